@@ -1,0 +1,63 @@
+/* rddl_b200.h -- C ABI of the B200 batched RDDL stepping backend.
+ *
+ * This is the boundary a pyRDDLGym maintainer binds (ctypes) to replace
+ * the NumPy evaluator behind RDDLSimulator.step and the check_* methods. Each entry point
+ * names the reference interface it replaces (paths relative to the pyRDDLGym repository).
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a
+ * negative error code, and rddl_last_error() describes the failure; no exceptions cross the
+ * ABI. All tensor pointers are DEVICE pointers owned by the caller (C-order, dtype per
+ * pyRDDLGym/core/compiler/initializer.py:16-23: bool = uint8, int = int64, real = float64),
+ * fluents carry a leading env axis [n_envs, ...], non-fluents are shared by all envs.
+ * Calls are asynchronous on the given CUDA stream.
+ */
+#ifndef RDDL_B200_H
+#define RDDL_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rddl_program rddl_program_t;
+
+enum { RDDL_PLAN_STEP = 0, RDDL_PLAN_TERMINAL = 1, RDDL_PLAN_INVARIANT = 2, RDDL_PLAN_PRECONDITION = 3 };
+enum { RDDL_OK = 0, RDDL_ERR_FORMAT = -1, RDDL_ERR_CUDA = -2, RDDL_ERR_ARG = -3 };
+
+/* Replaces RDDLSimulator._compile's product (pyRDDLGym/core/simulator.py:136-174): takes the
+ * lowered op table (pyrddlgym_b200/optable.py) and uploads it to `device`. */
+int rddl_program_create(const void* optable, size_t nbytes, int device, rddl_program_t** out);
+void rddl_program_destroy(rddl_program_t* prog);
+
+/* Text of the last error on this program (or of the last failed create if prog == NULL). */
+const char* rddl_last_error(const rddl_program_t* prog);
+
+/* what: 0 = #tensors, 1 = #variate slots, 2 = #launches of the step plan, 3 = total #instructions,
+ * 4 = kernel launches issued since create. */
+int64_t rddl_program_info(const rddl_program_t* prog, int what);
+
+/* Replaces RDDLSimulator.step (pyRDDLGym/core/simulator.py:442-502) for n_envs environments:
+ * evaluates every CPF in level order, the reward and the terminations on the new state.
+ *   tensors[id]  device pointer per op-table tensor id (state, next-state, action, interm,
+ *                non-fluent, then __reward f64[n], __done u8[n], __chk u8[n, width]);
+ *                next-state tensors are written, the caller swaps state/next pointers after.
+ *   injected     NULL, or per variate slot a device pointer to pre-drawn base variates
+ *                f64[n_envs, *scope] (NULL entries draw Philox4x32-10 keyed by
+ *                (seed, env_offset + env, step, node id, element)).
+ *   status       u32[n_envs] error bits OR-ed in (replaces the exceptions raised by
+ *                _check_positive/_check_bounds/_check_range, simulator.py:229-253). */
+int rddl_step(rddl_program_t* prog, void* const* tensors, const double* const* injected,
+              uint32_t* status, int64_t n_envs, int64_t env_offset, uint64_t seed, uint64_t step,
+              void* cuda_stream);
+
+/* Replaces check_state_invariants / check_action_preconditions / check_terminal_states
+ * (pyRDDLGym/core/simulator.py:362-399). which = RDDL_PLAN_INVARIANT | _PRECONDITION writes one
+ * bool per expression into __chk[n, width]; RDDL_PLAN_TERMINAL writes __done[n]. */
+int rddl_check(rddl_program_t* prog, int which, void* const* tensors, uint32_t* status,
+               int64_t n_envs, int64_t env_offset, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,84 @@
+// Op-table structs shared by host (C-ABI) and device (level interpreter).
+// Field-for-field mirror of pyrddlgym_b200/optable.py -- keep the two in sync.
+#pragma once
+#include <stdint.h>
+
+#define RDDL_MAGIC 0x31304C444452ll
+#define RDDL_VERSION 3
+#define RDDL_MAX_IDX 8
+#define RDDL_MAX_RED 8
+#define RDDL_MAX_REGS 96
+#define RDDL_MAX_TENSORS 120
+#define RDDL_MAX_VARIATES 64
+
+enum RddlOp : uint8_t {
+  OP_NOP, OP_CONST, OP_AXIS, OP_LOAD, OP_STORE, OP_MOV, OP_I2F, OP_F2I,
+  OP_FADD, OP_FSUB, OP_FMUL, OP_FDIV, OP_FNEG, OP_FABS, OP_FMIN, OP_FMAX, OP_FPOW, OP_FMOD, OP_FLOGB,
+  OP_FHYPOT, OP_COS, OP_SIN, OP_TAN, OP_ACOS, OP_ASIN, OP_ATAN, OP_COSH, OP_SINH, OP_TANH, OP_EXP, OP_LN,
+  OP_SQRT, OP_LNGAMMA, OP_GAMMA, OP_FSGN, OP_FROUND, OP_FFLOOR, OP_FCEIL,
+  OP_IADD, OP_ISUB, OP_IMUL, OP_INEG, OP_IABS, OP_IMIN, OP_IMAX, OP_IPOW, OP_IFLOORDIV, OP_IMOD, OP_ISGN,
+  OP_FLT, OP_FLE, OP_FGT, OP_FGE, OP_FEQ, OP_FNE, OP_ILT, OP_ILE, OP_IGT, OP_IGE, OP_IEQ, OP_INE,
+  OP_AND, OP_OR, OP_XOR, OP_NOT, OP_IMPLY,
+  OP_SEL,
+  OP_LOOP, OP_ENDLOOP, OP_CSRLOOP, OP_CSREND,
+  OP_RANDU, OP_RANDN, OP_RANDE, OP_RANDC,
+  OP_REDOUT, OP_REDIN, OP_STATUS,
+  OP_EXPM1, OP_LOG1P,
+  OP_COUNT_
+};
+
+enum RddlRed { RED_SUM_I, RED_SUM_F, RED_PROD_I, RED_PROD_F, RED_MIN_I, RED_MIN_F, RED_MAX_I, RED_MAX_F,
+               RED_AND, RED_OR };
+enum RddlDtype { DT_BOOL = 0, DT_INT = 1, DT_REAL = 2 };
+enum RddlKind { KIND_SHARED = 0, KIND_ENV = 1 };
+
+struct RddlInsn {      // 16 bytes
+  uint8_t op, flags;
+  uint16_t dst, a, b, c, pad;
+  uint32_t imm;
+};
+
+struct RddlAddr {      // 184 bytes: element offset = env*env_stride + c0 + sum coef*idx + sum clamp(reg)*rstride
+  int32_t tensor;      // >= 0 tensor id; < 0: variate slot -(1+slot)
+  int32_t naxis;
+  int64_t env_stride;
+  int64_t c0;
+  uint8_t axis[8];
+  int64_t coef[8];
+  int32_t nreg, pad;
+  int32_t reg[4];
+  int64_t rstride[4];
+  int64_t rextent[4];
+};
+
+struct RddlCsr {       // 152 bytes
+  int64_t rowptr_off;
+  int32_t ncols, pad;
+  int64_t col_off[4];
+  int32_t slot[4];
+  int64_t row_c0;
+  int32_t row_naxis, pad2;
+  uint8_t row_axis[8];
+  int64_t row_coef[8];
+};
+
+struct RddlTensor { int32_t dtype, kind; int64_t nelem; };
+
+struct RddlLaunch {    // 176 bytes
+  int32_t plan, rank;
+  int64_t extent[8];
+  int64_t E;
+  int32_t pc_begin, pc_end;
+  int32_t nred, G, ipt, chunks;
+  int32_t red_op[8];
+  int32_t red_slot[8];
+  int32_t nregs, pad;
+};
+
+struct RddlRedSlot { int32_t op, chunks; };
+struct RddlVariate { int32_t node, kind; int64_t nelem; };
+
+static_assert(sizeof(RddlInsn) == 16, "insn");
+static_assert(sizeof(RddlAddr) == 184, "addr");
+static_assert(sizeof(RddlCsr) == 152, "csr");
+static_assert(sizeof(RddlLaunch) == 176, "launch");

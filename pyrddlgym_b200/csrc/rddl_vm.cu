@@ -1,0 +1,563 @@
+// Fused level interpreter for batched RDDL stepping on sm_100a, and its C ABI.
+//
+// One thread evaluates the op-table program of one launch for one (env, scope element)
+// pair; the launches of a plan are the fused CPF levels produced by
+// pyrddlgym_b200/lowering.py. This replaces the recursive NumPy tree walk of
+// RDDLSimulator._sample (pyRDDLGym/core/simulator.py:508-537) and everything it dispatches to
+// (operators :584-952, distributions :958-1268).
+//
+// Thread mapping: a group of G consecutive threads works on one env (G = 1 for scope-free
+// programs, 256 for large scopes), a CTA holds 256/G envs; large scopes are split into
+// `chunks` CTAs per env, each thread visiting `ipt` elements strided by G so that
+// consecutive threads touch consecutive elements (coalesced loads of state / action planes).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/rddl_b200.h"
+#include "philox.cuh"
+#include "rddl_plan.h"
+
+struct VmArgs {
+  const RddlInsn* insns;
+  const uint64_t* consts;
+  const RddlAddr* addrs;
+  const RddlCsr* csrs;
+  const int32_t* pool;
+  const RddlVariate* variates;
+  const RddlRedSlot* redslots;
+  const int64_t* red_off;      // per slot: element offset (in units of n_envs) into `red`
+  uint64_t* red;
+  uint32_t* status;
+  int64_t n_envs, env_offset;
+  uint64_t seed, step;
+  RddlLaunch L;
+  void* tensors[RDDL_MAX_TENSORS];
+  uint8_t dtype[RDDL_MAX_TENSORS];
+  const double* inj[RDDL_MAX_VARIATES];
+};
+
+__device__ __forceinline__ double as_f(uint64_t v) { return __longlong_as_double((long long)v); }
+__device__ __forceinline__ uint64_t from_f(double v) { return (uint64_t)__double_as_longlong(v); }
+
+// simulator.py:1425-1441 (Stirling series after shifting the argument to >= 7)
+__device__ double rddl_lngamma(double x) {
+  double corr = 0.0;
+  for (int i = 0; i < 4; ++i) {
+    if (x < 7.0) {
+      corr += log(x) + log(x + 1.0);
+      x += 2.0;
+    }
+  }
+  double y2 = x * x;
+  double res = (x - 0.5) * log(x) - x + 0.5 * log(2.0 * 3.141592653589793) +
+               1.0 / (12.0 * x) *
+                   (1.0 + 1.0 / (30.0 * y2) *
+                              (-1.0 + 1.0 / (7.0 * y2 / 2.0) *
+                                          (1.0 + 1.0 / (4.0 * y2 / 3.0) *
+                                                     (-1.0 + 1.0 / (99.0 * y2 / 140.0) *
+                                                                 (1.0 + 1.0 / (910.0 * y2 / 3.0))))));
+  return res - corr;
+}
+
+__device__ __forceinline__ int64_t ipow64(int64_t a, int64_t b) {
+  if (b < 0) return a == 1 ? 1 : (a == -1 ? ((b & 1) ? -1 : 1) : 0);
+  int64_t r = 1;
+  while (b) {
+    if (b & 1) r *= a;
+    a *= a;
+    b >>= 1;
+  }
+  return r;
+}
+
+__device__ __forceinline__ uint64_t red_identity(int op) {
+  switch (op) {
+    case RED_SUM_I: return 0;
+    case RED_SUM_F: return from_f(0.0);
+    case RED_PROD_I: return 1;
+    case RED_PROD_F: return from_f(1.0);
+    case RED_MIN_I: return (uint64_t)INT64_MAX;
+    case RED_MIN_F: return from_f(INFINITY);
+    case RED_MAX_I: return (uint64_t)INT64_MIN;
+    case RED_MAX_F: return from_f(-INFINITY);
+    case RED_AND: return 1;
+    default: return 0;
+  }
+}
+
+__device__ __forceinline__ double np_fmin(double a, double b) {
+  return (isnan(a) || isnan(b)) ? NAN : fmin(a, b);
+}
+__device__ __forceinline__ double np_fmax(double a, double b) {
+  return (isnan(a) || isnan(b)) ? NAN : fmax(a, b);
+}
+
+__device__ __forceinline__ uint64_t red_combine(int op, uint64_t a, uint64_t b) {
+  switch (op) {
+    case RED_SUM_I: return (uint64_t)((int64_t)a + (int64_t)b);
+    case RED_SUM_F: return from_f(as_f(a) + as_f(b));
+    case RED_PROD_I: return (uint64_t)((int64_t)a * (int64_t)b);
+    case RED_PROD_F: return from_f(as_f(a) * as_f(b));
+    case RED_MIN_I: return (uint64_t)min((long long)a, (long long)b);
+    case RED_MIN_F: return from_f(np_fmin(as_f(a), as_f(b)));
+    case RED_MAX_I: return (uint64_t)max((long long)a, (long long)b);
+    case RED_MAX_F: return from_f(np_fmax(as_f(a), as_f(b)));
+    case RED_AND: return a & b;
+    default: return a | b;
+  }
+}
+
+template <int NREG>
+__global__ void __launch_bounds__(256) rddl_level_interp(const __grid_constant__ VmArgs A) {
+  const RddlLaunch& L = A.L;
+  const int G = L.G;
+  const int tid = threadIdx.x;
+  const int lane = tid & (G - 1);
+  const int envs_per_cta = 256 / G;
+  const int64_t chunk = blockIdx.x % L.chunks;
+  const int64_t env = (int64_t)(blockIdx.x / L.chunks) * envs_per_cta + tid / G;
+  const bool env_ok = env < A.n_envs;
+
+  uint64_t r[NREG];
+  int32_t idx[RDDL_MAX_IDX];
+  int32_t jcur[4], jend[4];
+  uint64_t redval[RDDL_MAX_RED];
+#pragma unroll
+  for (int j = 0; j < RDDL_MAX_RED; ++j) redval[j] = j < L.nred ? red_identity(L.red_op[j]) : 0;
+
+  const int npc = L.pc_end - L.pc_begin;
+  const RddlInsn* prog = A.insns + L.pc_begin;
+
+  for (int it = 0; it < L.ipt; ++it) {
+    const int64_t elem = chunk * ((int64_t)G * L.ipt) + (int64_t)it * G + lane;
+    if (!env_ok || elem >= L.E) continue;
+    {  // decode the element index into scope coordinates (C order)
+      int64_t rem = elem;
+      for (int k = L.rank - 1; k >= 0; --k) {
+        int64_t e = L.extent[k];
+        idx[k] = (int32_t)(rem % e);
+        rem /= e;
+      }
+    }
+    int pc = 0;
+    while (pc < npc) {
+      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(prog + pc));
+      const uint32_t op = raw.x & 0xff;
+      const uint32_t dst = raw.x >> 16;
+      const uint32_t ra = raw.y & 0xffff, rb = raw.y >> 16;
+      const uint32_t rc = raw.z & 0xffff;
+      const uint32_t imm = raw.w;
+      ++pc;
+#define RA r[ra]
+#define RB r[rb]
+#define FA as_f(r[ra])
+#define FB as_f(r[rb])
+#define IA ((int64_t)r[ra])
+#define IB ((int64_t)r[rb])
+#define SETF(v) r[dst] = from_f(v)
+#define SETI(v) r[dst] = (uint64_t)(int64_t)(v)
+      switch (op) {
+        case OP_NOP: break;
+        case OP_CONST: r[dst] = __ldg(A.consts + imm); break;
+        case OP_AXIS: SETI(idx[ra]); break;
+        case OP_MOV: r[dst] = RA; break;
+        case OP_I2F: SETF((double)IA); break;
+        case OP_F2I: SETI(__double2ll_rz(FA)); break;
+        case OP_LOAD:
+        case OP_STORE:
+        case OP_RANDU:
+        case OP_RANDN:
+        case OP_RANDE:
+        case OP_RANDC: {
+          const RddlAddr* ad = A.addrs + imm;
+          int64_t off = ad->c0;
+          const int na = ad->naxis;
+          for (int i = 0; i < na; ++i) off += ad->coef[i] * (int64_t)idx[ad->axis[i]];
+          const int nr = ad->nreg;
+          for (int i = 0; i < nr; ++i) {
+            int64_t v = (int64_t)r[ad->reg[i]];
+            const int64_t ext = ad->rextent[i];
+            if (v < 0 || v >= ext) {
+              atomicOr(A.status + env, 8u);
+              v = v < 0 ? 0 : ext - 1;
+            }
+            off += v * ad->rstride[i];
+          }
+          const int t = ad->tensor;
+          if (op == OP_LOAD) {
+            off += env * ad->env_stride;
+            const void* base = A.tensors[t];
+            const int dt = A.dtype[t];
+            if (dt == DT_BOOL) r[dst] = reinterpret_cast<const uint8_t*>(base)[off] != 0;
+            else r[dst] = reinterpret_cast<const uint64_t*>(base)[off];
+          } else if (op == OP_STORE) {
+            off += env * ad->env_stride;
+            void* base = A.tensors[t];
+            const int dt = A.dtype[t];
+            if (dt == DT_BOOL) reinterpret_cast<uint8_t*>(base)[off] = RA != 0;
+            else reinterpret_cast<uint64_t*>(base)[off] = RA;
+          } else {
+            const int slot = (int)ra;
+            const double* inj = A.inj[slot];
+            double v;
+            if (inj) {
+              v = inj[env * ad->env_stride + off];
+            } else {
+              const uint32_t node = (uint32_t)A.variates[slot].node;
+              uint4 x = rddl_philox_draw(A.seed, (uint64_t)(A.env_offset + env), A.step, node, (uint64_t)off);
+              const double u = rddl_u53(x.x, x.y);
+              if (op == OP_RANDU) v = u;
+              else if (op == OP_RANDN) v = sqrt(-2.0 * log(1.0 - u)) * cos(2.0 * 3.141592653589793 * rddl_u53(x.z, x.w));
+              else if (op == OP_RANDE) v = -log1p(-u);
+              else v = tan(3.141592653589793 * (u - 0.5));
+            }
+            SETF(v);
+          }
+          break;
+        }
+        case OP_FADD: SETF(FA + FB); break;
+        case OP_FSUB: SETF(FA - FB); break;
+        case OP_FMUL: SETF(FA * FB); break;
+        case OP_FDIV: SETF(FA / FB); break;
+        case OP_FNEG: SETF(-FA); break;
+        case OP_FABS: SETF(fabs(FA)); break;
+        case OP_FMIN: SETF(np_fmin(FA, FB)); break;
+        case OP_FMAX: SETF(np_fmax(FA, FB)); break;
+        case OP_FPOW: SETF(pow(FA, FB)); break;
+        case OP_FMOD: {  // np.mod (sign of the divisor), simulator.py:117-118
+          const double a = FA, b = FB;
+          double m = fmod(a, b);
+          if (b != 0.0) {
+            if (m != 0.0) { if ((b < 0) != (m < 0)) m += b; }
+            else m = copysign(0.0, b);
+          }
+          SETF(m);
+          break;
+        }
+        case OP_FLOGB: SETF(log(FA) / log(FB)); break;
+        case OP_FHYPOT: SETF(hypot(FA, FB)); break;
+        case OP_COS: SETF(cos(FA)); break;
+        case OP_SIN: SETF(sin(FA)); break;
+        case OP_TAN: SETF(tan(FA)); break;
+        case OP_ACOS: SETF(acos(FA)); break;
+        case OP_ASIN: SETF(asin(FA)); break;
+        case OP_ATAN: SETF(atan(FA)); break;
+        case OP_COSH: SETF(cosh(FA)); break;
+        case OP_SINH: SETF(sinh(FA)); break;
+        case OP_TANH: SETF(tanh(FA)); break;
+        case OP_EXP: SETF(exp(FA)); break;
+        case OP_LN: SETF(log(FA)); break;
+        case OP_SQRT: SETF(sqrt(FA)); break;
+        case OP_EXPM1: SETF(expm1(FA)); break;
+        case OP_LOG1P: SETF(log1p(FA)); break;
+        case OP_LNGAMMA: SETF(rddl_lngamma(FA)); break;
+        case OP_GAMMA: SETF(exp(rddl_lngamma(FA))); break;
+        case OP_FSGN: { const double a = FA; SETI((a > 0) - (a < 0)); break; }
+        case OP_FROUND: SETI(__double2ll_rn(FA)); break;
+        case OP_FFLOOR: SETI(__double2ll_rd(FA)); break;
+        case OP_FCEIL: SETI(__double2ll_ru(FA)); break;
+        case OP_IADD: SETI(IA + IB); break;
+        case OP_ISUB: SETI(IA - IB); break;
+        case OP_IMUL: SETI(IA * IB); break;
+        case OP_INEG: SETI(-IA); break;
+        case OP_IABS: SETI(llabs(IA)); break;
+        case OP_IMIN: SETI(min((long long)IA, (long long)IB)); break;
+        case OP_IMAX: SETI(max((long long)IA, (long long)IB)); break;
+        case OP_IPOW: SETI(ipow64(IA, IB)); break;
+        case OP_IFLOORDIV: {
+          const int64_t a = IA, b = IB;
+          int64_t q = 0;
+          if (b != 0) { q = a / b; if ((a % b != 0) && ((a < 0) != (b < 0))) --q; }
+          SETI(q);
+          break;
+        }
+        case OP_IMOD: {
+          const int64_t a = IA, b = IB;
+          int64_t m = 0;
+          if (b != 0) { m = a % b; if (m != 0 && ((m < 0) != (b < 0))) m += b; }
+          SETI(m);
+          break;
+        }
+        case OP_ISGN: { const int64_t a = IA; SETI((a > 0) - (a < 0)); break; }
+        case OP_FLT: SETI(FA < FB); break;
+        case OP_FLE: SETI(FA <= FB); break;
+        case OP_FGT: SETI(FA > FB); break;
+        case OP_FGE: SETI(FA >= FB); break;
+        case OP_FEQ: SETI(FA == FB); break;
+        case OP_FNE: SETI(FA != FB); break;
+        case OP_ILT: SETI(IA < IB); break;
+        case OP_ILE: SETI(IA <= IB); break;
+        case OP_IGT: SETI(IA > IB); break;
+        case OP_IGE: SETI(IA >= IB); break;
+        case OP_IEQ: SETI(IA == IB); break;
+        case OP_INE: SETI(IA != IB); break;
+        case OP_AND: r[dst] = (RA & RB) & 1; break;
+        case OP_OR: r[dst] = (RA | RB) & 1; break;
+        case OP_XOR: r[dst] = (RA ^ RB) & 1; break;
+        case OP_NOT: r[dst] = RA == 0; break;
+        case OP_IMPLY: r[dst] = ((RA == 0) | RB) & 1; break;
+        case OP_SEL: r[dst] = RA ? RB : r[rc]; break;
+        case OP_LOOP:
+          idx[ra] = 0;
+          if (imm == 0) pc = (int)rb;
+          break;
+        case OP_ENDLOOP:
+          if ((uint32_t)(++idx[ra]) < imm) pc = (int)rb;
+          break;
+        case OP_CSRLOOP:
+        case OP_CSREND: {
+          const RddlCsr* cs = A.csrs + imm;
+          int32_t j;
+          if (op == OP_CSRLOOP) {
+            int64_t row = cs->row_c0;
+            for (int i = 0; i < cs->row_naxis; ++i) row += cs->row_coef[i] * (int64_t)idx[cs->row_axis[i]];
+            j = __ldg(A.pool + cs->rowptr_off + row);
+            jend[ra] = __ldg(A.pool + cs->rowptr_off + row + 1);
+            jcur[ra] = j;
+            if (j >= jend[ra]) { pc = (int)rb; break; }
+          } else {
+            j = ++jcur[ra];
+            if (j >= jend[ra]) break;
+            pc = (int)rb;
+          }
+          for (int c = 0; c < cs->ncols; ++c) idx[cs->slot[c]] = __ldg(A.pool + cs->col_off[c] + j);
+          break;
+        }
+        case OP_REDOUT: redval[rb] = red_combine(L.red_op[rb], redval[rb], RA); break;
+        case OP_REDIN: {
+          const RddlRedSlot s = A.redslots[imm];
+          const uint64_t* base = A.red + (A.red_off[imm] * A.n_envs + env * s.chunks);
+          uint64_t acc = base[0];
+          for (int c = 1; c < s.chunks; ++c) acc = red_combine(s.op, acc, base[c]);
+          r[dst] = acc;
+          break;
+        }
+        case OP_STATUS:
+          if (RA) atomicOr(A.status + env, imm);
+          break;
+        default: break;
+      }
+    }
+  }
+
+  // per-env reductions: shuffle within the group, shared memory across warps when G = 256
+  if (L.nred > 0) {
+    __shared__ uint64_t sm[RDDL_MAX_RED][8];
+    for (int j = 0; j < L.nred; ++j) {
+      const int op = L.red_op[j];
+      uint64_t v = redval[j];
+      const int w = G < 32 ? G : 32;
+      for (int o = w >> 1; o > 0; o >>= 1) v = red_combine(op, v, __shfl_xor_sync(0xffffffffu, v, o, 32));
+      if (G > 32) {
+        if ((tid & 31) == 0) sm[j][tid >> 5] = v;
+      } else if (lane == 0 && env_ok) {
+        A.red[A.red_off[L.red_slot[j]] * A.n_envs + env * L.chunks + chunk] = v;
+      }
+    }
+    if (G > 32) {
+      __syncthreads();
+      const int nw = G / 32;  // warps per group
+      if (lane == 0 && env_ok) {
+        const int w0 = (tid / G) * nw;
+        for (int j = 0; j < L.nred; ++j) {
+          const int op = L.red_op[j];
+          uint64_t v = sm[j][w0];
+          for (int w = 1; w < nw; ++w) v = red_combine(op, v, sm[j][w0 + w]);
+          A.red[A.red_off[L.red_slot[j]] * A.n_envs + env * L.chunks + chunk] = v;
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side: op-table parsing and the C ABI
+// ---------------------------------------------------------------------------------------
+
+static thread_local std::string g_create_error;
+
+struct rddl_program {
+  int device = 0;
+  std::string err;
+  std::vector<RddlTensor> tensors;
+  std::vector<RddlLaunch> launches;
+  std::vector<RddlRedSlot> redslots;
+  std::vector<RddlVariate> variates;
+  std::vector<int64_t> red_off;
+  int64_t red_total = 0;  // sum of chunks over slots
+  int64_t n_insns = 0;
+  int64_t launches_issued = 0;
+  // device copies
+  RddlInsn* d_insns = nullptr;
+  uint64_t* d_consts = nullptr;
+  RddlAddr* d_addrs = nullptr;
+  RddlCsr* d_csrs = nullptr;
+  int32_t* d_pool = nullptr;
+  RddlVariate* d_variates = nullptr;
+  RddlRedSlot* d_redslots = nullptr;
+  int64_t* d_red_off = nullptr;
+  uint64_t* d_red = nullptr;
+  int64_t red_capacity_envs = 0;
+  uint32_t* d_status_dummy = nullptr;
+};
+
+#define CK(call)                                                                      \
+  do {                                                                                \
+    cudaError_t e_ = (call);                                                          \
+    if (e_ != cudaSuccess) {                                                          \
+      char buf_[512];                                                                 \
+      snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      *errp = buf_;                                                                   \
+      return RDDL_ERR_CUDA;                                                           \
+    }                                                                                 \
+  } while (0)
+
+template <typename T>
+static int upload(const void* src, int64_t n, T** dst, std::string* errp) {
+  *dst = nullptr;
+  CK(cudaMalloc((void**)dst, (size_t)(n > 0 ? n : 1) * sizeof(T)));
+  if (n > 0) CK(cudaMemcpy(*dst, src, (size_t)n * sizeof(T), cudaMemcpyHostToDevice));
+  return RDDL_OK;
+}
+
+extern "C" int rddl_program_create(const void* optable, size_t nbytes, int device, rddl_program_t** out) {
+  std::string* errp = &g_create_error;
+  if (!optable || !out || nbytes < 16 * sizeof(int64_t)) { *errp = "bad arguments"; return RDDL_ERR_ARG; }
+  const uint8_t* p = (const uint8_t*)optable;
+  int64_t hdr[16];
+  memcpy(hdr, p, sizeof hdr);
+  if (hdr[0] != RDDL_MAGIC || hdr[1] != RDDL_VERSION) { *errp = "op table: bad magic/version"; return RDDL_ERR_FORMAT; }
+  const size_t sizes[9] = {sizeof(RddlTensor), sizeof(RddlLaunch), sizeof(RddlInsn), 8, sizeof(RddlAddr),
+                           sizeof(RddlCsr), 4, sizeof(RddlRedSlot), sizeof(RddlVariate)};
+  const uint8_t* sec[9];
+  size_t off = sizeof hdr;
+  for (int i = 0; i < 9; ++i) {
+    sec[i] = p + off;
+    size_t b = (size_t)hdr[2 + i] * sizes[i];
+    off += (b + 7) & ~(size_t)7;
+  }
+  if (off > nbytes) { *errp = "op table: truncated"; return RDDL_ERR_FORMAT; }
+  if (hdr[2] > RDDL_MAX_TENSORS) { *errp = "op table: too many tensors"; return RDDL_ERR_FORMAT; }
+  if (hdr[10] > RDDL_MAX_VARIATES) { *errp = "op table: too many random nodes"; return RDDL_ERR_FORMAT; }
+  rddl_program* g = new rddl_program();
+  errp = &g->err;
+  g->device = device;
+  g->tensors.assign((const RddlTensor*)sec[0], (const RddlTensor*)sec[0] + hdr[2]);
+  g->launches.assign((const RddlLaunch*)sec[1], (const RddlLaunch*)sec[1] + hdr[3]);
+  g->redslots.assign((const RddlRedSlot*)sec[7], (const RddlRedSlot*)sec[7] + hdr[9]);
+  g->variates.assign((const RddlVariate*)sec[8], (const RddlVariate*)sec[8] + hdr[10]);
+  g->n_insns = hdr[4];
+  for (auto& L : g->launches) {
+    if (L.nregs > RDDL_MAX_REGS || L.G < 1 || L.G > 256 || (L.G & (L.G - 1)) || L.nred > RDDL_MAX_RED) {
+      g_create_error = "op table: launch out of limits";
+      delete g;
+      return RDDL_ERR_FORMAT;
+    }
+  }
+  int64_t acc = 0;
+  for (auto& s : g->redslots) { g->red_off.push_back(acc); acc += s.chunks; }
+  g->red_total = acc;
+  int rc = RDDL_OK;
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) { g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e); delete g; return RDDL_ERR_CUDA; }
+  if ((rc = upload<RddlInsn>(sec[2], hdr[4], &g->d_insns, errp)) ||
+      (rc = upload<uint64_t>(sec[3], hdr[5], &g->d_consts, errp)) ||
+      (rc = upload<RddlAddr>(sec[4], hdr[6], &g->d_addrs, errp)) ||
+      (rc = upload<RddlCsr>(sec[5], hdr[7], &g->d_csrs, errp)) ||
+      (rc = upload<int32_t>(sec[6], hdr[8], &g->d_pool, errp)) ||
+      (rc = upload<RddlVariate>(sec[8], hdr[10], &g->d_variates, errp)) ||
+      (rc = upload<RddlRedSlot>(sec[7], hdr[9], &g->d_redslots, errp)) ||
+      (rc = upload<int64_t>(g->red_off.data(), (int64_t)g->red_off.size(), &g->d_red_off, errp))) {
+    g_create_error = g->err;
+    rddl_program_destroy(g);
+    return rc;
+  }
+  *out = g;
+  return RDDL_OK;
+}
+
+extern "C" void rddl_program_destroy(rddl_program_t* g) {
+  if (!g) return;
+  cudaSetDevice(g->device);
+  cudaFree(g->d_insns); cudaFree(g->d_consts); cudaFree(g->d_addrs); cudaFree(g->d_csrs);
+  cudaFree(g->d_pool); cudaFree(g->d_variates); cudaFree(g->d_redslots); cudaFree(g->d_red_off);
+  cudaFree(g->d_red);
+  delete g;
+}
+
+extern "C" const char* rddl_last_error(const rddl_program_t* g) {
+  return g ? g->err.c_str() : g_create_error.c_str();
+}
+
+extern "C" int64_t rddl_program_info(const rddl_program_t* g, int what) {
+  if (!g) return -1;
+  switch (what) {
+    case 0: return (int64_t)g->tensors.size();
+    case 1: return (int64_t)g->variates.size();
+    case 2: { int64_t n = 0; for (auto& L : g->launches) n += L.plan == RDDL_PLAN_STEP; return n; }
+    case 3: return g->n_insns;
+    case 4: return g->launches_issued;
+    default: return -1;
+  }
+}
+
+static int run_plan(rddl_program* g, int plan, void* const* tensors, const double* const* injected,
+                    uint32_t* status, int64_t n_envs, int64_t env_offset, uint64_t seed, uint64_t step,
+                    cudaStream_t stream) {
+  std::string* errp = &g->err;
+  if (!tensors || n_envs <= 0 || !status) { g->err = "bad arguments"; return RDDL_ERR_ARG; }
+  CK(cudaSetDevice(g->device));
+  if (g->red_total > 0 && g->red_capacity_envs < n_envs) {
+    // grow the per-env reduction scratch (not capturable: size the first call like the largest)
+    CK(cudaStreamSynchronize(stream));
+    cudaFree(g->d_red);
+    g->d_red = nullptr;
+    CK(cudaMalloc((void**)&g->d_red, (size_t)(g->red_total * n_envs) * sizeof(uint64_t)));
+    g->red_capacity_envs = n_envs;
+  }
+  VmArgs A;
+  memset(&A, 0, sizeof A);
+  A.insns = g->d_insns; A.consts = g->d_consts; A.addrs = g->d_addrs; A.csrs = g->d_csrs;
+  A.pool = g->d_pool; A.variates = g->d_variates; A.redslots = g->d_redslots; A.red_off = g->d_red_off;
+  A.red = g->d_red; A.status = status; A.n_envs = n_envs; A.env_offset = env_offset;
+  A.seed = seed; A.step = step;
+  for (size_t i = 0; i < g->tensors.size(); ++i) { A.tensors[i] = tensors[i]; A.dtype[i] = (uint8_t)g->tensors[i].dtype; }
+  if (injected) for (size_t i = 0; i < g->variates.size(); ++i) A.inj[i] = injected[i];
+  for (const RddlLaunch& L : g->launches) {
+    if (L.plan != plan) continue;
+    A.L = L;
+    const int envs_per_cta = 256 / L.G;
+    const int64_t groups = (n_envs + envs_per_cta - 1) / envs_per_cta;
+    const int64_t blocks = groups * L.chunks;
+    if (blocks > 0x7fffffffll) { g->err = "grid too large"; return RDDL_ERR_ARG; }
+    if (L.nregs <= 16) rddl_level_interp<16><<<(unsigned)blocks, 256, 0, stream>>>(A);
+    else if (L.nregs <= 40) rddl_level_interp<40><<<(unsigned)blocks, 256, 0, stream>>>(A);
+    else rddl_level_interp<RDDL_MAX_REGS><<<(unsigned)blocks, 256, 0, stream>>>(A);
+    ++g->launches_issued;
+    CK(cudaGetLastError());
+  }
+  return RDDL_OK;
+}
+
+extern "C" int rddl_step(rddl_program_t* g, void* const* tensors, const double* const* injected,
+                         uint32_t* status, int64_t n_envs, int64_t env_offset, uint64_t seed,
+                         uint64_t step, void* cuda_stream) {
+  if (!g) return RDDL_ERR_ARG;
+  return run_plan(g, RDDL_PLAN_STEP, tensors, injected, status, n_envs, env_offset, seed, step,
+                  (cudaStream_t)cuda_stream);
+}
+
+extern "C" int rddl_check(rddl_program_t* g, int which, void* const* tensors, uint32_t* status,
+                          int64_t n_envs, int64_t env_offset, void* cuda_stream) {
+  if (!g) return RDDL_ERR_ARG;
+  if (which != RDDL_PLAN_TERMINAL && which != RDDL_PLAN_INVARIANT && which != RDDL_PLAN_PRECONDITION) {
+    g->err = "rddl_check: bad plan";
+    return RDDL_ERR_ARG;
+  }
+  return run_plan(g, which, tensors, nullptr, status, n_envs, env_offset, 0, 0, (cudaStream_t)cuda_stream);
+}
