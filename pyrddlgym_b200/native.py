@@ -1,0 +1,87 @@
+"""ctypes binding of the C ABI declared in include/rddl_b200.h (librddl_b200.so).
+
+The library is built in-tree by ``__graft_entry__.build()`` / ``pyrddlgym_b200.build``.
+There is no CPU execution path: if the library is missing or the device is not CUDA the
+binding raises.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'csrc', 'librddl_b200.so')
+
+_lib = None
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeError(
+            f'{LIB_PATH} not found: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+            '(the B200 backend has no CPU fallback)')
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i64, u64 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint64
+    lib.rddl_program_create.argtypes = [vp, ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(vp)]
+    lib.rddl_program_create.restype = ctypes.c_int
+    lib.rddl_program_destroy.argtypes = [vp]
+    lib.rddl_program_destroy.restype = None
+    lib.rddl_last_error.argtypes = [vp]
+    lib.rddl_last_error.restype = ctypes.c_char_p
+    lib.rddl_program_info.argtypes = [vp, ctypes.c_int]
+    lib.rddl_program_info.restype = i64
+    lib.rddl_step.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), vp, i64, i64, u64, u64, vp]
+    lib.rddl_step.restype = ctypes.c_int
+    lib.rddl_check.argtypes = [vp, ctypes.c_int, ctypes.POINTER(vp), vp, i64, i64, vp]
+    lib.rddl_check.restype = ctypes.c_int
+    _lib = lib
+    return lib
+
+
+EXPORTS = ['rddl_program_create', 'rddl_program_destroy', 'rddl_last_error', 'rddl_program_info',
+           'rddl_step', 'rddl_check']
+
+
+class NativeProgram:
+    """Owns one ``rddl_program_t``."""
+
+    def __init__(self, blob, device_index):
+        self.lib = load()
+        self.handle = ctypes.c_void_p()
+        buf = ctypes.create_string_buffer(blob, len(blob))
+        rc = self.lib.rddl_program_create(ctypes.cast(buf, ctypes.c_void_p), len(blob), int(device_index),
+                                          ctypes.byref(self.handle))
+        if rc != 0:
+            raise NativeError('rddl_program_create failed (%d): %s'
+                              % (rc, self.lib.rddl_last_error(None).decode()))
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise NativeError('%s failed (%d): %s' % (what, rc, self.lib.rddl_last_error(self.handle).decode()))
+
+    def info(self, what):
+        return int(self.lib.rddl_program_info(self.handle, what))
+
+    def step(self, ptrs, injected, status_ptr, n_envs, env_offset, seed, step, stream):
+        self._check(self.lib.rddl_step(self.handle, ptrs, injected, status_ptr, n_envs, env_offset,
+                                       seed, step, stream), 'rddl_step')
+
+    def check(self, which, ptrs, status_ptr, n_envs, env_offset, stream):
+        self._check(self.lib.rddl_check(self.handle, which, ptrs, status_ptr, n_envs, env_offset, stream),
+                    'rddl_check')
+
+    def close(self):
+        if self.handle:
+            self.lib.rddl_program_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

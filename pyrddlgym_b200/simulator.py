@@ -1,0 +1,197 @@
+"""Batched RDDL simulator on B200: the host-side mirror of ``RDDLSimulator``'s
+reset / step / check_* interface (/root/reference/pyRDDLGym/core/simulator.py:362-502)
+with a leading env axis on every fluent.
+
+State lives in torch CUDA tensors (bool / int64 / float64, C order -- the dtypes of
+compiler/initializer.py:16-23); each ``step`` issues the launches of the lowered op
+table through the C ABI (include/rddl_b200.h) on torch's current stream and then swaps
+the state / next-state buffers (the reference aliases them, simulator.py:463-466).
+There is no CPU execution path.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from pyrddlgym_b200 import lowering, native, optable as ot
+
+_TORCH_DT = {'b': torch.bool, 'i': torch.int64, 'f': torch.float64}
+
+
+class StatusError(RuntimeError):
+    """Raised by ``raise_for_status`` when a kernel flagged an invalid distribution parameter
+    (the reference raises RDDLValueOutOfRangeError from inside _sample_*, simulator.py:229-253)."""
+
+    def __init__(self, msg, status):
+        super().__init__(msg)
+        self.status = status
+
+
+class BatchedSimulator:
+    """N independent environments of one compiled RDDL problem, stepped in lock-step."""
+
+    def __init__(self, program, n_envs=1, device='cuda:0', seed=0, env_offset=0, optable=None):
+        self.program = program
+        self.n_envs = int(n_envs)
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise native.NativeError('the B200 backend runs on CUDA devices only (no CPU fallback)')
+        self.seed_value = int(seed)
+        self.env_offset = int(env_offset)
+        self.table = optable if optable is not None else lowering.lower(program)
+        index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.native = native.NativeProgram(self.table.blob, index)
+        self.names = list(self.table.tensor_names)
+        self.tid = self.table.tensor_id
+        self.state_names = list(program.next_state)
+        self.action_names = program.names_of_kind('action')
+        self.t = {}
+        with torch.cuda.device(self.device):
+            for name in self.names:
+                dt, kind, nelem = self.table.tensor_meta[name]
+                if name in program.tensors:
+                    shape = tuple(program.tensor_shape(name))
+                else:
+                    shape = (nelem,) if nelem > 1 else ()
+                if kind == ot.KIND_SHARED:
+                    v = torch.from_numpy(np.ascontiguousarray(program.init[name]))
+                    self.t[name] = v.to(self.device, dtype=_TORCH_DT[dt]).contiguous()
+                else:
+                    self.t[name] = torch.zeros((self.n_envs,) + shape, dtype=_TORCH_DT[dt], device=self.device)
+            self.status = torch.zeros(self.n_envs, dtype=torch.int32, device=self.device)
+        self._init = {name: torch.from_numpy(np.ascontiguousarray(program.init[name])).to(
+            self.device, dtype=_TORCH_DT[program.tensors[name].dtype])
+            for name in program.tensors if program.tensors[name].kind != 'nonfluent'}
+        self._ptrs = (ctypes.c_void_p * len(self.names))()
+        self._inj = (ctypes.c_void_p * max(1, len(self.table.variates)))()
+        self._external = {}
+        self.step_count = 0
+        self.reset()
+
+    # ------------------------------------------------------------------ plumbing
+    def _refresh_ptrs(self):
+        for i, name in enumerate(self.names):
+            self._ptrs[i] = self.t[name].data_ptr()
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def seed(self, seed):
+        self.seed_value = int(seed)
+
+    @property
+    def launches_issued(self):
+        return self.native.info(4)
+
+    # ------------------------------------------------------------------ reference API
+    def reset(self):
+        """simulator.py:405-440 -> (states, done[N])."""
+        for name, v in self._init.items():
+            self.t[name].copy_(v.expand_as(self.t[name]))
+        self.status.zero_()
+        self.step_count = 0
+        done = self.check_terminal_states()
+        return self.states, done
+
+    @property
+    def states(self):
+        """name -> tensor [N, *shape]; views of the live state buffers (valid until the next
+        step, like the reference's aliasing dict, simulator.py:176-179)."""
+        return {s: self.t[s] for s in self.state_names}
+
+    def fluent(self, name):
+        return self.t[name]
+
+    def set_actions(self, actions):
+        """simulator.py:259-327 for tensor inputs: each entry must be [N, *shape] (or
+        broadcastable); host arrays are copied to the device (pinned staging is the caller's
+        business), device tensors of the right dtype/layout are used in place."""
+        for name, v in actions.items():
+            if name not in self.tid or name not in self.action_names:
+                raise KeyError(f'<{name}> is not an action-fluent')
+            dst = self.t[name]
+            if isinstance(v, torch.Tensor):
+                if (v.device == dst.device and v.dtype == dst.dtype and v.shape == dst.shape
+                        and v.is_contiguous()):
+                    if v.data_ptr() != dst.data_ptr():
+                        self.t[name] = v          # zero-copy: read the caller's buffer directly
+                    continue
+                dst.copy_(v.to(dst.dtype).expand_as(dst) if v.shape != dst.shape else v, non_blocking=True)
+            else:
+                a = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(np.asarray(v), tuple(dst.shape))))
+                dst.copy_(a, non_blocking=True)
+
+    def step(self, actions=None, variates=None):
+        """simulator.py:442-502 for all envs -> (states, reward f64[N], done bool[N]).
+        ``variates``: AST node id -> pre-drawn base variates [N, *scope] (parity testing);
+        nodes not listed draw Philox."""
+        if actions:
+            self.set_actions(actions)
+        keep = []
+        for slot, (node, _, nelem) in enumerate(self.table.variates):
+            v = None if variates is None else variates.get(node, None)
+            if v is None:
+                self._inj[slot] = None
+            else:
+                tv = v if isinstance(v, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(v))
+                tv = tv.to(self.device, dtype=torch.float64).contiguous()
+                if tv.numel() != self.n_envs * nelem:
+                    raise ValueError(f'variates for node {node}: expected {self.n_envs * nelem} values')
+                keep.append(tv)
+                self._inj[slot] = tv.data_ptr()
+        self._refresh_ptrs()
+        self.native.step(self._ptrs, self._inj if variates else None, ctypes.c_void_p(self.status.data_ptr()),
+                         self.n_envs, self.env_offset, self.seed_value, self.step_count, self._stream())
+        for s, ns in self.program.next_state.items():
+            self.t[s], self.t[ns] = self.t[ns], self.t[s]
+        self.step_count += 1
+        self._keep = keep
+        return self.states, self.t['__reward'], self.t['__done']
+
+    def _run_check(self, plan):
+        self._refresh_ptrs()
+        self.native.check(plan, self._ptrs, ctypes.c_void_p(self.status.data_ptr()), self.n_envs,
+                          self.env_offset, self._stream())
+
+    def check_state_invariants(self):
+        """simulator.py:362-373 -> bool[N]."""
+        n = self.table.n_checks['invariant']
+        if n == 0:
+            return torch.ones(self.n_envs, dtype=torch.bool, device=self.device)
+        self._run_check(ot.PLAN_INVARIANT)
+        return self.t['__chk'].reshape(self.n_envs, -1)[:, :n].all(dim=1)
+
+    def check_action_preconditions(self, actions=None):
+        """simulator.py:375-389 (subs.update(actions) first) -> bool[N]."""
+        if actions:
+            self.set_actions(actions)
+        n = self.table.n_checks['precondition']
+        if n == 0:
+            return torch.ones(self.n_envs, dtype=torch.bool, device=self.device)
+        self._run_check(ot.PLAN_PRECONDITION)
+        return self.t['__chk'].reshape(self.n_envs, -1)[:, :n].all(dim=1)
+
+    def check_each(self, plan):
+        """bool[N, #expressions] of the last invariant / precondition evaluation."""
+        key = 'invariant' if plan == ot.PLAN_INVARIANT else 'precondition'
+        return self.t['__chk'].reshape(self.n_envs, -1)[:, :self.table.n_checks[key]]
+
+    def check_terminal_states(self):
+        """simulator.py:391-399 -> bool[N]."""
+        self._run_check(ot.PLAN_TERMINAL)
+        return self.t['__done']
+
+    def raise_for_status(self):
+        """Synchronises and raises if any env flagged an invalid distribution parameter."""
+        st = self.status.cpu().numpy().astype(np.uint32)
+        bad = np.nonzero(st)[0]
+        if len(bad):
+            bits = int(np.bitwise_or.reduce(st))
+            what = [n for (b, n) in [(ot.STATUS_OUT_OF_RANGE, 'distribution parameter out of range'),
+                                     (ot.STATUS_BAD_BOUNDS, 'Uniform bounds lb > ub'),
+                                     (ot.STATUS_BAD_PDF, 'Discrete probabilities do not sum to 1'),
+                                     (ot.STATUS_BAD_INDEX, 'object index out of range')] if bits & b]
+            raise StatusError('%s in %d env(s), first env %d' % ('; '.join(what), len(bad), int(bad[0])), st)
+
+    def close(self):
+        self.native.close()

@@ -546,3 +546,83 @@ WORKLOADS = {
     'pair_contraction': pair_contraction,
     'opzoo': opzoo,
 }
+
+
+# ---------------------------------------------------------------------------
+# instance tensors + compiled (lifted) programs
+# ---------------------------------------------------------------------------
+
+_DEFAULTS = {'bool': False, 'int': 0, 'real': 0.0}
+_NP_RANGE = {'bool': np.bool_, 'int': np.int64, 'real': np.float64}
+
+
+def instance_tensors(spec):
+    """Initial tensors of every pvariable of ``spec`` -- the same values
+    RDDLValueInitializer.initialize() produces
+    (/root/reference/pyRDDLGym/core/compiler/initializer.py:45-96,160-214): declared
+    default, overridden by the instance's init-non-fluent / init-state entries; object
+    valued fluents become canonical object indices (None -> 0); C order over parameters.
+    Primed copies of state fluents start from the same default."""
+    objects = {t: list(objs) for (t, objs) in spec['objects']}
+    enum_types = []
+    for (t, kind) in spec['types']:
+        if kind != 'object':
+            objects[t] = [o.lstrip('@') for o in kind]
+            enum_types.append(t)
+    index = {}
+    for t, objs in objects.items():
+        for i, o in enumerate(objs):
+            index[o.lstrip('@')] = i
+    sizes = {t: len(o) for t, o in objects.items()}
+    out = {}
+    meta = {}
+    for (name, ftype, rng, params, default) in spec['pvariables']:
+        shape = tuple(sizes[t] for t in (params or []))
+        if rng in _NP_RANGE:
+            dt = _NP_RANGE[rng]
+            dv = _DEFAULTS[rng] if default is None else default
+        else:
+            dt = np.int64
+            dv = 0 if default is None else index[str(default).lstrip('@')]
+        out[name] = np.full(shape, dv, dtype=dt)
+        meta[name] = (ftype, rng, params or [])
+        if ftype == 'state-fluent':
+            out[name + "'"] = np.full(shape, dv, dtype=dt)
+    for ((name, objs), value) in list(spec['init_non_fluent']) + list(spec['init_state']):
+        rng = meta[name][1]
+        if rng not in _NP_RANGE:
+            value = index[str(value).lstrip('@')]
+        pos = tuple(index[o.lstrip('@')] for o in (objs or []))
+        out[name][pos] = value
+    return out, objects, enum_types
+
+
+_PROGRAM_DIR = __import__('os').path.join(__import__('os').path.dirname(__import__('os').path.abspath(__file__)),
+                                          'programs')
+
+
+def program_path(spec_name):
+    import os
+    return os.path.join(_PROGRAM_DIR, spec_name + '.json')
+
+
+def load_program(spec):
+    """Compiled program for ``spec`` without the reference front end: the lifted HIR
+    (size independent; produced once from the reference's traced model by
+    oracle/gen_fixtures.py and stored in pyrddlgym_b200/programs/) re-instantiated with
+    this instance's object counts and initial tensors."""
+    import json
+    from pyrddlgym_b200 import hir
+    with open(program_path(spec['name'])) as f:
+        text = f.read()
+    init, objects, enum_types = instance_tensors(spec)
+    p = hir.Program.from_json(text, {})
+    p.types = {t: len(o) for t, o in objects.items()}
+    p.objects = objects
+    p.enum_types = sorted(enum_types)
+    p.init = {name: init[name] for name in p.tensors}
+    p.horizon = int(spec['horizon'])
+    p.discount = float(spec['discount'])
+    n_act = sum(int(np.prod(p.tensor_shape(n), dtype=np.int64)) for n in p.names_of_kind('action'))
+    p.max_allowed_actions = n_act if spec['max_nondef_actions'] == 'pos-inf' else int(spec['max_nondef_actions'])
+    return p

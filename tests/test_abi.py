@@ -1,0 +1,53 @@
+"""The C-ABI library builds, loads, and exports every symbol include/rddl_b200.h declares."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, 'include', 'rddl_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(rddl_[a-z_0-9]+)\s*\(', text)))
+
+
+def test_header_symbols_are_exported():
+    import __graft_entry__ as g
+    lib_path = g.build()
+    lib = ctypes.CDLL(lib_path)
+    names = _declared()
+    assert 'rddl_step' in names and 'rddl_program_create' in names
+    for n in names:
+        assert hasattr(lib, n), f'{n} declared in rddl_b200.h but not exported'
+    from pyrddlgym_b200 import native
+    assert sorted(native.EXPORTS) == [n for n in names if n in native.EXPORTS]
+    assert set(native.EXPORTS) <= set(names)
+
+
+def test_create_rejects_garbage_without_gpu():
+    from pyrddlgym_b200 import native
+    lib = native.load()
+    h = ctypes.c_void_p()
+    buf = ctypes.create_string_buffer(b'\0' * 256, 256)
+    rc = lib.rddl_program_create(ctypes.cast(buf, ctypes.c_void_p), 256, 0, ctypes.byref(h))
+    assert rc == -1
+    assert b'magic' in lib.rddl_last_error(None)
+
+
+def test_optable_structs_match_the_c_header():
+    from pyrddlgym_b200 import optable as ot
+    text = open(os.path.join(ROOT, 'pyrddlgym_b200', 'csrc', 'rddl_plan.h')).read()
+    ops = re.search(r'enum RddlOp : uint8_t \{(.*?)OP_COUNT_', text, re.S).group(1)
+    c_ops = [o.strip()[3:] for o in ops.replace('\n', ' ').split(',') if o.strip()]
+    assert c_ops == ot._OPS
+    assert int(re.search(r'RDDL_VERSION (\d+)', text).group(1)) == ot.VERSION
+
+
+def test_backend_refuses_cpu_device():
+    import pytest
+    from pyrddlgym_b200 import native, workloads
+    from pyrddlgym_b200.simulator import BatchedSimulator
+    p = workloads.load_program(workloads.cartpole())
+    with pytest.raises(native.NativeError):
+        BatchedSimulator(p, n_envs=2, device='cpu')

@@ -1,0 +1,173 @@
+"""GPU parity tests: the CUDA level interpreter, called through the C ABI, against
+(a) the reference-generated golden trajectories, (b) the NumPy oracle on seeded larger
+inputs, (c) the NumPy restatement of the Philox mapping, and (d) size-independent
+properties at sizes the oracle cannot reach."""
+import numpy as np
+import pytest
+
+import cases
+from oracle import harness
+from oracle.oracle_sim import OracleSimulator
+from pyrddlgym_b200 import workloads
+
+pytestmark = pytest.mark.gpu
+
+
+def _np(x):
+    import torch
+    return x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+
+
+def _make(p, n, **kw):
+    from pyrddlgym_b200.simulator import BatchedSimulator
+    return BatchedSimulator(p, n_envs=n, device='cuda:0', **kw)
+
+
+@pytest.mark.parametrize('case', sorted(cases.SPECS))
+def test_cuda_matches_reference_golden(case):
+    sim = cases.replay(case, _make, to_np=_np)
+    sim.raise_for_status()
+
+
+def _lockstep(spec, N, T, inject, seed=11, akw=None, rtol=cases.RTOL):
+    p = workloads.load_program(spec)
+    sim = _make(p, N, seed=seed)
+    ora = OracleSimulator(p, n_envs=N, seed=seed)
+    rng = np.random.default_rng(seed)
+    for t in range(T):
+        acts = harness.random_actions(p, N, rng, **(akw or {}))
+        var = harness.random_variates(p, N, rng) if inject else None
+        if p.preconditions:
+            cases.compare('pre', _np(sim.check_action_preconditions(acts)), ora.check_action_preconditions(acts))
+        _, r, d = sim.step(acts, var)
+        _, r0, d0 = ora.step(acts, var)
+        cases.compare(f'reward/{t}', _np(r), r0, rtol=rtol)
+        cases.compare(f'done/{t}', _np(d), d0)
+        if p.invariants:
+            cases.compare('inv', _np(sim.check_state_invariants()), ora.check_state_invariants())
+        for name, decl in p.tensors.items():
+            if decl.kind not in ('nonfluent', 'next', 'action'):
+                cases.compare(f'{name}/{t}', _np(sim.fluent(name)), ora.subs[name], rtol=rtol)
+    assert np.array_equal(_np(sim.status).astype(np.uint32), ora.status)
+    return sim, ora
+
+
+def test_wildfire32_injected_vs_oracle():
+    _lockstep(workloads.wildfire(32), N=8, T=6, inject=True, akw=dict(p_bool=0.05))
+
+
+def test_wildfire_separable_equals_4d_formulation():
+    # the two formulations agree wherever the neighbour aggregate is read
+    a = workloads.load_program(workloads.wildfire(16))
+    b = workloads.load_program(workloads.wildfire(16, separable=True))
+    N = 32
+    sa, sb = _make(a, N, seed=5), _make(b, N, seed=5)
+    rng = np.random.default_rng(0)
+    for t in range(10):
+        acts = harness.random_actions(a, N, rng, p_bool=0.03)
+        _, ra, _ = sa.step(acts)
+        _, rb, _ = sb.step(acts)
+        assert np.array_equal(_np(sa.fluent('burning')), _np(sb.fluent('burning')))
+        assert np.array_equal(_np(sa.fluent('out-of-fuel')), _np(sb.fluent('out-of-fuel')))
+        assert np.array_equal(_np(ra), _np(rb))
+
+
+@pytest.mark.parametrize('name,spec,akw', [
+    ('opzoo', lambda: workloads.opzoo(), {}),
+    ('cartpole', lambda: workloads.cartpole(), {}),
+    ('wildfire12', lambda: workloads.wildfire(12), dict(p_bool=0.05)),
+    ('reservoir', lambda: workloads.reservoir(64), {}),
+    ('reservoir_exp', lambda: workloads.reservoir(64, rain='exponential'), {}),
+    ('pair', lambda: workloads.pair_contraction(48), {}),
+])
+def test_native_philox_path_vs_oracle(name, spec, akw):
+    """No injected variates: both sides derive base variates from Philox4x32-10 counters
+    (oracle/philox_np.py restates csrc/philox.cuh); Bernoulli/Discrete draws are exact,
+    real-valued draws agree to libm rounding."""
+    _lockstep(spec(), N=5, T=4, inject=False, akw=akw)
+
+
+def test_shard_invariance():
+    """Results do not depend on how envs are split over devices: Philox counters use the
+    global env id (env_offset + local index)."""
+    p = workloads.load_program(workloads.wildfire(12))
+    N = 24
+    full = _make(p, N, seed=9)
+    lo = _make(p, N // 2, seed=9, env_offset=0)
+    hi = _make(p, N // 2, seed=9, env_offset=N // 2)
+    rng = np.random.default_rng(4)
+    for t in range(6):
+        acts = harness.random_actions(p, N, rng, p_bool=0.05)
+        full.step(acts)
+        lo.step({k: v[:N // 2] for k, v in acts.items()})
+        hi.step({k: v[N // 2:] for k, v in acts.items()})
+        for f in ('burning', 'out-of-fuel', '__reward'):
+            got = np.concatenate([_np(lo.fluent(f)), _np(hi.fluent(f))])
+            assert np.array_equal(got, _np(full.fluent(f))), f
+
+
+def test_bernoulli_moments_native_philox():
+    """Moment test of the native sampler path: fraction of ignitions next to k burning
+    neighbours ~ 1/(1+exp(4.5-k))."""
+    import torch
+    n = 16
+    p = workloads.load_program(workloads.wildfire(n))
+    N = 4096
+    sim = _make(p, N, seed=123)
+    burning0 = _np(sim.fluent('burning'))[0]
+    target = np.asarray(p.init['TARGET'])
+    sim.step({})
+    b1 = _np(sim.fluent('burning')).astype(np.float64).mean(axis=0)
+    pad = np.pad(burning0.astype(int), 1)
+    k = sum(pad[1 + dx:1 + dx + n, 1 + dy:1 + dy + n] for dx in (-1, 0, 1) for dy in (-1, 0, 1)
+            if (dx, dy) != (0, 0))
+    prob = 1.0 / (1.0 + np.exp(4.5 - k))
+    free = (~burning0) & ~(target & (k == 0))
+    sigma = np.sqrt(prob * (1 - prob) / N)
+    z = (b1 - prob)[free] / sigma[free]
+    assert np.abs(z).max() < 5.0, np.abs(z).max()
+    assert abs(z.mean()) < 0.5
+
+
+def test_full_size_properties_wildfire32_4096():
+    """BASELINE config 2 at full size: monotone fuel, fire only dies where put out,
+    reward equals its definition recomputed from the planes with torch."""
+    import torch
+    p = workloads.load_program(workloads.wildfire(32, separable=True))
+    N = 4096
+    sim = _make(p, N, seed=1)
+    g = torch.Generator(device='cuda').manual_seed(0)
+    target = torch.from_numpy(np.asarray(p.init['TARGET'])).cuda()
+    for t in range(5):
+        put = torch.rand((N, 32, 32), device='cuda', generator=g) < 0.05
+        cut = torch.rand((N, 32, 32), device='cuda', generator=g) < 0.05
+        b0 = sim.fluent('burning').clone()
+        f0 = sim.fluent('out-of-fuel').clone()
+        _, r, _ = sim.step({'put-out': put, 'cut-out': cut})
+        b1, f1 = sim.fluent('burning'), sim.fluent('out-of-fuel')
+        assert bool((f1 | ~f0).all())                                     # fuel never comes back
+        assert bool((f1 == (f0 | b0 | (~target & cut))).all())            # out-of-fuel' definition
+        assert not bool((b1 & put).any())                                 # put-out cells do not burn
+        assert bool((b1 | ~(b0 & ~put)).all())                            # burning persists unless put out
+        assert not bool((b1 & ~b0 & f0).any())                            # no ignition without fuel
+        want = (-5.0 * cut.sum((1, 2)) - 10.0 * put.sum((1, 2))
+                - 100.0 * ((b0 | f0) & target).sum((1, 2)) - 5.0 * (b0 & ~target).sum((1, 2))).double()
+        assert torch.equal(r, want)
+    sim.raise_for_status()
+
+
+def test_status_word_flags_invalid_distribution_parameters():
+    """Reservoir with a negative rain variance: the reference raises RDDLValueOutOfRangeError
+    (simulator.py:229-238); the kernels set the per-env status bit instead."""
+    from pyrddlgym_b200 import optable as ot
+    from pyrddlgym_b200.simulator import StatusError
+    spec = workloads.reservoir(8)
+    p = workloads.load_program(spec)
+    p.init['RAIN_VAR'] = np.asarray(p.init['RAIN_VAR']).copy()
+    p.init['RAIN_VAR'][3] = -1.0
+    sim = _make(p, 4)
+    sim.step({})
+    st = _np(sim.status)
+    assert (st & ot.STATUS_OUT_OF_RANGE).all()
+    with pytest.raises(StatusError):
+        sim.raise_for_status()
