@@ -1,0 +1,355 @@
+"""bench.py -- batched env-steps/sec of the B200 RDDL stepping backend (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload wildfire32]
+    python bench.py --impl reference ...        # CPU port of the reference algorithm (oracle)
+
+A "step" is one batched transition (RDDLSimulator.step for every env) of BASELINE.json
+config[1]: Wildfire 32x32, 4096 envs per GPU, random-policy actions (i.i.d. Bernoulli(0.05)
+put-out / cut-out per cell). `value` is timed with the action planes already resident in HBM
+(a rotating pool larger than L2); `e2e` goes through the host-facing call with pinned host
+action buffers copied H2D and the new state + reward + done copied D2H every step.
+Multi-GPU (torchrun): env batch sharded, 4096 envs per rank (weak scaling), one NCCL
+all-reduce of the return statistics at the end of the timed rollout.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = 'batched env-steps/sec'
+UNIT = 'env-steps/s'
+
+WORKLOADS = {
+    # name -> (spec factory kwargs, envs per GPU, algorithmic bytes per env-step)
+    'wildfire32': dict(n=32, separable=False, envs=4096),
+    'wildfire32_sep': dict(n=32, separable=True, envs=4096),
+    'wildfire1024': dict(n=1024, separable=True, envs=256),
+}
+
+
+def make_spec(name):
+    from pyrddlgym_b200 import workloads
+    w = WORKLOADS[name]
+    return workloads.wildfire(w['n'], separable=w['separable'])
+
+
+def algorithmic_bytes_per_env_step(name):
+    """read burning, out-of-fuel, put-out, cut-out + write burning', out-of-fuel'
+    (1 byte per bool cell) + reward f64 + done u8."""
+    n = WORKLOADS[name]['n']
+    return 6 * n * n + 9
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+                 '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for name, v in zip(['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'], r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------
+# CPU arm: the NumPy oracle port of the reference algorithm
+# ---------------------------------------------------------------------------------------
+
+def _cpu_worker(args):
+    name, n_envs, steps, seed = args
+    os.environ.setdefault('OMP_NUM_THREADS', '1')
+    from pyrddlgym_b200 import workloads
+    from oracle.oracle_sim import OracleSimulator
+    p = workloads.load_program(make_spec(name))
+    sim = OracleSimulator(p, n_envs=n_envs, seed=seed)
+    rng = np.random.default_rng(seed)
+    n = WORKLOADS[name]['n']
+    acts = [{'put-out': rng.random((n_envs, n, n)) < 0.05, 'cut-out': rng.random((n_envs, n, n)) < 0.05}
+            for _ in range(2)]
+    sim.step(acts[0])
+    t0 = time.perf_counter()
+    for t in range(steps):
+        sim.step(acts[t & 1])
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(name, cores=1, envs_per_core=4, steps=8):
+    """Oracle port timed on `cores` host cores (one process each, envs_per_core envs, `steps`
+    steps). Returns env-steps/s aggregated over cores."""
+    if WORKLOADS[name]['n'] > 64:
+        return None, 'reference formulation cannot run n>48 (O(n^4) temporaries)'
+    jobs = [(name, envs_per_core, steps, 100 + i) for i in range(cores)]
+    if cores == 1:
+        dts = [_cpu_worker(jobs[0])]
+    else:
+        import multiprocessing as mp
+        with mp.get_context('spawn').Pool(cores) as pool:
+            dts = pool.map(_cpu_worker, jobs)
+    total = cores * envs_per_core * steps
+    return total / max(dts), f'{cores} process(es) x {envs_per_core} envs x {steps} steps of {name} (NumPy oracle port)'
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    use = max(1, min(cores, 32))
+    per_step_envs = 4
+    t0 = time.perf_counter()
+    # warm-up + K timed "steps": each step = every core advancing per_step_envs envs once
+    v, sample = cpu_baseline(args.workload, cores=use, envs_per_core=per_step_envs,
+                             steps=max(1, args.steps))
+    wall = time.perf_counter() - t0
+    if v is None:
+        print(json.dumps({'impl': 'reference', 'unavailable': sample}))
+        return
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': 1e3 * use * per_step_envs / v, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'u8/f64', 'data': 'synthetic',
+        'config': {'workload': args.workload, 'envs_per_step': use * per_step_envs, 'wall_s': round(wall, 2)},
+        'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': use, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from pyrddlgym_b200 import workloads
+    from pyrddlgym_b200.simulator import BatchedSimulator
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    name = args.workload
+    w = WORKLOADS[name]
+    n, N = w['n'], args.envs or w['envs']
+    p = workloads.load_program(make_spec(name))
+    sim = BatchedSimulator(p, n_envs=N, device=dev, seed=42, env_offset=rank * N)
+    K, W = args.steps, args.warmup
+
+    # random-policy action planes, resident in HBM: a rotating pool larger than L2 (126 MB)
+    plane = N * n * n
+    pool_steps = max(4, min(K + W, -(-300_000_000 // (2 * plane))))
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    pool = [(torch.rand((N, n, n), device=dev, generator=g) < 0.05,
+             torch.rand((N, n, n), device=dev, generator=g) < 0.05) for _ in range(pool_steps)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(t):
+        put, cut = pool[t % pool_steps]
+        return sim.step({'put-out': put, 'cut-out': cut})
+
+    gamma = float(p.discount)
+    returns = torch.zeros(N, dtype=torch.float64, device=dev)
+
+    def rollout(k0, k):
+        disc = 1.0
+        for t in range(k0, k0 + k):
+            _, r, _ = one_step(t)
+            returns.add_(r, alpha=disc)
+            disc *= gamma
+
+    def reduce_stats():
+        # [sum, sum of squares, count] summed and [min, max] reduced over ranks (BaseAgent.evaluate
+        # statistics, pyRDDLGym/core/policy.py:120-126)
+        s = torch.stack([returns.sum(), (returns * returns).sum(),
+                         torch.tensor(float(N), dtype=torch.float64, device=dev)])
+        mm = torch.stack([returns.min(), -returns.max()])
+        if world > 1:
+            dist.all_reduce(s, op=dist.ReduceOp.SUM)
+            dist.all_reduce(mm, op=dist.ReduceOp.MIN)
+        return s, mm
+
+    rollout(0, W)
+    returns.zero_()
+    barrier()
+    l0 = sim.launches_issued
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    rollout(W, K)
+    stats = reduce_stats()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = sim.launches_issued - l0
+    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms.item())
+    value = world * N * K / (ms * 1e-3)
+
+    # dominant kernel: per-launch CUDA events on the launch stream (second pass, same inputs)
+    sim.native.profile(True)
+    rollout(W + K, K)
+    torch.cuda.synchronize()
+    prof = sim.native.profile_read(sim.table.launches)
+    sim.native.profile(False)
+    top = max(prof, key=lambda r: r['ms']) if prof else None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak = float(peaks.get('hbm_gbs', 6650.0))
+    peak_src = 'measured' if 'hbm_gbs' in peaks else 'fallback'
+    abytes = algorithmic_bytes_per_env_step(name) * N
+    roofline = None
+    if top:
+        per_launch_ms = top['ms'] / max(1, top['count'])
+        ach = abytes / (per_launch_ms * 1e-3) / 1e9
+        roofline = {'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
+                    'traffic': None, 'peak_source': peak_src, 'kernel': top['name'],
+                    'kernel_us': per_launch_ms * 1e3,
+                    'kernel_share_of_step': top['ms'] / max(1e-9, sum(r['ms'] for r in prof)),
+                    'algorithmic_bytes_per_launch': abytes}
+
+    # end-to-end through the host-facing call: pinned host actions -> H2D, step, new state +
+    # reward + done -> D2H, every step
+    host_pool = [tuple(x.cpu().pin_memory() for x in pool[i]) for i in range(min(4, pool_steps))]
+    h_state = {s: torch.empty((N, n, n), dtype=torch.bool).pin_memory() for s in sim.state_names}
+    h_reward = torch.empty(N, dtype=torch.float64).pin_memory()
+    h_done = torch.empty(N, dtype=torch.bool).pin_memory()
+    d_put, d_cut = torch.empty_like(pool[0][0]), torch.empty_like(pool[0][1])
+
+    def e2e_step(t):
+        hp, hc = host_pool[t % len(host_pool)]
+        d_put.copy_(hp, non_blocking=True)
+        d_cut.copy_(hc, non_blocking=True)
+        st, r, d = sim.step({'put-out': d_put, 'cut-out': d_cut})
+        for s in sim.state_names:
+            h_state[s].copy_(st[s], non_blocking=True)
+        h_reward.copy_(r, non_blocking=True)
+        h_done.copy_(d, non_blocking=True)
+        torch.cuda.current_stream().synchronize()      # the caller owns the result after step()
+
+    for t in range(W):
+        e2e_step(t)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for t in range(K):
+        e2e_step(t)
+    e1.record()
+    barrier()
+    ms_e2e = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = world * N * K / (float(ms_e2e.item()) * 1e-3)
+    h2d = 2 * plane
+    d2h = len(sim.state_names) * plane + 9 * N
+
+    if rank == 0:
+        cpu_v, cpu_sample = cpu_baseline(name, cores=1, envs_per_core=4, steps=16) if world == 1 else (None, None)
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
+            'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'u8/f64', 'data': 'synthetic',
+            'config': {'workload': f'Wildfire {n}x{n} ({"separable" if w["separable"] else "4-D NEIGHBOR"}), '
+                                   f'{N} envs/GPU, random policy Bernoulli(0.05)',
+                       'envs_per_gpu': N, 'global_envs': N * world, 'grid': n,
+                       'l2': f'action planes rotate through a {pool_steps}-step pool of '
+                             f'{pool_steps * 2 * plane / 1e6:.0f} MB (> 126 MB L2); state planes '
+                             f'({2 * plane / 1e6:.1f} MB) are rollout-resident',
+                       'parallelism': f'env-shard x{world}',
+                       'return_stats': [float(x) for x in stats[0].tolist()]},
+            'roofline': roofline,
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'ms_per_step': float(ms_e2e.item()) / K},
+            'gpu_launches': launches,
+            'clocks': clocks,
+        }
+        if cpu_v is not None:
+            line['cpu_baseline'] = {'value': cpu_v, 'unit': UNIT, 'cores': 1, 'kind': 'port', 'sample': cpu_sample}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=100)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default='wildfire32', choices=sorted(WORKLOADS))
+    ap.add_argument('--envs', type=int, default=0)
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -57,6 +57,13 @@ int rddl_step(rddl_program_t* prog, void* const* tensors, const double* const* i
 int rddl_check(rddl_program_t* prog, int which, void* const* tensors, uint32_t* status,
                int64_t n_envs, int64_t env_offset, void* cuda_stream);
 
+/* Measurement aid (no reference counterpart): when enabled, every kernel launch of this
+ * program is bracketed by CUDA events on its stream; rddl_profile_read synchronises them and
+ * returns, per launch index of the op table (n entries), the summed milliseconds and the
+ * number of launches since the last read. */
+int rddl_profile(rddl_program_t* prog, int enable);
+int rddl_profile_read(rddl_program_t* prog, double* ms, int64_t* count, int n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -403,7 +403,10 @@ struct rddl_program {
   int64_t* d_red_off = nullptr;
   uint64_t* d_red = nullptr;
   int64_t red_capacity_envs = 0;
-  uint32_t* d_status_dummy = nullptr;
+  // optional per-launch timing (rddl_profile): CUDA events on the launch stream
+  bool profiling = false;
+  struct Timed { int launch; cudaEvent_t e0, e1; };
+  std::vector<Timed> timed;
 };
 
 #define CK(call)                                                                      \
@@ -535,11 +538,22 @@ static int run_plan(rddl_program* g, int plan, void* const* tensors, const doubl
     const int64_t groups = (n_envs + envs_per_cta - 1) / envs_per_cta;
     const int64_t blocks = groups * L.chunks;
     if (blocks > 0x7fffffffll) { g->err = "grid too large"; return RDDL_ERR_ARG; }
+    rddl_program::Timed tm;
+    if (g->profiling) {
+      tm.launch = (int)(&L - g->launches.data());
+      CK(cudaEventCreate(&tm.e0));
+      CK(cudaEventCreate(&tm.e1));
+      CK(cudaEventRecord(tm.e0, stream));
+    }
     if (L.nregs <= 16) rddl_level_interp<16><<<(unsigned)blocks, 256, 0, stream>>>(A);
     else if (L.nregs <= 40) rddl_level_interp<40><<<(unsigned)blocks, 256, 0, stream>>>(A);
     else rddl_level_interp<RDDL_MAX_REGS><<<(unsigned)blocks, 256, 0, stream>>>(A);
     ++g->launches_issued;
     CK(cudaGetLastError());
+    if (g->profiling) {
+      CK(cudaEventRecord(tm.e1, stream));
+      g->timed.push_back(tm);
+    }
   }
   return RDDL_OK;
 }
@@ -560,4 +574,26 @@ extern "C" int rddl_check(rddl_program_t* g, int which, void* const* tensors, ui
     return RDDL_ERR_ARG;
   }
   return run_plan(g, which, tensors, nullptr, status, n_envs, env_offset, 0, 0, (cudaStream_t)cuda_stream);
+}
+
+extern "C" int rddl_profile(rddl_program_t* g, int enable) {
+  if (!g) return RDDL_ERR_ARG;
+  g->profiling = enable != 0;
+  return RDDL_OK;
+}
+
+extern "C" int rddl_profile_read(rddl_program_t* g, double* ms, int64_t* count, int n) {
+  if (!g || !ms || !count) return RDDL_ERR_ARG;
+  std::string* errp = &g->err;
+  for (int i = 0; i < n; ++i) { ms[i] = 0.0; count[i] = 0; }
+  for (auto& t : g->timed) {
+    CK(cudaEventSynchronize(t.e1));
+    float f = 0.f;
+    CK(cudaEventElapsedTime(&f, t.e0, t.e1));
+    if (t.launch < n) { ms[t.launch] += f; count[t.launch] += 1; }
+    cudaEventDestroy(t.e0);
+    cudaEventDestroy(t.e1);
+  }
+  g->timed.clear();
+  return RDDL_OK;
 }

@@ -39,12 +39,16 @@ def load():
     lib.rddl_step.restype = ctypes.c_int
     lib.rddl_check.argtypes = [vp, ctypes.c_int, ctypes.POINTER(vp), vp, i64, i64, vp]
     lib.rddl_check.restype = ctypes.c_int
+    lib.rddl_profile.argtypes = [vp, ctypes.c_int]
+    lib.rddl_profile.restype = ctypes.c_int
+    lib.rddl_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64), ctypes.c_int]
+    lib.rddl_profile_read.restype = ctypes.c_int
     _lib = lib
     return lib
 
 
 EXPORTS = ['rddl_program_create', 'rddl_program_destroy', 'rddl_last_error', 'rddl_program_info',
-           'rddl_step', 'rddl_check']
+           'rddl_step', 'rddl_check', 'rddl_profile', 'rddl_profile_read']
 
 
 class NativeProgram:
@@ -74,6 +78,24 @@ class NativeProgram:
     def check(self, which, ptrs, status_ptr, n_envs, env_offset, stream):
         self._check(self.lib.rddl_check(self.handle, which, ptrs, status_ptr, n_envs, env_offset, stream),
                     'rddl_check')
+
+    def profile(self, enable):
+        self._check(self.lib.rddl_profile(self.handle, 1 if enable else 0), 'rddl_profile')
+
+    def profile_read(self, launches=None):
+        """[{launch, ms, count, name}] for every launch index that ran since the last read."""
+        n = 256
+        ms = (ctypes.c_double * n)()
+        cnt = (ctypes.c_int64 * n)()
+        self._check(self.lib.rddl_profile_read(self.handle, ms, cnt, n), 'rddl_profile_read')
+        out = []
+        for i in range(n):
+            if cnt[i]:
+                name = 'rddl_level_interp[launch %d]' % i
+                if launches is not None and i < len(launches):
+                    name = launches[i].get('kernel', name)
+                out.append({'launch': i, 'ms': float(ms[i]), 'count': int(cnt[i]), 'name': name})
+        return out
 
     def close(self):
         if self.handle:

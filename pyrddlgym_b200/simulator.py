@@ -118,7 +118,7 @@ class BatchedSimulator:
                     continue
                 dst.copy_(v.to(dst.dtype).expand_as(dst) if v.shape != dst.shape else v, non_blocking=True)
             else:
-                a = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(np.asarray(v), tuple(dst.shape))))
+                a = torch.from_numpy(np.array(np.broadcast_to(np.asarray(v), tuple(dst.shape)), order='C'))
                 dst.copy_(a, non_blocking=True)
 
     def step(self, actions=None, variates=None):

@@ -57,19 +57,24 @@ def test_wildfire32_injected_vs_oracle():
 
 
 def test_wildfire_separable_equals_4d_formulation():
-    # the two formulations agree wherever the neighbour aggregate is read
+    # the two formulations agree wherever the neighbour aggregate is read;
+    # the Bernoulli node has a different AST id in each program, so the same uniforms are
+    # injected into both
     a = workloads.load_program(workloads.wildfire(16))
     b = workloads.load_program(workloads.wildfire(16, separable=True))
+    (na,), (nb,) = a.random_nodes(), b.random_nodes()
     N = 32
     sa, sb = _make(a, N, seed=5), _make(b, N, seed=5)
     rng = np.random.default_rng(0)
     for t in range(10):
         acts = harness.random_actions(a, N, rng, p_bool=0.03)
-        _, ra, _ = sa.step(acts)
-        _, rb, _ = sb.step(acts)
+        u = rng.random((N, 16, 16))
+        _, ra, _ = sa.step(acts, {na.id: u})
+        _, rb, _ = sb.step(acts, {nb.id: u})
         assert np.array_equal(_np(sa.fluent('burning')), _np(sb.fluent('burning')))
         assert np.array_equal(_np(sa.fluent('out-of-fuel')), _np(sb.fluent('out-of-fuel')))
         assert np.array_equal(_np(ra), _np(rb))
+    assert _np(sa.fluent('burning')).any()
 
 
 @pytest.mark.parametrize('name,spec,akw', [
