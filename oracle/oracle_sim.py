@@ -65,8 +65,11 @@ class OracleSimulator:
     """Batched CPU oracle. State lives in ``self.subs[name]``: arrays [N, *shape] for
     fluents, [*shape] for non-fluents."""
 
-    def __init__(self, program, n_envs=1, seed=0, env_offset=0):
+    def __init__(self, program, n_envs=1, seed=0, env_offset=0, bitsliced_nodes=()):
         self.p = program
+        # Bernoulli nodes the lowering mapped to the bit-sliced sampler (OpTable.plane_nodes):
+        # their *native* draw is defined by philox_np.bernoulli_bitsliced
+        self.bitsliced_nodes = set(int(x) for x in bitsliced_nodes)
         self.N = int(n_envs)
         self.seed = int(seed)
         self.env_offset = int(env_offset)
@@ -387,6 +390,12 @@ class OracleSimulator:
             if op == 'Bernoulli':                         # simulator.py:1045-1053 (note <=)
                 p, = args
                 self._flag(~((p >= 0) & (p <= 1)), rank, STATUS_OUT_OF_RANGE)
+                if n.id in self.bitsliced_nodes and self._variates.get(n.id, None) is None:
+                    shp = self._shape(n.scope)
+                    pf = np.broadcast_to(np.asarray(p, dtype=np.float64), (self.N,) + shp).reshape(self.N, -1)
+                    env_ids = self.env_offset + np.arange(self.N)
+                    draw = philox_np.bernoulli_bitsliced(self.seed, env_ids, self.step_count, n.id, pf)
+                    return draw.reshape((self.N,) + shp)
                 return self._base(n, 'U') <= p
             if op == 'Normal':                            # simulator.py:1055-1064 (variance)
                 m, var = args

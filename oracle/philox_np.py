@@ -72,3 +72,66 @@ def base_variates(kind, seed, env_ids, step, node_id, scope_shape):
     else:
         raise ValueError(kind)
     return out.reshape((len(env_ids),) + tuple(scope_shape))
+
+
+def bernoulli_thresholds(p):
+    """float64 probabilities -> (T uint64 = floor(p * 2^64) clipped, always = p >= 1).
+    Mirrors pyrddlgym_b200/plane_lowering.py:PlaneBuilder.fin_const."""
+    p = np.asarray(p, dtype=np.float64)
+    flat = p.reshape(-1)
+    T = np.zeros(flat.shape, dtype=np.uint64)
+    always = np.zeros(flat.shape, dtype=bool)
+    for i, pv in enumerate(flat.tolist()):
+        if not (pv >= 0.0 and pv <= 1.0):
+            pv = 0.0 if not (pv > 0.0) else 1.0
+        if pv >= 1.0:
+            always[i] = True
+            T[i] = np.uint64((1 << 64) - 1)
+        elif pv > 0.0:
+            T[i] = np.uint64(int(pv * float(1 << 64)))
+    return T.reshape(p.shape), always.reshape(p.shape)
+
+
+BERN_LEVELS = 8
+
+
+def bernoulli_bitsliced(seed, env_ids, step, node_id, p):
+    """Bit-sliced Bernoulli sampler of the plane interpreter (csrc/rddl_plane.cuh: PBERN).
+
+    p: float64 [len(env_ids), n_cells] with n_cells % 32 == 0 (C-order cells of the scope).
+    T = floor(p * 2^64). Cell c of env e first compares T's top BERN_LEVELS bits, MSB first,
+    against random bits: bit j of the cell is bit (c % 32) of word (j % 4) of
+    Philox4x32-10(key = seed, counter = (c // 32, e, step, (node & 0xffff) | ((0x8000 + j // 4) << 16))).
+    The first level where the random bit differs decides (random bit 0 -> True). A cell still
+    tied after BERN_LEVELS levels draws u64 = (x << 32) | y from
+    Philox4x32-10(counter = (c, e, step, (node & 0xffff) | (0xC000 << 16))) and is True iff
+    u64 < (T << BERN_LEVELS) mod 2^64. Cells with p >= 1 are always True."""
+    p = np.asarray(p, dtype=np.float64)
+    N, n_cells = p.shape
+    assert n_cells % 32 == 0
+    G = n_cells // 32
+    T, always = bernoulli_thresholds(p)
+    env = (np.asarray(env_ids, dtype=np.uint64)[:, None] & MASK).astype(np.uint32)
+    g = np.arange(G, dtype=np.uint32)[None, :]
+    lane = np.arange(32, dtype=np.uint32)
+    k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    st = np.uint32(step & 0xFFFFFFFF)
+    T3 = T.reshape(N, G, 32)
+    res = np.zeros((N, G, 32), dtype=bool)
+    und = np.ones((N, G, 32), dtype=bool)
+    for b in range(BERN_LEVELS // 4):
+        c3 = np.uint32((node_id & 0xFFFF) | ((0x8000 + b) << 16))
+        words = philox4x32_10(g, env, st, c3, k0, k1)
+        for q in range(4):
+            j = 4 * b + q
+            r = ((words[q][:, :, None] >> lane[None, None, :]) & np.uint32(1)).astype(bool)
+            t = ((T3 >> np.uint64(63 - j)) & np.uint64(1)).astype(bool)
+            res |= und & ~r & t
+            und &= ~(r ^ t)
+    cell = np.arange(n_cells, dtype=np.uint32)[None, :]
+    c3 = np.uint32((node_id & 0xFFFF) | (0xC000 << 16))
+    x, y, _, _ = philox4x32_10(cell, env, st, c3, k0, k1)
+    u64 = (x.astype(np.uint64) << np.uint64(32)) | y.astype(np.uint64)
+    tail = u64 < (T << np.uint64(BERN_LEVELS))
+    out = np.where(und.reshape(N, n_cells), tail, res.reshape(N, n_cells))
+    return out | always

@@ -4,7 +4,7 @@
 #include <stdint.h>
 
 #define RDDL_MAGIC 0x31304C444452ll
-#define RDDL_VERSION 3
+#define RDDL_VERSION 4
 #define RDDL_MAX_IDX 8
 #define RDDL_MAX_RED 8
 #define RDDL_MAX_REGS 96
@@ -24,6 +24,7 @@ enum RddlOp : uint8_t {
   OP_RANDU, OP_RANDN, OP_RANDE, OP_RANDC,
   OP_REDOUT, OP_REDIN, OP_STATUS,
   OP_EXPM1, OP_LOG1P,
+  OP_PLD, OP_PLDC, OP_PST, OP_PCONST, OP_PLUT, OP_PSHARE, OP_PCOUNT, OP_PBERN, OP_PRED,
   OP_COUNT_
 };
 
@@ -72,7 +73,7 @@ struct RddlLaunch {    // 176 bytes
   int32_t nred, G, ipt, chunks;
   int32_t red_op[8];
   int32_t red_slot[8];
-  int32_t nregs, pad;
+  int32_t nregs, kind;   // kind: 0 = scalar level interpreter, 1 = bit-plane interpreter
 };
 
 struct RddlRedSlot { int32_t op, chunks; };

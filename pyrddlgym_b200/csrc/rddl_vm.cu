@@ -41,6 +41,8 @@ struct VmArgs {
   const double* inj[RDDL_MAX_VARIATES];
 };
 
+#include "rddl_plane.cuh"
+
 __device__ __forceinline__ double as_f(uint64_t v) { return __longlong_as_double((long long)v); }
 __device__ __forceinline__ uint64_t from_f(double v) { return (uint64_t)__double_as_longlong(v); }
 
@@ -456,7 +458,9 @@ extern "C" int rddl_program_create(const void* optable, size_t nbytes, int devic
   g->variates.assign((const RddlVariate*)sec[8], (const RddlVariate*)sec[8] + hdr[10]);
   g->n_insns = hdr[4];
   for (auto& L : g->launches) {
-    if (L.nregs > RDDL_MAX_REGS || L.G < 1 || L.G > 256 || (L.G & (L.G - 1)) || L.nred > RDDL_MAX_RED) {
+    const bool bad_scalar = L.kind == 0 && (L.nregs > RDDL_MAX_REGS || L.G > 256 || (L.G & (L.G - 1)));
+    const bool bad_plane = L.kind == 1 && (L.nregs > PLANE_MAX_REGS || L.G > 32 || L.ipt > 1024 || (L.E & 31));
+    if (bad_scalar || bad_plane || L.kind > 1 || L.G < 1 || L.nred > RDDL_MAX_RED) {
       g_create_error = "op table: launch out of limits";
       delete g;
       return RDDL_ERR_FORMAT;
@@ -534,7 +538,7 @@ static int run_plan(rddl_program* g, int plan, void* const* tensors, const doubl
   for (const RddlLaunch& L : g->launches) {
     if (L.plan != plan) continue;
     A.L = L;
-    const int envs_per_cta = 256 / L.G;
+    const int envs_per_cta = L.kind == 1 ? L.G : 256 / L.G;
     const int64_t groups = (n_envs + envs_per_cta - 1) / envs_per_cta;
     const int64_t blocks = groups * L.chunks;
     if (blocks > 0x7fffffffll) { g->err = "grid too large"; return RDDL_ERR_ARG; }
@@ -545,7 +549,10 @@ static int run_plan(rddl_program* g, int plan, void* const* tensors, const doubl
       CK(cudaEventCreate(&tm.e1));
       CK(cudaEventRecord(tm.e0, stream));
     }
-    if (L.nregs <= 16) rddl_level_interp<16><<<(unsigned)blocks, 256, 0, stream>>>(A);
+    if (L.kind == 1) {
+      if (L.nregs <= 16) rddl_plane_interp<16><<<(unsigned)blocks, 256, 0, stream>>>(A);
+      else rddl_plane_interp<PLANE_MAX_REGS><<<(unsigned)blocks, 256, 0, stream>>>(A);
+    } else if (L.nregs <= 16) rddl_level_interp<16><<<(unsigned)blocks, 256, 0, stream>>>(A);
     else if (L.nregs <= 40) rddl_level_interp<40><<<(unsigned)blocks, 256, 0, stream>>>(A);
     else rddl_level_interp<RDDL_MAX_REGS><<<(unsigned)blocks, 256, 0, stream>>>(A);
     ++g->launches_issued;

@@ -821,6 +821,8 @@ class OpTable:
         self.launches = []           # dicts, for logging / tests
         self.n_checks = {}
         self.n_insns = 0
+        self.plane_nodes = []        # ids of Bernoulli nodes lowered to the bit-sliced sampler
+        self.plane_rejects = []      # (plan, scope, reason) of groups that stayed on the scalar path
 
 
 SPECIALS = ['__reward', '__done', '__chk']
@@ -828,8 +830,10 @@ SPECIALS = ['__reward', '__done', '__chk']
 
 class Lowerer:
 
-    def __init__(self, program):
+    def __init__(self, program, use_planes=True):
         self.p = program
+        self.use_planes = use_planes
+        self.csr_masks = {}
         self.rename = {}
         self.consts = []
         self.const_map = {}
@@ -966,7 +970,9 @@ class Lowerer:
             np.add.at(rowptr, rows + 1, 1)
             rowptr = np.cumsum(rowptr)
             cols = np.unravel_index(flat, [ext[a] for a in axes])
-            loops.append(('csr', self.csr_index(rowptr, cols, axes, row_axes, ext)))
+            ci = self.csr_index(rowptr, cols, axes, row_axes, ext)
+            self.csr_masks.setdefault(ci, (tuple(axes), tuple(row_axes), M2))
+            loops.append(('csr', ci))
         # rebuild the body from the remaining operands
         if mode == 'and':
             if not rest:
@@ -1084,34 +1090,68 @@ class Lowerer:
                 slots.append(x.value)
         return loads, slots
 
-    def schedule(self, plan, items):
+    def group_items(self, items):
+        """Splits the item list into launch groups (pure dependency analysis, no emission)."""
+        groups = []
         cur = None
         for it in items:
             self.rename = it.rename
             loads, slots = self.reads(it.expr)
-            fits = cur is not None and cur.scope == it.scope
+            fits = cur is not None and cur['scope'] == it.scope
             if fits:
                 for (name, node) in loads:
-                    if name in cur.written:
+                    if name in cur['written']:
                         # a value produced in this launch may only be read at the same element
-                        probe = Node('load', tensor=name, index=node.index)
-                        if name not in cur.stored or not cur.is_identity(probe):
+                        decl = self.p.tensors[name]
+                        ident = (list(decl.params) == it.scope and
+                                 [tuple(x) for x in node.index] == [('a', i) for i in range(len(it.scope))])
+                        if name not in cur['stored'] or not ident:
                             fits = False
                             break
-                if any(s in cur.produced_slots for s in slots):
+                if any(s in cur['slots'] for s in slots):
                     fits = False
-                if it.red is not None and len(cur.reds) >= ot.MAX_RED:
+                if it.red is not None and cur['nred'] >= ot.MAX_RED:
                     fits = False
             if not fits:
-                if cur is not None:
-                    self.finish_launch(cur)
-                cur = _LaunchBuilder(self, plan, it.scope)
-                cur.written = set()
-            cur.add_item(it)
+                cur = {'scope': list(it.scope), 'items': [], 'written': set(), 'stored': set(),
+                       'slots': set(), 'nred': 0}
+                groups.append(cur)
+            cur['items'].append(it)
             if it.store is not None:
-                cur.written.add(it.store)
-        if cur is not None:
-            self.finish_launch(cur)
+                cur['written'].add(it.store)
+                decl = self.p.tensors[it.store]
+                if it.scope == list(decl.params) and it.store_off == 0:
+                    cur['stored'].add(it.store)
+            if it.red is not None:
+                cur['slots'].add(it.red[0])
+                cur['nred'] += 1
+        self.rename = {}
+        return groups
+
+    def schedule(self, plan, items):
+        from pyrddlgym_b200 import plane_lowering
+        for grp in self.group_items(items):
+            lb = None
+            if self.use_planes and len(grp['scope']) in (1, 2):
+                mark = (len(self.consts), len(self.pool), self.pool_len)
+                try:
+                    lb = plane_lowering.PlaneBuilder(self, plan, grp['scope'])
+                    for it in grp['items']:
+                        self.rename = it.rename
+                        lb.add_item(it)
+                except plane_lowering.NotPlanar as e:
+                    self.out.plane_rejects.append((plan, list(grp['scope']), str(e)))
+                    lb = None
+                    del self.consts[mark[0]:]
+                    del self.pool[mark[1]:]
+                    self.pool_len = mark[2]
+                    self.const_map = {b: i for i, b in enumerate(self.consts)}
+            if lb is None:
+                lb = _LaunchBuilder(self, plan, grp['scope'])
+                for it in grp['items']:
+                    self.rename = it.rename
+                    lb.add_item(it)
+            self.finish_launch(lb)
         self.rename = {}
 
     def finish_launch(self, lb):
@@ -1125,17 +1165,25 @@ class Lowerer:
         self.insns.extend(lb.insns)
         row['pc_end'] = len(self.insns)
         row['nred'] = len(lb.reds)
-        G, ipt, chunks = self.geometry(lb.E, bool(lb.reds))
+        kind = getattr(lb, 'kind', 0)
+        if kind == 1:
+            G, ipt, chunks = lb.envs_per_tile, lb.tile_words, lb.chunks
+        else:
+            G, ipt, chunks = self.geometry(lb.E, bool(lb.reds))
         row['G'], row['ipt'], row['chunks'] = G, ipt, chunks
+        row['pad'] = kind
         for i, (rop, slot) in enumerate(lb.reds):
             row['red_op'][i] = rop
             row['red_slot'][i] = slot
-            assert self.redslots[slot][1] == chunks, 'reduction slot geometry mismatch'
+            self.redslots[slot] = (self.redslots[slot][0], chunks)
         row['nregs'] = max(lb.nregs, 1)
         self.launch_rows.append(row)
-        self.out.launches.append({'plan': lb.plan, 'scope': lb.scope, 'E': lb.E,
+        self.out.launches.append({'plan': lb.plan, 'scope': lb.scope, 'E': lb.E, 'kind': kind,
+                                  'kernel': 'rddl_plane_interp' if kind == 1 else 'rddl_level_interp',
                                   'n_insns': len(lb.insns), 'nregs': lb.nregs,
                                   'stores': sorted(lb.stored), 'nred': len(lb.reds)})
+        if kind == 1:
+            self.out.plane_nodes.extend(lb.variate_nodes)
 
     # ---- top level
     def lower(self):
@@ -1228,6 +1276,7 @@ class Lowerer:
                 self.schedule(plan, items)
 
 
-def lower(program):
-    """Lowers an HIR ``Program`` to an ``OpTable``."""
-    return Lowerer(program).lower()
+def lower(program, use_planes=True):
+    """Lowers an HIR ``Program`` to an ``OpTable``. ``use_planes=False`` keeps every launch on
+    the general scalar interpreter (used by tests to cross-check the two paths)."""
+    return Lowerer(program, use_planes=use_planes).lower()

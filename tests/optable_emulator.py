@@ -99,7 +99,99 @@ class Emulator:
             off += v * int(ad['rstride'][i])
         return off
 
+    # ---- bit-plane launches (mirrors csrc/rddl_plane.cu at the level of whole bool planes)
+    def _fin(self, ci):
+        m = int(self.consts[ci])
+        regs = int(self.consts[ci + 1])
+        idx = [(regs >> (8 * i)) & 0xFF for i in range(m)]
+        truth = int(self.consts[ci + 2])
+        bad, always = int(self.consts[ci + 3]), int(self.consts[ci + 4])
+        thr = np.array(self.consts[ci + 5:ci + 5 + (1 << m)], dtype=np.uint64)
+        vals = np.array(self.consts[ci + 5 + (1 << m):ci + 5 + 2 * (1 << m)], dtype=np.uint64)
+        return m, idx, truth, bad, always, thr, vals
+
+    def _plane_launch(self, L, bufs, N, status, injected, seed, step, env_offset, red):
+        E = int(L['E'])
+        rank = int(L['rank'])
+        H, W = (int(L['extent'][0]), int(L['extent'][1])) if rank == 2 else (1, int(L['extent'][0]))
+        chunks = int(L['chunks'])
+        tile_words = int(L['ipt'])
+        rows_per_tile = (tile_words * 32) // W
+        P = {}
+        shared = {}
+
+        def index_of(idx):
+            v = np.zeros((N, E), dtype=np.int64)
+            for i, r in enumerate(idx):
+                v |= P[r].astype(np.int64) << i
+            return v
+
+        for ins in self.insns[int(L['pc_begin']):int(L['pc_end'])]:
+            op = _OPNAME[int(ins['op'])]
+            dst, a, b, imm = int(ins['dst']), int(ins['a']), int(ins['b']), int(ins['imm'])
+            if op == 'PLD':
+                P[dst] = bufs[imm].reshape(N, E) != 0
+            elif op == 'PLDC':
+                words = self.pool[imm:imm + E // 32].view('<u4')
+                bits = np.unpackbits(words.view(np.uint8), bitorder='little').astype(bool)
+                P[dst] = np.broadcast_to(bits, (N, E))
+            elif op == 'PST':
+                bufs[imm][:] = P[a].reshape(-1).astype(bufs[imm].dtype)
+            elif op == 'PCONST':
+                P[dst] = np.full((N, E), bool(imm))
+            elif op == 'PLUT':
+                m, idx, truth, *_ = self._fin(imm)
+                tt = np.array([(truth >> v) & 1 for v in range(1 << m)], dtype=bool)
+                P[dst] = tt[index_of(idx)]
+            elif op == 'PSHARE':
+                shared[b] = P[a]
+            elif op == 'PCOUNT':
+                src = shared[b].reshape(N, H, W).astype(np.int64)
+                pad = np.pad(src, ((0, 0), (1, 1), (1, 1)))
+                cnt = np.zeros((N, H, W), dtype=np.int64)
+                for dx in (-1, 0, 1):
+                    for dy in (-1, 0, 1):
+                        if imm >> ((dx + 1) * 3 + (dy + 1)) & 1:
+                            cnt += pad[:, 1 + dx:1 + dx + H, 1 + dy:1 + dy + W]
+                cnt = cnt.reshape(N, E)
+                for i in range(4):
+                    P[dst + i] = ((cnt >> i) & 1).astype(bool)
+            elif op == 'PBERN':
+                m, idx, truth, bad, always, thr, vals = self._fin(imm)
+                v = index_of(idx)
+                pvals = vals.view(np.float64)[v]
+                badv = np.array([(bad >> k) & 1 for k in range(1 << m)], dtype=bool)[v]
+                status[badv.any(axis=1)] |= 1
+                inj = injected.get(a, None)
+                if inj is not None:
+                    P[dst] = np.asarray(inj, dtype=np.float64).reshape(N, E) <= pvals
+                else:
+                    node = int(self.variates[a]['node'])
+                    env_ids = env_offset + np.arange(N)
+                    P[dst] = philox_np.bernoulli_bitsliced(seed, env_ids, step, node, pvals)
+            elif op == 'PRED':
+                m, idx, truth, bad, always, thr, vals = self._fin(imm)
+                rop = int(L['red_op'][b])
+                v = index_of(idx).reshape(N, H, W)
+                for env in range(N):
+                    parts = []
+                    for c in range(chunks):
+                        blk = v[env, c * rows_per_tile:(c + 1) * rows_per_tile] if chunks > 1 else v[env]
+                        cnt = np.bincount(blk.reshape(-1), minlength=1 << m)
+                        if rop == 1:
+                            acc = np.float64(0.0)
+                            for k in range(1 << m):
+                                acc = acc + vals.view(np.float64)[k] * np.float64(cnt[k])
+                            parts.append(float(acc))
+                        else:
+                            parts.append(int((vals.view(np.int64) * cnt).sum()))
+                    red[(int(L['red_slot'][b]), env)] = parts
+            else:
+                raise NotImplementedError(op)
+
     def _launch(self, L, bufs, N, status, injected, seed, step, env_offset, red):
+        if int(L['pad']) == 1:
+            return self._plane_launch(L, bufs, N, status, injected, seed, step, env_offset, red)
         E = int(L['E'])
         rank = int(L['rank'])
         ext = [int(e) for e in L['extent'][:rank]]

@@ -15,3 +15,23 @@ class _Adapter(OracleSimulator):
 def test_oracle_matches_reference_golden(case):
     sim = cases.replay(case, lambda p, n: _Adapter(p, n))
     assert not sim.status.any()
+
+
+@pytest.mark.parametrize('case', ['wildfire8', 'wildfire8_sep', 'wildfire32'])
+def test_stencil_restatement_matches_reference_golden(case):
+    """Pins oracle/wildfire_stencil.py (used at grid sizes the reference cannot build)."""
+    from oracle.wildfire_stencil import wildfire_step
+    from pyrddlgym_b200 import workloads
+    g = cases.load_golden(case)
+    p = workloads.load_program(cases.SPECS[case]())
+    (node,) = p.random_nodes()
+    N = int(g['n_envs'])
+    target = np.asarray(p.init['TARGET'])
+    b = np.broadcast_to(np.asarray(p.init['burning']), (N,) + target.shape).copy()
+    f = np.broadcast_to(np.asarray(p.init['out-of-fuel']), (N,) + target.shape).copy()
+    for t in range(int(g['steps'])):
+        acts, var = cases.golden_step_inputs(g, t)
+        b, f, r = wildfire_step(b, f, acts['put-out'], acts['cut-out'], target, var[node.id])
+        assert np.array_equal(b, g[f'flu/{t}/burning'])
+        assert np.array_equal(f, g[f'flu/{t}/out-of-fuel'])
+        np.testing.assert_allclose(r, g[f'reward/{t}'], rtol=1e-12)
