@@ -1141,11 +1141,9 @@ class Lowerer:
                         lb.add_item(it)
                 except plane_lowering.NotPlanar as e:
                     self.out.plane_rejects.append((plan, list(grp['scope']), str(e)))
+                    # table entries (consts, CSR lists) added by the failed attempt stay: they are
+                    # shared with / deduplicated against the scalar lowering of the same group
                     lb = None
-                    del self.consts[mark[0]:]
-                    del self.pool[mark[1]:]
-                    self.pool_len = mark[2]
-                    self.const_map = {b: i for i, b in enumerate(self.consts)}
             if lb is None:
                 lb = _LaunchBuilder(self, plan, grp['scope'])
                 for it in grp['items']:
