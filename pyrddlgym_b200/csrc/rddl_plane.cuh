@@ -4,10 +4,13 @@
 // the reference boundary, pyRDDLGym/core/compiler/initializer.py:16-23); inside the kernel a
 // plane register is a packed 32-cell word, so one LOP3 evaluates a logical node for 32 cells.
 //
-// Tile: 256 threads x 4 words x 32 cells = 32768 cells of consecutive (env, cell) index space.
-// Thread t owns words w = j*256 + t (j = 0..3): each global access of a warp covers 1 KiB of
-// contiguous bytes (32 B per thread), i.e. fully coalesced 128-bit vector loads/stores.
-// Ops (one per op-table instruction, decoded once per thread for its 128 cells):
+// Tile: 256 threads x WPT words x 32 cells of consecutive (env, cell) index space (WPT = 4:
+// 32768 cells; WPT = 1 for small batches so that the grid still covers the 148 SMs).
+// Thread t owns words w = j*256 + t: every global access of a warp covers 1 KiB of contiguous
+// bytes (32 B per thread, two 128-bit vector accesses), i.e. fully coalesced.
+// The op table of the launch is pre-decoded on the host (PlaneProg, passed in the kernel
+// parameter constant bank): truth tables arrive expanded to 32-bit masks, so a table lookup
+// over m index planes is a (2^m - 1)-LOP3 multiplexer tree.
 //   PLD/PST   bytes <-> bits          PLDC    pre-packed non-fluent plane
 //   PLUT      m-input truth table     PSHARE  stage a plane (+ halo rows) in shared memory
 //   PCOUNT    3x3 stencil count as 4 bit-sliced planes (carry-save adders)
@@ -18,26 +21,23 @@
 #include "rddl_plan.h"
 
 #define PLANE_MAX_REGS 32
-#define PLANE_SMEM_WORDS 3072   // 1024 tile words + up to 1024 halo words on each side
+#define PLANE_MAX_OPS 40
+#define PLANE_WORDS 2048
 #define PLANE_BERN_LEVELS 8
+#define PLANE_QUEUE 96
 
-struct PlaneFin {
-  int m;
-  uint64_t regs, truth, bad, always;
-  const uint64_t* thr;
-  const uint64_t* vals;
-  const uint64_t* lev;
+struct PlaneOp {        // 16 bytes, pre-decoded from RddlInsn + its Fin descriptor
+  uint8_t op, dst, a, b, m;
+  uint8_t idx[5];
+  uint16_t off;         // offset of this op's tables in PlaneProg::words
+  uint32_t imm;
 };
 
-__device__ __forceinline__ PlaneFin plane_fin(const uint64_t* c) {
-  PlaneFin f;
-  f.m = (int)c[0];
-  f.regs = c[1]; f.truth = c[2]; f.bad = c[3]; f.always = c[4];
-  f.thr = c + 5;
-  f.vals = c + 5 + (1 << f.m);
-  f.lev = c + 5 + 2 * (1 << f.m);
-  return f;
-}
+struct PlaneProg {
+  int32_t nops, nshared, smem_bytes, pad;
+  PlaneOp ops[PLANE_MAX_OPS];
+  uint32_t words[PLANE_WORDS];
+};
 
 // 32 bool bytes (each 0/1) -> 32-bit word, cell i -> bit i
 __device__ __forceinline__ uint32_t plane_pack(const uint4 lo, const uint4 hi) {
@@ -60,16 +60,13 @@ __device__ __forceinline__ void plane_unpack(uint32_t w, uint4& lo, uint4& hi) {
   hi.z = plane_nib((w >> 24) & 15u);  hi.w = plane_nib(w >> 28);
 }
 
-__device__ __forceinline__ uint32_t bitmask(uint64_t tt, int v) { return 0u - (uint32_t)((tt >> v) & 1ull); }
-
-// value of the truth table tt (2^M bits) at the cell-wise index formed by planes x[0..M)
+// multiplexer tree: value of the table (2^M masks) at the cell-wise index formed by x[0..M)
 template <int M>
-__device__ __forceinline__ uint32_t plane_tt(uint64_t tt, const uint32_t* x) {
-  if (M == 0) return bitmask(tt, 0);
-  uint32_t v[M > 0 ? (1 << (M - 1)) : 1];
+__device__ __forceinline__ uint32_t plane_mux(const uint32_t* mk, const uint32_t* x) {
+  if (M == 0) return mk[0];
+  uint32_t v[M > 0 ? (1 << (M > 0 ? M - 1 : 0)) : 1];
 #pragma unroll
-  for (int i = 0; i < (1 << (M - 1)); ++i)
-    v[i] = (x[0] & bitmask(tt, 2 * i + 1)) | (~x[0] & bitmask(tt, 2 * i));
+  for (int i = 0; i < (1 << (M > 0 ? M - 1 : 0)); ++i) v[i] = (x[0] & mk[2 * i + 1]) | (~x[0] & mk[2 * i]);
 #pragma unroll
   for (int k = 1; k < M; ++k) {
 #pragma unroll
@@ -78,19 +75,165 @@ __device__ __forceinline__ uint32_t plane_tt(uint64_t tt, const uint32_t* x) {
   return v[0];
 }
 
-__device__ __forceinline__ uint32_t plane_tt_dyn(int m, uint64_t tt, const uint32_t* x) {
-  switch (m) {
-    case 0: return plane_tt<0>(tt, x);
-    case 1: return plane_tt<1>(tt, x);
-    case 2: return plane_tt<2>(tt, x);
-    case 3: return plane_tt<3>(tt, x);
-    case 4: return plane_tt<4>(tt, x);
-    default: return plane_tt<5>(tt, x);
+template <int NPR, int WPT>
+struct PlaneCtx {
+  uint32_t P[NPR][WPT];
+  int64_t env[WPT];
+  int wi[WPT], el[WPT];
+  bool valid[WPT];
+};
+
+// Bernoulli(table[idx]) for the thread's WPT words; M index planes
+template <int M, int NPR, int WPT>
+__device__ __forceinline__ void plane_bernoulli(PlaneCtx<NPR, WPT>& C, const VmArgs& A, const PlaneProg& G,
+                                                const PlaneOp& o, uint32_t* queue, int* qn, uint32_t* fix) {
+  const int TT = 1 << M;
+  const uint32_t* W = G.words + o.off;
+  const uint32_t* bad = W;
+  const uint32_t* always = W + TT;
+  const uint32_t* lev = W + 2 * TT;                    // [levels][TT]
+  const uint32_t* thr = W + (2 + PLANE_BERN_LEVELS) * TT;   // [TT][2] lo, hi
+  const uint32_t* pvl = thr + 2 * TT;                  // [TT][2] float64 probability
+  const double* inj = A.inj[o.a];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t x[WPT][M > 0 ? M : 1];
+  uint32_t res[WPT], und[WPT];
+#pragma unroll
+  for (int j = 0; j < WPT; ++j) {
+#pragma unroll
+    for (int i = 0; i < M; ++i) x[j][i] = C.P[o.idx[i]][j];
+    res[j] = 0;
+    und[j] = 0;
+  }
+  if (o.b) {   // some table entries are outside [0, 1]: flag the envs that select them
+#pragma unroll
+    for (int j = 0; j < WPT; ++j)
+      if (C.valid[j] && plane_mux<M>(bad, x[j])) atomicOr(A.status + C.env[j], 1u);
+  }
+  if (inj) {
+    // parity mode: the reference's U <= p on the same float64 values (simulator.py:1053)
+#pragma unroll 1
+    for (int j = 0; j < WPT; ++j) {
+      if (!C.valid[j]) continue;
+      const double* u = inj + C.env[j] * A.L.E + ((int64_t)C.wi[j] << 5);
+      for (int b = 0; b < 32; ++b) {
+        int v = 0;
+#pragma unroll
+        for (int i = 0; i < M; ++i) v |= ((x[j][i] >> b) & 1u) << i;
+        const double p = __hiloint2double((int)pvl[2 * v + 1], (int)pvl[2 * v]);
+        res[j] |= (uint32_t)(u[b] <= p) << b;
+      }
+    }
+  } else {
+    const uint2 key = make_uint2((uint32_t)A.seed, (uint32_t)(A.seed >> 32));
+    const uint32_t node = (uint32_t)A.variates[o.a].node & 0xffffu;
+#pragma unroll
+    for (int j = 0; j < WPT; ++j) {
+      const uint32_t al = plane_mux<M>(always, x[j]);
+      res[j] = C.valid[j] ? al : 0u;
+      und[j] = C.valid[j] ? ~al : 0u;
+    }
+#pragma unroll
+    for (int b = 0; b < PLANE_BERN_LEVELS / 4; ++b) {
+      uint32_t rw[WPT][4];
+#pragma unroll
+      for (int j = 0; j < WPT; ++j) {
+        const uint4 r4 = rddl_philox4x32_10(
+            make_uint4((uint32_t)C.wi[j], (uint32_t)(A.env_offset + C.env[j]), (uint32_t)A.step,
+                       node | ((0x8000u + b) << 16)), key);
+        rw[j][0] = r4.x; rw[j][1] = r4.y; rw[j][2] = r4.z; rw[j][3] = r4.w;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint32_t mk[TT];
+#pragma unroll
+        for (int i = 0; i < TT; ++i) mk[i] = lev[(4 * b + q) * TT + i];
+#pragma unroll
+        for (int j = 0; j < WPT; ++j) {
+          const uint32_t pj = plane_mux<M>(mk, x[j]);
+          res[j] |= und[j] & ~rw[j][q] & pj;
+          und[j] &= ~(rw[j][q] ^ pj);
+        }
+      }
+    }
+    // cells still tied after the first levels (2^-8 of them): queued per warp and finished
+    // cooperatively, one 64-bit Philox draw per cell
+    if (lane == 0) qn[warp] = 0;
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < WPT; ++j) {
+      fix[tid * WPT + j] = 0;
+      uint32_t u = und[j];
+      while (u) {
+        const int b = __ffs(u) - 1;
+        u &= u - 1;
+        int v = 0;
+#pragma unroll
+        for (int i = 0; i < M; ++i) v |= ((x[j][i] >> b) & 1u) << i;
+        const int slot = atomicAdd(&qn[warp], 1);
+        const uint32_t entry = (uint32_t)lane | ((uint32_t)j << 5) | ((uint32_t)b << 8) | ((uint32_t)v << 13);
+        if (slot < PLANE_QUEUE) {
+          queue[warp * PLANE_QUEUE + slot] = entry;
+        } else {   // queue full (practically never): finish inline
+          const uint4 r4 = rddl_philox4x32_10(
+              make_uint4(((uint32_t)C.wi[j] << 5) | b, (uint32_t)(A.env_offset + C.env[j]), (uint32_t)A.step,
+                         node | (0xC000u << 16)), key);
+          const uint64_t t64 = ((uint64_t)thr[2 * v + 1] << 32) | thr[2 * v];
+          if ((((uint64_t)r4.x << 32) | r4.y) < (t64 << PLANE_BERN_LEVELS)) res[j] |= 1u << b;
+        }
+      }
+    }
+    __syncwarp();
+    const int n = min(qn[warp], PLANE_QUEUE);
+    for (int i = lane; i < n; i += 32) {
+      const uint32_t e = queue[warp * PLANE_QUEUE + i];
+      const int ol = e & 31, oj = (e >> 5) & 7, b = (e >> 8) & 31, v = e >> 13;
+      // owner's word coordinates (shuffle-free: recomputed from the tile geometry)
+      const int w = oj * 256 + warp * 32 + ol;
+      int64_t oenv;
+      int owi;
+      if (A.L.chunks == 1) {
+        const int wpe = (int)(A.L.E >> 5);
+        const int oel = w / wpe;
+        owi = w - oel * wpe;
+        oenv = (int64_t)(blockIdx.x) * A.L.G + oel;
+      } else {
+        owi = (blockIdx.x % A.L.chunks) * A.L.ipt + w;
+        oenv = blockIdx.x / A.L.chunks;
+      }
+      const uint4 r4 = rddl_philox4x32_10(
+          make_uint4(((uint32_t)owi << 5) | b, (uint32_t)(A.env_offset + oenv), (uint32_t)A.step,
+                     node | (0xC000u << 16)), key);
+      const uint64_t t64 = ((uint64_t)thr[2 * v + 1] << 32) | thr[2 * v];
+      if ((((uint64_t)r4.x << 32) | r4.y) < (t64 << PLANE_BERN_LEVELS))
+        atomicOr(&fix[(warp * 32 + ol) * WPT + oj], 1u << b);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < WPT; ++j) res[j] |= fix[tid * WPT + j];
+  }
+#pragma unroll
+  for (int j = 0; j < WPT; ++j) C.P[o.dst][j] = res[j];
+}
+
+template <int M, int NPR, int WPT>
+__device__ __forceinline__ void plane_lut(PlaneCtx<NPR, WPT>& C, const PlaneProg& G, const PlaneOp& o) {
+  const int TT = 1 << M;
+  uint32_t mk[TT];
+#pragma unroll
+  for (int i = 0; i < TT; ++i) mk[i] = G.words[o.off + i];
+#pragma unroll
+  for (int j = 0; j < WPT; ++j) {
+    uint32_t x[M > 0 ? M : 1];
+#pragma unroll
+    for (int i = 0; i < M; ++i) x[i] = C.P[o.idx[i]][j];
+    C.P[o.dst][j] = plane_mux<M>(mk, x);
   }
 }
 
-template <int NPR>
-__global__ void __launch_bounds__(256) rddl_plane_interp(const __grid_constant__ VmArgs A) {
+template <int NPR, int WPT>
+__global__ void __launch_bounds__(256) rddl_plane_interp(const __grid_constant__ VmArgs A,
+                                                          const __grid_constant__ PlaneProg G) {
   const RddlLaunch& L = A.L;
   const int tid = threadIdx.x;
   const int H = L.rank == 2 ? (int)L.extent[0] : 1;
@@ -100,67 +243,69 @@ __global__ void __launch_bounds__(256) rddl_plane_interp(const __grid_constant__
   const int chunk = blockIdx.x % chunks;
   const int64_t envgrp = blockIdx.x / chunks;
 
-  __shared__ uint32_t S[2][PLANE_SMEM_WORDS];
-  __shared__ int32_t cnt[32][RDDL_MAX_RED][8];
-  for (int i = tid; i < 32 * RDDL_MAX_RED * 8; i += 256) (&cnt[0][0][0])[i] = 0;
+  // dynamic shared memory: [nshared][tile_words + 2*W32] stencil planes | cnt | queue | fix
+  extern __shared__ uint32_t smem[];
+  const int plane_stride = tile_words + 2 * W32;
+  uint32_t* S = smem;
+  int32_t* cnt = reinterpret_cast<int32_t*>(smem + G.nshared * plane_stride);   // [32][MAX_RED][2]
+  uint32_t* queue = reinterpret_cast<uint32_t*>(cnt + 32 * RDDL_MAX_RED * 2);    // [8][PLANE_QUEUE]
+  int* qn = reinterpret_cast<int*>(queue + 8 * PLANE_QUEUE);                     // [8]
+  uint32_t* fix = reinterpret_cast<uint32_t*>(qn + 8);                           // [256][WPT]
+  for (int i = tid; i < 32 * RDDL_MAX_RED * 2; i += 256) cnt[i] = 0;
 
-  uint32_t P[NPR][4];
-  int64_t env[4];
-  int wi[4], el[4];
-  bool valid[4];
+  PlaneCtx<NPR, WPT> C;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < WPT; ++j) {
     const int w = j * 256 + tid;
     bool ok = w < tile_words;
     if (chunks == 1) {
-      el[j] = w / wpe;
-      wi[j] = w - el[j] * wpe;
-      env[j] = envgrp * envs_per_tile + el[j];
+      C.el[j] = w / wpe;
+      C.wi[j] = w - C.el[j] * wpe;
+      C.env[j] = envgrp * envs_per_tile + C.el[j];
     } else {
-      el[j] = 0;
-      wi[j] = chunk * tile_words + w;
-      env[j] = envgrp;
-      ok = ok && wi[j] < wpe;
+      C.el[j] = 0;
+      C.wi[j] = chunk * tile_words + w;
+      C.env[j] = envgrp;
+      ok = ok && C.wi[j] < wpe;
     }
-    valid[j] = ok && env[j] < A.n_envs;
+    C.valid[j] = ok && C.env[j] < A.n_envs;
   }
   __syncthreads();
 
-  const RddlInsn* prog = A.insns + L.pc_begin;
-  const int npc = L.pc_end - L.pc_begin;
-  for (int pc = 0; pc < npc; ++pc) {
-    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(prog + pc));
-    const uint32_t op = raw.x & 0xff;
-    const uint32_t dst = raw.x >> 16;
-    const uint32_t ra = raw.y & 0xffff, rb = raw.y >> 16;
-    const uint32_t imm = raw.w;
-    switch (op) {
+  for (int pc = 0; pc < G.nops; ++pc) {
+    const PlaneOp o = G.ops[pc];
+    switch (o.op) {
       case OP_PLD: {
-        const uint8_t* base = reinterpret_cast<const uint8_t*>(A.tensors[imm]);
+        const uint8_t* base = reinterpret_cast<const uint8_t*>(A.tensors[o.imm]);
+        uint4 lo[WPT], hi[WPT];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint32_t word = 0;
-          if (valid[j]) {
-            const uint4* p = reinterpret_cast<const uint4*>(base + ((env[j] * wpe + wi[j]) << 5));
-            word = plane_pack(__ldcs(p), __ldcs(p + 1));
+        for (int j = 0; j < WPT; ++j) {
+          lo[j] = make_uint4(0, 0, 0, 0);
+          hi[j] = lo[j];
+          if (C.valid[j]) {
+            const uint4* p = reinterpret_cast<const uint4*>(base + ((C.env[j] * wpe + C.wi[j]) << 5));
+            lo[j] = __ldcs(p);
+            hi[j] = __ldcs(p + 1);
           }
-          P[dst][j] = word;
         }
+#pragma unroll
+        for (int j = 0; j < WPT; ++j) C.P[o.dst][j] = plane_pack(lo[j], hi[j]);
         break;
       }
       case OP_PLDC: {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) P[dst][j] = valid[j] ? (uint32_t)__ldg(A.pool + imm + wi[j]) : 0u;
+        for (int j = 0; j < WPT; ++j)
+          C.P[o.dst][j] = C.valid[j] ? (uint32_t)__ldg(A.pool + o.imm + C.wi[j]) : 0u;
         break;
       }
       case OP_PST: {
-        uint8_t* base = reinterpret_cast<uint8_t*>(A.tensors[imm]);
+        uint8_t* base = reinterpret_cast<uint8_t*>(A.tensors[o.imm]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (valid[j]) {
+        for (int j = 0; j < WPT; ++j) {
+          if (C.valid[j]) {
             uint4 lo, hi;
-            plane_unpack(P[ra][j], lo, hi);
-            uint4* p = reinterpret_cast<uint4*>(base + ((env[j] * wpe + wi[j]) << 5));
+            plane_unpack(C.P[o.a][j], lo, hi);
+            uint4* p = reinterpret_cast<uint4*>(base + ((C.env[j] * wpe + C.wi[j]) << 5));
             __stcs(p, lo);
             __stcs(p + 1, hi);
           }
@@ -169,37 +314,35 @@ __global__ void __launch_bounds__(256) rddl_plane_interp(const __grid_constant__
       }
       case OP_PCONST: {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) P[dst][j] = imm ? 0xffffffffu : 0u;
+        for (int j = 0; j < WPT; ++j) C.P[o.dst][j] = o.imm ? 0xffffffffu : 0u;
         break;
       }
       case OP_PLUT: {
-        const PlaneFin f = plane_fin(A.consts + imm);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint32_t x[5];
-#pragma unroll
-          for (int i = 0; i < 5; ++i) x[i] = i < f.m ? P[(f.regs >> (8 * i)) & 0xff][j] : 0u;
-          P[dst][j] = plane_tt_dyn(f.m, f.truth, x);
+        switch (o.m) {
+          case 1: plane_lut<1>(C, G, o); break;
+          case 2: plane_lut<2>(C, G, o); break;
+          case 3: plane_lut<3>(C, G, o); break;
+          case 4: plane_lut<4>(C, G, o); break;
+          default: plane_lut<5>(C, G, o); break;
         }
         break;
       }
       case OP_PSHARE: {
-        uint32_t* s = S[rb];
+        uint32_t* s = S + o.b * plane_stride;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < WPT; ++j) {
           const int w = j * 256 + tid;
-          if (w < tile_words) s[W32 + w] = valid[j] ? P[ra][j] : 0u;
+          if (w < tile_words) s[W32 + w] = C.valid[j] ? C.P[o.a][j] : 0u;
         }
         if (chunks > 1) {
           // halo rows above / below the tile, packed straight from the source tensor
-          const uint8_t* base = reinterpret_cast<const uint8_t*>(A.tensors[imm]);
-          const int64_t e = envgrp;
+          const uint8_t* base = reinterpret_cast<const uint8_t*>(A.tensors[o.imm]);
           for (int i = tid; i < 2 * W32; i += 256) {
             const bool top = i < W32;
             const int wsrc = top ? chunk * tile_words - W32 + i : (chunk + 1) * tile_words + (i - W32);
             uint32_t word = 0;
-            if (wsrc >= 0 && wsrc < wpe && e < A.n_envs) {
-              const uint4* p = reinterpret_cast<const uint4*>(base + ((e * wpe + wsrc) << 5));
+            if (wsrc >= 0 && wsrc < wpe && envgrp < A.n_envs) {
+              const uint4* p = reinterpret_cast<const uint4*>(base + ((envgrp * wpe + wsrc) << 5));
               word = plane_pack(__ldg(p), __ldg(p + 1));
             }
             s[top ? i : W32 + tile_words + (i - W32)] = word;
@@ -209,12 +352,12 @@ __global__ void __launch_bounds__(256) rddl_plane_interp(const __grid_constant__
         break;
       }
       case OP_PCOUNT: {
-        const uint32_t* s = S[rb];
+        const uint32_t* s = S + o.b * plane_stride;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < WPT; ++j) {
           uint32_t k0 = 0, k1 = 0, k2 = 0, k3 = 0;
-          if (valid[j]) {
-            const int x = wi[j] / W32, c = wi[j] - x * W32;
+          if (C.valid[j]) {
+            const int x = C.wi[j] / W32, c = C.wi[j] - x * W32;
             const int pos = W32 + j * 256 + tid;
             uint32_t sr[3], cr[3];   // per row: sum and carry of the (west, centre, east) planes
 #pragma unroll
@@ -227,7 +370,7 @@ __global__ void __launch_bounds__(256) rddl_plane_interp(const __grid_constant__
                 if (c > 0) Lw = s[q - 1];
                 if (c < W32 - 1) Rw = s[q + 1];
               }
-              const uint32_t m3 = imm >> (d * 3);
+              const uint32_t m3 = o.imm >> (d * 3);
               const uint32_t west = (m3 & 1u) ? ((Cw << 1) | (Lw >> 31)) : 0u;
               const uint32_t mid = (m3 & 2u) ? Cw : 0u;
               const uint32_t east = (m3 & 4u) ? ((Cw >> 1) | (Rw << 31)) : 0u;
@@ -243,87 +386,32 @@ __global__ void __launch_bounds__(256) rddl_plane_interp(const __grid_constant__
             k2 = u2 ^ v;
             k3 = u2 & v;
           }
-          P[dst][j] = k0; P[dst + 1][j] = k1; P[dst + 2][j] = k2; P[dst + 3][j] = k3;
+          C.P[o.dst][j] = k0; C.P[o.dst + 1][j] = k1; C.P[o.dst + 2][j] = k2; C.P[o.dst + 3][j] = k3;
         }
         break;
       }
       case OP_PBERN: {
-        const PlaneFin f = plane_fin(A.consts + imm);
-        const double* inj = A.inj[ra];
-        const uint32_t node = (uint32_t)A.variates[ra].node & 0xffffu;
-        const uint2 key = make_uint2((uint32_t)A.seed, (uint32_t)(A.seed >> 32));
-#pragma unroll 1
-        for (int j = 0; j < 4; ++j) {
-          uint32_t res = 0;
-          if (valid[j]) {
-            uint32_t x[5];
-#pragma unroll
-            for (int i = 0; i < 5; ++i) x[i] = i < f.m ? P[(f.regs >> (8 * i)) & 0xff][j] : 0u;
-            if (f.bad) {
-              if (plane_tt_dyn(f.m, f.bad, x)) atomicOr(A.status + env[j], 1u);
-            }
-            if (inj) {
-              // parity mode: the reference's U <= p on the same float64 values
-              const double* u = inj + env[j] * L.E + ((int64_t)wi[j] << 5);
-              for (int b = 0; b < 32; ++b) {
-                int v = 0;
-                for (int i = 0; i < f.m; ++i) v |= ((x[i] >> b) & 1u) << i;
-                res |= (uint32_t)(u[b] <= __longlong_as_double((long long)f.vals[v])) << b;
-              }
-            } else {
-              const uint32_t g = (uint32_t)wi[j];
-              const uint32_t e32 = (uint32_t)(A.env_offset + env[j]);
-              const uint32_t always = plane_tt_dyn(f.m, f.always, x);
-              res = always;
-              uint32_t und = ~always;
-#pragma unroll
-              for (int b = 0; b < PLANE_BERN_LEVELS / 4; ++b) {
-                const uint4 r4 = rddl_philox4x32_10(
-                    make_uint4(g, e32, (uint32_t)A.step, node | ((0x8000u + b) << 16)), key);
-                const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const uint32_t pj = plane_tt_dyn(f.m, f.lev[4 * b + q], x);
-                  res |= und & ~rw[q] & pj;
-                  und &= ~(rw[q] ^ pj);
-                }
-              }
-              // cells still tied after the first levels: finish each with one 64-bit draw
-              while (und) {
-                const int b = __ffs(und) - 1;
-                und &= und - 1;
-                int v = 0;
-                for (int i = 0; i < f.m; ++i) v |= ((x[i] >> b) & 1u) << i;
-                const uint4 r4 = rddl_philox4x32_10(
-                    make_uint4((g << 5) | b, e32, (uint32_t)A.step, node | ((0xC000u + (g >> 27)) << 16)), key);
-                const uint64_t u64 = ((uint64_t)r4.x << 32) | r4.y;
-                if (u64 < (f.thr[v] << PLANE_BERN_LEVELS)) res |= 1u << b;
-              }
-            }
-          }
-          P[dst][j] = res;
+        switch (o.m) {
+          case 0: plane_bernoulli<0>(C, A, G, o, queue, qn, fix); break;
+          case 1: plane_bernoulli<1>(C, A, G, o, queue, qn, fix); break;
+          case 2: plane_bernoulli<2>(C, A, G, o, queue, qn, fix); break;
+          case 3: plane_bernoulli<3>(C, A, G, o, queue, qn, fix); break;
+          default: plane_bernoulli<4>(C, A, G, o, queue, qn, fix); break;
         }
         break;
       }
       case OP_PRED: {
-        const PlaneFin f = plane_fin(A.consts + imm);
-        const bool warp_uniform_env = (wpe & 31) == 0;
-#pragma unroll 1
-        for (int j = 0; j < 4; ++j) {
-          uint32_t x[3];
+        // per-env popcount of a plane (m == 1) or of the valid cells (m == 0)
+        const bool warp_uniform_env = (wpe & 31) == 0 || chunks > 1;
 #pragma unroll
-          for (int i = 0; i < 3; ++i) x[i] = (valid[j] && i < f.m) ? P[(f.regs >> (8 * i)) & 0xff][j] : 0u;
-          for (int v = 0; v < (1 << f.m); ++v) {
-            if (f.vals[v] == 0ull || f.vals[v] == 0x8000000000000000ull) continue;   // +-0 contributes nothing
-            uint32_t mt = valid[j] ? 0xffffffffu : 0u;
-            for (int i = 0; i < f.m; ++i) mt &= ((v >> i) & 1) ? x[i] : ~x[i];
-            int c = __popc(mt);
-            if (warp_uniform_env) {
-              c = __reduce_add_sync(0xffffffffu, c);
-              if ((tid & 31) == 0 && c) atomicAdd(&cnt[el[j]][rb][v], c);
-            } else if (c) {
-              atomicAdd(&cnt[el[j]][rb][v], c);
-            }
+        for (int j = 0; j < WPT; ++j) {
+          const uint32_t x = o.m ? C.P[o.idx[0]][j] : 0xffffffffu;
+          int c = C.valid[j] ? __popc(x) : 0;
+          if (warp_uniform_env) {
+            c = __reduce_add_sync(0xffffffffu, c);
+            if ((tid & 31) == 0 && c) atomicAdd(&cnt[(C.el[j] * RDDL_MAX_RED + o.b) * 2], c);
+          } else if (c) {
+            atomicAdd(&cnt[(C.el[j] * RDDL_MAX_RED + o.b) * 2], c);
           }
         }
         break;
@@ -334,27 +422,26 @@ __global__ void __launch_bounds__(256) rddl_plane_interp(const __grid_constant__
 
   if (L.nred > 0) {
     __syncthreads();
+    const int64_t cells = chunks == 1 ? L.E : (int64_t)min(tile_words, wpe - chunk * tile_words) * 32;
     for (int i = tid; i < envs_per_tile * L.nred; i += 256) {
       const int e = i / L.nred, jr = i - e * L.nred;
       const int64_t ge = envgrp * envs_per_tile + e;
       if (ge >= A.n_envs) continue;
-      // locate the PRED instruction of reduction jr to read its value table
-      const uint64_t* fc = nullptr;
-      for (int pc = 0; pc < npc; ++pc) {
-        const RddlInsn in = prog[pc];
-        if (in.op == OP_PRED && in.b == jr) fc = A.consts + in.imm;
-      }
-      const PlaneFin f = plane_fin(fc);
+      // the PRED op of reduction jr carries (value at 0, value at 1) as raw 64-bit words
+      uint32_t off = 0, m = 0;
+      for (int pc = 0; pc < G.nops; ++pc)
+        if (G.ops[pc].op == OP_PRED && G.ops[pc].b == jr) { off = G.ops[pc].off; m = G.ops[pc].m; }
+      const uint64_t v0 = ((uint64_t)G.words[off + 1] << 32) | G.words[off];
+      const uint64_t v1 = ((uint64_t)G.words[off + 3] << 32) | G.words[off + 2];
+      const int64_t ones = cnt[(e * RDDL_MAX_RED + jr) * 2];
+      const int64_t n1 = m ? ones : 0, n0 = m ? cells - ones : cells;
       uint64_t out;
       if (L.red_op[jr] == RED_SUM_F) {
-        double acc = 0.0;
-        for (int v = 0; v < (1 << f.m); ++v)
-          acc = __dadd_rn(acc, __dmul_rn(__longlong_as_double((long long)f.vals[v]), (double)cnt[e][jr][v]));
+        double acc = __dmul_rn(__longlong_as_double((long long)v0), (double)n0);
+        acc = __dadd_rn(acc, __dmul_rn(__longlong_as_double((long long)v1), (double)n1));
         out = (uint64_t)__double_as_longlong(acc);
       } else {
-        int64_t acc = 0;
-        for (int v = 0; v < (1 << f.m); ++v) acc += (int64_t)f.vals[v] * (int64_t)cnt[e][jr][v];
-        out = (uint64_t)acc;
+        out = (uint64_t)((int64_t)v0 * n0 + (int64_t)v1 * n1);
       }
       A.red[A.red_off[L.red_slot[jr]] * A.n_envs + ge * chunks + chunk] = out;
     }

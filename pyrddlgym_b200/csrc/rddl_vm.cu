@@ -409,7 +409,55 @@ struct rddl_program {
   bool profiling = false;
   struct Timed { int launch; cudaEvent_t e0, e1; };
   std::vector<Timed> timed;
+  std::vector<PlaneProg> plane_progs;   // per launch index; pre-decoded programs of plane launches
 };
+
+// Pre-decodes the instructions of a plane launch (and the Fin descriptors they reference in the
+// const pool: [m, regs, truth, bad, always, thr[2^m], vals[2^m], lev[levels]]) into a PlaneProg.
+static bool decode_plane(const RddlLaunch& L, const RddlInsn* insns, const uint64_t* consts, int64_t n_consts,
+                         PlaneProg* G, std::string* err) {
+  memset(G, 0, sizeof *G);
+  int nw = 0;
+  auto need = [&](int n) { return nw + n <= PLANE_WORDS; };
+  for (int pc = L.pc_begin; pc < L.pc_end; ++pc) {
+    const RddlInsn& in = insns[pc];
+    if (G->nops >= PLANE_MAX_OPS) { *err = "plane program too long"; return false; }
+    PlaneOp& o = G->ops[G->nops++];
+    o.op = in.op; o.dst = (uint8_t)in.dst; o.a = (uint8_t)in.a; o.b = (uint8_t)in.b; o.imm = in.imm;
+    o.off = (uint16_t)nw;
+    if (in.op == OP_PSHARE && (int)in.b + 1 > G->nshared) G->nshared = in.b + 1;
+    if (in.op != OP_PLUT && in.op != OP_PBERN && in.op != OP_PRED) continue;
+    if ((int64_t)in.imm + 5 > n_consts) { *err = "plane op: bad Fin index"; return false; }
+    const uint64_t* c = consts + in.imm;
+    const int m = (int)c[0];
+    if (m < 0 || m > 5 || (int64_t)in.imm + 5 + 2 * (1 << m) > n_consts) { *err = "plane op: bad Fin"; return false; }
+    const int TT = 1 << m;
+    o.m = (uint8_t)m;
+    for (int i = 0; i < m; ++i) o.idx[i] = (uint8_t)((c[1] >> (8 * i)) & 0xff);
+    const uint64_t* thr = c + 5;
+    const uint64_t* vals = c + 5 + TT;
+    if (in.op == OP_PLUT) {
+      if (!need(TT)) { *err = "plane tables too large"; return false; }
+      for (int v = 0; v < TT; ++v) G->words[nw++] = ((c[2] >> v) & 1) ? 0xffffffffu : 0u;
+    } else if (in.op == OP_PBERN) {
+      if (m > 4 || !need((2 + PLANE_BERN_LEVELS) * TT + 4 * TT)) { *err = "plane tables too large"; return false; }
+      const uint64_t* lev = c + 5 + 2 * TT;
+      o.b = c[3] != 0;
+      for (int v = 0; v < TT; ++v) G->words[nw++] = ((c[3] >> v) & 1) ? 0xffffffffu : 0u;
+      for (int v = 0; v < TT; ++v) G->words[nw++] = ((c[4] >> v) & 1) ? 0xffffffffu : 0u;
+      for (int j = 0; j < PLANE_BERN_LEVELS; ++j)
+        for (int v = 0; v < TT; ++v) G->words[nw++] = ((lev[j] >> v) & 1) ? 0xffffffffu : 0u;
+      for (int v = 0; v < TT; ++v) { G->words[nw++] = (uint32_t)thr[v]; G->words[nw++] = (uint32_t)(thr[v] >> 32); }
+      for (int v = 0; v < TT; ++v) { G->words[nw++] = (uint32_t)vals[v]; G->words[nw++] = (uint32_t)(vals[v] >> 32); }
+    } else {
+      if (m > 1 || !need(4)) { *err = "plane reduction over more than one plane"; return false; }
+      G->words[nw++] = (uint32_t)vals[0]; G->words[nw++] = (uint32_t)(vals[0] >> 32);
+      const uint64_t v1 = m ? vals[1] : 0;
+      G->words[nw++] = (uint32_t)v1; G->words[nw++] = (uint32_t)(v1 >> 32);
+    }
+  }
+  return true;
+}
 
 #define CK(call)                                                                      \
   do {                                                                                \
@@ -457,6 +505,15 @@ extern "C" int rddl_program_create(const void* optable, size_t nbytes, int devic
   g->redslots.assign((const RddlRedSlot*)sec[7], (const RddlRedSlot*)sec[7] + hdr[9]);
   g->variates.assign((const RddlVariate*)sec[8], (const RddlVariate*)sec[8] + hdr[10]);
   g->n_insns = hdr[4];
+  g->plane_progs.resize(g->launches.size());
+  for (size_t i = 0; i < g->launches.size(); ++i) {
+    if (g->launches[i].kind != 1) continue;
+    if (!decode_plane(g->launches[i], (const RddlInsn*)sec[2], (const uint64_t*)sec[3], hdr[5],
+                      &g->plane_progs[i], &g_create_error)) {
+      delete g;
+      return RDDL_ERR_FORMAT;
+    }
+  }
   for (auto& L : g->launches) {
     const bool bad_scalar = L.kind == 0 && (L.nregs > RDDL_MAX_REGS || L.G > 256 || (L.G & (L.G - 1)));
     const bool bad_plane = L.kind == 1 && (L.nregs > PLANE_MAX_REGS || L.G > 32 || L.ipt > 1024 || (L.E & 31));
@@ -538,7 +595,19 @@ static int run_plan(rddl_program* g, int plan, void* const* tensors, const doubl
   for (const RddlLaunch& L : g->launches) {
     if (L.plan != plan) continue;
     A.L = L;
-    const int envs_per_cta = L.kind == 1 ? L.G : 256 / L.G;
+    int wpt = 4;
+    if (L.kind == 1 && L.chunks == 1 && L.E <= 8192) {
+      // small batch: one word per thread so that the grid still covers all SMs
+      const int64_t tiles4 = (n_envs + L.G - 1) / L.G;
+      if (tiles4 < 4 * 148) {
+        wpt = 1;
+        int ept = (int)(8192 / L.E);
+        if (ept > 32) ept = 32;
+        A.L.G = ept;
+        A.L.ipt = (int)(ept * (L.E >> 5));
+      }
+    }
+    const int envs_per_cta = L.kind == 1 ? A.L.G : 256 / L.G;
     const int64_t groups = (n_envs + envs_per_cta - 1) / envs_per_cta;
     const int64_t blocks = groups * L.chunks;
     if (blocks > 0x7fffffffll) { g->err = "grid too large"; return RDDL_ERR_ARG; }
@@ -550,8 +619,18 @@ static int run_plan(rddl_program* g, int plan, void* const* tensors, const doubl
       CK(cudaEventRecord(tm.e0, stream));
     }
     if (L.kind == 1) {
-      if (L.nregs <= 16) rddl_plane_interp<16><<<(unsigned)blocks, 256, 0, stream>>>(A);
-      else rddl_plane_interp<PLANE_MAX_REGS><<<(unsigned)blocks, 256, 0, stream>>>(A);
+      const PlaneProg& G = g->plane_progs[(size_t)(&L - g->launches.data())];
+      const int W32 = (int)((L.rank == 2 ? L.extent[1] : L.extent[0]) >> 5);
+      const size_t smem = sizeof(uint32_t) * ((size_t)G.nshared * (A.L.ipt + 2 * W32) + 32 * RDDL_MAX_RED * 2 +
+                                              8 * PLANE_QUEUE + 8 + 256 * wpt);
+      const bool small = L.nregs <= 16;
+      if (wpt == 1) {
+        if (small) rddl_plane_interp<16, 1><<<(unsigned)blocks, 256, smem, stream>>>(A, G);
+        else rddl_plane_interp<PLANE_MAX_REGS, 1><<<(unsigned)blocks, 256, smem, stream>>>(A, G);
+      } else {
+        if (small) rddl_plane_interp<16, 4><<<(unsigned)blocks, 256, smem, stream>>>(A, G);
+        else rddl_plane_interp<PLANE_MAX_REGS, 4><<<(unsigned)blocks, 256, smem, stream>>>(A, G);
+      }
     } else if (L.nregs <= 16) rddl_level_interp<16><<<(unsigned)blocks, 256, 0, stream>>>(A);
     else if (L.nregs <= 40) rddl_level_interp<40><<<(unsigned)blocks, 256, 0, stream>>>(A);
     else rddl_level_interp<RDDL_MAX_REGS><<<(unsigned)blocks, 256, 0, stream>>>(A);

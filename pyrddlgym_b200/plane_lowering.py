@@ -437,11 +437,15 @@ class PlaneBuilder:
                 raise NotPlanar('forall/exists plane reductions')      # TODO popcount compare
             if rop not in (RED['SUM_I'], RED['SUM_F']):
                 raise NotPlanar('reduction op')
-            if f.m > MAX_M_RED:
-                if f.cls == 'b':
-                    f = self.as_plane_fin(f)
-                else:
-                    raise NotPlanar('reduction value depends on too many bits')
+            if f.m > 1:
+                # value = c * [boolean expression]: reduce the popcount of the materialised plane
+                tab = np.asarray(_one(f.table))
+                nz = tab[tab != 0]
+                if len(nz) and not np.all(nz == nz[0]):
+                    raise NotPlanar('reduction value is not coefficient * boolean')
+                c = nz[0] if len(nz) else tab.dtype.type(0)
+                r = self.materialise(Fin(f.idx, tab != 0))
+                f = Fin((r,), np.array([tab.dtype.type(0), c]))
             if rop == RED['SUM_F']:
                 vals = np.asarray(_one(f.table), dtype=np.float64)
             else:
