@@ -430,7 +430,8 @@ static bool decode_plane(const RddlLaunch& L, const RddlInsn* insns, const uint6
     if ((int64_t)in.imm + 5 > n_consts) { *err = "plane op: bad Fin index"; return false; }
     const uint64_t* c = consts + in.imm;
     const int m = (int)c[0];
-    if (m < 0 || m > 5 || (int64_t)in.imm + 5 + 2 * (1 << m) > n_consts) { *err = "plane op: bad Fin"; return false; }
+    const int64_t fin_words = 5 + (in.op == OP_PLUT ? 0 : 2 * (1 << (m & 7))) + (in.op == OP_PBERN ? PLANE_BERN_LEVELS : 0);
+    if (m < 0 || m > 5 || (int64_t)in.imm + fin_words > n_consts) { *err = "plane op: bad Fin"; return false; }
     const int TT = 1 << m;
     o.m = (uint8_t)m;
     for (int i = 0; i < m; ++i) o.idx[i] = (uint8_t)((c[1] >> (8 * i)) & 0xff);

@@ -51,3 +51,23 @@ def test_backend_refuses_cpu_device():
     p = workloads.load_program(workloads.cartpole())
     with pytest.raises(native.NativeError):
         BatchedSimulator(p, n_envs=2, device='cpu')
+
+
+def test_every_workload_optable_decodes_on_the_host():
+    """rddl_program_create parses and pre-decodes the op table before touching CUDA: without a
+    GPU it must get past the format checks and fail at cudaSetDevice (RDDL_ERR_CUDA = -2)."""
+    import ctypes
+    import torch
+    from pyrddlgym_b200 import lowering, native, workloads
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip('host-only check')
+    lib = native.load()
+    specs = [workloads.cartpole(), workloads.opzoo(), workloads.wildfire(32), workloads.wildfire(64, separable=True),
+             workloads.reservoir(40), workloads.pair_contraction(24)]
+    for spec in specs:
+        blob = lowering.lower(workloads.load_program(spec)).blob
+        h = ctypes.c_void_p()
+        buf = ctypes.create_string_buffer(blob, len(blob))
+        rc = lib.rddl_program_create(ctypes.cast(buf, ctypes.c_void_p), len(blob), 0, ctypes.byref(h))
+        assert rc == -2, (spec['name'], rc, lib.rddl_last_error(None))
