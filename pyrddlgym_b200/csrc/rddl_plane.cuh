@@ -10,7 +10,8 @@
 // bytes (32 B per thread, two 128-bit vector accesses), i.e. fully coalesced.
 // The op table of the launch is pre-decoded on the host (PlaneProg, passed in the kernel
 // parameter constant bank): truth tables arrive expanded to 32-bit masks, so a table lookup
-// over m index planes is a (2^m - 1)-LOP3 multiplexer tree.
+// over m index planes is a (2^m - 1)-LOP3 multiplexer tree whose leaf masks are read
+// straight from the constant bank.
 //   PLD/PST   bytes <-> bits          PLDC    pre-packed non-fluent plane
 //   PLUT      m-input truth table     PSHARE  stage a plane (+ halo rows) in shared memory
 //   PCOUNT    3x3 stencil count as 4 bit-sliced planes (carry-save adders)
@@ -22,19 +23,20 @@
 
 #define PLANE_MAX_REGS 32
 #define PLANE_MAX_OPS 40
-#define PLANE_WORDS 2048
+#define PLANE_WORDS 1536
 #define PLANE_BERN_LEVELS 8
 #define PLANE_QUEUE 96
 
-struct PlaneOp {        // 16 bytes, pre-decoded from RddlInsn + its Fin descriptor
-  uint8_t op, dst, a, b, m;
-  uint8_t idx[5];
-  uint16_t off;         // offset of this op's tables in PlaneProg::words
+struct PlaneOp {        // 32 bytes, pre-decoded from RddlInsn + its Fin descriptor
+  int32_t op, dst, a, b;
+  int32_t m;            // index planes; bit 8: upper half of the table is constant
+  uint32_t idx;         // index plane registers, 6 bits each
+  int32_t off;          // offset of this op's tables in PlaneProg::words
   uint32_t imm;
 };
 
 struct PlaneProg {
-  int32_t nops, nshared, smem_bytes, pad;
+  int32_t nops, nshared, w32_shift, wpe_shift;   // shifts: log2 of words per row / per env, or -1
   PlaneOp ops[PLANE_MAX_OPS];
   uint32_t words[PLANE_WORDS];
 };
@@ -60,7 +62,7 @@ __device__ __forceinline__ void plane_unpack(uint32_t w, uint4& lo, uint4& hi) {
   hi.z = plane_nib((w >> 24) & 15u);  hi.w = plane_nib(w >> 28);
 }
 
-// multiplexer tree: value of the table (2^M masks) at the cell-wise index formed by x[0..M)
+// multiplexer tree: value of the table (2^M masks at mk[]) at the cell-wise index x[0..M)
 template <int M>
 __device__ __forceinline__ uint32_t plane_mux(const uint32_t* mk, const uint32_t* x) {
   if (M == 0) return mk[0];
@@ -75,165 +77,176 @@ __device__ __forceinline__ uint32_t plane_mux(const uint32_t* mk, const uint32_t
   return v[0];
 }
 
+// same, for tables whose upper half is the constant mk[1 << (M-1)] (HC) or general tables
+template <int M, bool HC>
+__device__ __forceinline__ uint32_t plane_mux_hc(const uint32_t* mk, const uint32_t* x) {
+  if (!HC || M == 0) return plane_mux<M>(mk, x);
+  const uint32_t lo = plane_mux<(M > 0 ? M - 1 : 0)>(mk, x);
+  return (x[M > 0 ? M - 1 : 0] & mk[1 << (M > 0 ? M - 1 : 0)]) | (~x[M > 0 ? M - 1 : 0] & lo);
+}
+
 template <int NPR, int WPT>
 struct PlaneCtx {
   uint32_t P[NPR][WPT];
-  int64_t env[WPT];
-  int wi[WPT], el[WPT];
-  bool valid[WPT];
+  int env[WPT];       // local env index (relative to the launch's first env)
+  int wi[WPT];        // word index inside the env
+  uint32_t valid;     // bit j: word j is inside the batch
 };
 
+__device__ __forceinline__ int plane_reg(uint32_t idx, int i) { return (idx >> (6 * i)) & 63; }
+
 // Bernoulli(table[idx]) for the thread's WPT words; M index planes
-template <int M, int NPR, int WPT>
-__device__ __forceinline__ void plane_bernoulli(PlaneCtx<NPR, WPT>& C, const VmArgs& A, const PlaneProg& G,
-                                                const PlaneOp& o, uint32_t* queue, int* qn, uint32_t* fix) {
+template <int M, bool HC, int NPR, int WPT>
+__device__ __noinline__ void plane_bernoulli(PlaneCtx<NPR, WPT>& C, const VmArgs& A, const PlaneProg& G,
+                                             const PlaneOp& o, uint32_t* queue, int* qn, uint32_t* fix,
+                                             int64_t env0) {
   const int TT = 1 << M;
   const uint32_t* W = G.words + o.off;
   const uint32_t* bad = W;
   const uint32_t* always = W + TT;
-  const uint32_t* lev = W + 2 * TT;                    // [levels][TT]
+  const uint32_t* lev = W + 2 * TT;                         // [levels][TT]
   const uint32_t* thr = W + (2 + PLANE_BERN_LEVELS) * TT;   // [TT][2] lo, hi
-  const uint32_t* pvl = thr + 2 * TT;                  // [TT][2] float64 probability
+  const uint32_t* pvl = thr + 2 * TT;                       // [TT][2] float64 probability
   const double* inj = A.inj[o.a];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  uint32_t x[WPT][M > 0 ? M : 1];
-  uint32_t res[WPT], und[WPT];
-#pragma unroll
-  for (int j = 0; j < WPT; ++j) {
-#pragma unroll
-    for (int i = 0; i < M; ++i) x[j][i] = C.P[o.idx[i]][j];
-    res[j] = 0;
-    und[j] = 0;
-  }
-  if (o.b) {   // some table entries are outside [0, 1]: flag the envs that select them
-#pragma unroll
-    for (int j = 0; j < WPT; ++j)
-      if (C.valid[j] && plane_mux<M>(bad, x[j])) atomicOr(A.status + C.env[j], 1u);
-  }
+  const bool has_bad = (o.b & 1) != 0, has_always = (o.b & 2) != 0;
   if (inj) {
     // parity mode: the reference's U <= p on the same float64 values (simulator.py:1053)
 #pragma unroll 1
     for (int j = 0; j < WPT; ++j) {
-      if (!C.valid[j]) continue;
-      const double* u = inj + C.env[j] * A.L.E + ((int64_t)C.wi[j] << 5);
-      for (int b = 0; b < 32; ++b) {
-        int v = 0;
+      uint32_t res = 0;
+      if ((C.valid >> j) & 1u) {
+        uint32_t x[M > 0 ? M : 1];
 #pragma unroll
-        for (int i = 0; i < M; ++i) v |= ((x[j][i] >> b) & 1u) << i;
-        const double p = __hiloint2double((int)pvl[2 * v + 1], (int)pvl[2 * v]);
-        res[j] |= (uint32_t)(u[b] <= p) << b;
+        for (int i = 0; i < M; ++i) x[i] = C.P[plane_reg(o.idx, i)][j];
+        if (has_bad && plane_mux<M>(bad, x)) atomicOr(A.status + env0 + C.env[j], 1u);
+        const double* u = inj + (env0 + C.env[j]) * A.L.E + ((int64_t)C.wi[j] << 5);
+        for (int b = 0; b < 32; ++b) {
+          int v = 0;
+#pragma unroll
+          for (int i = 0; i < M; ++i) v |= ((x[i] >> b) & 1u) << i;
+          const double p = __hiloint2double((int)pvl[2 * v + 1], (int)pvl[2 * v]);
+          res |= (uint32_t)(u[b] <= p) << b;
+        }
       }
+      C.P[o.dst][j] = res;
     }
-  } else {
-    const uint2 key = make_uint2((uint32_t)A.seed, (uint32_t)(A.seed >> 32));
-    const uint32_t node = (uint32_t)A.variates[o.a].node & 0xffffu;
+    return;
+  }
+  const uint2 key = make_uint2((uint32_t)A.seed, (uint32_t)(A.seed >> 32));
+  const uint32_t node = (uint32_t)A.variates[o.a].node & 0xffffu;
+  const uint32_t step = (uint32_t)A.step;
+  const uint32_t e0 = (uint32_t)(A.env_offset + env0);
+  if (lane == 0) qn[warp] = 0;
+  __syncwarp();
+  // two words at a time: bounds the live registers (index planes, random words, res/und)
+#pragma unroll 1
+  for (int j0 = 0; j0 < WPT; j0 += 2) {
+    constexpr int NW = WPT >= 2 ? 2 : 1;
+    uint32_t x[NW][M > 0 ? M : 1], res[NW], und[NW];
 #pragma unroll
-    for (int j = 0; j < WPT; ++j) {
-      const uint32_t al = plane_mux<M>(always, x[j]);
-      res[j] = C.valid[j] ? al : 0u;
-      und[j] = C.valid[j] ? ~al : 0u;
+    for (int jj = 0; jj < NW; ++jj) {
+      const int j = j0 + jj;
+#pragma unroll
+      for (int i = 0; i < M; ++i) x[jj][i] = C.P[plane_reg(o.idx, i)][j];
+      const bool ok = (C.valid >> j) & 1u;
+      if (has_bad && ok && plane_mux<M>(bad, x[jj])) atomicOr(A.status + env0 + C.env[j], 1u);
+      const uint32_t al = has_always ? plane_mux<M>(always, x[jj]) : 0u;
+      res[jj] = ok ? al : 0u;
+      und[jj] = ok ? ~al : 0u;
     }
 #pragma unroll
     for (int b = 0; b < PLANE_BERN_LEVELS / 4; ++b) {
-      uint32_t rw[WPT][4];
+      uint32_t rw[NW][4];
 #pragma unroll
-      for (int j = 0; j < WPT; ++j) {
+      for (int jj = 0; jj < NW; ++jj) {
         const uint4 r4 = rddl_philox4x32_10(
-            make_uint4((uint32_t)C.wi[j], (uint32_t)(A.env_offset + C.env[j]), (uint32_t)A.step,
-                       node | ((0x8000u + b) << 16)), key);
-        rw[j][0] = r4.x; rw[j][1] = r4.y; rw[j][2] = r4.z; rw[j][3] = r4.w;
+            make_uint4((uint32_t)C.wi[j0 + jj], e0 + (uint32_t)C.env[j0 + jj], step, node | ((0x8000u + b) << 16)),
+            key);
+        rw[jj][0] = r4.x; rw[jj][1] = r4.y; rw[jj][2] = r4.z; rw[jj][3] = r4.w;
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        uint32_t mk[TT];
+        const uint32_t* mk = lev + (4 * b + q) * TT;
 #pragma unroll
-        for (int i = 0; i < TT; ++i) mk[i] = lev[(4 * b + q) * TT + i];
-#pragma unroll
-        for (int j = 0; j < WPT; ++j) {
-          const uint32_t pj = plane_mux<M>(mk, x[j]);
-          res[j] |= und[j] & ~rw[j][q] & pj;
-          und[j] &= ~(rw[j][q] ^ pj);
+        for (int jj = 0; jj < NW; ++jj) {
+          const uint32_t pj = plane_mux_hc<M, HC>(mk, x[jj]);
+          res[jj] |= und[jj] & ~rw[jj][q] & pj;
+          und[jj] &= ~(rw[jj][q] ^ pj);
         }
       }
     }
-    // cells still tied after the first levels (2^-8 of them): queued per warp and finished
-    // cooperatively, one 64-bit Philox draw per cell
-    if (lane == 0) qn[warp] = 0;
-    __syncwarp();
+    // cells still tied after the first levels (2^-8 of them) are queued per warp and finished
+    // cooperatively below, one 64-bit Philox draw per cell
 #pragma unroll
-    for (int j = 0; j < WPT; ++j) {
+    for (int jj = 0; jj < NW; ++jj) {
+      const int j = j0 + jj;
+      C.P[o.dst][j] = res[jj];
       fix[tid * WPT + j] = 0;
-      uint32_t u = und[j];
+      uint32_t u = und[jj];
       while (u) {
         const int b = __ffs(u) - 1;
         u &= u - 1;
-        int v = 0;
+        uint32_t v = 0;
 #pragma unroll
-        for (int i = 0; i < M; ++i) v |= ((x[j][i] >> b) & 1u) << i;
+        for (int i = 0; i < M; ++i) v |= ((x[jj][i] >> b) & 1u) << i;
         const int slot = atomicAdd(&qn[warp], 1);
-        const uint32_t entry = (uint32_t)lane | ((uint32_t)j << 5) | ((uint32_t)b << 8) | ((uint32_t)v << 13);
         if (slot < PLANE_QUEUE) {
-          queue[warp * PLANE_QUEUE + slot] = entry;
+          queue[warp * PLANE_QUEUE + slot] = (uint32_t)lane | ((uint32_t)j << 5) | ((uint32_t)b << 8) | (v << 13);
         } else {   // queue full (practically never): finish inline
           const uint4 r4 = rddl_philox4x32_10(
-              make_uint4(((uint32_t)C.wi[j] << 5) | b, (uint32_t)(A.env_offset + C.env[j]), (uint32_t)A.step,
-                         node | (0xC000u << 16)), key);
+              make_uint4(((uint32_t)C.wi[j] << 5) | b, e0 + (uint32_t)C.env[j], step, node | (0xC000u << 16)), key);
           const uint64_t t64 = ((uint64_t)thr[2 * v + 1] << 32) | thr[2 * v];
-          if ((((uint64_t)r4.x << 32) | r4.y) < (t64 << PLANE_BERN_LEVELS)) res[j] |= 1u << b;
+          if ((((uint64_t)r4.x << 32) | r4.y) < (t64 << PLANE_BERN_LEVELS)) C.P[o.dst][j] |= 1u << b;
         }
       }
     }
-    __syncwarp();
-    const int n = min(qn[warp], PLANE_QUEUE);
+  }
+  __syncwarp();
+  const int n = min(qn[warp], PLANE_QUEUE);
+  if (n > 0) {
     for (int i = lane; i < n; i += 32) {
       const uint32_t e = queue[warp * PLANE_QUEUE + i];
-      const int ol = e & 31, oj = (e >> 5) & 7, b = (e >> 8) & 31, v = e >> 13;
-      // owner's word coordinates (shuffle-free: recomputed from the tile geometry)
-      const int w = oj * 256 + warp * 32 + ol;
-      int64_t oenv;
-      int owi;
+      const int ol = e & 31, oj = (e >> 5) & 7, b = (e >> 8) & 31;
+      const uint32_t v = e >> 13;
+      // the owner's word coordinates, recomputed from the tile geometry
+      const int ow = oj * 256 + warp * 32 + ol;
+      int env_l, wi_l;
       if (A.L.chunks == 1) {
         const int wpe = (int)(A.L.E >> 5);
-        const int oel = w / wpe;
-        owi = w - oel * wpe;
-        oenv = (int64_t)(blockIdx.x) * A.L.G + oel;
+        env_l = G.wpe_shift >= 0 ? (ow >> G.wpe_shift) : ow / wpe;
+        wi_l = ow - env_l * wpe;
       } else {
-        owi = (blockIdx.x % A.L.chunks) * A.L.ipt + w;
-        oenv = blockIdx.x / A.L.chunks;
+        env_l = 0;
+        wi_l = (blockIdx.x % A.L.chunks) * A.L.ipt + ow;
       }
       const uint4 r4 = rddl_philox4x32_10(
-          make_uint4(((uint32_t)owi << 5) | b, (uint32_t)(A.env_offset + oenv), (uint32_t)A.step,
-                     node | (0xC000u << 16)), key);
+          make_uint4(((uint32_t)wi_l << 5) | b, e0 + (uint32_t)env_l, step, node | (0xC000u << 16)), key);
       const uint64_t t64 = ((uint64_t)thr[2 * v + 1] << 32) | thr[2 * v];
       if ((((uint64_t)r4.x << 32) | r4.y) < (t64 << PLANE_BERN_LEVELS))
         atomicOr(&fix[(warp * 32 + ol) * WPT + oj], 1u << b);
     }
     __syncwarp();
 #pragma unroll
-    for (int j = 0; j < WPT; ++j) res[j] |= fix[tid * WPT + j];
+    for (int j = 0; j < WPT; ++j) C.P[o.dst][j] |= fix[tid * WPT + j];
   }
-#pragma unroll
-  for (int j = 0; j < WPT; ++j) C.P[o.dst][j] = res[j];
 }
 
 template <int M, int NPR, int WPT>
 __device__ __forceinline__ void plane_lut(PlaneCtx<NPR, WPT>& C, const PlaneProg& G, const PlaneOp& o) {
-  const int TT = 1 << M;
-  uint32_t mk[TT];
-#pragma unroll
-  for (int i = 0; i < TT; ++i) mk[i] = G.words[o.off + i];
+  const uint32_t* mk = G.words + o.off;
 #pragma unroll
   for (int j = 0; j < WPT; ++j) {
     uint32_t x[M > 0 ? M : 1];
 #pragma unroll
-    for (int i = 0; i < M; ++i) x[i] = C.P[o.idx[i]][j];
+    for (int i = 0; i < M; ++i) x[i] = C.P[plane_reg(o.idx, i)][j];
     C.P[o.dst][j] = plane_mux<M>(mk, x);
   }
 }
 
 template <int NPR, int WPT>
-__global__ void __launch_bounds__(256) rddl_plane_interp(const __grid_constant__ VmArgs A,
-                                                          const __grid_constant__ PlaneProg G) {
+__global__ void __launch_bounds__(256, 3) rddl_plane_interp(const __grid_constant__ VmArgs A,
+                                                             const __grid_constant__ PlaneProg G) {
   const RddlLaunch& L = A.L;
   const int tid = threadIdx.x;
   const int H = L.rank == 2 ? (int)L.extent[0] : 1;
@@ -241,49 +254,53 @@ __global__ void __launch_bounds__(256) rddl_plane_interp(const __grid_constant__
   const int wpe = (int)(L.E >> 5);              // words per env
   const int envs_per_tile = L.G, tile_words = L.ipt, chunks = L.chunks;
   const int chunk = blockIdx.x % chunks;
-  const int64_t envgrp = blockIdx.x / chunks;
+  const int64_t env0 = (int64_t)(blockIdx.x / chunks) * envs_per_tile;   // first env of this tile
 
-  // dynamic shared memory: [nshared][tile_words + 2*W32] stencil planes | cnt | queue | fix
+  // dynamic shared memory: [nshared][tile_words + 2*W32] stencil planes | cnt | queue | qn | fix
   extern __shared__ uint32_t smem[];
   const int plane_stride = tile_words + 2 * W32;
   uint32_t* S = smem;
-  int32_t* cnt = reinterpret_cast<int32_t*>(smem + G.nshared * plane_stride);   // [32][MAX_RED][2]
-  uint32_t* queue = reinterpret_cast<uint32_t*>(cnt + 32 * RDDL_MAX_RED * 2);    // [8][PLANE_QUEUE]
+  int32_t* cnt = reinterpret_cast<int32_t*>(smem + G.nshared * plane_stride);   // [32][MAX_RED]
+  uint32_t* queue = reinterpret_cast<uint32_t*>(cnt + 32 * RDDL_MAX_RED);        // [8][PLANE_QUEUE]
   int* qn = reinterpret_cast<int*>(queue + 8 * PLANE_QUEUE);                     // [8]
   uint32_t* fix = reinterpret_cast<uint32_t*>(qn + 8);                           // [256][WPT]
-  for (int i = tid; i < 32 * RDDL_MAX_RED * 2; i += 256) cnt[i] = 0;
+  if (L.nred > 0) cnt[tid] = 0;                                                  // 32 * MAX_RED == 256
 
   PlaneCtx<NPR, WPT> C;
+  C.valid = 0;
 #pragma unroll
   for (int j = 0; j < WPT; ++j) {
     const int w = j * 256 + tid;
     bool ok = w < tile_words;
     if (chunks == 1) {
-      C.el[j] = w / wpe;
-      C.wi[j] = w - C.el[j] * wpe;
-      C.env[j] = envgrp * envs_per_tile + C.el[j];
+      C.env[j] = G.wpe_shift >= 0 ? (w >> G.wpe_shift) : w / wpe;
+      C.wi[j] = w - C.env[j] * wpe;
     } else {
-      C.el[j] = 0;
+      C.env[j] = 0;
       C.wi[j] = chunk * tile_words + w;
-      C.env[j] = envgrp;
       ok = ok && C.wi[j] < wpe;
     }
-    C.valid[j] = ok && C.env[j] < A.n_envs;
+    if (ok && env0 + C.env[j] < A.n_envs) C.valid |= 1u << j;
   }
-  __syncthreads();
+  int racc[RDDL_MAX_RED];   // per-thread popcount accumulators (single-env tiles)
+#pragma unroll
+  for (int i = 0; i < RDDL_MAX_RED; ++i) racc[i] = 0;
+  const bool single_env = envs_per_tile == 1;
+  if (L.nred > 0) __syncthreads();
 
+#pragma unroll 1
   for (int pc = 0; pc < G.nops; ++pc) {
-    const PlaneOp o = G.ops[pc];
+    const PlaneOp& o = G.ops[pc];
     switch (o.op) {
       case OP_PLD: {
-        const uint8_t* base = reinterpret_cast<const uint8_t*>(A.tensors[o.imm]);
+        const uint8_t* base = reinterpret_cast<const uint8_t*>(A.tensors[o.imm]) + ((env0 * wpe) << 5);
         uint4 lo[WPT], hi[WPT];
 #pragma unroll
         for (int j = 0; j < WPT; ++j) {
           lo[j] = make_uint4(0, 0, 0, 0);
           hi[j] = lo[j];
-          if (C.valid[j]) {
-            const uint4* p = reinterpret_cast<const uint4*>(base + ((C.env[j] * wpe + C.wi[j]) << 5));
+          if ((C.valid >> j) & 1u) {
+            const uint4* p = reinterpret_cast<const uint4*>(base + ((int64_t)(C.env[j] * wpe + C.wi[j]) << 5));
             lo[j] = __ldcs(p);
             hi[j] = __ldcs(p + 1);
           }
@@ -295,17 +312,17 @@ __global__ void __launch_bounds__(256) rddl_plane_interp(const __grid_constant__
       case OP_PLDC: {
 #pragma unroll
         for (int j = 0; j < WPT; ++j)
-          C.P[o.dst][j] = C.valid[j] ? (uint32_t)__ldg(A.pool + o.imm + C.wi[j]) : 0u;
+          C.P[o.dst][j] = ((C.valid >> j) & 1u) ? (uint32_t)__ldg(A.pool + o.imm + C.wi[j]) : 0u;
         break;
       }
       case OP_PST: {
-        uint8_t* base = reinterpret_cast<uint8_t*>(A.tensors[o.imm]);
+        uint8_t* base = reinterpret_cast<uint8_t*>(A.tensors[o.imm]) + ((env0 * wpe) << 5);
 #pragma unroll
         for (int j = 0; j < WPT; ++j) {
-          if (C.valid[j]) {
+          if ((C.valid >> j) & 1u) {
             uint4 lo, hi;
             plane_unpack(C.P[o.a][j], lo, hi);
-            uint4* p = reinterpret_cast<uint4*>(base + ((C.env[j] * wpe + C.wi[j]) << 5));
+            uint4* p = reinterpret_cast<uint4*>(base + ((int64_t)(C.env[j] * wpe + C.wi[j]) << 5));
             __stcs(p, lo);
             __stcs(p + 1, hi);
           }
@@ -318,7 +335,7 @@ __global__ void __launch_bounds__(256) rddl_plane_interp(const __grid_constant__
         break;
       }
       case OP_PLUT: {
-        switch (o.m) {
+        switch (o.m & 0xff) {
           case 1: plane_lut<1>(C, G, o); break;
           case 2: plane_lut<2>(C, G, o); break;
           case 3: plane_lut<3>(C, G, o); break;
@@ -332,7 +349,7 @@ __global__ void __launch_bounds__(256) rddl_plane_interp(const __grid_constant__
 #pragma unroll
         for (int j = 0; j < WPT; ++j) {
           const int w = j * 256 + tid;
-          if (w < tile_words) s[W32 + w] = C.valid[j] ? C.P[o.a][j] : 0u;
+          if (w < tile_words) s[W32 + w] = ((C.valid >> j) & 1u) ? C.P[o.a][j] : 0u;
         }
         if (chunks > 1) {
           // halo rows above / below the tile, packed straight from the source tensor
@@ -341,8 +358,8 @@ __global__ void __launch_bounds__(256) rddl_plane_interp(const __grid_constant__
             const bool top = i < W32;
             const int wsrc = top ? chunk * tile_words - W32 + i : (chunk + 1) * tile_words + (i - W32);
             uint32_t word = 0;
-            if (wsrc >= 0 && wsrc < wpe && envgrp < A.n_envs) {
-              const uint4* p = reinterpret_cast<const uint4*>(base + ((envgrp * wpe + wsrc) << 5));
+            if (wsrc >= 0 && wsrc < wpe && env0 < A.n_envs) {
+              const uint4* p = reinterpret_cast<const uint4*>(base + ((env0 * wpe + wsrc) << 5));
               word = plane_pack(__ldg(p), __ldg(p + 1));
             }
             s[top ? i : W32 + tile_words + (i - W32)] = word;
@@ -353,12 +370,15 @@ __global__ void __launch_bounds__(256) rddl_plane_interp(const __grid_constant__
       }
       case OP_PCOUNT: {
         const uint32_t* s = S + o.b * plane_stride;
+        const uint32_t m9 = o.imm;
 #pragma unroll
         for (int j = 0; j < WPT; ++j) {
           uint32_t k0 = 0, k1 = 0, k2 = 0, k3 = 0;
-          if (C.valid[j]) {
-            const int x = C.wi[j] / W32, c = C.wi[j] - x * W32;
+          if ((C.valid >> j) & 1u) {
+            const int x = G.w32_shift >= 0 ? (C.wi[j] >> G.w32_shift) : C.wi[j] / W32;
+            const int c = C.wi[j] - x * W32;
             const int pos = W32 + j * 256 + tid;
+            const bool has_l = c > 0, has_r = c < W32 - 1;
             uint32_t sr[3], cr[3];   // per row: sum and carry of the (west, centre, east) planes
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
@@ -367,13 +387,13 @@ __global__ void __launch_bounds__(256) rddl_plane_interp(const __grid_constant__
               if (rowok) {
                 const int q = pos + (d - 1) * W32;
                 Cw = s[q];
-                if (c > 0) Lw = s[q - 1];
-                if (c < W32 - 1) Rw = s[q + 1];
+                if (has_l) Lw = s[q - 1];
+                if (has_r) Rw = s[q + 1];
               }
-              const uint32_t m3 = o.imm >> (d * 3);
-              const uint32_t west = (m3 & 1u) ? ((Cw << 1) | (Lw >> 31)) : 0u;
+              const uint32_t m3 = m9 >> (d * 3);
+              const uint32_t west = (m3 & 1u) ? __funnelshift_l(Lw, Cw, 1) : 0u;
               const uint32_t mid = (m3 & 2u) ? Cw : 0u;
-              const uint32_t east = (m3 & 4u) ? ((Cw >> 1) | (Rw << 31)) : 0u;
+              const uint32_t east = (m3 & 4u) ? __funnelshift_r(Cw, Rw, 1) : 0u;
               sr[d] = west ^ mid ^ east;
               cr[d] = (west & mid) | (east & (west ^ mid));
             }
@@ -392,26 +412,39 @@ __global__ void __launch_bounds__(256) rddl_plane_interp(const __grid_constant__
       }
       case OP_PBERN: {
         switch (o.m) {
-          case 0: plane_bernoulli<0>(C, A, G, o, queue, qn, fix); break;
-          case 1: plane_bernoulli<1>(C, A, G, o, queue, qn, fix); break;
-          case 2: plane_bernoulli<2>(C, A, G, o, queue, qn, fix); break;
-          case 3: plane_bernoulli<3>(C, A, G, o, queue, qn, fix); break;
-          default: plane_bernoulli<4>(C, A, G, o, queue, qn, fix); break;
+          case 0: plane_bernoulli<0, false>(C, A, G, o, queue, qn, fix, env0); break;
+          case 1: plane_bernoulli<1, false>(C, A, G, o, queue, qn, fix, env0); break;
+          case 2: plane_bernoulli<2, false>(C, A, G, o, queue, qn, fix, env0); break;
+          case 3: plane_bernoulli<3, false>(C, A, G, o, queue, qn, fix, env0); break;
+          case 4: plane_bernoulli<4, false>(C, A, G, o, queue, qn, fix, env0); break;
+          case 0x102: plane_bernoulli<2, true>(C, A, G, o, queue, qn, fix, env0); break;
+          case 0x103: plane_bernoulli<3, true>(C, A, G, o, queue, qn, fix, env0); break;
+          default: plane_bernoulli<4, true>(C, A, G, o, queue, qn, fix, env0); break;
         }
         break;
       }
       case OP_PRED: {
         // per-env popcount of a plane (m == 1) or of the valid cells (m == 0)
-        const bool warp_uniform_env = (wpe & 31) == 0 || chunks > 1;
+        const int r0 = plane_reg(o.idx, 0);
+        if (single_env) {
+          int c = 0;
 #pragma unroll
-        for (int j = 0; j < WPT; ++j) {
-          const uint32_t x = o.m ? C.P[o.idx[0]][j] : 0xffffffffu;
-          int c = C.valid[j] ? __popc(x) : 0;
-          if (warp_uniform_env) {
-            c = __reduce_add_sync(0xffffffffu, c);
-            if ((tid & 31) == 0 && c) atomicAdd(&cnt[(C.el[j] * RDDL_MAX_RED + o.b) * 2], c);
-          } else if (c) {
-            atomicAdd(&cnt[(C.el[j] * RDDL_MAX_RED + o.b) * 2], c);
+          for (int j = 0; j < WPT; ++j)
+            if ((C.valid >> j) & 1u) c += o.m ? __popc(C.P[r0][j]) : 32;
+#pragma unroll
+          for (int i = 0; i < RDDL_MAX_RED; ++i)
+            if (i == o.b) racc[i] += c;
+        } else {
+          const bool warp_uniform_env = (wpe & 31) == 0;
+#pragma unroll
+          for (int j = 0; j < WPT; ++j) {
+            int c = ((C.valid >> j) & 1u) ? (o.m ? __popc(C.P[r0][j]) : 32) : 0;
+            if (warp_uniform_env) {
+              c = __reduce_add_sync(0xffffffffu, c);
+              if ((tid & 31) == 0 && c) atomicAdd(&cnt[C.env[j] * RDDL_MAX_RED + o.b], c);
+            } else if (c) {
+              atomicAdd(&cnt[C.env[j] * RDDL_MAX_RED + o.b], c);
+            }
           }
         }
         break;
@@ -421,19 +454,28 @@ __global__ void __launch_bounds__(256) rddl_plane_interp(const __grid_constant__
   }
 
   if (L.nred > 0) {
+    if (single_env) {
+#pragma unroll
+      for (int i = 0; i < RDDL_MAX_RED; ++i) {
+        if (i < L.nred) {
+          const int c = __reduce_add_sync(0xffffffffu, racc[i]);
+          if ((tid & 31) == 0 && c) atomicAdd(&cnt[i], c);
+        }
+      }
+    }
     __syncthreads();
     const int64_t cells = chunks == 1 ? L.E : (int64_t)min(tile_words, wpe - chunk * tile_words) * 32;
     for (int i = tid; i < envs_per_tile * L.nred; i += 256) {
       const int e = i / L.nred, jr = i - e * L.nred;
-      const int64_t ge = envgrp * envs_per_tile + e;
+      const int64_t ge = env0 + e;
       if (ge >= A.n_envs) continue;
       // the PRED op of reduction jr carries (value at 0, value at 1) as raw 64-bit words
-      uint32_t off = 0, m = 0;
+      int off = 0, m = 0;
       for (int pc = 0; pc < G.nops; ++pc)
         if (G.ops[pc].op == OP_PRED && G.ops[pc].b == jr) { off = G.ops[pc].off; m = G.ops[pc].m; }
       const uint64_t v0 = ((uint64_t)G.words[off + 1] << 32) | G.words[off];
       const uint64_t v1 = ((uint64_t)G.words[off + 3] << 32) | G.words[off + 2];
-      const int64_t ones = cnt[(e * RDDL_MAX_RED + jr) * 2];
+      const int64_t ones = cnt[e * RDDL_MAX_RED + jr];
       const int64_t n1 = m ? ones : 0, n0 = m ? cells - ones : cells;
       uint64_t out;
       if (L.red_op[jr] == RED_SUM_F) {

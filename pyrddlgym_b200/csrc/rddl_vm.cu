@@ -414,36 +414,52 @@ struct rddl_program {
 
 // Pre-decodes the instructions of a plane launch (and the Fin descriptors they reference in the
 // const pool: [m, regs, truth, bad, always, thr[2^m], vals[2^m], lev[levels]]) into a PlaneProg.
+static int log2_or_neg(int64_t v) {
+  if (v <= 0 || (v & (v - 1))) return -1;
+  int s = 0;
+  while ((1ll << s) < v) ++s;
+  return s;
+}
+
 static bool decode_plane(const RddlLaunch& L, const RddlInsn* insns, const uint64_t* consts, int64_t n_consts,
                          PlaneProg* G, std::string* err) {
   memset(G, 0, sizeof *G);
+  G->w32_shift = log2_or_neg((L.rank == 2 ? L.extent[1] : L.extent[0]) >> 5);
+  G->wpe_shift = log2_or_neg(L.E >> 5);
   int nw = 0;
   auto need = [&](int n) { return nw + n <= PLANE_WORDS; };
   for (int pc = L.pc_begin; pc < L.pc_end; ++pc) {
     const RddlInsn& in = insns[pc];
     if (G->nops >= PLANE_MAX_OPS) { *err = "plane program too long"; return false; }
     PlaneOp& o = G->ops[G->nops++];
-    o.op = in.op; o.dst = (uint8_t)in.dst; o.a = (uint8_t)in.a; o.b = (uint8_t)in.b; o.imm = in.imm;
-    o.off = (uint16_t)nw;
+    o.op = in.op; o.dst = in.dst; o.a = in.a; o.b = in.b; o.imm = in.imm;
+    o.off = nw;
     if (in.op == OP_PSHARE && (int)in.b + 1 > G->nshared) G->nshared = in.b + 1;
     if (in.op != OP_PLUT && in.op != OP_PBERN && in.op != OP_PRED) continue;
     if ((int64_t)in.imm + 5 > n_consts) { *err = "plane op: bad Fin index"; return false; }
     const uint64_t* c = consts + in.imm;
-    const int m = (int)c[0];
+    const int m = (int)(c[0] & 0xff);
+    const bool hi_const = ((c[0] >> 8) & 1) != 0;
     const int64_t fin_words = 5 + (in.op == OP_PLUT ? 0 : 2 * (1 << (m & 7))) + (in.op == OP_PBERN ? PLANE_BERN_LEVELS : 0);
     if (m < 0 || m > 5 || (int64_t)in.imm + fin_words > n_consts) { *err = "plane op: bad Fin"; return false; }
     const int TT = 1 << m;
-    o.m = (uint8_t)m;
-    for (int i = 0; i < m; ++i) o.idx[i] = (uint8_t)((c[1] >> (8 * i)) & 0xff);
+    o.m = m;
+    o.idx = 0;
+    for (int i = 0; i < m; ++i) {
+      const uint32_t r = (uint32_t)((c[1] >> (8 * i)) & 0xff);
+      if (r >= PLANE_MAX_REGS) { *err = "plane op: register out of range"; return false; }
+      o.idx |= r << (6 * i);
+    }
     const uint64_t* thr = c + 5;
     const uint64_t* vals = c + 5 + TT;
     if (in.op == OP_PLUT) {
-      if (!need(TT)) { *err = "plane tables too large"; return false; }
+      if (m < 1 || !need(TT)) { *err = "plane tables too large"; return false; }
       for (int v = 0; v < TT; ++v) G->words[nw++] = ((c[2] >> v) & 1) ? 0xffffffffu : 0u;
     } else if (in.op == OP_PBERN) {
       if (m > 4 || !need((2 + PLANE_BERN_LEVELS) * TT + 4 * TT)) { *err = "plane tables too large"; return false; }
       const uint64_t* lev = c + 5 + 2 * TT;
-      o.b = c[3] != 0;
+      o.b = (c[3] != 0 ? 1 : 0) | (c[4] != 0 ? 2 : 0);
+      if (hi_const && m >= 2) o.m |= 0x100;
       for (int v = 0; v < TT; ++v) G->words[nw++] = ((c[3] >> v) & 1) ? 0xffffffffu : 0u;
       for (int v = 0; v < TT; ++v) G->words[nw++] = ((c[4] >> v) & 1) ? 0xffffffffu : 0u;
       for (int j = 0; j < PLANE_BERN_LEVELS; ++j)
@@ -622,7 +638,7 @@ static int run_plan(rddl_program* g, int plan, void* const* tensors, const doubl
     if (L.kind == 1) {
       const PlaneProg& G = g->plane_progs[(size_t)(&L - g->launches.data())];
       const int W32 = (int)((L.rank == 2 ? L.extent[1] : L.extent[0]) >> 5);
-      const size_t smem = sizeof(uint32_t) * ((size_t)G.nshared * (A.L.ipt + 2 * W32) + 32 * RDDL_MAX_RED * 2 +
+      const size_t smem = sizeof(uint32_t) * ((size_t)G.nshared * (A.L.ipt + 2 * W32) + 32 * RDDL_MAX_RED +
                                               8 * PLANE_QUEUE + 8 + 256 * wpt);
       const bool small = L.nregs <= 16;
       if (wpt == 1) {

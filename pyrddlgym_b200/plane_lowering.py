@@ -31,6 +31,7 @@ from pyrddlgym_b200 import optable as ot
 from pyrddlgym_b200.optable import OP, RED
 
 MAX_M = 5            # index planes of an intermediate Fin
+MAX_M_BOOL = 4       # ... of a boolean combination (a PLUT over m planes costs 2^m - 1 LOP3)
 MAX_M_BERN = 4
 MAX_M_RED = 3
 TILE_CELLS = 32768   # cells per CTA tile: 256 threads x 4 words x 32 cells
@@ -44,12 +45,15 @@ class NotPlanar(Exception):
 
 class Fin:
     """Finite-domain value: value(cell) = table[sum_i bit(idx[i], cell) << i]."""
-    __slots__ = ('idx', 'table')
+    __slots__ = ('idx', 'table', 'care')
 
-    def __init__(self, idx, table):
+    def __init__(self, idx, table, care=None):
         self.idx = tuple(idx)
         self.table = np.asarray(table)
         assert self.table.shape == (1 << len(self.idx),)
+        # care[v] == False: index value v cannot occur (e.g. a neighbour count above the
+        # stencil size); such entries may be filled freely to simplify the device tables
+        self.care = np.ones(self.table.shape, dtype=bool) if care is None else np.asarray(care, dtype=bool)
 
     @property
     def m(self):
@@ -72,7 +76,7 @@ def _expand(f, joint):
     sub = np.zeros_like(v)
     for i, p in enumerate(pos):
         sub |= ((v >> p) & 1) << i
-    return f.table[sub]
+    return f.table[sub], f.care[sub]
 
 
 def stencil_offsets(M, H, W):
@@ -179,7 +183,18 @@ class PlaneBuilder:
                     truth |= 1 << v
         words = [m, regs, truth, 0, 0]
         if thresholds:
-            p = np.asarray(f.table, dtype=np.float64)
+            p = np.asarray(f.table, dtype=np.float64).copy()
+            if m >= 2:
+                # fill impossible entries so that the upper half of the table is constant when
+                # it can be: the device then evaluates an (m-1)-input multiplexer + 1 select
+                half = 1 << (m - 1)
+                hi_care = f.care[half:]
+                if hi_care.any():
+                    vals_hi = p[half:][hi_care]
+                    if np.all(vals_hi == vals_hi[0]) or len(vals_hi) == 1:
+                        p[half:] = np.where(hi_care, p[half:], vals_hi[0])
+                if np.all(p[half:] == p[half]):
+                    words[0] |= 1 << 8          # hi-const flag
             bad = always = 0
             thr = []
             for v in range(1 << m):
@@ -213,7 +228,8 @@ class PlaneBuilder:
             for r in f.idx:
                 if r not in joint:
                     joint.append(r)
-        if len(joint) > MAX_M:
+        all_bool = all(f.cls == 'b' for f in fins)
+        if len(joint) > (MAX_M_BOOL if all_bool else MAX_M):
             # materialise boolean operands (largest first) until the joint domain fits
             order = sorted(range(len(fins)), key=lambda i: -fins[i].m)
             fins = list(fins)
@@ -222,10 +238,13 @@ class PlaneBuilder:
                     fins[i] = self.as_plane_fin(fins[i])
                     return self.combine(fins, fn)
             raise NotPlanar('value depends on more than %d bits per cell' % MAX_M)
-        tabs = [_expand(f, joint) for f in fins]
+        exp = [_expand(f, joint) for f in fins]
+        care = np.ones(1 << len(joint), dtype=bool)
+        for (_, c) in exp:
+            care &= c
         with np.errstate(all='ignore'):
-            out = fn(*tabs)
-        return Fin(joint, np.asarray(out))
+            out = fn(*[t for (t, _) in exp])
+        return Fin(joint, np.asarray(out), care)
 
     def materialise(self, f):
         """Returns a plane register holding the boolean Fin f."""
@@ -370,8 +389,8 @@ class PlaneBuilder:
             self.counts[key] = (k0, k0 + 1, k0 + 2, k0 + 3)
         planes = self.counts[key]
         if n.op == 'sum':
-            return Fin(planes, np.arange(16, dtype=np.int64))
-        return Fin(planes, np.arange(16) > 0)
+            return Fin(planes, np.arange(16, dtype=np.int64), np.arange(16) <= len(D))
+        return Fin(planes, np.arange(16) > 0, np.arange(16) <= len(D))
 
     def stencil_of(self, loops, rank):
         lw = self.lw
@@ -407,10 +426,10 @@ class PlaneBuilder:
             raise NotPlanar(f'distribution {n.op}')
         p = self.ev(n.args[0], base)
         if p.cls == 'b':
-            p = Fin(p.idx, p.table.astype(np.float64))
+            p = Fin(p.idx, p.table.astype(np.float64), p.care)
         if p.m > MAX_M_BERN:
             raise NotPlanar('Bernoulli parameter depends on too many bits')
-        p = Fin(p.idx, np.asarray(p.table, dtype=np.float64))
+        p = Fin(p.idx, np.asarray(p.table, dtype=np.float64), p.care)
         slot = self.lw.variate_slot(n.id, 'U', self.E)
         d = self.alloc()
         self.ins('PBERN', dst=d, a=slot, imm=self.fin_const(p, thresholds=True))

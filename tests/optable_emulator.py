@@ -101,7 +101,7 @@ class Emulator:
 
     # ---- bit-plane launches (mirrors csrc/rddl_plane.cu at the level of whole bool planes)
     def _fin(self, ci):
-        m = int(self.consts[ci])
+        m = int(self.consts[ci]) & 0xFF
         regs = int(self.consts[ci + 1])
         idx = [(regs >> (8 * i)) & 0xFF for i in range(m)]
         truth = int(self.consts[ci + 2])
