@@ -14,7 +14,6 @@ all-reduce of the return statistics at the end of the timed rollout.
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -49,54 +48,56 @@ def algorithmic_bytes_per_env_step(name):
 
 
 class ClockSampler:
-    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+    """Samples SM clock / throttle reasons through NVML from a background thread while the GPU
+    is under load (in-process: spawning nvidia-smi next to the timed region stalls launches)."""
 
-    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
-         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
-         'clocks_event_reasons.sw_power_cap')
+    REASONS = [('hw_slowdown', 0x8), ('sw_power_cap', 0x4), ('sw_thermal_slowdown', 0x20),
+               ('hw_thermal_slowdown', 0x40), ('hw_power_brake', 0x80)]
 
-    def __init__(self, index=0):
-        self.index = index
-        self.rows = []
-        self.proc = None
+    def __init__(self, index=0, period=0.02):
+        self.index, self.period = index, period
+        self.sm, self.reasons = [], set()
+        self.max_mhz = None
+        self.timed = False
+        self._stop = threading.Event()
+        self.thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
-                 '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
+        if self.nv is None:
+            return
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(',')])
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                if self.timed:
+                    self.sm.append(mhz)
+                    for name, bit in self.REASONS:
+                        if bits & bit:
+                            self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
 
     def stop(self):
-        if self.proc is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            if len(r) < 7:
-                continue
-            try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
-            except ValueError:
-                continue
-            for name, v in zip(['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'], r[3:7]):
-                if v.lower().startswith('active'):
-                    reasons.add(name)
-        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'samples': len(sm), 'reasons': sorted(reasons)}
+        if self.nv is None or self.thread is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvml unavailable']}
+        self._stop.set()
+        self.thread.join(timeout=1)
+        return {'sm_mhz': float(np.median(self.sm)) if self.sm else None, 'sm_max_mhz': self.max_mhz,
+                'samples': len(self.sm), 'reasons': sorted(self.reasons)}
 
 
 # ---------------------------------------------------------------------------------------
@@ -226,22 +227,27 @@ def run_gpu(args):
             dist.all_reduce(mm, op=dist.ReduceOp.MIN)
         return s, mm
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # bring the clocks up before the W warm-up steps (an idle GPU needs ~100 ms to boost)
+    t_spin = time.perf_counter()
+    while time.perf_counter() - t_spin < 0.3:
+        rollout(0, 8)
+        torch.cuda.synchronize()
     rollout(0, W)
     returns.zero_()
     barrier()
     l0 = sim.launches_issued
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.timed = True
     e0.record()
     rollout(W, K)
     stats = reduce_stats()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
     launches = sim.launches_issued - l0
     tms = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -255,6 +261,7 @@ def run_gpu(args):
     torch.cuda.synchronize()
     prof = sim.native.profile_read(sim.table.launches)
     sim.native.profile(False)
+    sampler.timed = False
     top = max(prof, key=lambda r: r['ms']) if prof else None
     peaks = {}
     try:
@@ -306,6 +313,7 @@ def run_gpu(args):
     if world > 1:
         dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
     e2e_value = world * N * K / (float(ms_e2e.item()) * 1e-3)
+    clocks = sampler.stop() if rank == 0 else None
     h2d = 2 * plane
     d2h = len(sim.state_names) * plane + 9 * N
 

@@ -57,6 +57,24 @@ int rddl_step(rddl_program_t* prog, void* const* tensors, const double* const* i
 int rddl_check(rddl_program_t* prog, int which, void* const* tensors, uint32_t* status,
                int64_t n_envs, int64_t env_offset, void* cuda_stream);
 
+/* Replaces the rollout loop of BaseAgent.evaluate (pyRDDLGym/core/policy.py:85-117: for each
+ * step, env.step(action); total_reward += reward * gamma^t; stop accumulating once done) for
+ * n_envs environments and n_steps steps with pre-drawn action sequences:
+ *   step_stride_bytes[id]  byte offset from one step's buffer of tensor id to the next step's
+ *                          (action sequences laid out [n_steps, n_envs, ...]); 0 = same buffer
+ *                          every step; NULL = all 0
+ *   returns                f64[n_envs], += discounted return of this rollout
+ *   rewards                NULL or f64[n_steps, n_envs], per-step rewards
+ *   state_in_next          out: 1 if the final state is in the next-state buffers (caller swaps
+ *                          state/next pointers, as after rddl_step), 0 if it is in the state buffers
+ * Step t draws Philox with step index step0 + t, so the result is identical to n_steps calls of
+ * rddl_step. When the whole step plan is one single-tile bit-plane launch, all steps run inside
+ * one kernel with the state held on chip (only the action planes stream from HBM). */
+int rddl_rollout(rddl_program_t* prog, void* const* tensors, uint32_t* status, int64_t n_envs,
+                 int64_t env_offset, uint64_t seed, uint64_t step0, int32_t n_steps,
+                 const int64_t* step_stride_bytes, double gamma, double* returns, double* rewards,
+                 int32_t* state_in_next, void* cuda_stream);
+
 /* Measurement aid (no reference counterpart): when enabled, every kernel launch of this
  * program is bracketed by CUDA events on its stream; rddl_profile_read synchronises them and
  * returns, per launch index of the op table (n entries), the summed milliseconds and the

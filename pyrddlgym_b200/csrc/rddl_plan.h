@@ -4,7 +4,7 @@
 #include <stdint.h>
 
 #define RDDL_MAGIC 0x31304C444452ll
-#define RDDL_VERSION 4
+#define RDDL_VERSION 5
 #define RDDL_MAX_IDX 8
 #define RDDL_MAX_RED 8
 #define RDDL_MAX_REGS 96
@@ -63,7 +63,7 @@ struct RddlCsr {       // 152 bytes
   int64_t row_coef[8];
 };
 
-struct RddlTensor { int32_t dtype, kind; int64_t nelem; };
+struct RddlTensor { int16_t dtype, pair; int32_t kind; int64_t nelem; };   // pair: next-state tensor id of a state fluent, else -1
 
 struct RddlLaunch {    // 176 bytes
   int32_t plan, rank;
@@ -73,7 +73,8 @@ struct RddlLaunch {    // 176 bytes
   int32_t nred, G, ipt, chunks;
   int32_t red_op[8];
   int32_t red_slot[8];
-  int32_t nregs, kind;   // kind: 0 = scalar level interpreter, 1 = bit-plane interpreter
+  int32_t nregs, kind;   // kind: 0 = scalar level interpreter, 1 = bit-plane interpreter,
+                         // 2 = scalar program fused into the epilogue of the preceding plane launch
 };
 
 struct RddlRedSlot { int32_t op, chunks; };

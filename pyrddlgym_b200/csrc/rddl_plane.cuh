@@ -37,6 +37,8 @@ struct PlaneOp {        // 32 bytes, pre-decoded from RddlInsn + its Fin descrip
 
 struct PlaneProg {
   int32_t nops, nshared, w32_shift, wpe_shift;   // shifts: log2 of words per row / per env, or -1
+  int32_t nfused, fused_nregs, rollout_ok, pad;  // scalar launches run in the epilogue (kind 2)
+  RddlLaunch fused[2];
   PlaneOp ops[PLANE_MAX_OPS];
   uint32_t words[PLANE_WORDS];
 };
@@ -99,7 +101,7 @@ __device__ __forceinline__ int plane_reg(uint32_t idx, int i) { return (idx >> (
 template <int M, bool HC, int NPR, int WPT>
 __device__ __noinline__ void plane_bernoulli(PlaneCtx<NPR, WPT>& C, const VmArgs& A, const PlaneProg& G,
                                              const PlaneOp& o, uint32_t* queue, int* qn, uint32_t* fix,
-                                             int64_t env0) {
+                                             int64_t env0, uint32_t step) {
   const int TT = 1 << M;
   const uint32_t* W = G.words + o.off;
   const uint32_t* bad = W;
@@ -135,7 +137,6 @@ __device__ __noinline__ void plane_bernoulli(PlaneCtx<NPR, WPT>& C, const VmArgs
   }
   const uint2 key = make_uint2((uint32_t)A.seed, (uint32_t)(A.seed >> 32));
   const uint32_t node = (uint32_t)A.variates[o.a].node & 0xffffu;
-  const uint32_t step = (uint32_t)A.step;
   const uint32_t e0 = (uint32_t)(A.env_offset + env0);
   if (lane == 0) qn[warp] = 0;
   __syncwarp();
@@ -288,12 +289,25 @@ __global__ void __launch_bounds__(256, 3) rddl_plane_interp(const __grid_constan
   const bool single_env = envs_per_tile == 1;
   if (L.nred > 0) __syncthreads();
 
+  // per-env rollout state of the thread that runs env (env0 + tid)'s scalar epilogue
+  double ret_acc = 0.0, disc = 1.0;
+  bool alive = true;
+  const int T = A.n_steps > 1 ? A.n_steps : 1;
+#pragma unroll 1
+  for (int t = 0; t < T; ++t) {
+  const bool last_step = t == T - 1;
 #pragma unroll 1
   for (int pc = 0; pc < G.nops; ++pc) {
     const PlaneOp& o = G.ops[pc];
     switch (o.op) {
       case OP_PLD: {
-        const uint8_t* base = reinterpret_cast<const uint8_t*>(A.tensors[o.imm]) + ((env0 * wpe) << 5);
+        if (t > 0 && o.a > 0) {   // state fluent: carried over from the value stored last step
+#pragma unroll
+          for (int j = 0; j < WPT; ++j) C.P[o.dst][j] = C.P[o.a - 1][j];
+          break;
+        }
+        const uint8_t* base = reinterpret_cast<const uint8_t*>(A.tensors[o.imm]) + t * A.tstride[o.imm] +
+                              ((env0 * wpe) << 5);
         uint4 lo[WPT], hi[WPT];
 #pragma unroll
         for (int j = 0; j < WPT; ++j) {
@@ -316,6 +330,7 @@ __global__ void __launch_bounds__(256, 3) rddl_plane_interp(const __grid_constan
         break;
       }
       case OP_PST: {
+        if (!last_step && o.b) break;   // carried state: only the final step reaches HBM
         uint8_t* base = reinterpret_cast<uint8_t*>(A.tensors[o.imm]) + ((env0 * wpe) << 5);
 #pragma unroll
         for (int j = 0; j < WPT; ++j) {
@@ -412,14 +427,14 @@ __global__ void __launch_bounds__(256, 3) rddl_plane_interp(const __grid_constan
       }
       case OP_PBERN: {
         switch (o.m) {
-          case 0: plane_bernoulli<0, false>(C, A, G, o, queue, qn, fix, env0); break;
-          case 1: plane_bernoulli<1, false>(C, A, G, o, queue, qn, fix, env0); break;
-          case 2: plane_bernoulli<2, false>(C, A, G, o, queue, qn, fix, env0); break;
-          case 3: plane_bernoulli<3, false>(C, A, G, o, queue, qn, fix, env0); break;
-          case 4: plane_bernoulli<4, false>(C, A, G, o, queue, qn, fix, env0); break;
-          case 0x102: plane_bernoulli<2, true>(C, A, G, o, queue, qn, fix, env0); break;
-          case 0x103: plane_bernoulli<3, true>(C, A, G, o, queue, qn, fix, env0); break;
-          default: plane_bernoulli<4, true>(C, A, G, o, queue, qn, fix, env0); break;
+          case 0: plane_bernoulli<0, false>(C, A, G, o, queue, qn, fix, env0, (uint32_t)(A.step + t)); break;
+          case 1: plane_bernoulli<1, false>(C, A, G, o, queue, qn, fix, env0, (uint32_t)(A.step + t)); break;
+          case 2: plane_bernoulli<2, false>(C, A, G, o, queue, qn, fix, env0, (uint32_t)(A.step + t)); break;
+          case 3: plane_bernoulli<3, false>(C, A, G, o, queue, qn, fix, env0, (uint32_t)(A.step + t)); break;
+          case 4: plane_bernoulli<4, false>(C, A, G, o, queue, qn, fix, env0, (uint32_t)(A.step + t)); break;
+          case 0x102: plane_bernoulli<2, true>(C, A, G, o, queue, qn, fix, env0, (uint32_t)(A.step + t)); break;
+          case 0x103: plane_bernoulli<3, true>(C, A, G, o, queue, qn, fix, env0, (uint32_t)(A.step + t)); break;
+          default: plane_bernoulli<4, true>(C, A, G, o, queue, qn, fix, env0, (uint32_t)(A.step + t)); break;
         }
         break;
       }
@@ -460,6 +475,7 @@ __global__ void __launch_bounds__(256, 3) rddl_plane_interp(const __grid_constan
         if (i < L.nred) {
           const int c = __reduce_add_sync(0xffffffffu, racc[i]);
           if ((tid & 31) == 0 && c) atomicAdd(&cnt[i], c);
+          racc[i] = 0;
         }
       }
     }
@@ -488,4 +504,31 @@ __global__ void __launch_bounds__(256, 3) rddl_plane_interp(const __grid_constan
       A.red[A.red_off[L.red_slot[jr]] * A.n_envs + ge * chunks + chunk] = out;
     }
   }
+  if (G.nfused > 0) {
+    // scope-free programs fused into this launch (reward / termination from the reductions):
+    // one thread per env of the tile runs them through the scalar interpreter
+    __threadfence_block();
+    __syncthreads();
+    if (tid < envs_per_tile && env0 + tid < A.n_envs) {
+      const int64_t ge = env0 + tid;
+      int32_t idx0[RDDL_MAX_IDX];
+      uint64_t rv[RDDL_MAX_RED];
+      for (int f = 0; f < G.nfused; ++f) vm_exec_element<40>(A, G.fused[f], ge, A.step + t, idx0, rv);
+      if (T > 1) {
+        // BaseAgent.evaluate (pyRDDLGym/core/policy.py:100-117): total += reward * gamma^t until done
+        const double rwd = __ldcg(reinterpret_cast<const double*>(A.tensors[G.pad]) + ge);
+        if (A.rewards) A.rewards[(int64_t)t * A.n_envs + ge] = rwd;
+        if (alive) ret_acc += rwd * disc;
+        disc *= A.gamma;
+        if (__ldcg(reinterpret_cast<const uint8_t*>(A.tensors[G.pad + 1]) + ge)) alive = false;
+      }
+    }
+  }
+  if (!last_step) {
+    __syncthreads();
+    if (L.nred > 0) cnt[tid] = 0;
+    __syncthreads();
+  }
+  }   // step loop
+  if (T > 1 && A.returns && tid < envs_per_tile && env0 + tid < A.n_envs) A.returns[env0 + tid] += ret_acc;
 }

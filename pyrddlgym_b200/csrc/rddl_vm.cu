@@ -39,9 +39,15 @@ struct VmArgs {
   void* tensors[RDDL_MAX_TENSORS];
   uint8_t dtype[RDDL_MAX_TENSORS];
   const double* inj[RDDL_MAX_VARIATES];
+  // multi-step rollouts fused into one plane launch (n_steps > 1): per-tensor byte stride from
+  // one step's inputs to the next (action sequences [T, n_envs, ...]), discounted return
+  // accumulators and optional per-step rewards [T, n_envs]
+  int32_t n_steps, pad0;
+  double gamma;
+  double* returns;
+  double* rewards;
+  int64_t tstride[RDDL_MAX_TENSORS];
 };
-
-#include "rddl_plane.cuh"
 
 __device__ __forceinline__ double as_f(uint64_t v) { return __longlong_as_double((long long)v); }
 __device__ __forceinline__ uint64_t from_f(double v) { return (uint64_t)__double_as_longlong(v); }
@@ -114,38 +120,16 @@ __device__ __forceinline__ uint64_t red_combine(int op, uint64_t a, uint64_t b) 
   }
 }
 
+// Interprets the program of launch L for one (env, element); idx[] holds the element's scope
+// coordinates. Shared by the scalar kernel below and by the plane kernel's fused epilogue.
 template <int NREG>
-__global__ void __launch_bounds__(256) rddl_level_interp(const __grid_constant__ VmArgs A) {
-  const RddlLaunch& L = A.L;
-  const int G = L.G;
-  const int tid = threadIdx.x;
-  const int lane = tid & (G - 1);
-  const int envs_per_cta = 256 / G;
-  const int64_t chunk = blockIdx.x % L.chunks;
-  const int64_t env = (int64_t)(blockIdx.x / L.chunks) * envs_per_cta + tid / G;
-  const bool env_ok = env < A.n_envs;
-
+__device__ __noinline__ void vm_exec_element(const VmArgs& A, const RddlLaunch& L, const int64_t env,
+                                             const uint64_t step, int32_t* idx, uint64_t* redval) {
   uint64_t r[NREG];
-  int32_t idx[RDDL_MAX_IDX];
   int32_t jcur[4], jend[4];
-  uint64_t redval[RDDL_MAX_RED];
-#pragma unroll
-  for (int j = 0; j < RDDL_MAX_RED; ++j) redval[j] = j < L.nred ? red_identity(L.red_op[j]) : 0;
-
   const int npc = L.pc_end - L.pc_begin;
   const RddlInsn* prog = A.insns + L.pc_begin;
-
-  for (int it = 0; it < L.ipt; ++it) {
-    const int64_t elem = chunk * ((int64_t)G * L.ipt) + (int64_t)it * G + lane;
-    if (!env_ok || elem >= L.E) continue;
-    {  // decode the element index into scope coordinates (C order)
-      int64_t rem = elem;
-      for (int k = L.rank - 1; k >= 0; --k) {
-        int64_t e = L.extent[k];
-        idx[k] = (int32_t)(rem % e);
-        rem /= e;
-      }
-    }
+  {
     int pc = 0;
     while (pc < npc) {
       const uint4 raw = __ldg(reinterpret_cast<const uint4*>(prog + pc));
@@ -211,7 +195,7 @@ __global__ void __launch_bounds__(256) rddl_level_interp(const __grid_constant__
               v = inj[env * ad->env_stride + off];
             } else {
               const uint32_t node = (uint32_t)A.variates[slot].node;
-              uint4 x = rddl_philox_draw(A.seed, (uint64_t)(A.env_offset + env), A.step, node, (uint64_t)off);
+              uint4 x = rddl_philox_draw(A.seed, (uint64_t)(A.env_offset + env), step, node, (uint64_t)off);
               const double u = rddl_u53(x.x, x.y);
               if (op == OP_RANDU) v = u;
               else if (op == OP_RANDN) v = sqrt(-2.0 * log(1.0 - u)) * cos(2.0 * 3.141592653589793 * rddl_u53(x.z, x.w));
@@ -334,8 +318,8 @@ __global__ void __launch_bounds__(256) rddl_level_interp(const __grid_constant__
         case OP_REDIN: {
           const RddlRedSlot s = A.redslots[imm];
           const uint64_t* base = A.red + (A.red_off[imm] * A.n_envs + env * s.chunks);
-          uint64_t acc = base[0];
-          for (int c = 1; c < s.chunks; ++c) acc = red_combine(s.op, acc, base[c]);
+          uint64_t acc = __ldcg(base);
+          for (int c = 1; c < s.chunks; ++c) acc = red_combine(s.op, acc, __ldcg(base + c));
           r[dst] = acc;
           break;
         }
@@ -345,6 +329,39 @@ __global__ void __launch_bounds__(256) rddl_level_interp(const __grid_constant__
         default: break;
       }
     }
+  }
+}
+
+#include "rddl_plane.cuh"
+
+template <int NREG>
+__global__ void __launch_bounds__(256) rddl_level_interp(const __grid_constant__ VmArgs A) {
+  const RddlLaunch& L = A.L;
+  const int G = L.G;
+  const int tid = threadIdx.x;
+  const int lane = tid & (G - 1);
+  const int envs_per_cta = 256 / G;
+  const int64_t chunk = blockIdx.x % L.chunks;
+  const int64_t env = (int64_t)(blockIdx.x / L.chunks) * envs_per_cta + tid / G;
+  const bool env_ok = env < A.n_envs;
+
+  int32_t idx[RDDL_MAX_IDX];
+  uint64_t redval[RDDL_MAX_RED];
+#pragma unroll
+  for (int j = 0; j < RDDL_MAX_RED; ++j) redval[j] = j < L.nred ? red_identity(L.red_op[j]) : 0;
+
+  for (int it = 0; it < L.ipt; ++it) {
+    const int64_t elem = chunk * ((int64_t)G * L.ipt) + (int64_t)it * G + lane;
+    if (!env_ok || elem >= L.E) continue;
+    {  // decode the element index into scope coordinates (C order)
+      int64_t rem = elem;
+      for (int k = L.rank - 1; k >= 0; --k) {
+        int64_t e = L.extent[k];
+        idx[k] = (int32_t)(rem % e);
+        rem /= e;
+      }
+    }
+    vm_exec_element<NREG>(A, L, env, A.step, idx, redval);
   }
 
   // per-env reductions: shuffle within the group, shared memory across warps when G = 256
@@ -410,6 +427,8 @@ struct rddl_program {
   struct Timed { int launch; cudaEvent_t e0, e1; };
   std::vector<Timed> timed;
   std::vector<PlaneProg> plane_progs;   // per launch index; pre-decoded programs of plane launches
+  uint8_t* d_alive = nullptr;           // rollout (general path): env still running
+  int64_t alive_capacity = 0;
 };
 
 // Pre-decodes the instructions of a plane launch (and the Fin descriptors they reference in the
@@ -523,18 +542,45 @@ extern "C" int rddl_program_create(const void* optable, size_t nbytes, int devic
   g->variates.assign((const RddlVariate*)sec[8], (const RddlVariate*)sec[8] + hdr[10]);
   g->n_insns = hdr[4];
   g->plane_progs.resize(g->launches.size());
+  const int reward_tensor = (int)g->tensors.size() - 3;   // specials: __reward, __done, __chk
   for (size_t i = 0; i < g->launches.size(); ++i) {
     if (g->launches[i].kind != 1) continue;
-    if (!decode_plane(g->launches[i], (const RddlInsn*)sec[2], (const uint64_t*)sec[3], hdr[5],
-                      &g->plane_progs[i], &g_create_error)) {
+    PlaneProg* G = &g->plane_progs[i];
+    if (!decode_plane(g->launches[i], (const RddlInsn*)sec[2], (const uint64_t*)sec[3], hdr[5], G,
+                      &g_create_error)) {
       delete g;
       return RDDL_ERR_FORMAT;
     }
+    G->pad = reward_tensor;
+    // scalar programs fused into this launch's epilogue
+    for (size_t k = i + 1; k < g->launches.size() && g->launches[k].kind == 2; ++k) {
+      if (G->nfused >= 2 || g->launches[k].plan != g->launches[i].plan || g->launches[k].nregs > 40) {
+        g_create_error = "op table: too many fused scalar launches";
+        delete g;
+        return RDDL_ERR_FORMAT;
+      }
+      G->fused[G->nfused++] = g->launches[k];
+    }
+    // state carry for multi-step rollouts: PLD of a state fluent whose primed partner is stored
+    // by this launch takes last step's stored register instead of reloading from HBM
+    bool ok = g->launches[i].chunks == 1 && G->nfused > 0;
+    for (int a = 0; a < G->nops; ++a) {
+      PlaneOp& o = G->ops[a];
+      if (o.op != OP_PLD) continue;
+      const int pair = g->tensors[o.imm].pair;
+      if (pair < 0) continue;
+      int src = -1;
+      for (int b = 0; b < G->nops; ++b)
+        if (G->ops[b].op == OP_PST && (int)G->ops[b].imm == pair) { src = G->ops[b].a; G->ops[b].b = 1; }
+      if (src < 0) ok = false;
+      else o.a = src + 1;
+    }
+    G->rollout_ok = ok;
   }
   for (auto& L : g->launches) {
-    const bool bad_scalar = L.kind == 0 && (L.nregs > RDDL_MAX_REGS || L.G > 256 || (L.G & (L.G - 1)));
+    const bool bad_scalar = L.kind != 1 && (L.nregs > RDDL_MAX_REGS || L.G > 256 || (L.G & (L.G - 1)));
     const bool bad_plane = L.kind == 1 && (L.nregs > PLANE_MAX_REGS || L.G > 32 || L.ipt > 1024 || (L.E & 31));
-    if (bad_scalar || bad_plane || L.kind > 1 || L.G < 1 || L.nred > RDDL_MAX_RED) {
+    if (bad_scalar || bad_plane || L.kind > 2 || L.G < 1 || L.nred > RDDL_MAX_RED) {
       g_create_error = "op table: launch out of limits";
       delete g;
       return RDDL_ERR_FORMAT;
@@ -568,6 +614,7 @@ extern "C" void rddl_program_destroy(rddl_program_t* g) {
   cudaFree(g->d_insns); cudaFree(g->d_consts); cudaFree(g->d_addrs); cudaFree(g->d_csrs);
   cudaFree(g->d_pool); cudaFree(g->d_variates); cudaFree(g->d_redslots); cudaFree(g->d_red_off);
   cudaFree(g->d_red);
+  cudaFree(g->d_alive);
   delete g;
 }
 
@@ -587,9 +634,17 @@ extern "C" int64_t rddl_program_info(const rddl_program_t* g, int what) {
   }
 }
 
+struct RolloutArgs {
+  int n_steps;
+  double gamma;
+  double* returns;
+  double* rewards;
+  const int64_t* stride_bytes;
+};
+
 static int run_plan(rddl_program* g, int plan, void* const* tensors, const double* const* injected,
                     uint32_t* status, int64_t n_envs, int64_t env_offset, uint64_t seed, uint64_t step,
-                    cudaStream_t stream) {
+                    cudaStream_t stream, const RolloutArgs* ro = nullptr) {
   std::string* errp = &g->err;
   if (!tensors || n_envs <= 0 || !status) { g->err = "bad arguments"; return RDDL_ERR_ARG; }
   CK(cudaSetDevice(g->device));
@@ -607,10 +662,15 @@ static int run_plan(rddl_program* g, int plan, void* const* tensors, const doubl
   A.pool = g->d_pool; A.variates = g->d_variates; A.redslots = g->d_redslots; A.red_off = g->d_red_off;
   A.red = g->d_red; A.status = status; A.n_envs = n_envs; A.env_offset = env_offset;
   A.seed = seed; A.step = step;
+  A.n_steps = 1;
+  if (ro) {
+    A.n_steps = ro->n_steps; A.gamma = ro->gamma; A.returns = ro->returns; A.rewards = ro->rewards;
+    if (ro->stride_bytes) for (size_t i = 0; i < g->tensors.size(); ++i) A.tstride[i] = ro->stride_bytes[i];
+  }
   for (size_t i = 0; i < g->tensors.size(); ++i) { A.tensors[i] = tensors[i]; A.dtype[i] = (uint8_t)g->tensors[i].dtype; }
   if (injected) for (size_t i = 0; i < g->variates.size(); ++i) A.inj[i] = injected[i];
   for (const RddlLaunch& L : g->launches) {
-    if (L.plan != plan) continue;
+    if (L.plan != plan || L.kind == 2) continue;   // kind 2 runs inside the preceding plane launch
     A.L = L;
     int wpt = 4;
     if (L.kind == 1 && L.chunks == 1 && L.E <= 8192) {
@@ -667,6 +727,72 @@ extern "C" int rddl_step(rddl_program_t* g, void* const* tensors, const double* 
   if (!g) return RDDL_ERR_ARG;
   return run_plan(g, RDDL_PLAN_STEP, tensors, injected, status, n_envs, env_offset, seed, step,
                   (cudaStream_t)cuda_stream);
+}
+
+__global__ void rddl_accumulate_returns(double* returns, double* rewards_t, const double* reward,
+                                        const uint8_t* done, uint8_t* alive, double disc, int64_t n, int first) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const bool live = first ? true : alive[i] != 0;
+  const double r = reward[i];
+  if (rewards_t) rewards_t[i] = r;
+  if (live) returns[i] += r * disc;
+  alive[i] = live && !done[i];
+}
+
+extern "C" int rddl_rollout(rddl_program_t* g, void* const* tensors, uint32_t* status, int64_t n_envs,
+                            int64_t env_offset, uint64_t seed, uint64_t step0, int32_t n_steps,
+                            const int64_t* step_stride_bytes, double gamma, double* returns, double* rewards,
+                            int32_t* state_in_next, void* cuda_stream) {
+  if (!g) return RDDL_ERR_ARG;
+  if (n_steps < 1 || !returns || !state_in_next) { g->err = "rddl_rollout: bad arguments"; return RDDL_ERR_ARG; }
+  cudaStream_t stream = (cudaStream_t)cuda_stream;
+  std::string* errp = &g->err;
+  // fused path: the step plan is one single-tile plane launch (+ its fused scalar epilogue)
+  int n_step_launches = 0;
+  const PlaneProg* G = nullptr;
+  for (size_t i = 0; i < g->launches.size(); ++i) {
+    if (g->launches[i].plan != RDDL_PLAN_STEP || g->launches[i].kind == 2) continue;
+    ++n_step_launches;
+    if (g->launches[i].kind == 1) G = &g->plane_progs[i];
+  }
+  if (n_step_launches == 1 && G && G->rollout_ok) {
+    RolloutArgs ro{n_steps, gamma, returns, rewards, step_stride_bytes};
+    *state_in_next = 1;
+    return run_plan(g, RDDL_PLAN_STEP, tensors, nullptr, status, n_envs, env_offset, seed, step0, stream, &ro);
+  }
+  // general path: one step plan per step, state / next-state pointers swapped on the host
+  CK(cudaSetDevice(g->device));
+  if (g->alive_capacity < n_envs) {
+    CK(cudaStreamSynchronize(stream));
+    cudaFree(g->d_alive);
+    g->d_alive = nullptr;
+    CK(cudaMalloc((void**)&g->d_alive, (size_t)n_envs));
+    g->alive_capacity = n_envs;
+  }
+  const size_t nt = g->tensors.size();
+  std::vector<void*> cur(tensors, tensors + nt);
+  const int reward_tensor = (int)nt - 3;
+  double disc = 1.0;
+  for (int t = 0; t < n_steps; ++t) {
+    std::vector<void*> at(cur);
+    if (step_stride_bytes)
+      for (size_t i = 0; i < nt; ++i) at[i] = (uint8_t*)cur[i] + (int64_t)t * step_stride_bytes[i];
+    int rc = run_plan(g, RDDL_PLAN_STEP, at.data(), nullptr, status, n_envs, env_offset, seed, step0 + t, stream);
+    if (rc) return rc;
+    rddl_accumulate_returns<<<(unsigned)((n_envs + 255) / 256), 256, 0, stream>>>(
+        returns, rewards ? rewards + (int64_t)t * n_envs : nullptr, (const double*)cur[reward_tensor],
+        (const uint8_t*)cur[reward_tensor + 1], g->d_alive, disc, n_envs, t == 0);
+    CK(cudaGetLastError());
+    ++g->launches_issued;
+    disc *= gamma;
+    for (size_t i = 0; i < nt; ++i) {
+      const int pair = g->tensors[i].pair;
+      if (pair >= 0) std::swap(cur[i], cur[pair]);
+    }
+  }
+  *state_in_next = n_steps & 1;
+  return RDDL_OK;
 }
 
 extern "C" int rddl_check(rddl_program_t* g, int which, void* const* tensors, uint32_t* status,

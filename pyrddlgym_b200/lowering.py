@@ -834,6 +834,7 @@ class Lowerer:
         self.p = program
         self.use_planes = use_planes
         self.csr_masks = {}
+        self._plane_ctx = None
         self.rename = {}
         self.consts = []
         self.const_map = {}
@@ -1169,6 +1170,23 @@ class Lowerer:
         else:
             G, ipt, chunks = self.geometry(lb.E, bool(lb.reds))
         row['G'], row['ipt'], row['chunks'] = G, ipt, chunks
+        # a scope-free program that only consumes reductions of the preceding single-tile plane
+        # launch runs in that kernel's epilogue (kind 2): one launch per step instead of two
+        if kind == 1:
+            self._plane_ctx = None
+            if chunks == 1:
+                self._plane_ctx = (lb.plan, set(lb.produced_slots),
+                                   {self.tensor_id[n] for n in lb.written})
+        elif self._plane_ctx is not None and self._plane_ctx[0] == lb.plan and lb.E == 1 \
+                and not lb.reds and lb.nregs <= 40:
+            redin = {i[7] for i in lb.insns if i[0] == OP['REDIN']}
+            touched = {int(self.addrs[i[7]]['tensor']) for i in lb.insns if i[0] in (OP['LOAD'], OP['STORE'])}
+            if redin <= self._plane_ctx[1] and not (touched & self._plane_ctx[2]):
+                kind = 2
+            else:
+                self._plane_ctx = None
+        else:
+            self._plane_ctx = None
         row['pad'] = kind
         for i, (rop, slot) in enumerate(lb.reds):
             row['red_op'][i] = rop
@@ -1177,7 +1195,8 @@ class Lowerer:
         row['nregs'] = max(lb.nregs, 1)
         self.launch_rows.append(row)
         self.out.launches.append({'plan': lb.plan, 'scope': lb.scope, 'E': lb.E, 'kind': kind,
-                                  'kernel': 'rddl_plane_interp' if kind == 1 else 'rddl_level_interp',
+                                  'kernel': {0: 'rddl_level_interp', 1: 'rddl_plane_interp',
+                                             2: 'fused into rddl_plane_interp'}[kind],
                                   'n_insns': len(lb.insns), 'nregs': lb.nregs,
                                   'stores': sorted(lb.stored), 'nred': len(lb.reds)})
         if kind == 1:
@@ -1193,12 +1212,13 @@ class Lowerer:
             nelem = int(np.prod(shape, dtype=np.int64)) if shape else 1
             self.tensor_id[name] = i
             kind = ot.KIND_SHARED if d.kind == 'nonfluent' else ot.KIND_ENV
-            self.tensor_rows.append((ot.DT[d.dtype], kind, nelem))
+            pair = names.index(p.next_state[name]) if name in p.next_state else -1
+            self.tensor_rows.append((ot.DT[d.dtype], pair, kind, nelem))
             self.out.tensor_meta[name] = (d.dtype, kind, nelem)
         n_chk = max(1, len(p.invariants), len(p.preconditions), len(p.terminations))
         for (name, dt, nelem) in [('__reward', 'f', 1), ('__done', 'b', 1), ('__chk', 'b', n_chk)]:
             self.tensor_id[name] = len(self.tensor_rows)
-            self.tensor_rows.append((ot.DT[dt], ot.KIND_ENV, nelem))
+            self.tensor_rows.append((ot.DT[dt], -1, ot.KIND_ENV, nelem))
             p.tensors[name] = hir.TensorDecl(name, 'output', dt, [], 'special')
             self.out.tensor_meta[name] = (dt, ot.KIND_ENV, nelem)
             names.append(name)

@@ -39,6 +39,9 @@ def load():
     lib.rddl_step.restype = ctypes.c_int
     lib.rddl_check.argtypes = [vp, ctypes.c_int, ctypes.POINTER(vp), vp, i64, i64, vp]
     lib.rddl_check.restype = ctypes.c_int
+    lib.rddl_rollout.argtypes = [vp, ctypes.POINTER(vp), vp, i64, i64, u64, u64, ctypes.c_int32,
+                                 ctypes.POINTER(i64), ctypes.c_double, vp, vp, ctypes.POINTER(ctypes.c_int32), vp]
+    lib.rddl_rollout.restype = ctypes.c_int
     lib.rddl_profile.argtypes = [vp, ctypes.c_int]
     lib.rddl_profile.restype = ctypes.c_int
     lib.rddl_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64), ctypes.c_int]
@@ -48,7 +51,7 @@ def load():
 
 
 EXPORTS = ['rddl_program_create', 'rddl_program_destroy', 'rddl_last_error', 'rddl_program_info',
-           'rddl_step', 'rddl_check', 'rddl_profile', 'rddl_profile_read']
+           'rddl_step', 'rddl_check', 'rddl_rollout', 'rddl_profile', 'rddl_profile_read']
 
 
 class NativeProgram:
@@ -78,6 +81,14 @@ class NativeProgram:
     def check(self, which, ptrs, status_ptr, n_envs, env_offset, stream):
         self._check(self.lib.rddl_check(self.handle, which, ptrs, status_ptr, n_envs, env_offset, stream),
                     'rddl_check')
+
+    def rollout(self, ptrs, status_ptr, n_envs, env_offset, seed, step0, n_steps, strides, gamma,
+                returns_ptr, rewards_ptr, stream):
+        swapped = ctypes.c_int32(0)
+        self._check(self.lib.rddl_rollout(self.handle, ptrs, status_ptr, n_envs, env_offset, seed, step0,
+                                          n_steps, strides, gamma, returns_ptr, rewards_ptr,
+                                          ctypes.byref(swapped), stream), 'rddl_rollout')
+        return bool(swapped.value)
 
     def profile(self, enable):
         self._check(self.lib.rddl_profile(self.handle, 1 if enable else 0), 'rddl_profile')

@@ -149,6 +149,49 @@ class BatchedSimulator:
         self._keep = keep
         return self.states, self.t['__reward'], self.t['__done']
 
+    def rollout(self, actions, n_steps, gamma=None, returns=None, keep_rewards=False):
+        """``n_steps`` transitions with pre-drawn action sequences -- the loop of
+        BaseAgent.evaluate (/root/reference/pyRDDLGym/core/policy.py:85-117) for all envs.
+
+        actions: name -> device tensor [n_steps, N, *shape] (one slice per step) or [N, *shape]
+        (same every step). Returns (returns f64[N], rewards f64[n_steps, N] or None); the
+        discounted return is accumulated while an env is not done. Identical, step for step, to
+        ``n_steps`` calls of ``step`` (same Philox counters)."""
+        gamma = float(self.program.discount) if gamma is None else float(gamma)
+        strides = (ctypes.c_int64 * len(self.names))()
+        keep = []
+        for name, v in actions.items():
+            if name not in self.action_names:
+                raise KeyError(f'<{name}> is not an action-fluent')
+            dst = self.t[name]
+            v = v if isinstance(v, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(v))
+            v = v.to(self.device, dtype=dst.dtype).contiguous()
+            if tuple(v.shape) == (n_steps,) + tuple(dst.shape):
+                strides[self.tid[name]] = dst.numel() * dst.element_size()
+            elif tuple(v.shape) != tuple(dst.shape):
+                raise ValueError(f'<{name}>: expected shape {(n_steps,) + tuple(dst.shape)} or {tuple(dst.shape)}')
+            keep.append(v)
+            self.t[name] = v
+        if returns is None:
+            returns = torch.zeros(self.n_envs, dtype=torch.float64, device=self.device)
+        rewards = torch.empty((n_steps, self.n_envs), dtype=torch.float64, device=self.device) if keep_rewards else None
+        self._refresh_ptrs()
+        swapped = self.native.rollout(
+            self._ptrs, ctypes.c_void_p(self.status.data_ptr()), self.n_envs, self.env_offset, self.seed_value,
+            self.step_count, int(n_steps), strides, gamma, ctypes.c_void_p(returns.data_ptr()),
+            ctypes.c_void_p(rewards.data_ptr()) if rewards is not None else None, self._stream())
+        if swapped:
+            for s, ns in self.program.next_state.items():
+                self.t[s], self.t[ns] = self.t[ns], self.t[s]
+        self.step_count += int(n_steps)
+        # action buffers go back to owned [N, ...] storage (the sequence tensor may be freed)
+        for name in actions:
+            dst_shape = (self.n_envs,) + tuple(self.program.tensor_shape(name))
+            if tuple(self.t[name].shape) != dst_shape:
+                self.t[name] = self.t[name][-1]
+        self._keep = keep
+        return returns, rewards
+
     def _run_check(self, plan):
         self._refresh_ptrs()
         self.native.check(plan, self._ptrs, ctypes.c_void_p(self.status.data_ptr()), self.n_envs,

@@ -237,3 +237,47 @@ def test_wildfire1024_vs_independent_stencil_restatement():
         assert np.array_equal(_np(sim.fluent('burning')), burning)
         assert np.array_equal(_np(sim.fluent('out-of-fuel')), oof)
         np.testing.assert_allclose(_np(r), reward, rtol=1e-12)
+
+
+@pytest.mark.parametrize('name,spec,T,fused', [
+    ('wildfire32', lambda: workloads.wildfire(32), 7, True),
+    ('wildfire64_sep', lambda: workloads.wildfire(64, separable=True), 4, True),
+    ('wildfire256_sep', lambda: workloads.wildfire(256, separable=True), 3, False),
+    ('reservoir', lambda: workloads.reservoir(64), 5, False),
+    ('cartpole', lambda: workloads.cartpole(), 60, False),
+])
+def test_rollout_equals_repeated_steps(name, spec, T, fused):
+    """rddl_rollout (policy.py:85-117 for all envs; for single-tile plane programs: every step
+    inside one kernel with the state carried on chip) == T calls of rddl_step + host-side
+    discounted accumulation that stops at done."""
+    import torch
+    p = workloads.load_program(spec())
+    N = 37
+    a = _make(p, N, seed=21)
+    b = _make(p, N, seed=21)
+    rng = np.random.default_rng(5)
+    seq = {}
+    for an in p.names_of_kind('action'):
+        shp = (T, N) + tuple(p.tensor_shape(an))
+        if p.tensors[an].dtype == 'b':
+            seq[an] = rng.random(shp) < 0.05
+        else:
+            seq[an] = rng.uniform(-12.0, 12.0, size=shp) if name == 'cartpole' else rng.uniform(0.0, 5.0, size=shp)
+    gamma = 0.9
+    la0 = a.launches_issued
+    ret, rew = a.rollout({k: torch.from_numpy(v).cuda() for k, v in seq.items()}, T, gamma=gamma, keep_rewards=True)
+    la = a.launches_issued - la0
+    want = np.zeros(N)
+    alive = np.ones(N, dtype=bool)
+    for t in range(T):
+        _, r, d = b.step({k: v[t] for k, v in seq.items()})
+        r, d = _np(r), _np(d)
+        np.testing.assert_array_equal(_np(rew[t]), r)
+        want += np.where(alive, r * gamma ** t, 0.0)
+        alive &= ~d
+    np.testing.assert_allclose(_np(ret), want, rtol=1e-12, atol=1e-12)
+    for s in p.next_state:
+        assert torch.equal(a.fluent(s), b.fluent(s)), s
+    if name == 'cartpole':
+        assert not alive.all()          # some episodes terminated inside the rollout
+    assert (la == 1) == fused, la
