@@ -189,36 +189,30 @@ def run_gpu(args):
     p = workloads.load_program(make_spec(name))
     sim = BatchedSimulator(p, n_envs=N, device=dev, seed=42, env_offset=rank * N)
     K, W = args.steps, args.warmup
-
-    # random-policy action planes, resident in HBM: a rotating pool larger than L2 (126 MB)
+    gamma = float(p.discount)
     plane = N * n * n
-    pool_steps = max(4, min(K + W, -(-300_000_000 // (2 * plane))))
+
+    # random-policy action sequence for the timed rollout, resident in HBM: [K, N, n, n] x 2
+    # planes (larger than the 126 MB L2 unless K is tiny); the warm-up uses its own sequence
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    pool = [(torch.rand((N, n, n), device=dev, generator=g) < 0.05,
-             torch.rand((N, n, n), device=dev, generator=g) < 0.05) for _ in range(pool_steps)]
+
+    def draw(k):
+        return {'put-out': torch.rand((k, N, n, n), device=dev, generator=g) < 0.05,
+                'cut-out': torch.rand((k, N, n, n), device=dev, generator=g) < 0.05}
+
+    seq = draw(K)
+    warm = draw(max(W, 1))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def one_step(t):
-        put, cut = pool[t % pool_steps]
-        return sim.step({'put-out': put, 'cut-out': cut})
-
-    gamma = float(p.discount)
     returns = torch.zeros(N, dtype=torch.float64, device=dev)
 
-    def rollout(k0, k):
-        disc = 1.0
-        for t in range(k0, k0 + k):
-            _, r, _ = one_step(t)
-            returns.add_(r, alpha=disc)
-            disc *= gamma
-
     def reduce_stats():
-        # [sum, sum of squares, count] summed and [min, max] reduced over ranks (BaseAgent.evaluate
-        # statistics, pyRDDLGym/core/policy.py:120-126)
+        # [sum, sum of squares, count] summed and [min, -max] reduced over ranks: the statistics of
+        # BaseAgent.evaluate (pyRDDLGym/core/policy.py:120-126)
         s = torch.stack([returns.sum(), (returns * returns).sum(),
                          torch.tensor(float(N), dtype=torch.float64, device=dev)])
         mm = torch.stack([returns.min(), -returns.max()])
@@ -233,9 +227,10 @@ def run_gpu(args):
     # bring the clocks up before the W warm-up steps (an idle GPU needs ~100 ms to boost)
     t_spin = time.perf_counter()
     while time.perf_counter() - t_spin < 0.3:
-        rollout(0, 8)
+        sim.rollout(warm, max(W, 1), gamma=gamma)
         torch.cuda.synchronize()
-    rollout(0, W)
+    sim.reset()
+    sim.rollout(warm, max(W, 1), gamma=gamma)                      # W untimed warm-up steps
     returns.zero_()
     barrier()
     l0 = sim.launches_issued
@@ -243,7 +238,7 @@ def run_gpu(args):
     barrier()
     sampler.timed = True
     e0.record()
-    rollout(W, K)
+    sim.rollout(seq, K, gamma=gamma, returns=returns)              # exactly K timed steps
     stats = reduce_stats()
     e1.record()
     barrier()
@@ -255,9 +250,22 @@ def run_gpu(args):
     ms = float(tms.item())
     value = world * N * K / (ms * 1e-3)
 
+    # the same K steps through the per-step call (rddl_step per transition), for comparison
+    sim.reset()
+    for t in range(min(W, K)):
+        sim.step({k: v[t] for k, v in seq.items()})
+    barrier()
+    e0.record()
+    for t in range(K):
+        sim.step({k: v[t] for k, v in seq.items()})
+    e1.record()
+    barrier()
+    step_api_value = N * K / (e0.elapsed_time(e1) * 1e-3)
+
     # dominant kernel: per-launch CUDA events on the launch stream (second pass, same inputs)
+    sim.reset()
     sim.native.profile(True)
-    rollout(W + K, K)
+    sim.rollout(seq, K, gamma=gamma)
     torch.cuda.synchronize()
     prof = sim.native.profile_read(sim.table.launches)
     sim.native.profile(False)
@@ -270,43 +278,45 @@ def run_gpu(args):
         pass
     peak = float(peaks.get('hbm_gbs', 6650.0))
     peak_src = 'measured' if 'hbm_gbs' in peaks else 'fallback'
-    abytes = algorithmic_bytes_per_env_step(name) * N
     roofline = None
     if top:
-        per_launch_ms = top['ms'] / max(1, top['count'])
+        steps_per_launch = K / top['count']
+        abytes = algorithmic_bytes_per_env_step(name) * N * steps_per_launch
+        per_launch_ms = top['ms'] / top['count']
         ach = abytes / (per_launch_ms * 1e-3) / 1e9
         roofline = {'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
                     'traffic': None, 'peak_source': peak_src, 'kernel': top['name'],
-                    'kernel_us': per_launch_ms * 1e3,
+                    'kernel_us': per_launch_ms * 1e3, 'steps_per_launch': steps_per_launch,
                     'kernel_share_of_step': top['ms'] / max(1e-9, sum(r['ms'] for r in prof)),
-                    'algorithmic_bytes_per_launch': abytes}
+                    'algorithmic_bytes_per_launch': abytes,
+                    'note': 'algorithmic bytes = (4 planes read + 2 written + reward + done) per env-step; '
+                            'a fused multi-step launch keeps the state planes on chip, so its DRAM '
+                            'traffic is below this figure'}
 
-    # end-to-end through the host-facing call: pinned host actions -> H2D, step, new state +
-    # reward + done -> D2H, every step
-    host_pool = [tuple(x.cpu().pin_memory() for x in pool[i]) for i in range(min(4, pool_steps))]
+    # end-to-end through the host-facing call: pinned host action sequence -> H2D, rollout,
+    # per-step rewards + returns + final state -> D2H
+    h_seq = {k: v.cpu().pin_memory() for k, v in seq.items()}
+    d_seq = {k: torch.empty_like(v) for k, v in seq.items()}
     h_state = {s: torch.empty((N, n, n), dtype=torch.bool).pin_memory() for s in sim.state_names}
-    h_reward = torch.empty(N, dtype=torch.float64).pin_memory()
-    h_done = torch.empty(N, dtype=torch.bool).pin_memory()
-    d_put, d_cut = torch.empty_like(pool[0][0]), torch.empty_like(pool[0][1])
+    h_rew = torch.empty((K, N), dtype=torch.float64).pin_memory()
+    h_ret = torch.empty(N, dtype=torch.float64).pin_memory()
 
-    def e2e_step(t):
-        hp, hc = host_pool[t % len(host_pool)]
-        d_put.copy_(hp, non_blocking=True)
-        d_cut.copy_(hc, non_blocking=True)
-        st, r, d = sim.step({'put-out': d_put, 'cut-out': d_cut})
+    def e2e_rollout():
+        for k in d_seq:
+            d_seq[k].copy_(h_seq[k], non_blocking=True)
+        ret, rew = sim.rollout(d_seq, K, gamma=gamma, keep_rewards=True)
         for s in sim.state_names:
-            h_state[s].copy_(st[s], non_blocking=True)
-        h_reward.copy_(r, non_blocking=True)
-        h_done.copy_(d, non_blocking=True)
-        torch.cuda.current_stream().synchronize()      # the caller owns the result after step()
+            h_state[s].copy_(sim.fluent(s), non_blocking=True)
+        h_rew.copy_(rew, non_blocking=True)
+        h_ret.copy_(ret, non_blocking=True)
+        torch.cuda.current_stream().synchronize()      # the caller owns the results after the call
 
-    for t in range(W):
-        e2e_step(t)
+    sim.reset()
+    e2e_rollout()
+    sim.reset()
     barrier()
-    t0 = time.perf_counter()
     e0.record()
-    for t in range(K):
-        e2e_step(t)
+    e2e_rollout()
     e1.record()
     barrier()
     ms_e2e = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -315,7 +325,7 @@ def run_gpu(args):
     e2e_value = world * N * K / (float(ms_e2e.item()) * 1e-3)
     clocks = sampler.stop() if rank == 0 else None
     h2d = 2 * plane
-    d2h = len(sim.state_names) * plane + 9 * N
+    d2h = (len(sim.state_names) * plane + 8 * N) // K + 8 * N
 
     if rank == 0:
         cpu_v, cpu_sample = cpu_baseline(name, cores=1, envs_per_core=4, steps=16) if world == 1 else (None, None)
@@ -324,12 +334,14 @@ def run_gpu(args):
             'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'u8/f64', 'data': 'synthetic',
             'config': {'workload': f'Wildfire {n}x{n} ({"separable" if w["separable"] else "4-D NEIGHBOR"}), '
-                                   f'{N} envs/GPU, random policy Bernoulli(0.05)',
+                                   f'{N} envs/GPU, {K}-step random-policy rollout, Bernoulli(0.05) actions',
                        'envs_per_gpu': N, 'global_envs': N * world, 'grid': n,
-                       'l2': f'action planes rotate through a {pool_steps}-step pool of '
-                             f'{pool_steps * 2 * plane / 1e6:.0f} MB (> 126 MB L2); state planes '
-                             f'({2 * plane / 1e6:.1f} MB) are rollout-resident',
-                       'parallelism': f'env-shard x{world}',
+                       'api': 'rddl_rollout (K steps per call); per-step rddl_step loop reported as step_api_value',
+                       'step_api_value': step_api_value,
+                       'l2': f'inputs larger than L2: the action sequence read by the timed rollout is '
+                             f'{2 * K * plane / 1e6:.0f} MB (L2 = 126 MB); state planes {2 * plane / 1e6:.1f} MB',
+                       'parallelism': f'env-shard x{world}, return statistics all-reduced (NCCL) once per rollout',
+                       'launches': [l['kernel'] for l in sim.table.launches if l['plan'] == 0],
                        'return_stats': [float(x) for x in stats[0].tolist()]},
             'roofline': roofline,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
