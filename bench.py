@@ -230,7 +230,8 @@ def run_gpu(args):
         sim.rollout(warm, max(W, 1), gamma=gamma)
         torch.cuda.synchronize()
     sim.reset()
-    sim.rollout(warm, max(W, 1), gamma=gamma)                      # W untimed warm-up steps
+    sim.rollout(warm, max(W, 1), gamma=gamma, returns=returns)     # W untimed warm-up steps
+    reduce_stats()                                                 # (loads torch's reduction kernels)
     returns.zero_()
     barrier()
     l0 = sim.launches_issued

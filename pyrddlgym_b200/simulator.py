@@ -63,6 +63,7 @@ class BatchedSimulator:
         self._init = {name: torch.from_numpy(np.ascontiguousarray(program.init[name])).to(
             self.device, dtype=_TORCH_DT[program.tensors[name].dtype])
             for name in program.tensors if program.tensors[name].kind != 'nonfluent'}
+        self._owned_actions = {name: self.t[name] for name in self.action_names}
         self._ptrs = (ctypes.c_void_p * len(self.names))()
         self._inj = (ctypes.c_void_p * max(1, len(self.table.variates)))()
         self._external = {}
@@ -87,6 +88,8 @@ class BatchedSimulator:
     # ------------------------------------------------------------------ reference API
     def reset(self):
         """simulator.py:405-440 -> (states, done[N])."""
+        for name, own in self._owned_actions.items():
+            self.t[name] = own          # never write into caller-owned action tensors
         for name, v in self._init.items():
             self.t[name].copy_(v.expand_as(self.t[name]))
         self.status.zero_()
@@ -110,17 +113,17 @@ class BatchedSimulator:
         for name, v in actions.items():
             if name not in self.tid or name not in self.action_names:
                 raise KeyError(f'<{name}> is not an action-fluent')
-            dst = self.t[name]
+            dst = self._owned_actions[name]
             if isinstance(v, torch.Tensor):
                 if (v.device == dst.device and v.dtype == dst.dtype and v.shape == dst.shape
                         and v.is_contiguous()):
-                    if v.data_ptr() != dst.data_ptr():
-                        self.t[name] = v          # zero-copy: read the caller's buffer directly
+                    self.t[name] = v              # zero-copy: read the caller's buffer directly
                     continue
                 dst.copy_(v.to(dst.dtype).expand_as(dst) if v.shape != dst.shape else v, non_blocking=True)
             else:
                 a = torch.from_numpy(np.array(np.broadcast_to(np.asarray(v), tuple(dst.shape)), order='C'))
                 dst.copy_(a, non_blocking=True)
+            self.t[name] = dst
 
     def step(self, actions=None, variates=None):
         """simulator.py:442-502 for all envs -> (states, reward f64[N], done bool[N]).
@@ -163,7 +166,7 @@ class BatchedSimulator:
         for name, v in actions.items():
             if name not in self.action_names:
                 raise KeyError(f'<{name}> is not an action-fluent')
-            dst = self.t[name]
+            dst = self._owned_actions[name]
             v = v if isinstance(v, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(v))
             v = v.to(self.device, dtype=dst.dtype).contiguous()
             if tuple(v.shape) == (n_steps,) + tuple(dst.shape):
@@ -184,11 +187,11 @@ class BatchedSimulator:
             for s, ns in self.program.next_state.items():
                 self.t[s], self.t[ns] = self.t[ns], self.t[s]
         self.step_count += int(n_steps)
-        # action buffers go back to owned [N, ...] storage (the sequence tensor may be freed)
+        # action fluents go back to owned [N, ...] storage holding the last step's actions
         for name in actions:
-            dst_shape = (self.n_envs,) + tuple(self.program.tensor_shape(name))
-            if tuple(self.t[name].shape) != dst_shape:
-                self.t[name] = self.t[name][-1]
+            last = self.t[name]
+            self.t[name] = self._owned_actions[name]
+            self.t[name].copy_(last[-1] if last.dim() == self.t[name].dim() + 1 else last, non_blocking=True)
         self._keep = keep
         return returns, rewards
 
