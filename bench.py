@@ -211,15 +211,10 @@ def run_gpu(args):
     returns = torch.zeros(N, dtype=torch.float64, device=dev)
 
     def reduce_stats():
-        # [sum, sum of squares, count] summed and [min, -max] reduced over ranks: the statistics of
-        # BaseAgent.evaluate (pyRDDLGym/core/policy.py:120-126)
-        s = torch.stack([returns.sum(), (returns * returns).sum(),
-                         torch.tensor(float(N), dtype=torch.float64, device=dev)])
-        mm = torch.stack([returns.min(), -returns.max()])
-        if world > 1:
-            dist.all_reduce(s, op=dist.ReduceOp.SUM)
-            dist.all_reduce(mm, op=dist.ReduceOp.MIN)
-        return s, mm
+        # statistics of BaseAgent.evaluate (pyRDDLGym/core/policy.py:120-126) over all ranks:
+        # two NCCL all-reduces of a few scalars (pyrddlgym_b200/parallel.py)
+        from pyrddlgym_b200 import parallel
+        return parallel.reduce_return_stats(returns)
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -343,7 +338,7 @@ def run_gpu(args):
                              f'{2 * K * plane / 1e6:.0f} MB (L2 = 126 MB); state planes {2 * plane / 1e6:.1f} MB',
                        'parallelism': f'env-shard x{world}, return statistics all-reduced (NCCL) once per rollout',
                        'launches': [l['kernel'] for l in sim.table.launches if l['plan'] == 0],
-                       'return_stats': [float(x) for x in stats[0].tolist()]},
+                       'return_stats': stats},
             'roofline': roofline,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': float(ms_e2e.item()) / K},
