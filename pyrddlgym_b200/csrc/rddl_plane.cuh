@@ -87,6 +87,41 @@ __device__ __forceinline__ uint32_t plane_mux_hc(const uint32_t* mk, const uint3
   return (x[M > 0 ? M - 1 : 0] & mk[1 << (M > 0 ? M - 1 : 0)]) | (~x[M > 0 ? M - 1 : 0] & lo);
 }
 
+// batched over NW words, leaf-major: every table mask is fetched once and applied to all NW words
+template <int M, bool HC, int NW>
+__device__ __forceinline__ void plane_mux_n(const uint32_t* mk, const uint32_t (*x)[M > 0 ? M : 1], uint32_t* out) {
+  constexpr int ME = (HC && M > 0) ? M - 1 : M;      // depth of the non-constant part of the table
+  if (ME == 0) {
+#pragma unroll
+    for (int jj = 0; jj < NW; ++jj) out[jj] = mk[0];
+  } else {
+    constexpr int NL = 1 << (ME > 0 ? ME - 1 : 0);
+    uint32_t v[NW][NL];
+#pragma unroll
+    for (int i = 0; i < NL; ++i) {
+      const uint32_t m1 = mk[2 * i + 1], m0 = mk[2 * i];
+#pragma unroll
+      for (int jj = 0; jj < NW; ++jj) v[jj][i] = (x[jj][0] & m1) | (~x[jj][0] & m0);
+    }
+#pragma unroll
+    for (int k = 1; k < ME; ++k) {
+#pragma unroll
+      for (int i = 0; i < (NL >> k); ++i) {
+#pragma unroll
+        for (int jj = 0; jj < NW; ++jj) v[jj][i] = (x[jj][k] & v[jj][2 * i + 1]) | (~x[jj][k] & v[jj][2 * i]);
+      }
+    }
+#pragma unroll
+    for (int jj = 0; jj < NW; ++jj) out[jj] = v[jj][0];
+  }
+  if (HC && M > 0) {
+    const uint32_t c = mk[1 << (M > 0 ? M - 1 : 0)];
+#pragma unroll
+    for (int jj = 0; jj < NW; ++jj)
+      out[jj] = (x[jj][M > 0 ? M - 1 : 0] & c) | (~x[jj][M > 0 ? M - 1 : 0] & out[jj]);
+  }
+}
+
 template <int NPR, int WPT>
 struct PlaneCtx {
   uint32_t P[NPR][WPT];
@@ -168,12 +203,12 @@ __device__ __noinline__ void plane_bernoulli(PlaneCtx<NPR, WPT>& C, const VmArgs
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const uint32_t* mk = lev + (4 * b + q) * TT;
+        uint32_t pj[NW];
+        plane_mux_n<M, HC, NW>(lev + (4 * b + q) * TT, x, pj);
 #pragma unroll
         for (int jj = 0; jj < NW; ++jj) {
-          const uint32_t pj = plane_mux_hc<M, HC>(mk, x[jj]);
-          res[jj] |= und[jj] & ~rw[jj][q] & pj;
-          und[jj] &= ~(rw[jj][q] ^ pj);
+          res[jj] |= und[jj] & ~rw[jj][q] & pj[jj];
+          und[jj] &= ~(rw[jj][q] ^ pj[jj]);
         }
       }
     }
@@ -235,14 +270,15 @@ __device__ __noinline__ void plane_bernoulli(PlaneCtx<NPR, WPT>& C, const VmArgs
 
 template <int M, int NPR, int WPT>
 __device__ __forceinline__ void plane_lut(PlaneCtx<NPR, WPT>& C, const PlaneProg& G, const PlaneOp& o) {
-  const uint32_t* mk = G.words + o.off;
+  uint32_t x[WPT][M > 0 ? M : 1], out[WPT];
 #pragma unroll
   for (int j = 0; j < WPT; ++j) {
-    uint32_t x[M > 0 ? M : 1];
 #pragma unroll
-    for (int i = 0; i < M; ++i) x[i] = C.P[plane_reg(o.idx, i)][j];
-    C.P[o.dst][j] = plane_mux<M>(mk, x);
+    for (int i = 0; i < M; ++i) x[j][i] = C.P[plane_reg(o.idx, i)][j];
   }
+  plane_mux_n<M, false, WPT>(G.words + o.off, x, out);
+#pragma unroll
+  for (int j = 0; j < WPT; ++j) C.P[o.dst][j] = out[j];
 }
 
 template <int NPR, int WPT>
