@@ -124,7 +124,10 @@ __device__ __forceinline__ void plane_mux_n(const uint32_t* mk, const uint32_t (
 
 template <int NPR, int WPT>
 struct PlaneCtx {
-  uint32_t P[NPR][WPT];
+  // virtual plane registers live in shared memory, [reg][word][thread]: conflict-free, never
+  // evicted (a local-memory register file of this size thrashes L1 at 3 CTAs per SM)
+  uint32_t* P;
+  __device__ __forceinline__ uint32_t& at(int r, int j) { return P[(r * WPT + j) * 256 + threadIdx.x]; }
   int env[WPT];       // local env index (relative to the launch's first env)
   int wi[WPT];        // word index inside the env
   uint32_t valid;     // bit j: word j is inside the batch
@@ -155,7 +158,7 @@ __device__ __noinline__ void plane_bernoulli(PlaneCtx<NPR, WPT>& C, const VmArgs
       if ((C.valid >> j) & 1u) {
         uint32_t x[M > 0 ? M : 1];
 #pragma unroll
-        for (int i = 0; i < M; ++i) x[i] = C.P[plane_reg(o.idx, i)][j];
+        for (int i = 0; i < M; ++i) x[i] = C.at(plane_reg(o.idx, i), j);
         if (has_bad && plane_mux<M>(bad, x)) atomicOr(A.status + env0 + C.env[j], 1u);
         const double* u = inj + (env0 + C.env[j]) * A.L.E + ((int64_t)C.wi[j] << 5);
         for (int b = 0; b < 32; ++b) {
@@ -166,7 +169,7 @@ __device__ __noinline__ void plane_bernoulli(PlaneCtx<NPR, WPT>& C, const VmArgs
           res |= (uint32_t)(u[b] <= p) << b;
         }
       }
-      C.P[o.dst][j] = res;
+      C.at(o.dst, j) = res;
     }
     return;
   }
@@ -184,7 +187,7 @@ __device__ __noinline__ void plane_bernoulli(PlaneCtx<NPR, WPT>& C, const VmArgs
     for (int jj = 0; jj < NW; ++jj) {
       const int j = j0 + jj;
 #pragma unroll
-      for (int i = 0; i < M; ++i) x[jj][i] = C.P[plane_reg(o.idx, i)][j];
+      for (int i = 0; i < M; ++i) x[jj][i] = C.at(plane_reg(o.idx, i), j);
       const bool ok = (C.valid >> j) & 1u;
       if (has_bad && ok && plane_mux<M>(bad, x[jj])) atomicOr(A.status + env0 + C.env[j], 1u);
       const uint32_t al = has_always ? plane_mux<M>(always, x[jj]) : 0u;
@@ -217,7 +220,7 @@ __device__ __noinline__ void plane_bernoulli(PlaneCtx<NPR, WPT>& C, const VmArgs
 #pragma unroll
     for (int jj = 0; jj < NW; ++jj) {
       const int j = j0 + jj;
-      C.P[o.dst][j] = res[jj];
+      C.at(o.dst, j) = res[jj];
       fix[tid * WPT + j] = 0;
       uint32_t u = und[jj];
       while (u) {
@@ -233,7 +236,7 @@ __device__ __noinline__ void plane_bernoulli(PlaneCtx<NPR, WPT>& C, const VmArgs
           const uint4 r4 = rddl_philox4x32_10(
               make_uint4(((uint32_t)C.wi[j] << 5) | b, e0 + (uint32_t)C.env[j], step, node | (0xC000u << 16)), key);
           const uint64_t t64 = ((uint64_t)thr[2 * v + 1] << 32) | thr[2 * v];
-          if ((((uint64_t)r4.x << 32) | r4.y) < (t64 << PLANE_BERN_LEVELS)) C.P[o.dst][j] |= 1u << b;
+          if ((((uint64_t)r4.x << 32) | r4.y) < (t64 << PLANE_BERN_LEVELS)) C.at(o.dst, j) |= 1u << b;
         }
       }
     }
@@ -264,7 +267,7 @@ __device__ __noinline__ void plane_bernoulli(PlaneCtx<NPR, WPT>& C, const VmArgs
     }
     __syncwarp();
 #pragma unroll
-    for (int j = 0; j < WPT; ++j) C.P[o.dst][j] |= fix[tid * WPT + j];
+    for (int j = 0; j < WPT; ++j) C.at(o.dst, j) |= fix[tid * WPT + j];
   }
 }
 
@@ -274,11 +277,11 @@ __device__ __forceinline__ void plane_lut(PlaneCtx<NPR, WPT>& C, const PlaneProg
 #pragma unroll
   for (int j = 0; j < WPT; ++j) {
 #pragma unroll
-    for (int i = 0; i < M; ++i) x[j][i] = C.P[plane_reg(o.idx, i)][j];
+    for (int i = 0; i < M; ++i) x[j][i] = C.at(plane_reg(o.idx, i), j);
   }
   plane_mux_n<M, false, WPT>(G.words + o.off, x, out);
 #pragma unroll
-  for (int j = 0; j < WPT; ++j) C.P[o.dst][j] = out[j];
+  for (int j = 0; j < WPT; ++j) C.at(o.dst, j) = out[j];
 }
 
 template <int NPR, int WPT>
@@ -293,17 +296,19 @@ __global__ void __launch_bounds__(256, 3) rddl_plane_interp(const __grid_constan
   const int chunk = blockIdx.x % chunks;
   const int64_t env0 = (int64_t)(blockIdx.x / chunks) * envs_per_tile;   // first env of this tile
 
-  // dynamic shared memory: [nshared][tile_words + 2*W32] stencil planes | cnt | queue | qn | fix
+  // dynamic shared memory: plane registers [nregs][WPT][256] | [nshared][tile_words + 2*W32] stencil
+  // planes | cnt | queue | qn | fix
   extern __shared__ uint32_t smem[];
   const int plane_stride = tile_words + 2 * W32;
-  uint32_t* S = smem;
-  int32_t* cnt = reinterpret_cast<int32_t*>(smem + G.nshared * plane_stride);   // [32][MAX_RED]
+  uint32_t* S = smem + L.nregs * WPT * 256;
+  int32_t* cnt = reinterpret_cast<int32_t*>(S + G.nshared * plane_stride);      // [32][MAX_RED]
   uint32_t* queue = reinterpret_cast<uint32_t*>(cnt + 32 * RDDL_MAX_RED);        // [8][PLANE_QUEUE]
   int* qn = reinterpret_cast<int*>(queue + 8 * PLANE_QUEUE);                     // [8]
   uint32_t* fix = reinterpret_cast<uint32_t*>(qn + 8);                           // [256][WPT]
   if (L.nred > 0) cnt[tid] = 0;                                                  // 32 * MAX_RED == 256
 
   PlaneCtx<NPR, WPT> C;
+  C.P = smem;
   C.valid = 0;
 #pragma unroll
   for (int j = 0; j < WPT; ++j) {
@@ -339,7 +344,7 @@ __global__ void __launch_bounds__(256, 3) rddl_plane_interp(const __grid_constan
       case OP_PLD: {
         if (t > 0 && o.a > 0) {   // state fluent: carried over from the value stored last step
 #pragma unroll
-          for (int j = 0; j < WPT; ++j) C.P[o.dst][j] = C.P[o.a - 1][j];
+          for (int j = 0; j < WPT; ++j) C.at(o.dst, j) = C.at(o.a - 1, j);
           break;
         }
         const uint8_t* base = reinterpret_cast<const uint8_t*>(A.tensors[o.imm]) + t * A.tstride[o.imm] +
@@ -356,13 +361,13 @@ __global__ void __launch_bounds__(256, 3) rddl_plane_interp(const __grid_constan
           }
         }
 #pragma unroll
-        for (int j = 0; j < WPT; ++j) C.P[o.dst][j] = plane_pack(lo[j], hi[j]);
+        for (int j = 0; j < WPT; ++j) C.at(o.dst, j) = plane_pack(lo[j], hi[j]);
         break;
       }
       case OP_PLDC: {
 #pragma unroll
         for (int j = 0; j < WPT; ++j)
-          C.P[o.dst][j] = ((C.valid >> j) & 1u) ? (uint32_t)__ldg(A.pool + o.imm + C.wi[j]) : 0u;
+          C.at(o.dst, j) = ((C.valid >> j) & 1u) ? (uint32_t)__ldg(A.pool + o.imm + C.wi[j]) : 0u;
         break;
       }
       case OP_PST: {
@@ -372,7 +377,7 @@ __global__ void __launch_bounds__(256, 3) rddl_plane_interp(const __grid_constan
         for (int j = 0; j < WPT; ++j) {
           if ((C.valid >> j) & 1u) {
             uint4 lo, hi;
-            plane_unpack(C.P[o.a][j], lo, hi);
+            plane_unpack(C.at(o.a, j), lo, hi);
             uint4* p = reinterpret_cast<uint4*>(base + ((int64_t)(C.env[j] * wpe + C.wi[j]) << 5));
             __stcs(p, lo);
             __stcs(p + 1, hi);
@@ -382,7 +387,7 @@ __global__ void __launch_bounds__(256, 3) rddl_plane_interp(const __grid_constan
       }
       case OP_PCONST: {
 #pragma unroll
-        for (int j = 0; j < WPT; ++j) C.P[o.dst][j] = o.imm ? 0xffffffffu : 0u;
+        for (int j = 0; j < WPT; ++j) C.at(o.dst, j) = o.imm ? 0xffffffffu : 0u;
         break;
       }
       case OP_PLUT: {
@@ -400,7 +405,7 @@ __global__ void __launch_bounds__(256, 3) rddl_plane_interp(const __grid_constan
 #pragma unroll
         for (int j = 0; j < WPT; ++j) {
           const int w = j * 256 + tid;
-          if (w < tile_words) s[W32 + w] = ((C.valid >> j) & 1u) ? C.P[o.a][j] : 0u;
+          if (w < tile_words) s[W32 + w] = ((C.valid >> j) & 1u) ? C.at(o.a, j) : 0u;
         }
         if (chunks > 1) {
           // halo rows above / below the tile, packed straight from the source tensor
@@ -457,7 +462,7 @@ __global__ void __launch_bounds__(256, 3) rddl_plane_interp(const __grid_constan
             k2 = u2 ^ v;
             k3 = u2 & v;
           }
-          C.P[o.dst][j] = k0; C.P[o.dst + 1][j] = k1; C.P[o.dst + 2][j] = k2; C.P[o.dst + 3][j] = k3;
+          C.at(o.dst, j) = k0; C.at(o.dst + 1, j) = k1; C.at(o.dst + 2, j) = k2; C.at(o.dst + 3, j) = k3;
         }
         break;
       }
@@ -481,7 +486,7 @@ __global__ void __launch_bounds__(256, 3) rddl_plane_interp(const __grid_constan
           int c = 0;
 #pragma unroll
           for (int j = 0; j < WPT; ++j)
-            if ((C.valid >> j) & 1u) c += o.m ? __popc(C.P[r0][j]) : 32;
+            if ((C.valid >> j) & 1u) c += o.m ? __popc(C.at(r0, j)) : 32;
 #pragma unroll
           for (int i = 0; i < RDDL_MAX_RED; ++i)
             if (i == o.b) racc[i] += c;
@@ -489,7 +494,7 @@ __global__ void __launch_bounds__(256, 3) rddl_plane_interp(const __grid_constan
           const bool warp_uniform_env = (wpe & 31) == 0;
 #pragma unroll
           for (int j = 0; j < WPT; ++j) {
-            int c = ((C.valid >> j) & 1u) ? (o.m ? __popc(C.P[r0][j]) : 32) : 0;
+            int c = ((C.valid >> j) & 1u) ? (o.m ? __popc(C.at(r0, j)) : 32) : 0;
             if (warp_uniform_env) {
               c = __reduce_add_sync(0xffffffffu, c);
               if ((tid & 31) == 0 && c) atomicAdd(&cnt[C.env[j] * RDDL_MAX_RED + o.b], c);

@@ -586,6 +586,15 @@ extern "C" int rddl_program_create(const void* optable, size_t nbytes, int devic
       return RDDL_ERR_FORMAT;
     }
   }
+  // the plane kernels keep their virtual register file in dynamic shared memory (> 48 KB)
+  {
+    const int max_smem = 200 * 1024;
+    cudaFuncSetAttribute(rddl_plane_interp<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(rddl_plane_interp<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(rddl_plane_interp<PLANE_MAX_REGS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(rddl_plane_interp<PLANE_MAX_REGS, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaGetLastError();   // no device in CPU-only builds: ignored here, create fails at cudaSetDevice below
+  }
   int64_t acc = 0;
   for (auto& s : g->redslots) { g->red_off.push_back(acc); acc += s.chunks; }
   g->red_total = acc;
@@ -698,7 +707,8 @@ static int run_plan(rddl_program* g, int plan, void* const* tensors, const doubl
     if (L.kind == 1) {
       const PlaneProg& G = g->plane_progs[(size_t)(&L - g->launches.data())];
       const int W32 = (int)((L.rank == 2 ? L.extent[1] : L.extent[0]) >> 5);
-      const size_t smem = sizeof(uint32_t) * ((size_t)G.nshared * (A.L.ipt + 2 * W32) + 32 * RDDL_MAX_RED +
+      const size_t smem = sizeof(uint32_t) * ((size_t)L.nregs * wpt * 256 +
+                                              (size_t)G.nshared * (A.L.ipt + 2 * W32) + 32 * RDDL_MAX_RED +
                                               8 * PLANE_QUEUE + 8 + 256 * wpt);
       const bool small = L.nregs <= 16;
       if (wpt == 1) {

@@ -835,6 +835,7 @@ class Lowerer:
         self.use_planes = use_planes
         self.csr_masks = {}
         self._plane_ctx = None
+        self.tensor_names_by_id = {}
         self.rename = {}
         self.consts = []
         self.const_map = {}
@@ -1140,6 +1141,7 @@ class Lowerer:
                     for it in grp['items']:
                         self.rename = it.rename
                         lb.add_item(it)
+                    lb.finalize()
                 except plane_lowering.NotPlanar as e:
                     self.out.plane_rejects.append((plan, list(grp['scope']), str(e)))
                     # table entries (consts, CSR lists) added by the failed attempt stay: they are
@@ -1211,6 +1213,7 @@ class Lowerer:
             shape = p.tensor_shape(name)
             nelem = int(np.prod(shape, dtype=np.int64)) if shape else 1
             self.tensor_id[name] = i
+            self.tensor_names_by_id[i] = name
             kind = ot.KIND_SHARED if d.kind == 'nonfluent' else ot.KIND_ENV
             pair = names.index(p.next_state[name]) if name in p.next_state else -1
             self.tensor_rows.append((ot.DT[d.dtype], pair, kind, nelem))

@@ -136,6 +136,7 @@ class PlaneBuilder:
             raise NotPlanar('row length must be a multiple of 32')
         self.E = self.H * self.W
         self.insns = []
+        self.ops = []
         self.reds = []
         self.stored = {}
         self.written = set()
@@ -166,8 +167,77 @@ class PlaneBuilder:
             raise NotPlanar('too many plane registers')
         return r
 
-    def ins(self, op, dst=0, a=0, b=0, c=0, imm=0, flags=0):
-        self.insns.append((OP[op], flags, dst, a, b, c, 0, imm))
+    def ins(self, op, dst=0, a=0, b=0, c=0, imm=0, flags=0, fin=None):
+        """Records one plane op over *virtual* registers; ``fin``: (Fin, kwargs of fin_const),
+        serialised by finalize() once physical registers are known."""
+        self.ops.append({'op': op, 'dst': dst, 'a': a, 'b': b, 'imm': imm, 'fin': fin})
+
+    def finalize(self):
+        """Liveness-based register allocation (the virtual register file lives in shared
+        memory: fewer registers = more resident CTAs), then emission of the instructions."""
+        ops = self.ops
+        nxt = set(self.lw.p.next_state.values())
+        INF = len(ops) + 1
+        defs, uses = [], []
+        for o in ops:
+            op = o['op']
+            d = [o['dst'] + k for k in range(4)] if op == 'PCOUNT' else (
+                [o['dst']] if op in ('PLD', 'PLDC', 'PCONST', 'PLUT', 'PBERN') else [])
+            u = [o['a']] if op in ('PST', 'PSHARE') else []
+            if o['fin'] is not None:
+                u += list(o['fin'][0].idx)
+            defs.append(d)
+            uses.append(u)
+        last = {}
+        for i, (d, u) in enumerate(zip(defs, uses)):
+            for v in d + u:
+                last[v] = max(last.get(v, -1), i)
+        for i, o in enumerate(ops):
+            # a state plane stored this step is re-read by next step's PLD in fused rollouts
+            if o['op'] == 'PST' and self.lw.tensor_names_by_id[o['imm']] in nxt:
+                last[o['a']] = INF
+        phys, free, top = {}, set(), 0
+        for i, (d, u) in enumerate(zip(defs, uses)):
+            for v in set(u):
+                if last[v] == i and v in phys:
+                    free.add(phys[v])
+            if len(d) == 4:
+                k = 0
+                while not all((k + t) in free or (k + t) >= top for t in range(4)):
+                    k += 1
+                for t in range(4):
+                    free.discard(k + t)
+                    phys[d[t]] = k + t
+                top = max(top, k + 4)
+            elif d:
+                if last[d[0]] == INF:
+                    # carried across steps: a register of its own, never shared with an earlier
+                    # value (that value's next-step write would clobber the carry before its PLD)
+                    r = top
+                    top += 1
+                elif free:
+                    r = min(free)
+                    free.discard(r)
+                else:
+                    r = top
+                    top += 1
+                phys[d[0]] = r
+            for v in d:
+                if last[v] == i:
+                    free.add(phys[v])          # defined but never read
+        if top > MAX_PREGS:
+            raise NotPlanar('too many plane registers')
+        self.nregs = top
+        self.insns = []
+        for o in ops:
+            op = o['op']
+            dst = phys.get(o['dst'], 0) if op in ('PLD', 'PLDC', 'PCONST', 'PLUT', 'PBERN', 'PCOUNT') else o['dst']
+            a = phys[o['a']] if op in ('PST', 'PSHARE') else o['a']
+            imm = o['imm']
+            if o['fin'] is not None:
+                f, kw = o['fin']
+                imm = self.fin_const(Fin([phys[r] for r in f.idx], f.table, f.care), **kw)
+            self.insns.append((OP[op], 0, dst, a, o['b'], 0, 0, imm))
 
     def fin_const(self, f, thresholds=False, values=None):
         """Serialises a Fin descriptor into the const pool; returns its index."""
@@ -256,7 +326,7 @@ class PlaneBuilder:
         if f.m == 0:
             self.ins('PCONST', dst=d, imm=int(bool(f.table[0])))
         else:
-            self.ins('PLUT', dst=d, imm=self.fin_const(f))
+            self.ins('PLUT', dst=d, fin=(f, {}))
         return d
 
     def as_plane_fin(self, f):
@@ -432,7 +502,7 @@ class PlaneBuilder:
         p = Fin(p.idx, np.asarray(p.table, dtype=np.float64), p.care)
         slot = self.lw.variate_slot(n.id, 'U', self.E)
         d = self.alloc()
-        self.ins('PBERN', dst=d, a=slot, imm=self.fin_const(p, thresholds=True))
+        self.ins('PBERN', dst=d, a=slot, fin=(p, {'thresholds': True}))
         self.variate_nodes.append(int(n.id))
         return Fin((d,), np.array([False, True]))
 
@@ -473,6 +543,6 @@ class PlaneBuilder:
                 vals = np.asarray(_one(f.table), dtype=np.int64)
             if len(self.reds) >= ot.MAX_RED:
                 raise NotPlanar('too many reductions')
-            self.ins('PRED', b=len(self.reds), imm=self.fin_const(f, values=vals))
+            self.ins('PRED', b=len(self.reds), fin=(f, {'values': vals}))
             self.reds.append((rop, slot))
             self.produced_slots.add(slot)
