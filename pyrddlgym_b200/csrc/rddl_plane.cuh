@@ -284,9 +284,21 @@ __device__ __forceinline__ void plane_lut(PlaneCtx<NPR, WPT>& C, const PlaneProg
   for (int j = 0; j < WPT; ++j) C.at(o.dst, j) = out[j];
 }
 
+#ifndef PLANE_MIN_BLOCKS
+#define PLANE_MIN_BLOCKS 2
+#endif
+
+// Shared-memory layout of a staged stencil plane: rows are padded with one zero word on each
+// side and separated (per env) by a zero row, so that PCOUNT needs no boundary conditionals:
+//   index(row r of the tile, word c) = (r + 1 + r / H_rows_per_env) * (W32 + 2) + c + 1   (chunks == 1)
+//   index(r, c) = (r + 1) * (W32 + 2) + c + 1, halo rows at r = -1 and r = rows             (chunks > 1)
+__device__ __forceinline__ int plane_spos(int row, int c, int env_l, int pitch) {
+  return (row + 1 + env_l) * pitch + c + 1;
+}
+
 template <int NPR, int WPT>
-__global__ void __launch_bounds__(256, 3) rddl_plane_interp(const __grid_constant__ VmArgs A,
-                                                             const __grid_constant__ PlaneProg G) {
+__global__ void __launch_bounds__(256, WPT == 1 ? 4 : PLANE_MIN_BLOCKS) rddl_plane_interp(const __grid_constant__ VmArgs A,
+                                                                          const __grid_constant__ PlaneProg G) {
   const RddlLaunch& L = A.L;
   const int tid = threadIdx.x;
   const int H = L.rank == 2 ? (int)L.extent[0] : 1;
@@ -295,21 +307,25 @@ __global__ void __launch_bounds__(256, 3) rddl_plane_interp(const __grid_constan
   const int envs_per_tile = L.G, tile_words = L.ipt, chunks = L.chunks;
   const int chunk = blockIdx.x % chunks;
   const int64_t env0 = (int64_t)(blockIdx.x / chunks) * envs_per_tile;   // first env of this tile
+  const int pitch = W32 + 2;
+  const int tile_rows = tile_words / W32;
 
-  // dynamic shared memory: plane registers [nregs][WPT][256] | [nshared][tile_words + 2*W32] stencil
-  // planes | cnt | queue | qn | fix
+  // dynamic shared memory: plane registers [nregs][WPT][256] | [nshared] padded stencil planes |
+  // cnt | queue | qn | fix
   extern __shared__ uint32_t smem[];
-  const int plane_stride = tile_words + 2 * W32;
+  const int plane_stride = (tile_rows + envs_per_tile + 2) * pitch;
   uint32_t* S = smem + L.nregs * WPT * 256;
   int32_t* cnt = reinterpret_cast<int32_t*>(S + G.nshared * plane_stride);      // [32][MAX_RED]
   uint32_t* queue = reinterpret_cast<uint32_t*>(cnt + 32 * RDDL_MAX_RED);        // [8][PLANE_QUEUE]
   int* qn = reinterpret_cast<int*>(queue + 8 * PLANE_QUEUE);                     // [8]
   uint32_t* fix = reinterpret_cast<uint32_t*>(qn + 8);                           // [256][WPT]
   if (L.nred > 0) cnt[tid] = 0;                                                  // 32 * MAX_RED == 256
+  for (int i = tid; i < G.nshared * plane_stride; i += 256) S[i] = 0u;           // zero padding, once
 
   PlaneCtx<NPR, WPT> C;
   C.P = smem;
   C.valid = 0;
+  int spos[WPT];      // shared-memory index of the word inside a staged plane
 #pragma unroll
   for (int j = 0; j < WPT; ++j) {
     const int w = j * 256 + tid;
@@ -323,12 +339,17 @@ __global__ void __launch_bounds__(256, 3) rddl_plane_interp(const __grid_constan
       ok = ok && C.wi[j] < wpe;
     }
     if (ok && env0 + C.env[j] < A.n_envs) C.valid |= 1u << j;
+    const int row = G.w32_shift >= 0 ? (w >> G.w32_shift) : w / W32;        // row inside the tile
+    spos[j] = plane_spos(row, w - row * W32, C.env[j], pitch);
   }
+  // whole tile inside the batch (the common case): no per-word validity handling below
+  const bool full = __syncthreads_and(C.valid == ((1u << WPT) - 1u)) != 0;
+  // byte offset of this thread's first word (word j is 256 words further), valid when `full`
+  const int64_t tile_byte0 = ((env0 * wpe + (int64_t)chunk * tile_words + tid) << 5);
   int racc[RDDL_MAX_RED];   // per-thread popcount accumulators (single-env tiles)
 #pragma unroll
   for (int i = 0; i < RDDL_MAX_RED; ++i) racc[i] = 0;
   const bool single_env = envs_per_tile == 1;
-  if (L.nred > 0) __syncthreads();
 
   // per-env rollout state of the thread that runs env (env0 + tid)'s scalar epilogue
   double ret_acc = 0.0, disc = 1.0;
@@ -347,17 +368,26 @@ __global__ void __launch_bounds__(256, 3) rddl_plane_interp(const __grid_constan
           for (int j = 0; j < WPT; ++j) C.at(o.dst, j) = C.at(o.a - 1, j);
           break;
         }
-        const uint8_t* base = reinterpret_cast<const uint8_t*>(A.tensors[o.imm]) + t * A.tstride[o.imm] +
-                              ((env0 * wpe) << 5);
+        const uint8_t* base = reinterpret_cast<const uint8_t*>(A.tensors[o.imm]) + t * A.tstride[o.imm];
         uint4 lo[WPT], hi[WPT];
+        if (full) {
+          const uint4* p = reinterpret_cast<const uint4*>(base + tile_byte0);
 #pragma unroll
-        for (int j = 0; j < WPT; ++j) {
-          lo[j] = make_uint4(0, 0, 0, 0);
-          hi[j] = lo[j];
-          if ((C.valid >> j) & 1u) {
-            const uint4* p = reinterpret_cast<const uint4*>(base + ((int64_t)(C.env[j] * wpe + C.wi[j]) << 5));
-            lo[j] = __ldcs(p);
-            hi[j] = __ldcs(p + 1);
+          for (int j = 0; j < WPT; ++j) {
+            lo[j] = __ldcs(p + j * 512);
+            hi[j] = __ldcs(p + j * 512 + 1);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < WPT; ++j) {
+            lo[j] = make_uint4(0, 0, 0, 0);
+            hi[j] = lo[j];
+            if ((C.valid >> j) & 1u) {
+              const uint4* p = reinterpret_cast<const uint4*>(
+                  base + (((env0 + C.env[j]) * wpe + C.wi[j]) << 5));
+              lo[j] = __ldcs(p);
+              hi[j] = __ldcs(p + 1);
+            }
           }
         }
 #pragma unroll
@@ -367,20 +397,31 @@ __global__ void __launch_bounds__(256, 3) rddl_plane_interp(const __grid_constan
       case OP_PLDC: {
 #pragma unroll
         for (int j = 0; j < WPT; ++j)
-          C.at(o.dst, j) = ((C.valid >> j) & 1u) ? (uint32_t)__ldg(A.pool + o.imm + C.wi[j]) : 0u;
+          C.at(o.dst, j) = (full || ((C.valid >> j) & 1u)) ? (uint32_t)__ldg(A.pool + o.imm + C.wi[j]) : 0u;
         break;
       }
       case OP_PST: {
         if (!last_step && o.b) break;   // carried state: only the final step reaches HBM
-        uint8_t* base = reinterpret_cast<uint8_t*>(A.tensors[o.imm]) + ((env0 * wpe) << 5);
+        uint8_t* base = reinterpret_cast<uint8_t*>(A.tensors[o.imm]);
+        if (full) {
+          uint4* p = reinterpret_cast<uint4*>(base + tile_byte0);
 #pragma unroll
-        for (int j = 0; j < WPT; ++j) {
-          if ((C.valid >> j) & 1u) {
+          for (int j = 0; j < WPT; ++j) {
             uint4 lo, hi;
             plane_unpack(C.at(o.a, j), lo, hi);
-            uint4* p = reinterpret_cast<uint4*>(base + ((int64_t)(C.env[j] * wpe + C.wi[j]) << 5));
-            __stcs(p, lo);
-            __stcs(p + 1, hi);
+            __stcs(p + j * 512, lo);
+            __stcs(p + j * 512 + 1, hi);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < WPT; ++j) {
+            if ((C.valid >> j) & 1u) {
+              uint4 lo, hi;
+              plane_unpack(C.at(o.a, j), lo, hi);
+              uint4* p = reinterpret_cast<uint4*>(base + (((env0 + C.env[j]) * wpe + C.wi[j]) << 5));
+              __stcs(p, lo);
+              __stcs(p + 1, hi);
+            }
           }
         }
         break;
@@ -402,23 +443,25 @@ __global__ void __launch_bounds__(256, 3) rddl_plane_interp(const __grid_constan
       }
       case OP_PSHARE: {
         uint32_t* s = S + o.b * plane_stride;
+        if (t > 0) __syncthreads();      // every warp is done reading last step's plane
 #pragma unroll
         for (int j = 0; j < WPT; ++j) {
           const int w = j * 256 + tid;
-          if (w < tile_words) s[W32 + w] = ((C.valid >> j) & 1u) ? C.at(o.a, j) : 0u;
+          if (w < tile_words) s[spos[j]] = (full || ((C.valid >> j) & 1u)) ? C.at(o.a, j) : 0u;
         }
         if (chunks > 1) {
           // halo rows above / below the tile, packed straight from the source tensor
-          const uint8_t* base = reinterpret_cast<const uint8_t*>(A.tensors[o.imm]);
+          const uint8_t* base = reinterpret_cast<const uint8_t*>(A.tensors[o.imm]) + t * A.tstride[o.imm];
           for (int i = tid; i < 2 * W32; i += 256) {
             const bool top = i < W32;
-            const int wsrc = top ? chunk * tile_words - W32 + i : (chunk + 1) * tile_words + (i - W32);
+            const int c = top ? i : i - W32;
+            const int wsrc = top ? chunk * tile_words - W32 + c : (chunk + 1) * tile_words + c;
             uint32_t word = 0;
             if (wsrc >= 0 && wsrc < wpe && env0 < A.n_envs) {
               const uint4* p = reinterpret_cast<const uint4*>(base + ((env0 * wpe + wsrc) << 5));
               word = plane_pack(__ldg(p), __ldg(p + 1));
             }
-            s[top ? i : W32 + tile_words + (i - W32)] = word;
+            s[plane_spos(top ? -1 : tile_rows, c, 0, pitch)] = word;
           }
         }
         __syncthreads();
@@ -427,42 +470,33 @@ __global__ void __launch_bounds__(256, 3) rddl_plane_interp(const __grid_constan
       case OP_PCOUNT: {
         const uint32_t* s = S + o.b * plane_stride;
         const uint32_t m9 = o.imm;
+        // uniform masks of the stencil offsets (all-ones for the common full neighbourhoods)
+        uint32_t mk[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) mk[i] = ((m9 >> i) & 1u) ? 0xffffffffu : 0u;
 #pragma unroll
         for (int j = 0; j < WPT; ++j) {
-          uint32_t k0 = 0, k1 = 0, k2 = 0, k3 = 0;
-          if ((C.valid >> j) & 1u) {
-            const int x = G.w32_shift >= 0 ? (C.wi[j] >> G.w32_shift) : C.wi[j] / W32;
-            const int c = C.wi[j] - x * W32;
-            const int pos = W32 + j * 256 + tid;
-            const bool has_l = c > 0, has_r = c < W32 - 1;
-            uint32_t sr[3], cr[3];   // per row: sum and carry of the (west, centre, east) planes
+          const int q0 = spos[j];
+          uint32_t sr[3], cr[3];   // per row: sum and carry of the (west, centre, east) planes
 #pragma unroll
-            for (int d = 0; d < 3; ++d) {
-              const bool rowok = (d == 0) ? x > 0 : (d == 2 ? x < H - 1 : true);
-              uint32_t Cw = 0, Lw = 0, Rw = 0;
-              if (rowok) {
-                const int q = pos + (d - 1) * W32;
-                Cw = s[q];
-                if (has_l) Lw = s[q - 1];
-                if (has_r) Rw = s[q + 1];
-              }
-              const uint32_t m3 = m9 >> (d * 3);
-              const uint32_t west = (m3 & 1u) ? __funnelshift_l(Lw, Cw, 1) : 0u;
-              const uint32_t mid = (m3 & 2u) ? Cw : 0u;
-              const uint32_t east = (m3 & 4u) ? __funnelshift_r(Cw, Rw, 1) : 0u;
-              sr[d] = west ^ mid ^ east;
-              cr[d] = (west & mid) | (east & (west ^ mid));
-            }
-            k0 = sr[0] ^ sr[1] ^ sr[2];
-            const uint32_t t1 = (sr[0] & sr[1]) | (sr[2] & (sr[0] ^ sr[1]));   // weight 2
-            const uint32_t u1 = cr[0] ^ cr[1] ^ cr[2];                         // weight 2
-            const uint32_t u2 = (cr[0] & cr[1]) | (cr[2] & (cr[0] ^ cr[1]));   // weight 4
-            k1 = t1 ^ u1;
-            const uint32_t v = t1 & u1;                                        // weight 4
-            k2 = u2 ^ v;
-            k3 = u2 & v;
+          for (int d = 0; d < 3; ++d) {
+            const int q = q0 + (d - 1) * pitch;
+            const uint32_t Cw = s[q], Lw = s[q - 1], Rw = s[q + 1];
+            const uint32_t west = __funnelshift_l(Lw, Cw, 1) & mk[3 * d];
+            const uint32_t mid = Cw & mk[3 * d + 1];
+            const uint32_t east = __funnelshift_r(Cw, Rw, 1) & mk[3 * d + 2];
+            sr[d] = west ^ mid ^ east;
+            cr[d] = (west & mid) | (east & (west ^ mid));
           }
-          C.at(o.dst, j) = k0; C.at(o.dst + 1, j) = k1; C.at(o.dst + 2, j) = k2; C.at(o.dst + 3, j) = k3;
+          const uint32_t k0 = sr[0] ^ sr[1] ^ sr[2];
+          const uint32_t t1 = (sr[0] & sr[1]) | (sr[2] & (sr[0] ^ sr[1]));   // weight 2
+          const uint32_t u1 = cr[0] ^ cr[1] ^ cr[2];                         // weight 2
+          const uint32_t u2 = (cr[0] & cr[1]) | (cr[2] & (cr[0] ^ cr[1]));   // weight 4
+          const uint32_t v = t1 & u1;                                        // weight 4
+          C.at(o.dst, j) = k0;
+          C.at(o.dst + 1, j) = t1 ^ u1;
+          C.at(o.dst + 2, j) = u2 ^ v;
+          C.at(o.dst + 3, j) = u2 & v;
         }
         break;
       }
@@ -486,7 +520,7 @@ __global__ void __launch_bounds__(256, 3) rddl_plane_interp(const __grid_constan
           int c = 0;
 #pragma unroll
           for (int j = 0; j < WPT; ++j)
-            if ((C.valid >> j) & 1u) c += o.m ? __popc(C.at(r0, j)) : 32;
+            if (full || ((C.valid >> j) & 1u)) c += o.m ? __popc(C.at(r0, j)) : 32;
 #pragma unroll
           for (int i = 0; i < RDDL_MAX_RED; ++i)
             if (i == o.b) racc[i] += c;
@@ -494,7 +528,7 @@ __global__ void __launch_bounds__(256, 3) rddl_plane_interp(const __grid_constan
           const bool warp_uniform_env = (wpe & 31) == 0;
 #pragma unroll
           for (int j = 0; j < WPT; ++j) {
-            int c = ((C.valid >> j) & 1u) ? (o.m ? __popc(C.at(r0, j)) : 32) : 0;
+            int c = (full || ((C.valid >> j) & 1u)) ? (o.m ? __popc(C.at(r0, j)) : 32) : 0;
             if (warp_uniform_env) {
               c = __reduce_add_sync(0xffffffffu, c);
               if ((tid & 31) == 0 && c) atomicAdd(&cnt[C.env[j] * RDDL_MAX_RED + o.b], c);

@@ -708,7 +708,8 @@ static int run_plan(rddl_program* g, int plan, void* const* tensors, const doubl
       const PlaneProg& G = g->plane_progs[(size_t)(&L - g->launches.data())];
       const int W32 = (int)((L.rank == 2 ? L.extent[1] : L.extent[0]) >> 5);
       const size_t smem = sizeof(uint32_t) * ((size_t)L.nregs * wpt * 256 +
-                                              (size_t)G.nshared * (A.L.ipt + 2 * W32) + 32 * RDDL_MAX_RED +
+                                              (size_t)G.nshared * ((A.L.ipt / W32 + A.L.G + 2) * (W32 + 2)) +
+                                              32 * RDDL_MAX_RED +
                                               8 * PLANE_QUEUE + 8 + 256 * wpt);
       const bool small = L.nregs <= 16;
       if (wpt == 1) {
