@@ -39,6 +39,7 @@ struct PlaneProg {
   int32_t nops, nshared, w32_shift, wpe_shift;   // shifts: log2 of words per row / per env, or -1
   int32_t nfused, fused_nregs, rollout_ok, pad;  // scalar launches run in the epilogue (kind 2)
   RddlLaunch fused[2];
+  int32_t red_off[RDDL_MAX_RED], red_m[RDDL_MAX_RED];   // PRED op of reduction j: table offset, #planes
   PlaneOp ops[PLANE_MAX_OPS];
   uint32_t words[PLANE_WORDS];
 };
@@ -122,12 +123,12 @@ __device__ __forceinline__ void plane_mux_n(const uint32_t* mk, const uint32_t (
   }
 }
 
-template <int NPR, int WPT>
+template <int WPT, int BLOCK>
 struct PlaneCtx {
   // virtual plane registers live in shared memory, [reg][word][thread]: conflict-free, never
   // evicted (a local-memory register file of this size thrashes L1 at 3 CTAs per SM)
   uint32_t* P;
-  __device__ __forceinline__ uint32_t& at(int r, int j) { return P[(r * WPT + j) * 256 + threadIdx.x]; }
+  __device__ __forceinline__ uint32_t& at(int r, int j) { return P[(r * WPT + j) * BLOCK + threadIdx.x]; }
   int env[WPT];       // local env index (relative to the launch's first env)
   int wi[WPT];        // word index inside the env
   uint32_t valid;     // bit j: word j is inside the batch
@@ -136,8 +137,8 @@ struct PlaneCtx {
 __device__ __forceinline__ int plane_reg(uint32_t idx, int i) { return (idx >> (6 * i)) & 63; }
 
 // Bernoulli(table[idx]) for the thread's WPT words; M index planes
-template <int M, bool HC, int NPR, int WPT>
-__device__ __noinline__ void plane_bernoulli(PlaneCtx<NPR, WPT>& C, const VmArgs& A, const PlaneProg& G,
+template <int M, bool HC, int WPT, int BLOCK>
+__device__ __noinline__ void plane_bernoulli(PlaneCtx<WPT, BLOCK>& C, const VmArgs& A, const PlaneProg& G,
                                              const PlaneOp& o, uint32_t* queue, int* qn, uint32_t* fix,
                                              int64_t env0, uint32_t step) {
   const int TT = 1 << M;
@@ -249,7 +250,7 @@ __device__ __noinline__ void plane_bernoulli(PlaneCtx<NPR, WPT>& C, const VmArgs
       const int ol = e & 31, oj = (e >> 5) & 7, b = (e >> 8) & 31;
       const uint32_t v = e >> 13;
       // the owner's word coordinates, recomputed from the tile geometry
-      const int ow = oj * 256 + warp * 32 + ol;
+      const int ow = oj * BLOCK + warp * 32 + ol;
       int env_l, wi_l;
       if (A.L.chunks == 1) {
         const int wpe = (int)(A.L.E >> 5);
@@ -271,17 +272,51 @@ __device__ __noinline__ void plane_bernoulli(PlaneCtx<NPR, WPT>& C, const VmArgs
   }
 }
 
-template <int M, int NPR, int WPT>
-__device__ __forceinline__ void plane_lut(PlaneCtx<NPR, WPT>& C, const PlaneProg& G, const PlaneOp& o) {
-  uint32_t x[WPT][M > 0 ? M : 1], out[WPT];
+template <int M, int WPT, int BLOCK>
+__device__ __forceinline__ void plane_lut(PlaneCtx<WPT, BLOCK>& C, const PlaneProg& G, const PlaneOp& o) {
+  constexpr int CH = WPT < 4 ? WPT : 4;
 #pragma unroll
-  for (int j = 0; j < WPT; ++j) {
+  for (int j0 = 0; j0 < WPT; j0 += CH) {
+    uint32_t x[CH][M > 0 ? M : 1], out[CH];
 #pragma unroll
-    for (int i = 0; i < M; ++i) x[j][i] = C.at(plane_reg(o.idx, i), j);
+    for (int j = 0; j < CH; ++j) {
+#pragma unroll
+      for (int i = 0; i < M; ++i) x[j][i] = C.at(plane_reg(o.idx, i), j0 + j);
+    }
+    plane_mux_n<M, false, CH>(G.words + o.off, x, out);
+#pragma unroll
+    for (int j = 0; j < CH; ++j) C.at(o.dst, j0 + j) = out[j];
   }
-  plane_mux_n<M, false, WPT>(G.words + o.off, x, out);
-#pragma unroll
-  for (int j = 0; j < WPT; ++j) C.at(o.dst, j) = out[j];
+}
+
+// Partial tiles (last CTA of the batch / of an env): per-word validity and 64-bit addressing.
+// Kept out of line so that their address arithmetic is not hoisted into the dispatch loop.
+template <int WPT, int BLOCK>
+__device__ __noinline__ void plane_ld_partial(PlaneCtx<WPT, BLOCK>& C, const uint8_t* base, int64_t env0, int wpe,
+                                              int dst) {
+#pragma unroll 1
+  for (int j = 0; j < WPT; ++j) {
+    uint32_t word = 0;
+    if ((C.valid >> j) & 1u) {
+      const uint4* p = reinterpret_cast<const uint4*>(base + (((env0 + C.env[j]) * wpe + C.wi[j]) << 5));
+      word = plane_pack(__ldcs(p), __ldcs(p + 1));
+    }
+    C.at(dst, j) = word;
+  }
+}
+
+template <int WPT, int BLOCK>
+__device__ __noinline__ void plane_st_partial(PlaneCtx<WPT, BLOCK>& C, uint8_t* base, int64_t env0, int wpe, int src) {
+#pragma unroll 1
+  for (int j = 0; j < WPT; ++j) {
+    if ((C.valid >> j) & 1u) {
+      uint4 lo, hi;
+      plane_unpack(C.at(src, j), lo, hi);
+      uint4* p = reinterpret_cast<uint4*>(base + (((env0 + C.env[j]) * wpe + C.wi[j]) << 5));
+      __stcs(p, lo);
+      __stcs(p + 1, hi);
+    }
+  }
 }
 
 #ifndef PLANE_MIN_BLOCKS
@@ -296,8 +331,8 @@ __device__ __forceinline__ int plane_spos(int row, int c, int env_l, int pitch) 
   return (row + 1 + env_l) * pitch + c + 1;
 }
 
-template <int NPR, int WPT>
-__global__ void __launch_bounds__(256, WPT == 1 ? 4 : PLANE_MIN_BLOCKS) rddl_plane_interp(const __grid_constant__ VmArgs A,
+template <int WPT, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, WPT == 1 ? 4 : PLANE_MIN_BLOCKS) rddl_plane_interp(const __grid_constant__ VmArgs A,
                                                                           const __grid_constant__ PlaneProg G) {
   const RddlLaunch& L = A.L;
   const int tid = threadIdx.x;
@@ -314,21 +349,22 @@ __global__ void __launch_bounds__(256, WPT == 1 ? 4 : PLANE_MIN_BLOCKS) rddl_pla
   // cnt | queue | qn | fix
   extern __shared__ uint32_t smem[];
   const int plane_stride = (tile_rows + envs_per_tile + 2) * pitch;
-  uint32_t* S = smem + L.nregs * WPT * 256;
+  uint32_t* S = smem + L.nregs * WPT * BLOCK;
   int32_t* cnt = reinterpret_cast<int32_t*>(S + G.nshared * plane_stride);      // [32][MAX_RED]
   uint32_t* queue = reinterpret_cast<uint32_t*>(cnt + 32 * RDDL_MAX_RED);        // [8][PLANE_QUEUE]
   int* qn = reinterpret_cast<int*>(queue + 8 * PLANE_QUEUE);                     // [8]
   uint32_t* fix = reinterpret_cast<uint32_t*>(qn + 8);                           // [256][WPT]
-  if (L.nred > 0) cnt[tid] = 0;                                                  // 32 * MAX_RED == 256
-  for (int i = tid; i < G.nshared * plane_stride; i += 256) S[i] = 0u;           // zero padding, once
+  if (L.nred > 0)
+    for (int i = tid; i < 32 * RDDL_MAX_RED; i += BLOCK) cnt[i] = 0;
+  for (int i = tid; i < G.nshared * plane_stride; i += BLOCK) S[i] = 0u;           // zero padding, once
 
-  PlaneCtx<NPR, WPT> C;
+  PlaneCtx<WPT, BLOCK> C;
   C.P = smem;
   C.valid = 0;
   int spos[WPT];      // shared-memory index of the word inside a staged plane
 #pragma unroll
   for (int j = 0; j < WPT; ++j) {
-    const int w = j * 256 + tid;
+    const int w = j * BLOCK + tid;
     bool ok = w < tile_words;
     if (chunks == 1) {
       C.env[j] = G.wpe_shift >= 0 ? (w >> G.wpe_shift) : w / wpe;
@@ -346,6 +382,17 @@ __global__ void __launch_bounds__(256, WPT == 1 ? 4 : PLANE_MIN_BLOCKS) rddl_pla
   const bool full = __syncthreads_and(C.valid == ((1u << WPT) - 1u)) != 0;
   // byte offset of this thread's first word (word j is 256 words further), valid when `full`
   const int64_t tile_byte0 = ((env0 * wpe + (int64_t)chunk * tile_words + tid) << 5);
+  if (full) {
+    // issue the DRAM requests of every plane this tile reads up front (L2 prefetch): the loads of
+    // the later PLD ops then hit L2 and the compute of this CTA overlaps its own memory traffic
+    for (int pc = 0; pc < G.nops; ++pc) {
+      if (G.ops[pc].op != OP_PLD) continue;
+      const uint8_t* p = reinterpret_cast<const uint8_t*>(A.tensors[G.ops[pc].imm]) + tile_byte0;
+#pragma unroll
+      for (int j = 0; j < WPT; ++j)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p + (int64_t)j * (BLOCK * 32)));
+    }
+  }
   int racc[RDDL_MAX_RED];   // per-thread popcount accumulators (single-env tiles)
 #pragma unroll
   for (int i = 0; i < RDDL_MAX_RED; ++i) racc[i] = 0;
@@ -358,6 +405,17 @@ __global__ void __launch_bounds__(256, WPT == 1 ? 4 : PLANE_MIN_BLOCKS) rddl_pla
 #pragma unroll 1
   for (int t = 0; t < T; ++t) {
   const bool last_step = t == T - 1;
+  if (full && !last_step) {
+    // next step's action planes: start their DRAM reads now (L2 prefetch)
+    for (int pc = 0; pc < G.nops; ++pc) {
+      const PlaneOp& q = G.ops[pc];
+      if (q.op != OP_PLD || q.a > 0 || A.tstride[q.imm] == 0) continue;
+      const uint8_t* p = reinterpret_cast<const uint8_t*>(A.tensors[q.imm]) + (t + 1) * A.tstride[q.imm] + tile_byte0;
+#pragma unroll
+      for (int j = 0; j < WPT; ++j)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p + (int64_t)j * (BLOCK * 32)));
+    }
+  }
 #pragma unroll 1
   for (int pc = 0; pc < G.nops; ++pc) {
     const PlaneOp& o = G.ops[pc];
@@ -369,29 +427,23 @@ __global__ void __launch_bounds__(256, WPT == 1 ? 4 : PLANE_MIN_BLOCKS) rddl_pla
           break;
         }
         const uint8_t* base = reinterpret_cast<const uint8_t*>(A.tensors[o.imm]) + t * A.tstride[o.imm];
-        uint4 lo[WPT], hi[WPT];
-        if (full) {
-          const uint4* p = reinterpret_cast<const uint4*>(base + tile_byte0);
-#pragma unroll
-          for (int j = 0; j < WPT; ++j) {
-            lo[j] = __ldcs(p + j * 512);
-            hi[j] = __ldcs(p + j * 512 + 1);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < WPT; ++j) {
-            lo[j] = make_uint4(0, 0, 0, 0);
-            hi[j] = lo[j];
-            if ((C.valid >> j) & 1u) {
-              const uint4* p = reinterpret_cast<const uint4*>(
-                  base + (((env0 + C.env[j]) * wpe + C.wi[j]) << 5));
-              lo[j] = __ldcs(p);
-              hi[j] = __ldcs(p + 1);
-            }
-          }
+        if (!full) {
+          plane_ld_partial<WPT, BLOCK>(C, base, env0, wpe, o.dst);
+          break;
         }
+        const uint4* p = reinterpret_cast<const uint4*>(base + tile_byte0);
+        constexpr int CH = WPT < 4 ? WPT : 4;     // loads in flight per thread: 2 * CH x 16 B
 #pragma unroll
-        for (int j = 0; j < WPT; ++j) C.at(o.dst, j) = plane_pack(lo[j], hi[j]);
+        for (int j0 = 0; j0 < WPT; j0 += CH) {
+          uint4 lo[CH], hi[CH];
+#pragma unroll
+          for (int j = 0; j < CH; ++j) {
+            lo[j] = __ldcs(p + (j0 + j) * (BLOCK * 2));
+            hi[j] = __ldcs(p + (j0 + j) * (BLOCK * 2) + 1);
+          }
+#pragma unroll
+          for (int j = 0; j < CH; ++j) C.at(o.dst, j0 + j) = plane_pack(lo[j], hi[j]);
+        }
         break;
       }
       case OP_PLDC: {
@@ -403,26 +455,17 @@ __global__ void __launch_bounds__(256, WPT == 1 ? 4 : PLANE_MIN_BLOCKS) rddl_pla
       case OP_PST: {
         if (!last_step && o.b) break;   // carried state: only the final step reaches HBM
         uint8_t* base = reinterpret_cast<uint8_t*>(A.tensors[o.imm]);
-        if (full) {
-          uint4* p = reinterpret_cast<uint4*>(base + tile_byte0);
+        if (!full) {
+          plane_st_partial<WPT, BLOCK>(C, base, env0, wpe, o.a);
+          break;
+        }
+        uint4* p = reinterpret_cast<uint4*>(base + tile_byte0);
 #pragma unroll
-          for (int j = 0; j < WPT; ++j) {
-            uint4 lo, hi;
-            plane_unpack(C.at(o.a, j), lo, hi);
-            __stcs(p + j * 512, lo);
-            __stcs(p + j * 512 + 1, hi);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < WPT; ++j) {
-            if ((C.valid >> j) & 1u) {
-              uint4 lo, hi;
-              plane_unpack(C.at(o.a, j), lo, hi);
-              uint4* p = reinterpret_cast<uint4*>(base + (((env0 + C.env[j]) * wpe + C.wi[j]) << 5));
-              __stcs(p, lo);
-              __stcs(p + 1, hi);
-            }
-          }
+        for (int j = 0; j < WPT; ++j) {
+          uint4 lo, hi;
+          plane_unpack(C.at(o.a, j), lo, hi);
+          __stcs(p + j * (BLOCK * 2), lo);
+          __stcs(p + j * (BLOCK * 2) + 1, hi);
         }
         break;
       }
@@ -432,6 +475,10 @@ __global__ void __launch_bounds__(256, WPT == 1 ? 4 : PLANE_MIN_BLOCKS) rddl_pla
         break;
       }
       case OP_PLUT: {
+#if defined(PLANE_ABLATE) && (PLANE_ABLATE & 2)
+        for (int j = 0; j < WPT; ++j) C.at(o.dst, j) = C.at(plane_reg(o.idx, 0), j);
+        break;
+#endif
         switch (o.m & 0xff) {
           case 1: plane_lut<1>(C, G, o); break;
           case 2: plane_lut<2>(C, G, o); break;
@@ -443,16 +490,15 @@ __global__ void __launch_bounds__(256, WPT == 1 ? 4 : PLANE_MIN_BLOCKS) rddl_pla
       }
       case OP_PSHARE: {
         uint32_t* s = S + o.b * plane_stride;
-        if (t > 0) __syncthreads();      // every warp is done reading last step's plane
 #pragma unroll
         for (int j = 0; j < WPT; ++j) {
-          const int w = j * 256 + tid;
+          const int w = j * BLOCK + tid;
           if (w < tile_words) s[spos[j]] = (full || ((C.valid >> j) & 1u)) ? C.at(o.a, j) : 0u;
         }
         if (chunks > 1) {
           // halo rows above / below the tile, packed straight from the source tensor
           const uint8_t* base = reinterpret_cast<const uint8_t*>(A.tensors[o.imm]) + t * A.tstride[o.imm];
-          for (int i = tid; i < 2 * W32; i += 256) {
+          for (int i = tid; i < 2 * W32; i += BLOCK) {
             const bool top = i < W32;
             const int c = top ? i : i - W32;
             const int wsrc = top ? chunk * tile_words - W32 + c : (chunk + 1) * tile_words + c;
@@ -468,6 +514,10 @@ __global__ void __launch_bounds__(256, WPT == 1 ? 4 : PLANE_MIN_BLOCKS) rddl_pla
         break;
       }
       case OP_PCOUNT: {
+#if defined(PLANE_ABLATE) && (PLANE_ABLATE & 8)
+        for (int j = 0; j < WPT; ++j) { C.at(o.dst, j) = 0; C.at(o.dst + 1, j) = 0; C.at(o.dst + 2, j) = 0; C.at(o.dst + 3, j) = 0; }
+        break;
+#endif
         const uint32_t* s = S + o.b * plane_stride;
         const uint32_t m9 = o.imm;
         // uniform masks of the stencil offsets (all-ones for the common full neighbourhoods)
@@ -501,6 +551,10 @@ __global__ void __launch_bounds__(256, WPT == 1 ? 4 : PLANE_MIN_BLOCKS) rddl_pla
         break;
       }
       case OP_PBERN: {
+#if defined(PLANE_ABLATE) && (PLANE_ABLATE & 1)
+        for (int j = 0; j < WPT; ++j) C.at(o.dst, j) = C.at(plane_reg(o.idx, 0), j);
+        break;
+#endif
         switch (o.m) {
           case 0: plane_bernoulli<0, false>(C, A, G, o, queue, qn, fix, env0, (uint32_t)(A.step + t)); break;
           case 1: plane_bernoulli<1, false>(C, A, G, o, queue, qn, fix, env0, (uint32_t)(A.step + t)); break;
@@ -514,6 +568,9 @@ __global__ void __launch_bounds__(256, WPT == 1 ? 4 : PLANE_MIN_BLOCKS) rddl_pla
         break;
       }
       case OP_PRED: {
+#if defined(PLANE_ABLATE) && (PLANE_ABLATE & 4)
+        break;
+#endif
         // per-env popcount of a plane (m == 1) or of the valid cells (m == 0)
         const int r0 = plane_reg(o.idx, 0);
         if (single_env) {
@@ -556,17 +613,16 @@ __global__ void __launch_bounds__(256, WPT == 1 ? 4 : PLANE_MIN_BLOCKS) rddl_pla
     }
     __syncthreads();
     const int64_t cells = chunks == 1 ? L.E : (int64_t)min(tile_words, wpe - chunk * tile_words) * 32;
-    for (int i = tid; i < envs_per_tile * L.nred; i += 256) {
+    for (int i = tid; i < envs_per_tile * L.nred; i += BLOCK) {
       const int e = i / L.nred, jr = i - e * L.nred;
       const int64_t ge = env0 + e;
       if (ge >= A.n_envs) continue;
       // the PRED op of reduction jr carries (value at 0, value at 1) as raw 64-bit words
-      int off = 0, m = 0;
-      for (int pc = 0; pc < G.nops; ++pc)
-        if (G.ops[pc].op == OP_PRED && G.ops[pc].b == jr) { off = G.ops[pc].off; m = G.ops[pc].m; }
+      const int off = G.red_off[jr], m = G.red_m[jr];
       const uint64_t v0 = ((uint64_t)G.words[off + 1] << 32) | G.words[off];
       const uint64_t v1 = ((uint64_t)G.words[off + 3] << 32) | G.words[off + 2];
       const int64_t ones = cnt[e * RDDL_MAX_RED + jr];
+      cnt[e * RDDL_MAX_RED + jr] = 0;      // ready for the next step of a fused rollout
       const int64_t n1 = m ? ones : 0, n0 = m ? cells - ones : cells;
       uint64_t out;
       if (L.red_op[jr] == RED_SUM_F) {
@@ -598,11 +654,6 @@ __global__ void __launch_bounds__(256, WPT == 1 ? 4 : PLANE_MIN_BLOCKS) rddl_pla
         if (__ldcg(reinterpret_cast<const uint8_t*>(A.tensors[G.pad + 1]) + ge)) alive = false;
       }
     }
-  }
-  if (!last_step) {
-    __syncthreads();
-    if (L.nred > 0) cnt[tid] = 0;
-    __syncthreads();
   }
   }   // step loop
   if (T > 1 && A.returns && tid < envs_per_tile && env0 + tid < A.n_envs) A.returns[env0 + tid] += ret_acc;

@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -490,6 +491,7 @@ static bool decode_plane(const RddlLaunch& L, const RddlInsn* insns, const uint6
       G->words[nw++] = (uint32_t)vals[0]; G->words[nw++] = (uint32_t)(vals[0] >> 32);
       const uint64_t v1 = m ? vals[1] : 0;
       G->words[nw++] = (uint32_t)v1; G->words[nw++] = (uint32_t)(v1 >> 32);
+      if (in.b < RDDL_MAX_RED) { G->red_off[in.b] = o.off; G->red_m[in.b] = m; }
     }
   }
   return true;
@@ -589,10 +591,11 @@ extern "C" int rddl_program_create(const void* optable, size_t nbytes, int devic
   // the plane kernels keep their virtual register file in dynamic shared memory (> 48 KB)
   {
     const int max_smem = 200 * 1024;
-    cudaFuncSetAttribute(rddl_plane_interp<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    cudaFuncSetAttribute(rddl_plane_interp<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    cudaFuncSetAttribute(rddl_plane_interp<PLANE_MAX_REGS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    cudaFuncSetAttribute(rddl_plane_interp<PLANE_MAX_REGS, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    const void* fns[3] = {(const void*)rddl_plane_interp<1, 256>, (const void*)rddl_plane_interp<2, 256>,
+                          (const void*)rddl_plane_interp<4, 256>};
+    for (const void* f : fns) {
+      cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    }
     cudaGetLastError();   // no device in CPU-only builds: ignored here, create fails at cudaSetDevice below
   }
   int64_t acc = 0;
@@ -681,14 +684,19 @@ static int run_plan(rddl_program* g, int plan, void* const* tensors, const doubl
   for (const RddlLaunch& L : g->launches) {
     if (L.plan != plan || L.kind == 2) continue;   // kind 2 runs inside the preceding plane launch
     A.L = L;
-    int wpt = 4;
-    if (L.kind == 1 && L.chunks == 1 && L.E <= 8192) {
-      // small batch: one word per thread so that the grid still covers all SMs
-      const int64_t tiles4 = (n_envs + L.G - 1) / L.G;
-      if (tiles4 < 4 * 148) {
-        wpt = 1;
-        int ept = (int)(8192 / L.E);
+    // words per thread: the tile geometry of the op table (4 words, 32768 cells per CTA: big tiles
+    // amortise the per-thread interpretation overhead); for very small batches of small grids
+    // one word per thread, so that the grid still spans the SMs. RDDL_PLANE_FORCE_WPT overrides.
+    int wpt = L.ipt <= 256 ? 1 : (L.ipt <= 512 ? 2 : 4);
+    const int block = 256;
+    if (L.kind == 1 && L.chunks == 1 && wpt > 1) {
+      const char* force = getenv("RDDL_PLANE_FORCE_WPT");
+      int want = force ? atoi(force) : ((n_envs + L.G - 1) / L.G < 74 ? 1 : wpt);
+      if (want != 1 && want != 2 && want != 4) want = wpt;
+      if (want < wpt && L.E <= 8192 * want) {
+        int ept = (int)((8192 * want) / L.E);
         if (ept > 32) ept = 32;
+        wpt = want;
         A.L.G = ept;
         A.L.ipt = (int)(ept * (L.E >> 5));
       }
@@ -707,18 +715,13 @@ static int run_plan(rddl_program* g, int plan, void* const* tensors, const doubl
     if (L.kind == 1) {
       const PlaneProg& G = g->plane_progs[(size_t)(&L - g->launches.data())];
       const int W32 = (int)((L.rank == 2 ? L.extent[1] : L.extent[0]) >> 5);
-      const size_t smem = sizeof(uint32_t) * ((size_t)L.nregs * wpt * 256 +
+      const size_t smem = sizeof(uint32_t) * ((size_t)L.nregs * wpt * block +
                                               (size_t)G.nshared * ((A.L.ipt / W32 + A.L.G + 2) * (W32 + 2)) +
                                               32 * RDDL_MAX_RED +
-                                              8 * PLANE_QUEUE + 8 + 256 * wpt);
-      const bool small = L.nregs <= 16;
-      if (wpt == 1) {
-        if (small) rddl_plane_interp<16, 1><<<(unsigned)blocks, 256, smem, stream>>>(A, G);
-        else rddl_plane_interp<PLANE_MAX_REGS, 1><<<(unsigned)blocks, 256, smem, stream>>>(A, G);
-      } else {
-        if (small) rddl_plane_interp<16, 4><<<(unsigned)blocks, 256, smem, stream>>>(A, G);
-        else rddl_plane_interp<PLANE_MAX_REGS, 4><<<(unsigned)blocks, 256, smem, stream>>>(A, G);
-      }
+                                              8 * PLANE_QUEUE + 8 + block * wpt);
+      if (wpt == 1) rddl_plane_interp<1, 256><<<(unsigned)blocks, 256, smem, stream>>>(A, G);
+      else if (wpt == 2) rddl_plane_interp<2, 256><<<(unsigned)blocks, 256, smem, stream>>>(A, G);
+      else rddl_plane_interp<4, 256><<<(unsigned)blocks, 256, smem, stream>>>(A, G);
     } else if (L.nregs <= 16) rddl_level_interp<16><<<(unsigned)blocks, 256, 0, stream>>>(A);
     else if (L.nregs <= 40) rddl_level_interp<40><<<(unsigned)blocks, 256, 0, stream>>>(A);
     else rddl_level_interp<RDDL_MAX_REGS><<<(unsigned)blocks, 256, 0, stream>>>(A);

@@ -34,7 +34,10 @@ MAX_M = 5            # index planes of an intermediate Fin
 MAX_M_BOOL = 4       # ... of a boolean combination (a PLUT over m planes costs 2^m - 1 LOP3)
 MAX_M_BERN = 4
 MAX_M_RED = 3
-TILE_CELLS = 32768   # cells per CTA tile: 256 threads x 4 words x 32 cells
+import os as _os
+
+# cells per CTA tile: 256 threads x WPT words x 32 cells (WPT in {1, 2, 4}; RDDL_PLANE_WPT overrides)
+TILE_CELLS = 8192 * int(_os.environ.get('RDDL_PLANE_WPT', '4'))
 MAX_PREGS = 32
 BERN_LEVELS = 8      # bit-serial levels before the per-cell tail (csrc/rddl_plane.cuh)
 
