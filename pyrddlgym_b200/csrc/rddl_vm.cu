@@ -327,6 +327,62 @@ __device__ __noinline__ void vm_exec_element(const VmArgs& A, const RddlLaunch& 
         case OP_STATUS:
           if (RA) atomicOr(A.status + env, imm);
           break;
+        case OP_SUMLOOP: {
+          // sum over one loop variable of t1 [* t2], t = plain tensor reads: native MAC loop.
+          // data word (next instruction): dst | a << 16 = extent or CSR id, imm = address of t2
+          const uint4 raw2 = __ldg(reinterpret_cast<const uint4*>(prog + pc));
+          ++pc;
+          const uint32_t arg = (raw2.x >> 16) | ((raw2.y & 0xffff) << 16);
+          const bool is_csr = rb & 1u, two = rb & 2u, flt = rb & 4u;
+          const int slot = (int)ra;
+          int64_t base[2], stride[2];
+          const void* ptr[2];
+          int dts[2];
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const RddlAddr* ad = A.addrs + (k == 0 ? imm : raw2.w);
+            int64_t off = ad->c0 + env * ad->env_stride, st = 0;
+            for (int i = 0; i < ad->naxis; ++i) {
+              if (ad->axis[i] == slot) st = ad->coef[i];
+              else off += ad->coef[i] * (int64_t)idx[ad->axis[i]];
+            }
+            base[k] = off; stride[k] = st;
+            ptr[k] = A.tensors[ad->tensor];
+            dts[k] = A.dtype[ad->tensor];
+          }
+          int32_t j0 = 0, j1 = (int32_t)arg;
+          const int32_t* cols = nullptr;
+          if (is_csr) {
+            const RddlCsr* cs = A.csrs + arg;
+            int64_t row = cs->row_c0;
+            for (int i = 0; i < cs->row_naxis; ++i) row += cs->row_coef[i] * (int64_t)idx[cs->row_axis[i]];
+            j0 = __ldg(A.pool + cs->rowptr_off + row);
+            j1 = __ldg(A.pool + cs->rowptr_off + row + 1);
+            cols = A.pool + cs->col_off[0];
+          }
+          double facc = 0.0;
+          int64_t iacc = 0;
+          for (int32_t j = j0; j < j1; ++j) {
+            const int64_t k = is_csr ? (int64_t)__ldg(cols + j) : (int64_t)j;
+            double fv[2] = {1.0, 1.0};
+            int64_t iv[2] = {1, 1};
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              if (q == 1 && !two) break;
+              const int64_t o = base[q] + stride[q] * k;
+              if (dts[q] == DT_REAL) fv[q] = reinterpret_cast<const double*>(ptr[q])[o];
+              else {
+                iv[q] = dts[q] == DT_BOOL ? (int64_t)(reinterpret_cast<const uint8_t*>(ptr[q])[o] != 0)
+                                          : reinterpret_cast<const int64_t*>(ptr[q])[o];
+                fv[q] = (double)iv[q];
+              }
+            }
+            if (flt) facc = __dadd_rn(facc, two ? __dmul_rn(fv[0], fv[1]) : fv[0]);
+            else iacc += two ? iv[0] * iv[1] : iv[0];
+          }
+          r[dst] = flt ? from_f(facc) : (uint64_t)iacc;
+          break;
+        }
         default: break;
       }
     }

@@ -502,6 +502,48 @@ class _LaunchBuilder:
             o[4] = end                      # field b = pc after the loop
             self.insns[pc] = tuple(o)
 
+    def emit_sumloop(self, n, loops, body):
+        """``sum_{v} t1`` / ``sum_{v} t1 * t2`` with t1, t2 plain pvariable reads and a single
+        (dense or CSR) loop becomes one SUMLOOP superinstruction: the kernel runs the
+        multiply-accumulate loop natively instead of interpreting ~5 ops per iteration
+        (the Reservoir inflow sum and the pair sum-product contraction)."""
+        lw = self.lw
+        p = lw.p
+        if len(loops) != 1:
+            return None
+        terms = [body]
+        if body.kind == 'bin' and body.op == 'mul':
+            terms = list(body.args)
+        if not 1 <= len(terms) <= 2:
+            return None
+        for t in terms:
+            if t.kind != 'load' or any(k not in ('a', 'c') for (k, _) in t.index):
+                return None
+            name = lw.rename.get(t.tensor, t.tensor)
+            if name in self.stored or (p.tensors[name].kind == 'nonfluent' and not t.index):
+                return None
+        cls = _num(body.dtype)
+        if cls not in ('i', 'f'):
+            return None
+        lp = loops[0]
+        if lp[0] == 'csr' and int(lw.csrs[lp[1]]['ncols']) != 1:
+            return None
+        ais = []
+        for t in terms:
+            name = lw.rename.get(t.tensor, t.tensor)
+            decl = p.tensors[name]
+            shape = p.tensor_shape(name)
+            nelem = int(np.prod(shape, dtype=np.int64)) if shape else 1
+            env_stride = 0 if decl.kind == 'nonfluent' else nelem
+            ais.append(self.addr_for(lw.tensor_id[name], shape, t.index, env_stride, []))
+        flags = (1 if lp[0] == 'csr' else 0) | (2 if len(terms) == 2 else 0) | (4 if cls == 'f' else 0)
+        slot = lp[1] if lp[0] == 'dense' else int(lw.csrs[lp[1]]['slot'][0])
+        arg = int(lp[2]) if lp[0] == 'dense' else int(lp[1])        # extent | csr id
+        d = self.alloc()
+        self.ins('SUMLOOP', dst=d, a=slot, b=flags, imm=ais[0])
+        self.ins('NOP', dst=arg & 0xFFFF, a=(arg >> 16) & 0xFFFF, imm=ais[1] if len(ais) == 2 else 0)
+        return d, cls
+
     def emit_agg(self, n):
         lw = self.lw
         op = n.op
@@ -514,6 +556,9 @@ class _LaunchBuilder:
         count = int(np.prod(ext[outer:], dtype=np.int64))
         loops, body = lw.plan_loops(n)
         bcls = body.dtype
+        fused = self.emit_sumloop(n, loops, body) if op == 'sum' else None
+        if fused is not None:
+            return fused
         if op in ('forall', 'exists'):
             acc = self.const(op == 'forall', 'b')
             cls = 'b'

@@ -13,7 +13,7 @@ slots the kernels need. It is a flat little-endian blob:
 import numpy as np
 
 MAGIC = 0x31304C444452  # "RDDL01"
-VERSION = 5
+VERSION = 6
 MAX_IDX = 8          # index variables per thread: scope axes + nested loop axes
 MAX_RED = 8          # reduction outputs per launch
 MAX_REGS = 96        # virtual 64-bit registers per thread
@@ -42,6 +42,8 @@ _OPS = [
     'EXPM1', 'LOG1P',
     # bit-plane ops (rddl_plane_interp)
     'PLD', 'PLDC', 'PST', 'PCONST', 'PLUT', 'PSHARE', 'PCOUNT', 'PBERN', 'PRED',
+    # scalar superinstruction: native multiply-accumulate loop (followed by one NOP data word)
+    'SUMLOOP',
 ]
 OP = {name: i for i, name in enumerate(_OPS)}
 

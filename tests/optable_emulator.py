@@ -276,6 +276,45 @@ class Emulator:
                     for v in vals[1:]:
                         acc = _red_comb(rop, acc, v)
                     r[dst] = _bits_f(acc) if rop in (1, 3, 5, 7) else _bits_i(acc)
+                elif op == 'SUMLOOP':
+                    ins2 = prog[pc]
+                    pc += 1
+                    arg = int(ins2['dst']) | (int(ins2['a']) << 16)
+                    is_csr, two, flt = b & 1, b & 2, b & 4
+                    terms = []
+                    for ai in ([imm, int(ins2['imm'])] if two else [imm]):
+                        ad = self.addrs[ai]
+                        off = int(ad['c0']) + env * int(ad['env_stride'])
+                        st = 0
+                        for i in range(int(ad['naxis'])):
+                            if int(ad['axis'][i]) == a:
+                                st = int(ad['coef'][i])
+                            else:
+                                off += int(ad['coef'][i]) * idx[int(ad['axis'][i])]
+                        t = int(ad['tensor'])
+                        terms.append((bufs[t], int(self.tensors[t]['dtype']), off, st))
+                    if is_csr:
+                        cs = self.csrs[arg]
+                        row = int(cs['row_c0'])
+                        for i in range(int(cs['row_naxis'])):
+                            row += int(cs['row_coef'][i]) * idx[int(cs['row_axis'][i])]
+                        j0 = int(self.pool[int(cs['rowptr_off']) + row])
+                        j1 = int(self.pool[int(cs['rowptr_off']) + row + 1])
+                        ks = [int(self.pool[int(cs['col_off'][0]) + j]) for j in range(j0, j1)]
+                    else:
+                        ks = range(arg)
+                    facc, iacc = np.float64(0.0), 0
+                    for k in ks:
+                        vals = []
+                        for (buf, dt, off, st) in terms:
+                            v = buf[off + st * k]
+                            vals.append(np.float64(v) if dt == 2 else int(v != 0) if dt == 0 else int(v))
+                        if flt:
+                            fv = [np.float64(x) for x in vals]
+                            facc = facc + (fv[0] * fv[1] if two else fv[0])
+                        else:
+                            iacc += vals[0] * vals[1] if two else vals[0]
+                    r[dst] = _bits_f(facc) if flt else _bits_i(iacc)
                 elif op == 'STATUS':
                     if r[a]:
                         status[env] |= imm
