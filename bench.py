@@ -27,24 +27,59 @@ METRIC = 'batched env-steps/sec'
 UNIT = 'env-steps/s'
 
 WORKLOADS = {
-    # name -> (spec factory kwargs, envs per GPU, algorithmic bytes per env-step)
-    'wildfire32': dict(n=32, separable=False, envs=4096),
-    'wildfire32_sep': dict(n=32, separable=True, envs=4096),
-    'wildfire1024': dict(n=1024, separable=True, envs=256),
+    # BASELINE.json configs: [1] wildfire32 (the default), [2] reservoir1000, [3] wildfire1024, [4] pair512
+    'wildfire32': dict(kind='wildfire', n=32, separable=False, envs=4096),
+    'wildfire32_sep': dict(kind='wildfire', n=32, separable=True, envs=4096),
+    'wildfire1024': dict(kind='wildfire', n=1024, separable=True, envs=256),
+    'reservoir1000': dict(kind='reservoir', n=1000, envs=4096),
+    'pair512': dict(kind='pair', n=512, envs=1024),
 }
 
 
 def make_spec(name):
     from pyrddlgym_b200 import workloads
     w = WORKLOADS[name]
-    return workloads.wildfire(w['n'], separable=w['separable'])
+    if w['kind'] == 'wildfire':
+        return workloads.wildfire(w['n'], separable=w['separable'])
+    if w['kind'] == 'reservoir':
+        return workloads.reservoir(w['n'])
+    return workloads.pair_contraction(w['n'])
 
 
 def algorithmic_bytes_per_env_step(name):
-    """read burning, out-of-fuel, put-out, cut-out + write burning', out-of-fuel'
-    (1 byte per bool cell) + reward f64 + done u8."""
-    n = WORKLOADS[name]['n']
-    return 6 * n * n + 9
+    """SURVEY 8(d). Wildfire: read burning, out-of-fuel, put-out, cut-out + write burning',
+    out-of-fuel' (1 byte per bool cell) + reward f64 + done u8. Reservoir (f64): read rlevel,
+    release + write rlevel' (interm fluents counted as on-chip). Pair contraction: read x, u +
+    write x' (W is shared by all envs)."""
+    w = WORKLOADS[name]
+    if w['kind'] == 'wildfire':
+        return 6 * w['n'] * w['n'] + 9
+    return 24 * w['n'] + 9
+
+
+def workload_label(name):
+    w = WORKLOADS[name]
+    if w['kind'] == 'wildfire':
+        return f"Wildfire {w['n']}x{w['n']} ({'separable' if w['separable'] else '4-D NEIGHBOR'})"
+    if w['kind'] == 'reservoir':
+        return f"Reservoir R={w['n']} (sum-over-upstream, Normal rain)"
+    return f"Pair sum-product contraction {w['n']}x{w['n']} + invariants"
+
+
+def draw_actions(name, p, k, N, dev, g):
+    """Random-policy action sequence [k, N, ...] resident on the device."""
+    import torch
+    w = WORKLOADS[name]
+    out = {}
+    for an in p.names_of_kind('action'):
+        shp = (k, N) + tuple(p.tensor_shape(an))
+        if p.tensors[an].dtype == 'b':
+            out[an] = torch.rand(shp, device=dev, generator=g) < 0.05
+        elif w['kind'] == 'reservoir':
+            out[an] = torch.rand(shp, device=dev, generator=g, dtype=torch.float64) * 10.0
+        else:
+            out[an] = torch.rand(shp, device=dev, generator=g, dtype=torch.float64) * 2.0 - 1.0
+    return out
 
 
 class ClockSampler:
@@ -112,9 +147,13 @@ def _cpu_worker(args):
     p = workloads.load_program(make_spec(name))
     sim = OracleSimulator(p, n_envs=n_envs, seed=seed)
     rng = np.random.default_rng(seed)
-    n = WORKLOADS[name]['n']
-    acts = [{'put-out': rng.random((n_envs, n, n)) < 0.05, 'cut-out': rng.random((n_envs, n, n)) < 0.05}
-            for _ in range(2)]
+    acts = []
+    for _ in range(2):
+        a = {}
+        for an in p.names_of_kind('action'):
+            shp = (n_envs,) + tuple(p.tensor_shape(an))
+            a[an] = (rng.random(shp) < 0.05) if p.tensors[an].dtype == 'b' else rng.random(shp) * 5.0
+        acts.append(a)
     sim.step(acts[0])
     t0 = time.perf_counter()
     for t in range(steps):
@@ -125,7 +164,7 @@ def _cpu_worker(args):
 def cpu_baseline(name, cores=1, envs_per_core=4, steps=8):
     """Oracle port timed on `cores` host cores (one process each, envs_per_core envs, `steps`
     steps). Returns env-steps/s aggregated over cores."""
-    if WORKLOADS[name]['n'] > 64:
+    if WORKLOADS[name]['kind'] == 'wildfire' and WORKLOADS[name]['n'] > 64:
         return None, 'reference formulation cannot run n>48 (O(n^4) temporaries)'
     jobs = [(name, envs_per_core, steps, 100 + i) for i in range(cores)]
     if cores == 1:
@@ -190,15 +229,17 @@ def run_gpu(args):
     sim = BatchedSimulator(p, n_envs=N, device=dev, seed=42, env_offset=rank * N)
     K, W = args.steps, args.warmup
     gamma = float(p.discount)
-    plane = N * n * n
+    act_bytes = sum(N * int(np.prod(p.tensor_shape(a), dtype=np.int64)) * (1 if p.tensors[a].dtype == 'b' else 8)
+                    for a in p.names_of_kind('action'))       # action bytes per step
+    state_bytes = sum(N * int(np.prod(p.tensor_shape(a), dtype=np.int64)) * (1 if p.tensors[a].dtype == 'b' else 8)
+                      for a in p.next_state)
 
     # random-policy action sequence for the timed rollout, resident in HBM: [K, N, n, n] x 2
     # planes (larger than the 126 MB L2 unless K is tiny); the warm-up uses its own sequence
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
 
     def draw(k):
-        return {'put-out': torch.rand((k, N, n, n), device=dev, generator=g) < 0.05,
-                'cut-out': torch.rand((k, N, n, n), device=dev, generator=g) < 0.05}
+        return draw_actions(name, p, k, N, dev, g)
 
     seq = draw(K)
     warm = draw(max(W, 1))
@@ -285,7 +326,7 @@ def run_gpu(args):
                     'kernel_us': per_launch_ms * 1e3, 'steps_per_launch': steps_per_launch,
                     'kernel_share_of_step': top['ms'] / max(1e-9, sum(r['ms'] for r in prof)),
                     'algorithmic_bytes_per_launch': abytes,
-                    'note': 'algorithmic bytes = (4 planes read + 2 written + reward + done) per env-step; '
+                    'note': 'algorithmic bytes per env-step as in SURVEY 8(d) (state + action reads, next-state writes, reward, done); '
                             'a fused multi-step launch keeps the state planes on chip, so its DRAM '
                             'traffic is below this figure'}
 
@@ -293,7 +334,7 @@ def run_gpu(args):
     # per-step rewards + returns + final state -> D2H
     h_seq = {k: v.cpu().pin_memory() for k, v in seq.items()}
     d_seq = {k: torch.empty_like(v) for k, v in seq.items()}
-    h_state = {s: torch.empty((N, n, n), dtype=torch.bool).pin_memory() for s in sim.state_names}
+    h_state = {s: torch.empty_like(sim.fluent(s), device='cpu').pin_memory() for s in sim.state_names}
     h_rew = torch.empty((K, N), dtype=torch.float64).pin_memory()
     h_ret = torch.empty(N, dtype=torch.float64).pin_memory()
 
@@ -320,8 +361,8 @@ def run_gpu(args):
         dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
     e2e_value = world * N * K / (float(ms_e2e.item()) * 1e-3)
     clocks = sampler.stop() if rank == 0 else None
-    h2d = 2 * plane
-    d2h = (len(sim.state_names) * plane + 8 * N) // K + 8 * N
+    h2d = act_bytes
+    d2h = (state_bytes + 8 * N) // K + 8 * N
 
     if rank == 0:
         cpu_v, cpu_sample = cpu_baseline(name, cores=1, envs_per_core=4, steps=16) if world == 1 else (None, None)
@@ -329,13 +370,13 @@ def run_gpu(args):
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
             'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'u8/f64', 'data': 'synthetic',
-            'config': {'workload': f'Wildfire {n}x{n} ({"separable" if w["separable"] else "4-D NEIGHBOR"}), '
-                                   f'{N} envs/GPU, {K}-step random-policy rollout, Bernoulli(0.05) actions',
+            'config': {'workload': f'{workload_label(name)}, '
+                                   f'{N} envs/GPU, {K}-step random-policy rollout',
                        'envs_per_gpu': N, 'global_envs': N * world, 'grid': n,
                        'api': 'rddl_rollout (K steps per call); per-step rddl_step loop reported as step_api_value',
                        'step_api_value': step_api_value,
                        'l2': f'inputs larger than L2: the action sequence read by the timed rollout is '
-                             f'{2 * K * plane / 1e6:.0f} MB (L2 = 126 MB); state planes {2 * plane / 1e6:.1f} MB',
+                             f'{K * act_bytes / 1e6:.0f} MB (L2 = 126 MB); state tensors {state_bytes / 1e6:.1f} MB',
                        'parallelism': f'env-shard x{world}, return statistics all-reduced (NCCL) once per rollout',
                        'launches': [l['kernel'] for l in sim.table.launches if l['plan'] == 0],
                        'return_stats': stats},

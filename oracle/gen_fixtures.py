@@ -33,6 +33,9 @@ CASES = {
     'pair16': (lambda: workloads.pair_contraction(16), 3, 6, dict(real=(-12.0, 12.0))),
 }
 
+# programs without golden trajectories (natively sampled distributions: moment / KS tests only)
+PROGRAM_ONLY = {'distzoo': lambda: workloads.distzoo()}
+
 
 def reference_program(spec):
     model = ast_builders.build_model(spec)
@@ -91,6 +94,13 @@ def main():
         np.savez_compressed(os.path.join(ROOT, 'tests', 'golden', name + '.npz'), **out)
         print(name, '->', os.path.relpath(path, ROOT), os.path.getsize(path), 'B;',
               'golden', os.path.getsize(os.path.join(ROOT, 'tests', 'golden', name + '.npz')), 'B')
+    for name, factory in PROGRAM_ONLY.items():
+        p = reference_program(factory())
+        path = workloads.program_path(p.name)
+        p.types, p.objects = {}, {}
+        with open(path, 'w') as f:
+            f.write(p.to_json())
+        print(name, '->', os.path.relpath(path, ROOT))
 
 
 if __name__ == '__main__':

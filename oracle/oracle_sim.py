@@ -360,6 +360,40 @@ class OracleSimulator:
         env_ids = self.env_offset + np.arange(self.N)
         return philox_np.base_variates(kind, self.seed, env_ids, self.step_count, n.id, shp)
 
+    def _native(self, n, op, args, rank):
+        """simulator.py:1066-1221: the distributions NumPy draws by rejection / search. No base
+        variate can be shared with the device samplers (csrc/rddl_samplers.cuh), so this draws
+        from NumPy's own generators on a stream keyed by (seed, step, node): same distribution,
+        different numbers -- compared through moments / KS tests only."""
+        full = (self.N,) + self._shape(n.scope)
+        rng = np.random.default_rng([self.seed & 0xFFFFFFFF, self.step_count, int(n.id), self.env_offset])
+        a = np.broadcast_to(args[0], full)
+        b = np.broadcast_to(args[1], full) if len(args) > 1 else None
+        pos = lambda x, strict: ~((x > 0) if strict else (x >= 0))
+        if op == 'Poisson':
+            self._flag(pos(a, False), rank, STATUS_OUT_OF_RANGE)
+            return rng.poisson(np.maximum(a, 0.0))
+        if op == 'Gamma':
+            self._flag(pos(a, True) | pos(b, True), rank, STATUS_OUT_OF_RANGE)
+            return rng.gamma(np.where(a > 0, a, 1.0), np.where(b > 0, b, 1.0))
+        if op == 'Binomial':
+            self._flag(pos(a, False) | ~((b >= 0) & (b <= 1)), rank, STATUS_OUT_OF_RANGE)
+            return rng.binomial(np.maximum(a, 0), np.clip(b, 0.0, 1.0))
+        if op == 'NegativeBinomial':
+            self._flag(pos(a, True) | ~((b >= 0) & (b <= 1)), rank, STATUS_OUT_OF_RANGE)
+            return rng.negative_binomial(np.where(a > 0, a, 1.0), np.clip(b, 1e-12, 1.0))
+        if op == 'Beta':
+            self._flag(pos(a, True) | pos(b, True), rank, STATUS_OUT_OF_RANGE)
+            return rng.beta(np.where(a > 0, a, 1.0), np.where(b > 0, b, 1.0))
+        if op == 'Geometric':
+            self._flag(~((a >= 0) & (a <= 1)), rank, STATUS_OUT_OF_RANGE)
+            return rng.geometric(np.clip(a, 1e-12, 1.0))
+        if op == 'Student':
+            self._flag(pos(a, True), rank, STATUS_OUT_OF_RANGE)
+            return rng.standard_t(np.where(a > 0, a, 1.0))
+        self._flag(pos(a, True), rank, STATUS_OUT_OF_RANGE)
+        return rng.chisquare(np.where(a > 0, a, 1.0))
+
     def _random(self, n):
         op = n.op
         rank = len(n.scope)
@@ -382,6 +416,8 @@ class OracleSimulator:
             U = self._base(n, 'U')[..., np.newaxis]
             return np.argmax(U < cdf, axis=-1)            # simulator.py:1255-1256
         args = [np.asarray(self.ev(a)) for a in n.args]
+        if op in ('Poisson', 'Gamma', 'Binomial', 'NegativeBinomial', 'Beta', 'Geometric', 'Student', 'ChiSquare'):
+            return self._native(n, op, args, rank)
         with np.errstate(all='ignore'):
             if op == 'Uniform':                           # simulator.py:1035-1043
                 lb, ub = args

@@ -4,7 +4,7 @@
 #include <stdint.h>
 
 #define RDDL_MAGIC 0x31304C444452ll
-#define RDDL_VERSION 6
+#define RDDL_VERSION 7
 #define RDDL_MAX_IDX 8
 #define RDDL_MAX_RED 8
 #define RDDL_MAX_REGS 96
@@ -26,6 +26,7 @@ enum RddlOp : uint8_t {
   OP_EXPM1, OP_LOG1P,
   OP_PLD, OP_PLDC, OP_PST, OP_PCONST, OP_PLUT, OP_PSHARE, OP_PCOUNT, OP_PBERN, OP_PRED,
   OP_SUMLOOP,
+  OP_SAMPLE,
   OP_COUNT_
 };
 

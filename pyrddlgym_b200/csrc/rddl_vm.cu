@@ -22,6 +22,7 @@
 #include "../../include/rddl_b200.h"
 #include "philox.cuh"
 #include "rddl_plan.h"
+#include "rddl_samplers.cuh"
 
 struct VmArgs {
   const RddlInsn* insns;
@@ -327,6 +328,16 @@ __device__ __noinline__ void vm_exec_element(const VmArgs& A, const RddlLaunch& 
         case OP_STATUS:
           if (RA) atomicOr(A.status + env, imm);
           break;
+        case OP_SAMPLE: {
+          // rejection / search samplers: one private Philox stream per (env, step, node, element)
+          const RddlAddr* ad = A.addrs + imm;
+          int64_t off = ad->c0;
+          for (int i = 0; i < ad->naxis; ++i) off += ad->coef[i] * (int64_t)idx[ad->axis[i]];
+          const uint32_t node = (uint32_t)A.variates[rc].node;
+          r[dst] = rddl_sample((int)((raw.x >> 8) & 0xff), RA, RB, A.seed, (uint64_t)(A.env_offset + env), step,
+                               node, (uint64_t)off);
+          break;
+        }
         case OP_SUMLOOP: {
           // sum over one loop variable of t1 [* t2], t = plain tensor reads: native MAC loop.
           // data word (next instruction): dst | a << 16 = extent or CSR id, imm = address of t2

@@ -243,6 +243,14 @@ class _Converter:
             body, = args
             return Node('rand', op=name, args=[self.conv(body)], red=[typ], dtype='i', scope=scope,
                         id=nid, obj_type=self.traced.cached_object_type(expr))
+        if name in hir.DIST_NATIVE:
+            arity, dt = hir.DIST_NATIVE[name]
+            args = [self.conv(a) for a in expr.args]
+            if len(args) != arity:
+                raise exc.RDDLInvalidNumberOfArgumentsError(f'{name} requires {arity} argument(s).')
+            if name == 'Binomial' and args[0].dtype == 'f':
+                self.fail_type('Binomial count must evaluate to int.')
+            return Node('rand', op=name, args=args, dtype=dt, scope=scope, id=nid)
         if name not in hir.DIST_BASE:
             raise exc.RDDLNotImplementedError(
                 f'Distribution {name} is not supported by the B200 backend (no CPU fallback).')

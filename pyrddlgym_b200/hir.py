@@ -37,6 +37,10 @@ DIST_BASE = {
     'Kumaraswamy': 'U', 'Discrete': 'U', 'UnnormDiscrete': 'U',
     'Discrete(p)': 'U', 'UnnormDiscrete(p)': 'U',
 }
+# distributions NumPy draws by rejection / search: sampled natively (no shared base variate);
+#   name -> (arity, result dtype)
+DIST_NATIVE = {'Poisson': (1, 'i'), 'Gamma': (2, 'f'), 'Binomial': (2, 'i'), 'NegativeBinomial': (2, 'i'),
+               'Beta': (2, 'f'), 'Geometric': (1, 'i'), 'Student': (1, 'f'), 'ChiSquare': (1, 'f')}
 DIST_DTYPE = {'Bernoulli': 'b', 'Discrete': 'i', 'UnnormDiscrete': 'i',
               'Discrete(p)': 'i', 'UnnormDiscrete(p)': 'i'}
 

@@ -650,6 +650,8 @@ class _LaunchBuilder:
         if op in ('Discrete', 'UnnormDiscrete', 'Discrete(p)', 'UnnormDiscrete(p)'):
             return self.emit_discrete(n)
         RANGE = ot.STATUS_OUT_OF_RANGE
+        if op in hir.DIST_NATIVE:
+            return self.emit_sample(n)
         if op == 'Uniform':
             lb = self.emit_f(n.args[0])
             ub = self.emit_f(n.args[1])
@@ -746,6 +748,44 @@ class _LaunchBuilder:
             t = self.op2('FSUB', one(), t)
             return self.op2('FPOW', t, self.op2('FDIV', one(), a)), 'f'
         raise LoweringError(f'distribution {op}')
+
+    def emit_sample(self, n):
+        """Poisson / Gamma / Binomial / NegativeBinomial / Beta / Geometric / Student / ChiSquare:
+        parameter checks as status bits (simulator.py:1066-1221), then one SAMPLE op."""
+        op = n.op
+        RANGE = ot.STATUS_OUT_OF_RANGE
+        arity, dt = hir.DIST_NATIVE[op]
+        if op == 'Binomial':
+            a, ca = self.emit(n.args[0])
+            af = self.alloc()
+            self.ins('I2F', dst=af, a=a)
+            self.check('FGE', af, 0.0, RANGE)
+            self.release(af)
+        else:
+            a = self.emit_f(n.args[0])
+            self.check('FGE' if op == 'Poisson' else 'FGT', a, 0.0, RANGE) if op != 'Geometric' else None
+        b = a
+        if arity == 2:
+            b = self.emit_f(n.args[1])
+        if op in ('Binomial', 'NegativeBinomial'):
+            self.check('FGE', b, 0.0, RANGE)
+            self.check('FLE', b, 1.0, RANGE)
+        elif op == 'Geometric':
+            self.check('FGE', a, 0.0, RANGE)
+            self.check('FLE', a, 1.0, RANGE)
+        elif op in ('Gamma', 'Beta'):
+            self.check('FGT', b, 0.0, RANGE)
+        lw = self.lw
+        shape = lw.p.shape_of(n.scope)
+        nelem = int(np.prod(shape, dtype=np.int64)) if shape else 1
+        slot = lw.variate_slot(n.id, 'U', nelem)
+        ai = self.addr_for(-(1 + slot), shape, [('a', i) for i in range(len(shape))], nelem, [])
+        d = self.alloc()
+        self.ins('SAMPLE', dst=d, a=a, b=b, c=slot, imm=ai, flags=ot.SAMPLE_DIST[op])
+        self.release(a)
+        if b != a:
+            self.release(b)
+        return d, dt
 
     def emit_discrete(self, n):
         """simulator.py:1240-1256: cdf = cumsum(pdf) [/ cdf[-1]]; argmax(U < cdf)."""

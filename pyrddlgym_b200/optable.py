@@ -13,7 +13,7 @@ slots the kernels need. It is a flat little-endian blob:
 import numpy as np
 
 MAGIC = 0x31304C444452  # "RDDL01"
-VERSION = 6
+VERSION = 7
 MAX_IDX = 8          # index variables per thread: scope axes + nested loop axes
 MAX_RED = 8          # reduction outputs per launch
 MAX_REGS = 96        # virtual 64-bit registers per thread
@@ -44,6 +44,8 @@ _OPS = [
     'PLD', 'PLDC', 'PST', 'PCONST', 'PLUT', 'PSHARE', 'PCOUNT', 'PBERN', 'PRED',
     # scalar superinstruction: native multiply-accumulate loop (followed by one NOP data word)
     'SUMLOOP',
+    # rejection / search samplers on a private Philox stream (flags = distribution id)
+    'SAMPLE',
 ]
 OP = {name: i for i, name in enumerate(_OPS)}
 
@@ -99,3 +101,7 @@ def pack(tensors, launches, insns, consts, addrs, csrs, pool, redslots, variates
         if len(b) % 8:
             out.append(b'\0' * (8 - len(b) % 8))
     return b''.join(out)
+
+# distribution ids of the SAMPLE op (csrc/rddl_samplers.cuh: enum RddlDist)
+SAMPLE_DIST = {'Poisson': 0, 'Gamma': 1, 'Binomial': 2, 'NegativeBinomial': 3, 'Beta': 4, 'Geometric': 5,
+               'Student': 6, 'ChiSquare': 7}

@@ -539,12 +539,48 @@ def opzoo(n=5, m=4, seed=3):
     )
 
 
+# ---------------------------------------------------------------------------
+# distribution zoo: one state fluent per natively sampled distribution
+# (/root/reference/pyRDDLGym/core/simulator.py:1066-1221), parameters from non-fluents
+# ---------------------------------------------------------------------------
+
+DISTZOO_PARAMS = {
+    'poisson-small': ('Poisson', (3.5,)), 'poisson-large': ('Poisson', (47.0,)),
+    'gamma-small': ('Gamma', (0.6, 2.0)), 'gamma-large': ('Gamma', (4.5, 0.5)),
+    'binomial-small': ('Binomial', (12, 0.3)), 'binomial-large': ('Binomial', (400, 0.62)),
+    'negbinomial': ('NegativeBinomial', (5.0, 0.4)), 'beta': ('Beta', (2.0, 5.0)),
+    'geometric': ('Geometric', (0.2,)), 'student': ('Student', (7.0,)), 'chisquare': ('ChiSquare', (3.0,)),
+}
+
+
+def distzoo(n=4):
+    objs = [f'o{i + 1}' for i in range(n)]
+    pvars, cpfs = [], []
+    for key, (dist, params) in DISTZOO_PARAMS.items():
+        is_int = dist in ('Poisson', 'Binomial', 'NegativeBinomial', 'Geometric')
+        pvars.append((key, 'state-fluent', 'int' if is_int else 'real', ['obj'], 0 if is_int else 0.0))
+        args = []
+        for j, v in enumerate(params):
+            pname = f'P-{key}-{j}'
+            pvars.append((pname, 'non-fluent', 'int' if isinstance(v, int) else 'real', None, v))
+            args.append(pv(pname))
+        cpfs.append(((key + "'", ['?o']), rand(dist, *args)))
+    pvars.append(('nudge', 'action-fluent', 'real', None, 0.0))
+    reward = add(pv('nudge'), agg('sum', [('?o', 'obj')], pv("student'", '?o')))
+    return dict(
+        name='distzoo', types=[('obj', 'object')], pvariables=pvars, cpfs=cpfs, reward=reward,
+        preconds=[], invariants=[], terminals=[], objects=[('obj', objs)], init_non_fluent=[], init_state=[],
+        max_nondef_actions='pos-inf', horizon=10, discount=1.0,
+    )
+
+
 WORKLOADS = {
     'cartpole': cartpole,
     'wildfire': wildfire,
     'reservoir': reservoir,
     'pair_contraction': pair_contraction,
     'opzoo': opzoo,
+    'distzoo': distzoo,
 }
 
 

@@ -276,6 +276,31 @@ class Emulator:
                     for v in vals[1:]:
                         acc = _red_comb(rop, acc, v)
                     r[dst] = _bits_f(acc) if rop in (1, 3, 5, 7) else _bits_i(acc)
+                elif op == 'SAMPLE':
+                    # same distributions as csrc/rddl_samplers.cuh, NumPy's generators (other stream)
+                    ad = self.addrs[imm]
+                    off = self._addr(ad, idx, r, status, env)
+                    node = int(self.variates[c]['node'])
+                    rng = np.random.default_rng([seed & 0xFFFFFFFF, env_offset + env, step, node, off])
+                    dist = int(ins['flags'])
+                    fa, fb = float(_f(r[a])), float(_f(r[b]))
+                    if dist == 0:
+                        v = _bits_i(rng.poisson(max(fa, 0.0)))
+                    elif dist == 1:
+                        v = _bits_f(fb * rng.standard_gamma(fa if fa > 0 else 1.0))
+                    elif dist == 2:
+                        v = _bits_i(rng.binomial(max(_i(r[a]), 0), min(max(fb, 0.0), 1.0)))
+                    elif dist == 3:
+                        v = _bits_i(rng.negative_binomial(fa if fa > 0 else 1.0, min(max(fb, 1e-12), 1.0)))
+                    elif dist == 4:
+                        v = _bits_f(rng.beta(fa if fa > 0 else 1.0, fb if fb > 0 else 1.0))
+                    elif dist == 5:
+                        v = _bits_i(rng.geometric(min(max(fa, 1e-12), 1.0)))
+                    elif dist == 6:
+                        v = _bits_f(rng.standard_t(fa if fa > 0 else 1.0))
+                    else:
+                        v = _bits_f(rng.chisquare(fa if fa > 0 else 1.0))
+                    r[dst] = v
                 elif op == 'SUMLOOP':
                     ins2 = prog[pc]
                     pc += 1

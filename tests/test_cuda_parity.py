@@ -281,3 +281,52 @@ def test_rollout_equals_repeated_steps(name, spec, T, fused):
     if name == 'cartpole':
         assert not alive.all()          # some episodes terminated inside the rollout
     assert (la == 1) == fused, la
+
+
+def _dist_reference(dist, params):
+    from scipy import stats
+    if dist == 'Poisson':
+        return stats.poisson(params[0]), True
+    if dist == 'Gamma':
+        return stats.gamma(params[0], scale=params[1]), False
+    if dist == 'Binomial':
+        return stats.binom(params[0], params[1]), True
+    if dist == 'NegativeBinomial':
+        return stats.nbinom(params[0], params[1]), True
+    if dist == 'Beta':
+        return stats.beta(params[0], params[1]), False
+    if dist == 'Geometric':
+        return stats.geom(params[0]), True
+    if dist == 'Student':
+        return stats.t(params[0]), False
+    return stats.chi2(params[0]), False
+
+
+def test_native_rejection_samplers_match_their_distributions():
+    """Poisson / Gamma / Binomial / NegativeBinomial / Beta / Geometric / Student / ChiSquare
+    (simulator.py:1066-1221) cannot share base variates with NumPy: the device samplers
+    (csrc/rddl_samplers.cuh) are checked through moments and a KS / chi-square distance against
+    scipy.stats, and for shard invariance (streams keyed by the global env id)."""
+    from scipy import stats
+    p = workloads.load_program(workloads.distzoo(4))
+    N = 8192
+    sim = _make(p, N, seed=77)
+    sim.step({})
+    sim.raise_for_status()
+    half = _make(p, N // 2, seed=77, env_offset=N // 2)
+    half.step({})
+    for key, (dist, params) in workloads.DISTZOO_PARAMS.items():
+        x = _np(sim.fluent(key)).reshape(-1).astype(np.float64)
+        assert np.array_equal(_np(half.fluent(key)), _np(sim.fluent(key))[N // 2:]), key
+        ref, discrete = _dist_reference(dist, params)
+        n = x.size
+        mean, var = float(ref.mean()), float(ref.var())
+        assert abs(x.mean() - mean) < 6.0 * np.sqrt(var / n), (key, x.mean(), mean)
+        if dist != 'Student':
+            assert abs(x.var() - var) < 0.1 * var, (key, x.var(), var)
+        if discrete:
+            ks = np.arange(int(x.min()), int(x.max()) + 1)
+            emp = np.array([(x == k).mean() for k in ks])
+            assert np.abs(np.cumsum(emp) - ref.cdf(ks)).max() < 0.02, key
+        else:
+            assert stats.kstest(x, ref.cdf).statistic < 0.02, key

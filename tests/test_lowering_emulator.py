@@ -46,3 +46,17 @@ def test_wildfire_neighbour_mask_becomes_csr():
         em = EmulatedSimulator(p, tab, 1)
         names = [ot._OPS[int(i['op'])] for i in em.em.insns]
         assert 'CSRLOOP' in names and 'LOOP' not in names
+
+
+def test_native_samplers_lower_to_sample_ops_and_run_in_the_emulator():
+    from pyrddlgym_b200 import workloads
+    p = workloads.load_program(workloads.distzoo(3))
+    tab = lowering.lower(p)
+    em = EmulatedSimulator(p, tab, 40, seed=3)
+    names = [ot._OPS[int(i['op'])] for i in em.em.insns]
+    assert names.count('SAMPLE') == len(workloads.DISTZOO_PARAMS)
+    em.step({})
+    assert not em.status.any()
+    x = em.fluent('poisson-large').astype(np.float64)
+    assert abs(x.mean() - 47.0) < 4.0
+    assert (em.fluent('geometric') >= 1).all() and (em.fluent('beta') > 0).all() and (em.fluent('beta') < 1).all()
