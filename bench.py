@@ -57,6 +57,14 @@ def algorithmic_bytes_per_env_step(name):
     return 24 * w['n'] + 9
 
 
+# DRAM traffic of the dominant kernel per env-step, from `ncu --set full` captures
+# (dram__bytes_read.sum + dram__bytes_write.sum; profiles/r01_ncu_full_*.csv). None = not captured.
+MEASURED_TRAFFIC_BYTES_PER_ENV_STEP = {
+    'wildfire32': (176.496128e6 + 7.141888e6) / (20 * 4096),      # fused 20-step rollout, plane_c2_v6
+    'wildfire1024': (537.102592e6 + 223.248384e6) / 128,          # one step, plane_1024_v5
+}
+
+
 def workload_label(name):
     w = WORKLOADS[name]
     if w['kind'] == 'wildfire':
@@ -322,7 +330,9 @@ def run_gpu(args):
         per_launch_ms = top['ms'] / top['count']
         ach = abytes / (per_launch_ms * 1e-3) / 1e9
         roofline = {'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
-                    'traffic': None, 'peak_source': peak_src, 'kernel': top['name'],
+                    'traffic': (MEASURED_TRAFFIC_BYTES_PER_ENV_STEP[name] * N * steps_per_launch
+                                if name in MEASURED_TRAFFIC_BYTES_PER_ENV_STEP else None),
+                    'peak_source': peak_src, 'kernel': top['name'],
                     'kernel_us': per_launch_ms * 1e3, 'steps_per_launch': steps_per_launch,
                     'kernel_share_of_step': top['ms'] / max(1e-9, sum(r['ms'] for r in prof)),
                     'algorithmic_bytes_per_launch': abytes,

@@ -330,3 +330,25 @@ def test_native_rejection_samplers_match_their_distributions():
             assert np.abs(np.cumsum(emp) - ref.cdf(ks)).max() < 0.02, key
         else:
             assert stats.kstest(x, ref.cdf).statistic < 0.02, key
+
+
+def test_batched_evaluate_random_and_noop_policies():
+    """policy.py:45-126 for all envs at once: statistics dict of the discounted returns."""
+    from pyrddlgym_b200.policy import NoOpPolicy, RandomPolicy, evaluate
+    p = workloads.load_program(workloads.cartpole())
+    sim = _make(p, 512, seed=4)
+    st = evaluate(sim, RandomPolicy(bounds={'force': (-10.0, 10.0)}), seed=1)
+    # reward 1 per step while the pole is up; a random policy drops it after a few dozen steps
+    assert set(st) == {'mean', 'median', 'min', 'max', 'std'}
+    assert 5.0 < st['mean'] < 80.0 and st['min'] >= 1.0 and st['max'] <= p.horizon
+    st0 = evaluate(sim, NoOpPolicy())
+    assert st0['std'] == 0.0 and st0['mean'] == p.horizon      # zero force from rest: never falls
+    # Wildfire: at most max-nondef-actions non-default groundings per env and step
+    spec = workloads.wildfire(32, max_nondef=3)
+    pw = workloads.load_program(spec)
+    simw = _make(pw, 64, seed=2)
+    acts = RandomPolicy().sample(simw, 5)
+    n_on = sum(a.reshape(5, 64, -1).sum(-1) for a in acts.values())
+    assert int(n_on.max()) <= 3
+    stw = evaluate(simw, RandomPolicy(), n_steps=10, seed=3)
+    assert stw['max'] <= 0.0 and stw['mean'] < 0.0

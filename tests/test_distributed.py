@@ -36,6 +36,7 @@ def _worker(rank, world, port, out):
     n_local, off = parallel.shard_envs(6, world, rank)
     ret = _rollout_returns(n_local, off)
     stats = parallel.reduce_return_stats(torch.from_numpy(ret))
+    stats['median'] = parallel.gather_median(torch.from_numpy(ret))
     if rank == 0:
         torch.save(stats, out)
     dist.destroy_process_group()
@@ -61,5 +62,6 @@ def test_return_statistics_are_shard_invariant(tmp_path):
     np.testing.assert_allclose(got['mean'], full.mean(), rtol=1e-12)
     np.testing.assert_allclose(got['std'], full.std(), rtol=1e-9, atol=1e-9)
     assert got['min'] == full.min() and got['max'] == full.max()
+    np.testing.assert_allclose(got['median'], np.median(full), rtol=1e-12)
     single = parallel.reduce_return_stats(torch.from_numpy(full))
     np.testing.assert_allclose(single['mean'], got['mean'], rtol=1e-12)
