@@ -4,7 +4,7 @@
 #include <stdint.h>
 
 #define RDDL_MAGIC 0x31304C444452ll
-#define RDDL_VERSION 7
+#define RDDL_VERSION 8
 #define RDDL_MAX_IDX 8
 #define RDDL_MAX_RED 8
 #define RDDL_MAX_REGS 96
@@ -76,7 +76,9 @@ struct RddlLaunch {    // 176 bytes
   int32_t red_op[8];
   int32_t red_slot[8];
   int32_t nregs, kind;   // kind: 0 = scalar level interpreter, 1 = bit-plane interpreter,
-                         // 2 = scalar program fused into the epilogue of the preceding plane launch
+                         // 2 = scalar program fused into the epilogue of the preceding plane launch,
+                         // 3 = FP64 contraction out[e,n] = sum_k x[e,k] W(k,n): extent = {N, K},
+                         //     red_slot = {W, x, out} tensor ids, red_op = {W stride of k, of n}
 };
 
 struct RddlRedSlot { int32_t op, chunks; };

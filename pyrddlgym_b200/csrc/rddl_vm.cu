@@ -22,6 +22,7 @@
 #include "../../include/rddl_b200.h"
 #include "philox.cuh"
 #include "rddl_plan.h"
+#include "rddl_contract.cuh"
 #include "rddl_samplers.cuh"
 
 struct VmArgs {
@@ -647,9 +648,9 @@ extern "C" int rddl_program_create(const void* optable, size_t nbytes, int devic
     G->rollout_ok = ok;
   }
   for (auto& L : g->launches) {
-    const bool bad_scalar = L.kind != 1 && (L.nregs > RDDL_MAX_REGS || L.G > 256 || (L.G & (L.G - 1)));
+    const bool bad_scalar = L.kind != 1 && L.kind != 3 && (L.nregs > RDDL_MAX_REGS || L.G > 256 || (L.G & (L.G - 1)));
     const bool bad_plane = L.kind == 1 && (L.nregs > PLANE_MAX_REGS || L.G > 32 || L.ipt > 1024 || (L.E & 31));
-    if (bad_scalar || bad_plane || L.kind > 2 || L.G < 1 || L.nred > RDDL_MAX_RED) {
+    if (bad_scalar || bad_plane || L.kind > 3 || L.G < 1 || L.nred > RDDL_MAX_RED) {
       g_create_error = "op table: launch out of limits";
       delete g;
       return RDDL_ERR_FORMAT;
@@ -779,7 +780,14 @@ static int run_plan(rddl_program* g, int plan, void* const* tensors, const doubl
       CK(cudaEventCreate(&tm.e1));
       CK(cudaEventRecord(tm.e0, stream));
     }
-    if (L.kind == 1) {
+    if (L.kind == 3) {
+      const int N = (int)L.extent[0], K = (int)L.extent[1];
+      dim3 grid((unsigned)((N + CT_BN - 1) / CT_BN), (unsigned)((n_envs + CT_BM - 1) / CT_BM));
+      rddl_contract_f64<<<grid, 128, 0, stream>>>((const double*)tensors[L.red_slot[1]],
+                                                  (const double*)tensors[L.red_slot[0]],
+                                                  (double*)tensors[L.red_slot[2]], n_envs, N, K,
+                                                  (int64_t)L.red_op[0], (int64_t)L.red_op[1]);
+    } else if (L.kind == 1) {
       const PlaneProg& G = g->plane_progs[(size_t)(&L - g->launches.data())];
       const int W32 = (int)((L.rank == 2 ? L.extent[1] : L.extent[0]) >> 5);
       const size_t smem = sizeof(uint32_t) * ((size_t)L.nregs * wpt * block +

@@ -157,7 +157,8 @@ def _flatten(n, kind_op):
 class _Item:
     """One schedulable root: evaluate ``expr`` over ``scope`` and sink the value."""
 
-    def __init__(self, scope, expr, store=None, store_off=0, red=None, rename=None):
+    def __init__(self, scope, expr, store=None, store_off=0, red=None, rename=None, contract=None):
+        self.contract = contract    # (W name, x name, out name, stride_k, stride_n, N, K) or None
         self.scope = list(scope)
         self.expr = expr
         self.store = store          # tensor name or None
@@ -915,9 +916,11 @@ SPECIALS = ['__reward', '__done', '__chk']
 
 class Lowerer:
 
-    def __init__(self, program, use_planes=True):
+    def __init__(self, program, use_planes=True, use_contract=True):
         self.p = program
         self.use_planes = use_planes
+        self.use_contract = use_contract
+        self.contract_items = {}
         self.csr_masks = {}
         self._plane_ctx = None
         self.tensor_names_by_id = {}
@@ -1182,6 +1185,11 @@ class Lowerer:
         groups = []
         cur = None
         for it in items:
+            if it.contract is not None:
+                groups.append({'scope': list(it.scope), 'items': [it], 'written': {it.contract[2]},
+                               'stored': set(), 'slots': set(), 'nred': 0, 'contract': True})
+                cur = None
+                continue
             self.rename = it.rename
             loads, slots = self.reads(it.expr)
             fits = cur is not None and cur['scope'] == it.scope
@@ -1218,6 +1226,9 @@ class Lowerer:
     def schedule(self, plan, items):
         from pyrddlgym_b200 import plane_lowering
         for grp in self.group_items(items):
+            if grp.get('contract'):
+                self.finish_contract(plan, grp['items'][0])
+                continue
             lb = None
             if self.use_planes and len(grp['scope']) in (1, 2):
                 mark = (len(self.consts), len(self.pool), self.pool_len)
@@ -1239,6 +1250,25 @@ class Lowerer:
                     lb.add_item(it)
             self.finish_launch(lb)
         self.rename = {}
+
+    def finish_contract(self, plan, it):
+        (w, x, out, sk, sn, N, K) = it.contract
+        row = np.zeros((), dtype=ot.LAUNCH)
+        row['plan'] = plan
+        row['rank'] = 1
+        row['extent'][0], row['extent'][1] = N, K
+        row['E'] = N
+        row['pc_begin'] = row['pc_end'] = len(self.insns)
+        row['G'], row['ipt'], row['chunks'] = 1, 1, 1
+        row['red_slot'][0], row['red_slot'][1], row['red_slot'][2] = (self.tensor_id[w], self.tensor_id[x],
+                                                                      self.tensor_id[out])
+        row['red_op'][0], row['red_op'][1] = sk, sn
+        row['nregs'] = 1
+        row['pad'] = 3
+        self._plane_ctx = None
+        self.launch_rows.append(row)
+        self.out.launches.append({'plan': plan, 'scope': it.scope, 'E': N, 'kind': 3, 'kernel': 'rddl_contract_f64',
+                                  'n_insns': 0, 'nregs': 0, 'stores': [out], 'nred': 0, 'K': K})
 
     def finish_launch(self, lb):
         row = np.zeros((), dtype=ot.LAUNCH)
@@ -1290,7 +1320,77 @@ class Lowerer:
             self.out.plane_nodes.extend(lb.variate_nodes)
 
     # ---- top level
+    # ---- dense two-operand contractions  out(?b) = sum_{?a} W(?a, ?b) * x(?a)
+    def _extract_contractions(self):
+        """Rewrites the program (on a copy): every dense real contraction over a shared object
+        axis with a non-fluent matrix operand is computed by the FP64 tensor-core kernel
+        (csrc/rddl_contract.cuh) into a scratch fluent that the CPF then reads at the same element.
+        Small contractions stay on the scalar SUMLOOP path."""
+        import copy
+        src = self.p
+        p = copy.copy(src)
+        p.tensors = dict(src.tensors)
+        p.init = dict(src.init)
+        self.contract_items = {}       # root index -> [_Item]
+        counter = [0]
+
+        def match(n):
+            if n.kind != 'agg' or n.op != 'sum' or len(n.scope) != 1 or len(n.red) != 1:
+                return None
+            body = n.args[0]
+            if body.kind != 'bin' or body.op != 'mul' or body.dtype != 'f':
+                return None
+            ops = list(body.args)
+            if any(o.kind != 'load' or o.dtype != 'f' for o in ops):
+                return None
+            for (w, x) in (ops, ops[::-1]):
+                dw, dx = p.tensors.get(w.tensor), p.tensors.get(x.tensor)
+                if dw is None or dx is None or dw.kind != 'nonfluent' or dx.kind == 'nonfluent':
+                    continue
+                if [tuple(i) for i in x.index] != [('a', 1)]:
+                    continue
+                wi = [tuple(i) for i in w.index]
+                if sorted(wi) != [('a', 0), ('a', 1)]:
+                    continue
+                N = p.types[n.scope[0]]
+                K = p.types[n.red[0]]
+                if N < 32 or K < 32:
+                    return None
+                if wi == [('a', 1), ('a', 0)]:      # W[a][b]: k-major
+                    sk, sn = N, 1
+                else:                                # W[b][a]
+                    sk, sn = 1, K
+                return (w.tensor, x.tensor, sk, sn, N, K)
+            return None
+
+        def rec(n, root_index):
+            m = match(n)
+            if m is not None:
+                name = '__ct%d' % counter[0]
+                counter[0] += 1
+                p.tensors[name] = hir.TensorDecl(name, 'interm', 'f', [n.scope[0]], 'real')
+                p.init[name] = np.zeros(m[4], dtype=np.float64)
+                self.contract_items.setdefault(root_index, []).append(
+                    _Item(n.scope, None, contract=(m[0], m[1], name, m[2], m[3], m[4], m[5])))
+                return Node('load', tensor=name, index=[('a', 0)], dtype='f', scope=n.scope, id=n.id)
+            if n.kind in ('const', 'axis', 'redin'):
+                return n
+            q = Node(n.kind, op=n.op, args=[rec(a, root_index) for a in n.args], dtype=n.dtype, scope=n.scope,
+                     id=n.id, value=n.value, tensor=n.tensor, red=n.red, obj_type=n.obj_type)
+            if n.index is not None:
+                q.index = [(k, (rec(v, root_index) if k == 'e' else v)) for (k, v) in n.index]
+            if n.cases is not None:
+                q.cases = [None if c is None else rec(c, root_index) for c in n.cases]
+            if n.default is not None:
+                q.default = rec(n.default, root_index)
+            return q
+
+        if self.use_contract:
+            p.cpfs = [hir.Root(r.name, r.level, r.scope, rec(r.expr, i)) for i, r in enumerate(src.cpfs)]
+        self.p = p
+
     def lower(self):
+        self._extract_contractions()
         p = self.p
         names = list(p.tensors)
         for i, name in enumerate(names):
@@ -1347,7 +1447,8 @@ class Lowerer:
         p = self.p
         # --- step plan (simulator.py:442-502)
         items = []
-        for root in p.cpfs:
+        for ri, root in enumerate(p.cpfs):
+            items.extend(self.contract_items.get(ri, []))
             e = self.hoist(root.expr, items)
             items.append(_Item(root.scope, e, store=root.name))
         e = self.hoist(p.reward, items)
@@ -1382,7 +1483,7 @@ class Lowerer:
                 self.schedule(plan, items)
 
 
-def lower(program, use_planes=True):
+def lower(program, use_planes=True, use_contract=True):
     """Lowers an HIR ``Program`` to an ``OpTable``. ``use_planes=False`` keeps every launch on
     the general scalar interpreter (used by tests to cross-check the two paths)."""
-    return Lowerer(program, use_planes=use_planes).lower()
+    return Lowerer(program, use_planes=use_planes, use_contract=use_contract).lower()

@@ -13,7 +13,7 @@ slots the kernels need. It is a flat little-endian blob:
 import numpy as np
 
 MAGIC = 0x31304C444452  # "RDDL01"
-VERSION = 7
+VERSION = 8
 MAX_IDX = 8          # index variables per thread: scope axes + nested loop axes
 MAX_RED = 8          # reduction outputs per launch
 MAX_REGS = 96        # virtual 64-bit registers per thread

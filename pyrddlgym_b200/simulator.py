@@ -31,7 +31,7 @@ class BatchedSimulator:
     """N independent environments of one compiled RDDL problem, stepped in lock-step."""
 
     def __init__(self, program, n_envs=1, device='cuda:0', seed=0, env_offset=0, optable=None,
-                 use_planes=True):
+                 use_planes=True, use_contract=True):
         self.program = program
         self.n_envs = int(n_envs)
         self.device = torch.device(device)
@@ -39,7 +39,8 @@ class BatchedSimulator:
             raise native.NativeError('the B200 backend runs on CUDA devices only (no CPU fallback)')
         self.seed_value = int(seed)
         self.env_offset = int(env_offset)
-        self.table = optable if optable is not None else lowering.lower(program, use_planes=use_planes)
+        self.table = optable if optable is not None else lowering.lower(program, use_planes=use_planes,
+                                                                             use_contract=use_contract)
         index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self.native = native.NativeProgram(self.table.blob, index)
         self.names = list(self.table.tensor_names)

@@ -192,6 +192,13 @@ class Emulator:
     def _launch(self, L, bufs, N, status, injected, seed, step, env_offset, red):
         if int(L['pad']) == 1:
             return self._plane_launch(L, bufs, N, status, injected, seed, step, env_offset, red)
+        if int(L['pad']) == 3:      # dense FP64 contraction out[e, n] = sum_k x[e, k] W(k, n)
+            Nn, K = int(L['extent'][0]), int(L['extent'][1])
+            w, x, o = [int(v) for v in L['red_slot'][:3]]
+            sk, sn = int(L['red_op'][0]), int(L['red_op'][1])
+            W = np.lib.stride_tricks.as_strided(bufs[w], shape=(K, Nn), strides=(8 * sk, 8 * sn))
+            bufs[o][:] = (bufs[x].reshape(N, K) @ W).reshape(-1)
+            return
         E = int(L['E'])
         rank = int(L['rank'])
         ext = [int(e) for e in L['extent'][:rank]]
