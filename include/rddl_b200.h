@@ -53,9 +53,10 @@ int rddl_step(rddl_program_t* prog, void* const* tensors, const double* const* i
 
 /* Replaces check_state_invariants / check_action_preconditions / check_terminal_states
  * (pyRDDLGym/core/simulator.py:362-399). which = RDDL_PLAN_INVARIANT | _PRECONDITION writes one
- * bool per expression into __chk[n, width]; RDDL_PLAN_TERMINAL writes __done[n]. */
+ * bool per expression into __chk[n, width]; RDDL_PLAN_TERMINAL writes __done[n]. Random variables
+ * inside a constraint (legal RDDL) draw Philox with (seed, step) like rddl_step. */
 int rddl_check(rddl_program_t* prog, int which, void* const* tensors, uint32_t* status,
-               int64_t n_envs, int64_t env_offset, void* cuda_stream);
+               int64_t n_envs, int64_t env_offset, uint64_t seed, uint64_t step, void* cuda_stream);
 
 /* Replaces the rollout loop of BaseAgent.evaluate (pyRDDLGym/core/policy.py:85-117: for each
  * step, env.step(action); total_reward += reward * gamma^t; stop accumulating once done) for

@@ -115,7 +115,9 @@ class OracleSimulator:
         reward = np.broadcast_to(np.asarray(self.ev(p.reward), dtype=np.float64).reshape(-1), (self.N,)).copy()
         for s, ns in p.next_state.items():
             self.subs[s] = self.subs[ns]
-        done = self.check_terminal_states()
+        # terminations on the new state (simulator.py:501); a random variable inside a termination
+        # draws like any other node of this step (injected variate of its node id, else Philox)
+        done = self.check_terminal_states(keep_variates=True)
         self.step_count += 1
         return self.states(), reward, done
 
@@ -142,9 +144,10 @@ class OracleSimulator:
         self._variates = {}
         return self._all_of(self.p.preconditions)[0]
 
-    def check_terminal_states(self):
+    def check_terminal_states(self, keep_variates=False):
         """simulator.py:391-399 -> bool[N] (any termination true)."""
-        self._variates = {}
+        if not keep_variates:
+            self._variates = {}
         done = np.zeros(self.N, dtype=bool)
         for e in self.p.terminations:
             done |= np.broadcast_to(np.asarray(self.ev(e)).reshape(-1), (self.N,))

@@ -885,13 +885,13 @@ extern "C" int rddl_rollout(rddl_program_t* g, void* const* tensors, uint32_t* s
 }
 
 extern "C" int rddl_check(rddl_program_t* g, int which, void* const* tensors, uint32_t* status,
-                          int64_t n_envs, int64_t env_offset, void* cuda_stream) {
+                          int64_t n_envs, int64_t env_offset, uint64_t seed, uint64_t step, void* cuda_stream) {
   if (!g) return RDDL_ERR_ARG;
   if (which != RDDL_PLAN_TERMINAL && which != RDDL_PLAN_INVARIANT && which != RDDL_PLAN_PRECONDITION) {
     g->err = "rddl_check: bad plan";
     return RDDL_ERR_ARG;
   }
-  return run_plan(g, which, tensors, nullptr, status, n_envs, env_offset, 0, 0, (cudaStream_t)cuda_stream);
+  return run_plan(g, which, tensors, nullptr, status, n_envs, env_offset, seed, step, (cudaStream_t)cuda_stream);
 }
 
 extern "C" int rddl_profile(rddl_program_t* g, int enable) {

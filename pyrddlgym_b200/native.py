@@ -37,7 +37,7 @@ def load():
     lib.rddl_program_info.restype = i64
     lib.rddl_step.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), vp, i64, i64, u64, u64, vp]
     lib.rddl_step.restype = ctypes.c_int
-    lib.rddl_check.argtypes = [vp, ctypes.c_int, ctypes.POINTER(vp), vp, i64, i64, vp]
+    lib.rddl_check.argtypes = [vp, ctypes.c_int, ctypes.POINTER(vp), vp, i64, i64, u64, u64, vp]
     lib.rddl_check.restype = ctypes.c_int
     lib.rddl_rollout.argtypes = [vp, ctypes.POINTER(vp), vp, i64, i64, u64, u64, ctypes.c_int32,
                                  ctypes.POINTER(i64), ctypes.c_double, vp, vp, ctypes.POINTER(ctypes.c_int32), vp]
@@ -78,9 +78,9 @@ class NativeProgram:
         self._check(self.lib.rddl_step(self.handle, ptrs, injected, status_ptr, n_envs, env_offset,
                                        seed, step, stream), 'rddl_step')
 
-    def check(self, which, ptrs, status_ptr, n_envs, env_offset, stream):
-        self._check(self.lib.rddl_check(self.handle, which, ptrs, status_ptr, n_envs, env_offset, stream),
-                    'rddl_check')
+    def check(self, which, ptrs, status_ptr, n_envs, env_offset, seed, step, stream):
+        self._check(self.lib.rddl_check(self.handle, which, ptrs, status_ptr, n_envs, env_offset, seed, step,
+                                        stream), 'rddl_check')
 
     def rollout(self, ptrs, status_ptr, n_envs, env_offset, seed, step0, n_steps, strides, gamma,
                 returns_ptr, rewards_ptr, stream):

@@ -199,7 +199,7 @@ class BatchedSimulator:
     def _run_check(self, plan):
         self._refresh_ptrs()
         self.native.check(plan, self._ptrs, ctypes.c_void_p(self.status.data_ptr()), self.n_envs,
-                          self.env_offset, self._stream())
+                          self.env_offset, self.seed_value, self.step_count, self._stream())
 
     def check_state_invariants(self):
         """simulator.py:362-373 -> bool[N]."""

@@ -474,7 +474,7 @@ class EmulatedSimulator:
                 self.bufs[tid] = np.zeros(self.N * nelem, dtype=npdt)
         self.status = np.zeros(self.N, dtype=np.uint32)
         self.step_count = 0
-        self.em.run(ot.PLAN_TERMINAL, self.bufs, self.N, self.status)
+        self.em.run(ot.PLAN_TERMINAL, self.bufs, self.N, self.status, None, self.seed, self.step_count, self.env_offset)
         return self.fluent('__done').astype(bool).reshape(-1)
 
     def fluent(self, name):
@@ -509,7 +509,7 @@ class EmulatedSimulator:
     def check(self, plan, actions=None):
         if actions:
             self.set_actions(actions)
-        self.em.run(plan, self.bufs, self.N, self.status)
+        self.em.run(plan, self.bufs, self.N, self.status, None, self.seed, self.step_count, self.env_offset)
         key = 'invariant' if plan == ot.PLAN_INVARIANT else 'precondition'
         n = self.ot.n_checks[key]
         return self.fluent('__chk')[:, :n].astype(bool).all(axis=1)
