@@ -451,8 +451,8 @@ class PlaneBuilder:
                 mask |= 1 << ((dx + 1) * 3 + (dy + 1))
             slot = self.shared_slots
             self.shared_slots += 1
-            if slot >= 2:
-                raise NotPlanar('more than 2 stencil source planes')
+            if slot >= 4:
+                raise NotPlanar('more than 4 stencil source planes')
             tensor = getattr(self, 'load_tensor_of_reg', {}).get(reg, None)
             if self.chunks > 1 and tensor is None:
                 raise NotPlanar('stencil over a computed plane needs whole envs per tile')
@@ -500,13 +500,26 @@ class PlaneBuilder:
         p = self.ev(n.args[0], base)
         if p.cls == 'b':
             p = Fin(p.idx, p.table.astype(np.float64), p.care)
-        if p.m > MAX_M_BERN:
-            raise NotPlanar('Bernoulli parameter depends on too many bits')
         p = Fin(p.idx, np.asarray(p.table, dtype=np.float64), p.care)
         slot = self.lw.variate_slot(n.id, 'U', self.E)
+        self.variate_nodes.append(int(n.id))
+        return self.bernoulli(p, slot)
+
+    def bernoulli(self, p, slot):
+        """PBERN of a probability table; tables over more than MAX_M_BERN planes are split on
+        their last index plane x: Bern(p) = x ? Bern(p | x=1) : Bern(p | x=0). Both halves read the
+        same Philox words (same node, same counters), so the split does not change the draw."""
+        if p.m > MAX_M_BERN:
+            if p.m > MAX_M_BERN + 3:
+                raise NotPlanar('Bernoulli parameter depends on too many bits')
+            half = 1 << (p.m - 1)
+            x = p.idx[-1]
+            b0 = self.bernoulli(Fin(p.idx[:-1], p.table[:half], p.care[:half]), slot)
+            b1 = self.bernoulli(Fin(p.idx[:-1], p.table[half:], p.care[half:]), slot)
+            sel = Fin((x,), np.array([False, True]))
+            return self.as_plane_fin(self.combine([sel, b1, b0], lambda c, a, b: np.where(c, a, b)))
         d = self.alloc()
         self.ins('PBERN', dst=d, a=slot, fin=(p, {'thresholds': True}))
-        self.variate_nodes.append(int(n.id))
         return Fin((d,), np.array([False, True]))
 
     # ---- sinks

@@ -240,3 +240,117 @@ class Gen:
 
 def random_program(seed, depth=3):
     return Gen(seed).build(depth)
+
+
+# ---------------------------------------------------------------------------------------
+# random cellular (boolean-grid) programs: the class pyrddlgym_b200/plane_lowering.py targets
+# ---------------------------------------------------------------------------------------
+
+class GridGen:
+    """Random Wildfire-like programs over an H x W grid: bool planes, 3x3-stencil neighbour
+    counts through separable band masks, Bernoulli of a function of count and planes, reward
+    sums of coefficient * boolean expression."""
+
+    def __init__(self, seed, H=4, W=32):
+        self.rng = rng = np.random.default_rng(seed)
+        self.next_id = 0
+        self.H, self.W = H, W
+        self.p = p = Program()
+        p.name = f'gridfuzz{seed}'
+        p.types = {'x_pos': H, 'y_pos': W}
+        p.objects = {'x_pos': [f'x{i}' for i in range(H)], 'y_pos': [f'y{i}' for i in range(W)]}
+        XY = ['x_pos', 'y_pos']
+
+        def band(n, offs):
+            B = np.zeros((n, n), dtype=bool)
+            for d in offs:
+                i = np.arange(max(0, -d), min(n, n - d))
+                B[i, i + d] = True
+            return B
+
+        offx = [d for d in (-1, 0, 1) if rng.random() < 0.8] or [0]
+        offy = [d for d in (-1, 0, 1) if rng.random() < 0.8] or [1]
+        decl = [('XN', 'nonfluent', 'b', ['x_pos', 'x_pos'], band(H, offx)),
+                ('YN', 'nonfluent', 'b', ['y_pos', 'y_pos'], band(W, offy)),
+                ('NA', 'nonfluent', 'b', XY, rng.random((H, W)) < 0.3),
+                ('C0', 'nonfluent', 'f', [], np.float64(np.round(rng.uniform(-9, -1), 1))),
+                ('C1', 'nonfluent', 'f', [], np.float64(np.round(rng.uniform(0.5, 4), 2)))]
+        for k in range(3):
+            decl.append((f's{k}', 'state', 'b', XY, rng.random((H, W)) < 0.25))
+            decl.append((f"s{k}'", 'next', 'b', XY, np.zeros((H, W), dtype=bool)))
+        for k in range(2):
+            decl.append((f'a{k}', 'action', 'b', XY, np.zeros((H, W), dtype=bool)))
+        for (name, kind, dt, params, init) in decl:
+            p.tensors[name] = TensorDecl(name, kind, dt, params, {'f': 'real', 'b': 'bool'}[dt])
+            p.init[name] = np.asarray(init, dtype=hir.NP_DTYPE[dt])
+        p.next_state = {f's{k}': f"s{k}'" for k in range(3)}
+        p.horizon, p.discount, p.max_allowed_actions = 10, 1.0, 2 * H * W
+        self.XY = XY
+
+    def nid(self):
+        self.next_id += 1
+        return self.next_id
+
+    def plane(self, name, scope=None, at=(0, 1)):
+        scope = self.XY if scope is None else scope
+        return Node('load', tensor=name, index=[('a', at[0]), ('a', at[1])], dtype='b', scope=scope, id=self.nid())
+
+    def count(self, src):
+        """sum_{x2,y2} XN(x,x2) ^ YN(y,y2) ^ src(x2,y2) -> int count in 0..9."""
+        inner = self.XY + self.XY
+        xn = Node('load', tensor='XN', index=[('a', 0), ('a', 2)], dtype='b', scope=inner, id=self.nid())
+        yn = Node('load', tensor='YN', index=[('a', 1), ('a', 3)], dtype='b', scope=inner, id=self.nid())
+        body = Node('bin', op='and', args=[Node('bin', op='and', args=[xn, yn], dtype='b', scope=inner, id=self.nid()),
+                                           self.plane(src, inner, (2, 3))], dtype='b', scope=inner, id=self.nid())
+        return body, inner
+
+    def boolean(self, depth, avail):
+        rng = self.rng
+        r = rng.random()
+        if depth <= 0 or r < 0.2:
+            return self.plane(avail[rng.integers(len(avail))])
+        B = lambda: self.boolean(depth - 1, avail)
+        mk = lambda **kw: Node(scope=self.XY, id=self.nid(), **kw)
+        if r < 0.5:
+            return mk(kind='bin', op=['and', 'or', 'xor', 'imply', 'eqv'][rng.integers(5)], args=[B(), B()], dtype='b')
+        if r < 0.6:
+            return mk(kind='un', op='not', args=[B()], dtype='b')
+        if r < 0.7:
+            return mk(kind='if', args=[B(), B(), B()], dtype='b')
+        src = [s for s in avail if s.startswith('s') and not s.endswith("'")] or ['s0']
+        body, inner = self.count(src[rng.integers(len(src))])
+        if r < 0.8:
+            return Node('agg', op='exists', args=[body], red=self.XY, dtype='b', scope=self.XY, id=self.nid())
+        cnt = Node('agg', op='sum', args=[body], red=self.XY, dtype='i', scope=self.XY, id=self.nid())
+        if r < 0.9:
+            k = mk(kind='const', value=int(rng.integers(0, 4)), dtype='i')
+            return mk(kind='bin', op=['gt', 'ge', 'eq', 'lt'][rng.integers(4)], args=[cnt, k], dtype='b')
+        # Bernoulli(1 / (1 + exp(c1 - k * w)))  [optionally modulated by a plane]
+        c = lambda v: mk(kind='const', value=float(v), dtype='f')
+        w = mk(kind='bin', op='mul', args=[cnt, c(np.round(rng.uniform(0.3, 1.5), 2))], dtype='f')
+        e = mk(kind='un', op='exp', args=[mk(kind='bin', op='sub', args=[Node('load', tensor='C1', index=[], dtype='f', scope=self.XY, id=self.nid()), w], dtype='f')], dtype='f')
+        pr = mk(kind='bin', op='div', args=[c(1.0), mk(kind='bin', op='add', args=[c(1.0), e], dtype='f')], dtype='f')
+        if rng.random() < 0.4:
+            pr = mk(kind='if', args=[self.plane(avail[rng.integers(len(avail))]), pr, c(np.round(rng.uniform(0, 1), 2))], dtype='f')
+        return mk(kind='rand', op='Bernoulli', args=[pr], dtype='b')
+
+    def build(self, depth=3):
+        p = self.p
+        avail = ['s0', 's1', 's2', 'a0', 'a1', 'NA']
+        for k in range(3):
+            p.cpfs.append(Root(f"s{k}'", 0, list(self.XY), self.boolean(depth, avail)))
+        terms = []
+        for k in range(int(self.rng.integers(1, 4))):
+            coef = Node('load', tensor='C0', index=[], dtype='f', scope=self.XY, id=self.nid()) if k == 0 else \
+                Node('const', value=float(np.round(self.rng.uniform(-5, 5), 1)), dtype='f', scope=self.XY, id=self.nid())
+            body = Node('bin', op='mul', args=[coef, self.boolean(1, avail)], dtype='f', scope=self.XY, id=self.nid())
+            terms.append(Node('agg', op='sum', args=[body], red=list(self.XY), dtype='f', scope=[], id=self.nid()))
+        r = terms[0]
+        for t in terms[1:]:
+            r = Node('bin', op='add', args=[r, t], dtype='f', scope=[], id=self.nid())
+        p.reward = r
+        return p
+
+
+def random_grid_program(seed, H=4, W=32, depth=3):
+    return GridGen(seed, H, W).build(depth)

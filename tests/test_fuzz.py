@@ -59,3 +59,69 @@ def test_fuzz_cuda_vs_oracle(seed):
            (lambda a: to_np(sim.check_action_preconditions(a)), lambda: to_np(sim.check_state_invariants())),
            ora, N, 3, np.random.default_rng(seed))
     assert np.array_equal(to_np(sim.status).astype(np.uint32), ora.status)
+
+
+def _grid_drive(p, table, make, N, steps, seed, inject):
+    ora = OracleSimulator(p, n_envs=N, seed=3, bitsliced_nodes=table.plane_nodes)
+    sim = make(p, table, N)
+    rng = np.random.default_rng(seed)
+    for t in range(steps):
+        acts = harness.random_actions(p, N, rng, p_bool=0.2)
+        var = harness.random_variates(p, N, rng) if inject else None
+        r, d = sim.step(acts, var)
+        _, r0, d0 = ora.step(acts, var)
+        for k in range(3):
+            assert np.array_equal(np.asarray(sim.fluent(f's{k}')).astype(bool), ora.subs[f's{k}']), (f's{k}', t)
+        np.testing.assert_allclose(r, r0, rtol=1e-9, atol=1e-9)
+    return sim
+
+
+@pytest.mark.parametrize('seed', range(16))
+def test_fuzz_grid_programs_take_the_plane_path_and_match_the_oracle(seed):
+    from fuzz_programs import random_grid_program
+    from optable_emulator import EmulatedSimulator
+    p = random_grid_program(seed)
+    tab = lowering.lower(p)
+    kinds = [l['kernel'] for l in tab.launches if l['plan'] == ot.PLAN_STEP]
+    assert kinds[0] == 'rddl_plane_interp', (kinds, tab.plane_rejects)
+    for inject in (True, False):
+        _grid_drive(p, tab, lambda p_, t_, n: EmulatedSimulator(p_, t_, n, seed=3), 2, 2, seed, inject)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('seed', range(200, 240))
+def test_fuzz_grid_cuda_plane_vs_scalar_vs_oracle(seed):
+    import torch
+    from fuzz_programs import random_grid_program
+    from pyrddlgym_b200.simulator import BatchedSimulator
+    H, W = [(4, 32), (3, 64), (33, 32), (5, 96)][seed % 4]
+    p = random_grid_program(seed, H=H, W=W)
+    N = 37
+
+    class _S:
+        def __init__(self, sim):
+            self.sim = sim
+
+        def step(self, a, v):
+            _, r, d = self.sim.step(a, v)
+            return r.cpu().numpy(), d.cpu().numpy()
+
+        def fluent(self, n):
+            return self.sim.fluent(n).cpu().numpy()
+
+    tab = lowering.lower(p)
+    assert tab.launches[0]['kernel'] == 'rddl_plane_interp', tab.plane_rejects
+    for inject in (True, False):
+        _grid_drive(p, tab, lambda p_, t_, n: _S(BatchedSimulator(p_, n_envs=n, seed=3, optable=t_)), N, 3, seed, inject)
+    # scalar interpreter on the same program (injected uniforms): bit-identical planes
+    a = BatchedSimulator(p, n_envs=N, seed=3)
+    b = BatchedSimulator(p, n_envs=N, seed=3, use_planes=False)
+    rng = np.random.default_rng(seed)
+    for t in range(3):
+        acts = harness.random_actions(p, N, rng, p_bool=0.2)
+        var = harness.random_variates(p, N, rng)
+        _, ra, _ = a.step(acts, var)
+        _, rb, _ = b.step(acts, var)
+        for k in range(3):
+            assert torch.equal(a.fluent(f's{k}'), b.fluent(f's{k}'))
+        np.testing.assert_allclose(ra.cpu().numpy(), rb.cpu().numpy(), rtol=1e-9)
