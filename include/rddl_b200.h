@@ -9,6 +9,9 @@
  * ABI. All tensor pointers are DEVICE pointers owned by the caller (C-order, dtype per
  * pyRDDLGym/core/compiler/initializer.py:16-23: bool = uint8, int = int64, real = float64),
  * fluents carry a leading env axis [n_envs, ...], non-fluents are shared by all envs.
+ * Exception: bool state fluents that the op table marks with dtype code 3 (OpTable.packed --
+ * those only the bit-plane kernel writes) are stored BIT-PACKED, uint32[n_envs, cells / 32], cell i in
+ * bit (i % 32) of word i / 32; the host mirror converts to the byte layout on demand.
  * Calls are asynchronous on the given CUDA stream.
  */
 #ifndef RDDL_B200_H

@@ -4,7 +4,7 @@
 #include <stdint.h>
 
 #define RDDL_MAGIC 0x31304C444452ll
-#define RDDL_VERSION 8
+#define RDDL_VERSION 9
 #define RDDL_MAX_IDX 8
 #define RDDL_MAX_RED 8
 #define RDDL_MAX_REGS 96
@@ -32,7 +32,8 @@ enum RddlOp : uint8_t {
 
 enum RddlRed { RED_SUM_I, RED_SUM_F, RED_PROD_I, RED_PROD_F, RED_MIN_I, RED_MIN_F, RED_MAX_I, RED_MAX_F,
                RED_AND, RED_OR };
-enum RddlDtype { DT_BOOL = 0, DT_INT = 1, DT_REAL = 2 };
+enum RddlDtype { DT_BOOL = 0, DT_INT = 1, DT_REAL = 2,
+                 DT_PACKED = 3 };   // bool fluent stored bit-packed: cell i -> bit (i % 32) of uint32 word i / 32
 enum RddlKind { KIND_SHARED = 0, KIND_ENV = 1 };
 
 struct RddlInsn {      // 16 bytes

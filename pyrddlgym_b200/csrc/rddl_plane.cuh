@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(BLOCK, WPT == 1 ? 4 : PLANE_MIN_BLOCKS) rddl_p
     // issue the DRAM requests of every plane this tile reads up front (L2 prefetch): the loads of
     // the later PLD ops then hit L2 and the compute of this CTA overlaps its own memory traffic
     for (int pc = 0; pc < G.nops; ++pc) {
-      if (G.ops[pc].op != OP_PLD) continue;
+      if (G.ops[pc].op != OP_PLD || A.dtype[G.ops[pc].imm] == DT_PACKED) continue;
       const uint8_t* p = reinterpret_cast<const uint8_t*>(A.tensors[G.ops[pc].imm]) + tile_byte0;
 #pragma unroll
       for (int j = 0; j < WPT; ++j)
@@ -427,6 +427,13 @@ __global__ void __launch_bounds__(BLOCK, WPT == 1 ? 4 : PLANE_MIN_BLOCKS) rddl_p
           break;
         }
         const uint8_t* base = reinterpret_cast<const uint8_t*>(A.tensors[o.imm]) + t * A.tstride[o.imm];
+        if (A.dtype[o.imm] == DT_PACKED) {   // state kept bit-packed in HBM: one word per 32 cells
+          const uint32_t* wp = reinterpret_cast<const uint32_t*>(base) + (tile_byte0 >> 5);
+#pragma unroll
+          for (int j = 0; j < WPT; ++j)
+            C.at(o.dst, j) = (full || ((C.valid >> j) & 1u)) ? __ldcs(wp + j * BLOCK) : 0u;
+          break;
+        }
         if (!full) {
           plane_ld_partial<WPT, BLOCK>(C, base, env0, wpe, o.dst);
           break;
@@ -455,6 +462,13 @@ __global__ void __launch_bounds__(BLOCK, WPT == 1 ? 4 : PLANE_MIN_BLOCKS) rddl_p
       case OP_PST: {
         if (!last_step && o.b) break;   // carried state: only the final step reaches HBM
         uint8_t* base = reinterpret_cast<uint8_t*>(A.tensors[o.imm]);
+        if (A.dtype[o.imm] == DT_PACKED) {
+          uint32_t* wp = reinterpret_cast<uint32_t*>(base) + (tile_byte0 >> 5);
+#pragma unroll
+          for (int j = 0; j < WPT; ++j)
+            if (full || ((C.valid >> j) & 1u)) __stcs(wp + j * BLOCK, C.at(o.a, j));
+          break;
+        }
         if (!full) {
           plane_st_partial<WPT, BLOCK>(C, base, env0, wpe, o.a);
           break;
@@ -504,8 +518,12 @@ __global__ void __launch_bounds__(BLOCK, WPT == 1 ? 4 : PLANE_MIN_BLOCKS) rddl_p
             const int wsrc = top ? chunk * tile_words - W32 + c : (chunk + 1) * tile_words + c;
             uint32_t word = 0;
             if (wsrc >= 0 && wsrc < wpe && env0 < A.n_envs) {
-              const uint4* p = reinterpret_cast<const uint4*>(base + ((env0 * wpe + wsrc) << 5));
-              word = plane_pack(__ldg(p), __ldg(p + 1));
+              if (A.dtype[o.imm] == DT_PACKED) {
+                word = __ldg(reinterpret_cast<const uint32_t*>(base) + env0 * wpe + wsrc);
+              } else {
+                const uint4* p = reinterpret_cast<const uint4*>(base + ((env0 * wpe + wsrc) << 5));
+                word = plane_pack(__ldg(p), __ldg(p + 1));
+              }
             }
             s[plane_spos(top ? -1 : tile_rows, c, 0, pitch)] = word;
           }

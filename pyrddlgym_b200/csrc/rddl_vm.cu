@@ -183,6 +183,7 @@ __device__ __noinline__ void vm_exec_element(const VmArgs& A, const RddlLaunch& 
             const void* base = A.tensors[t];
             const int dt = A.dtype[t];
             if (dt == DT_BOOL) r[dst] = reinterpret_cast<const uint8_t*>(base)[off] != 0;
+            else if (dt == DT_PACKED) r[dst] = (reinterpret_cast<const uint32_t*>(base)[off >> 5] >> (off & 31)) & 1u;
             else r[dst] = reinterpret_cast<const uint64_t*>(base)[off];
           } else if (op == OP_STORE) {
             off += env * ad->env_stride;

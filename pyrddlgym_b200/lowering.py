@@ -909,6 +909,7 @@ class OpTable:
         self.n_insns = 0
         self.plane_nodes = []        # ids of Bernoulli nodes lowered to the bit-sliced sampler
         self.plane_rejects = []      # (plan, scope, reason) of groups that stayed on the scalar path
+        self.packed = []             # bool state fluents stored bit-packed in HBM (dtype code 3)
 
 
 SPECIALS = ['__reward', '__done', '__chk']
@@ -916,8 +917,9 @@ SPECIALS = ['__reward', '__done', '__chk']
 
 class Lowerer:
 
-    def __init__(self, program, use_planes=True, use_contract=True):
+    def __init__(self, program, use_planes=True, use_contract=True, use_packed=True):
         self.p = program
+        self.use_packed = use_packed
         self.use_planes = use_planes
         self.use_contract = use_contract
         self.contract_items = {}
@@ -1417,6 +1419,7 @@ class Lowerer:
         finally:
             for s in SPECIALS:
                 del p.tensors[s]
+        self._choose_packed()
         out = self.out
         out.tensor_names = names
         out.tensor_id = dict(self.tensor_id)
@@ -1436,6 +1439,54 @@ class Lowerer:
             np.array(self.redslots, dtype=ot.REDSLOT) if self.redslots else np.zeros(0, ot.REDSLOT),
             np.array(self.variates, dtype=ot.VARIATE) if self.variates else np.zeros(0, ot.VARIATE))
         return out
+
+    def _choose_packed(self):
+        """Bool state fluents that only the plane interpreter writes are kept BIT-PACKED in HBM
+        (32 cells per uint32 word; tensor dtype code 3): a step then moves 1/8 of the state bytes
+        and skips the byte<->bit conversion. The byte layout of the reference boundary is
+        produced on demand by the host mirror (BatchedSimulator.fluent). A state / next-state
+        pair is packed together or not at all."""
+        self.out.packed = []
+        if not self.use_packed:
+            return
+        p = self.p
+        plane_rw, scalar_w, other = set(), set(), set()
+        for L in self.launch_rows:
+            kind = int(L['pad'])
+            ins = self.insns[int(L['pc_begin']):int(L['pc_end'])]
+            if kind == 1:
+                for i in ins:
+                    if i[0] in (OP['PLD'], OP['PST']):
+                        plane_rw.add(int(i[7]))
+                    elif i[0] == OP['PSHARE'] and int(i[7]) != 0xFFFFFFFF:
+                        plane_rw.add(int(i[7]))
+            elif kind == 3:
+                other.update(int(t) for t in L['red_slot'][:3])
+            else:
+                k = 0
+                while k < len(ins):
+                    i = ins[k]
+                    if i[0] == OP['STORE']:
+                        scalar_w.add(int(self.addrs[i[7]]['tensor']))
+                    elif i[0] == OP['SUMLOOP']:
+                        other.add(int(self.addrs[i[7]]['tensor']))
+                        if i[4] & 2:
+                            other.add(int(self.addrs[ins[k + 1][7]]['tensor']))
+                        k += 1
+                    k += 1
+        for s_name, n_name in p.next_state.items():
+            ids = (self.tensor_id[s_name], self.tensor_id[n_name])
+            d = p.tensors[s_name]
+            nelem = self.out.tensor_meta[s_name][2]
+            if d.dtype != 'b' or nelem % 32 or any(t in scalar_w or t in other for t in ids):
+                continue
+            if not all(t in plane_rw for t in ids):
+                continue
+            for name, t in ((s_name, ids[0]), (n_name, ids[1])):
+                row = list(self.tensor_rows[t])
+                row[0] = 3
+                self.tensor_rows[t] = tuple(row)
+                self.out.packed.append(name)
 
     def _or_all(self, exprs):
         out = exprs[0]
@@ -1483,7 +1534,7 @@ class Lowerer:
                 self.schedule(plan, items)
 
 
-def lower(program, use_planes=True, use_contract=True):
+def lower(program, use_planes=True, use_contract=True, use_packed=True):
     """Lowers an HIR ``Program`` to an ``OpTable``. ``use_planes=False`` keeps every launch on
     the general scalar interpreter (used by tests to cross-check the two paths)."""
-    return Lowerer(program, use_planes=use_planes, use_contract=use_contract).lower()
+    return Lowerer(program, use_planes=use_planes, use_contract=use_contract, use_packed=use_packed).lower()

@@ -13,7 +13,7 @@ slots the kernels need. It is a flat little-endian blob:
 import numpy as np
 
 MAGIC = 0x31304C444452  # "RDDL01"
-VERSION = 8
+VERSION = 9
 MAX_IDX = 8          # index variables per thread: scope axes + nested loop axes
 MAX_RED = 8          # reduction outputs per launch
 MAX_REGS = 96        # virtual 64-bit registers per thread
@@ -52,7 +52,7 @@ OP = {name: i for i, name in enumerate(_OPS)}
 RED = {'SUM_I': 0, 'SUM_F': 1, 'PROD_I': 2, 'PROD_F': 3, 'MIN_I': 4, 'MIN_F': 5, 'MAX_I': 6,
        'MAX_F': 7, 'AND': 8, 'OR': 9}
 
-DT = {'b': 0, 'i': 1, 'f': 2, 'u32': 3}
+DT = {'b': 0, 'i': 1, 'f': 2, 'packed': 3}      # 3: bool fluent stored as bits, 32 cells per uint32 word
 KIND_SHARED, KIND_ENV = 0, 1
 
 PLAN_STEP, PLAN_TERMINAL, PLAN_INVARIANT, PLAN_PRECONDITION = 0, 1, 2, 3

@@ -8,6 +8,7 @@ table through the C ABI (include/rddl_b200.h) on torch's current stream and then
 the state / next-state buffers (the reference aliases them, simulator.py:463-466).
 There is no CPU execution path.
 """
+import collections.abc
 import ctypes
 
 import numpy as np
@@ -27,11 +28,29 @@ class StatusError(RuntimeError):
         self.status = status
 
 
+class _States(collections.abc.Mapping):
+    """Lazy name -> tensor view of the current state (bit-packed fluents unpack on access)."""
+
+    def __init__(self, sim):
+        self._sim = sim
+
+    def __getitem__(self, name):
+        if name not in self._sim.state_names:
+            raise KeyError(name)
+        return self._sim.fluent(name)
+
+    def __iter__(self):
+        return iter(self._sim.state_names)
+
+    def __len__(self):
+        return len(self._sim.state_names)
+
+
 class BatchedSimulator:
     """N independent environments of one compiled RDDL problem, stepped in lock-step."""
 
     def __init__(self, program, n_envs=1, device='cuda:0', seed=0, env_offset=0, optable=None,
-                 use_planes=True, use_contract=True):
+                 use_planes=True, use_contract=True, use_packed=True):
         self.program = program
         self.n_envs = int(n_envs)
         self.device = torch.device(device)
@@ -39,11 +58,12 @@ class BatchedSimulator:
             raise native.NativeError('the B200 backend runs on CUDA devices only (no CPU fallback)')
         self.seed_value = int(seed)
         self.env_offset = int(env_offset)
-        self.table = optable if optable is not None else lowering.lower(program, use_planes=use_planes,
-                                                                             use_contract=use_contract)
+        self.table = optable if optable is not None else lowering.lower(
+            program, use_planes=use_planes, use_contract=use_contract, use_packed=use_packed)
         index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self.native = native.NativeProgram(self.table.blob, index)
         self.names = list(self.table.tensor_names)
+        self.packed = set(self.table.packed)
         self.tid = self.table.tensor_id
         self.state_names = list(program.next_state)
         self.action_names = program.names_of_kind('action')
@@ -58,6 +78,9 @@ class BatchedSimulator:
                 if kind == ot.KIND_SHARED:
                     v = torch.from_numpy(np.ascontiguousarray(program.init[name]))
                     self.t[name] = v.to(self.device, dtype=_TORCH_DT[dt]).contiguous()
+                elif name in self.packed:
+                    # bool state kept bit-packed in HBM (32 cells per int32 word); see fluent()
+                    self.t[name] = torch.zeros((self.n_envs, nelem // 32), dtype=torch.int32, device=self.device)
                 else:
                     self.t[name] = torch.zeros((self.n_envs,) + shape, dtype=_TORCH_DT[dt], device=self.device)
             self.status = torch.zeros(self.n_envs, dtype=torch.int32, device=self.device)
@@ -92,19 +115,37 @@ class BatchedSimulator:
         for name, own in self._owned_actions.items():
             self.t[name] = own          # never write into caller-owned action tensors
         for name, v in self._init.items():
-            self.t[name].copy_(v.expand_as(self.t[name]))
+            if name in self.packed:
+                self.t[name].copy_(self._pack(v.reshape(1, -1)).expand_as(self.t[name]))
+            else:
+                self.t[name].copy_(v.expand_as(self.t[name]))
         self.status.zero_()
         self.step_count = 0
         done = self.check_terminal_states()
         return self.states, done
 
+    @staticmethod
+    def _pack(x):
+        """bool [n, cells] -> int32 [n, cells / 32], cell i -> bit (i % 32) of word i / 32."""
+        n = x.shape[0]
+        w = x.reshape(n, -1, 32).to(torch.int64) << torch.arange(32, device=x.device, dtype=torch.int64)
+        return w.sum(-1).to(torch.int32)
+
+    @staticmethod
+    def _unpack(w, shape):
+        bits = (w.unsqueeze(-1) >> torch.arange(32, device=w.device, dtype=torch.int32)) & 1
+        return bits.to(torch.bool).reshape((w.shape[0],) + tuple(shape))
+
     @property
     def states(self):
-        """name -> tensor [N, *shape]; views of the live state buffers (valid until the next
-        step, like the reference's aliasing dict, simulator.py:176-179)."""
-        return {s: self.t[s] for s in self.state_names}
+        """name -> tensor [N, *shape] of the current state. Byte / int64 / float64 fluents are
+        views of the live buffers (valid until the next step, like the reference's aliasing dict,
+        simulator.py:176-179); bit-packed bool fluents are unpacked into a fresh tensor."""
+        return _States(self)
 
     def fluent(self, name):
+        if name in self.packed:
+            return self._unpack(self.t[name], self.program.tensor_shape(name))
         return self.t[name]
 
     def set_actions(self, actions):

@@ -250,12 +250,12 @@ class Emulator:
                     dt = int(self.tensors[t]['dtype'])
                     buf = bufs[t]
                     if op == 'LOAD':
-                        if dt == 0:
+                        if dt in (0, 3):
                             r[dst] = int(buf[off] != 0)
                         else:
                             r[dst] = int(buf.view('<u8')[off])
                     else:
-                        if dt == 0:
+                        if dt in (0, 3):
                             buf[off] = 1 if r[a] != 0 else 0
                         else:
                             buf.view('<u8')[off] = r[a]
@@ -340,7 +340,7 @@ class Emulator:
                         vals = []
                         for (buf, dt, off, st) in terms:
                             v = buf[off + st * k]
-                            vals.append(np.float64(v) if dt == 2 else int(v != 0) if dt == 0 else int(v))
+                            vals.append(np.float64(v) if dt == 2 else int(v != 0) if dt in (0, 3) else int(v))
                         if flt:
                             fv = [np.float64(x) for x in vals]
                             facc = facc + (fv[0] * fv[1] if two else fv[0])
