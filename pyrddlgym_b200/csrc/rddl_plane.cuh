@@ -128,7 +128,12 @@ struct PlaneCtx {
   // virtual plane registers live in shared memory, [reg][word][thread]: conflict-free, never
   // evicted (a local-memory register file of this size thrashes L1 at 3 CTAs per SM)
   uint32_t* P;
-  __device__ __forceinline__ uint32_t& at(int r, int j) { return P[(r * WPT + j) * BLOCK + threadIdx.x]; }
+  __device__ __forceinline__ uint32_t& at(int r, int j) {
+    // the register file starts at offset 0 of the dynamic shared memory; naming the extern array
+    // here keeps the accesses in the shared address space (LDS/STS instead of generic LD/ST)
+    extern __shared__ uint32_t plane_smem_base[];
+    return plane_smem_base[(r * WPT + j) * BLOCK + threadIdx.x];
+  }
   int env[WPT];       // local env index (relative to the launch's first env)
   int wi[WPT];        // word index inside the env
   uint32_t valid;     // bit j: word j is inside the batch
@@ -393,9 +398,6 @@ __global__ void __launch_bounds__(BLOCK, WPT == 1 ? 4 : PLANE_MIN_BLOCKS) rddl_p
         asm volatile("prefetch.global.L2 [%0];" ::"l"(p + (int64_t)j * (BLOCK * 32)));
     }
   }
-  int racc[RDDL_MAX_RED];   // per-thread popcount accumulators (single-env tiles)
-#pragma unroll
-  for (int i = 0; i < RDDL_MAX_RED; ++i) racc[i] = 0;
   const bool single_env = envs_per_tile == 1;
 
   // per-env rollout state of the thread that runs env (env0 + tid)'s scalar epilogue
@@ -596,9 +598,8 @@ __global__ void __launch_bounds__(BLOCK, WPT == 1 ? 4 : PLANE_MIN_BLOCKS) rddl_p
 #pragma unroll
           for (int j = 0; j < WPT; ++j)
             if (full || ((C.valid >> j) & 1u)) c += o.m ? __popc(C.at(r0, j)) : 32;
-#pragma unroll
-          for (int i = 0; i < RDDL_MAX_RED; ++i)
-            if (i == o.b) racc[i] += c;
+          c = __reduce_add_sync(0xffffffffu, c);
+          if ((tid & 31) == 0 && c) atomicAdd(&cnt[o.b], c);
         } else {
           const bool warp_uniform_env = (wpe & 31) == 0;
 #pragma unroll
@@ -619,16 +620,6 @@ __global__ void __launch_bounds__(BLOCK, WPT == 1 ? 4 : PLANE_MIN_BLOCKS) rddl_p
   }
 
   if (L.nred > 0) {
-    if (single_env) {
-#pragma unroll
-      for (int i = 0; i < RDDL_MAX_RED; ++i) {
-        if (i < L.nred) {
-          const int c = __reduce_add_sync(0xffffffffu, racc[i]);
-          if ((tid & 31) == 0 && c) atomicAdd(&cnt[i], c);
-          racc[i] = 0;
-        }
-      }
-    }
     __syncthreads();
     const int64_t cells = chunks == 1 ? L.E : (int64_t)min(tile_words, wpe - chunk * tile_words) * 32;
     for (int i = tid; i < envs_per_tile * L.nred; i += BLOCK) {

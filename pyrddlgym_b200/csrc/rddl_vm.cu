@@ -664,6 +664,8 @@ extern "C" int rddl_program_create(const void* optable, size_t nbytes, int devic
                           (const void*)rddl_plane_interp<4, 256>};
     for (const void* f : fns) {
       cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+      if (getenv("RDDL_PLANE_CARVEOUT"))   // experiment knob: shared-memory share of the unified L1 array, percent
+        cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("RDDL_PLANE_CARVEOUT")));
     }
     cudaGetLastError();   // no device in CPU-only builds: ignored here, create fails at cudaSetDevice below
   }
