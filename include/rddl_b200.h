@@ -37,7 +37,7 @@ void rddl_program_destroy(rddl_program_t* prog);
 const char* rddl_last_error(const rddl_program_t* prog);
 
 /* what: 0 = #tensors, 1 = #variate slots, 2 = #launches of the step plan, 3 = total #instructions,
- * 4 = kernel launches issued since create. */
+ * 4 = kernel launches issued since create, 5-7 = specialisation counters (below). */
 int64_t rddl_program_info(const rddl_program_t* prog, int what);
 
 /* Replaces RDDLSimulator.step (pyRDDLGym/core/simulator.py:442-502) for n_envs environments:
@@ -78,6 +78,27 @@ int rddl_rollout(rddl_program_t* prog, void* const* tensors, uint32_t* status, i
                  int64_t env_offset, uint64_t seed, uint64_t step0, int32_t n_steps,
                  const int64_t* step_stride_bytes, double gamma, double* returns, double* rewards,
                  int32_t* state_in_next, void* cuda_stream);
+
+/* Run-time specialisation of the bit-plane kernels (no reference counterpart; the closest analogue
+ * is the reference's JAX backend jit-compiling a model once, pyRDDLGym-jax, docs/jax.rst). On the
+ * first run of a plane launch the library recompiles its kernel source for sm_100a with NVRTC, with
+ * the launch's program and geometry as constants (pyrddlgym_b200/csrc/rddl_jit.h); results are
+ * bit-identical to the interpreter kernel's, which runs instead whenever NVRTC is unavailable.
+ *   rddl_program_option(prog, 0, v)  v = 0: interpreter kernels only; 1 (default unless the
+ *                                    environment has RDDL_B200_JIT=0): specialise
+ *   rddl_program_info(prog, 5 | 6 | 7)  specialised kernels in use | launches that fell back to the
+ *                                    interpreter (rddl_jit_error has the compiler log) | cubins
+ *                                    taken from the disk cache (<library dir>/jit_cache or
+ *                                    $RDDL_B200_JIT_CACHE)
+ *   rddl_plane_precompile            host only (no device needed): fills the disk cache with the
+ *                                    kernels an op table needs for batches of n_envs; returns the
+ *                                    number of kernels, < 0 on error (rddl_last_error(NULL))
+ *   rddl_plane_source                inspection aid: the generated constants of plane launch `launch`;
+ *                                    returns the text length, writes at most cap - 1 bytes + NUL */
+int rddl_program_option(rddl_program_t* prog, int what, int64_t value);
+const char* rddl_jit_error(const rddl_program_t* prog);
+int rddl_plane_precompile(const void* optable, size_t nbytes, int64_t n_envs);
+int64_t rddl_plane_source(const void* optable, size_t nbytes, int launch, int64_t n_envs, char* out, size_t cap);
 
 /* Measurement aid (no reference counterpart): when enabled, every kernel launch of this
  * program is bracketed by CUDA events on its stream; rddl_profile_read synchronises them and

@@ -27,7 +27,7 @@ def build(force=False, verbose=False):
         return LIB
     nvcc = os.environ.get('NVCC', 'nvcc')
     srcs = [f for f in sorted(os.listdir(CSRC)) if f.endswith('.cu')]
-    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB] + srcs
+    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB] + srcs + ['-ldl']
     res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

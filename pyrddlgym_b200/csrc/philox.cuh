@@ -7,7 +7,7 @@
 // so a draw depends only on (seed, env, step, AST node, element): results are invariant to how
 // envs are sharded over GPUs.
 #pragma once
-#include <stdint.h>
+#include "rddl_stdint.h"
 
 __device__ __forceinline__ uint4 rddl_philox4x32_10(uint4 c, uint2 k) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;

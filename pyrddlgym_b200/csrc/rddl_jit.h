@@ -1,0 +1,264 @@
+// Run-time specialisation of the bit-plane kernel (host side).
+//
+// rddl_plane.cuh is written once and built twice: ahead of time as an interpreter whose program
+// arrives in the kernel parameter bank, and -- here -- per plane launch of a created program, with
+// the pre-decoded PlaneProg, the launch geometry and the tensor dtypes emitted as constants
+// ("plane_static_data.inc") and the file recompiled for sm_100a by NVRTC. The op loop then unrolls,
+// the dispatch switches fold, truth-table masks turn into LOP3 immediates and the plane registers
+// into machine registers. Same source, same Philox counters: results are bit-identical to the
+// interpreter's (tests/test_cuda_parity.py::test_specialised_*).
+//
+// NVRTC and the driver entry points are bound lazily (dlopen / cudaGetDriverEntryPoint): the
+// library keeps loading on machines without a driver, and when NVRTC is missing the interpreter
+// kernels run instead (rddl_program_info(prog, 5) reports how many launches are specialised).
+// Compiled cubins are cached on disk, keyed by a hash of every source byte and option.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+static std::string jit_fmt(const char* f, long long v) {
+  char b[64];
+  snprintf(b, sizeof b, f, v);
+  return b;
+}
+
+static void jit_launch_init(std::string& s, const RddlLaunch& L) {
+  s += "{" + jit_fmt("%lld,", L.plan) + jit_fmt("%lld,{", L.rank);
+  for (int i = 0; i < 8; ++i) s += jit_fmt("%lldll,", (long long)L.extent[i]);
+  s += "}," + jit_fmt("%lldll,", (long long)L.E) + jit_fmt("%lld,", L.pc_begin) + jit_fmt("%lld,", L.pc_end) +
+       jit_fmt("%lld,", L.nred) + jit_fmt("%lld,", L.G) + jit_fmt("%lld,", L.ipt) + jit_fmt("%lld,{", L.chunks);
+  for (int i = 0; i < 8; ++i) s += jit_fmt("%lld,", L.red_op[i]);
+  s += "},{";
+  for (int i = 0; i < 8; ++i) s += jit_fmt("%lld,", L.red_slot[i]);
+  s += "}," + jit_fmt("%lld,", L.nregs) + jit_fmt("%lld}", L.kind);
+}
+
+// The constants of one (plane launch, words per thread) pair, as C++ source.
+static std::string plane_static_data(const PlaneProg& G, const RddlLaunch& L, const uint8_t* dtype, int wpt,
+                                     int min_blocks) {
+  std::string s;
+  s += jit_fmt("#define PS_WPT %lld\n", wpt) + jit_fmt("#define PS_NREGS %lld\n", L.nregs > 0 ? L.nregs : 1) +
+       jit_fmt("#define PS_NOPS %lld\n", G.nops) + jit_fmt("#define PS_MINB %lld\n", min_blocks);
+  s += "__device__ constexpr PlaneProg kG = {" + jit_fmt("%lld,", G.nops) + jit_fmt("%lld,", G.nshared) +
+       jit_fmt("%lld,", G.w32_shift) + jit_fmt("%lld,", G.wpe_shift) + jit_fmt("%lld,", G.nfused) +
+       jit_fmt("%lld,", G.fused_nregs) + jit_fmt("%lld,", G.rollout_ok) + jit_fmt("%lld,\n{", G.pad);
+  jit_launch_init(s, G.fused[0]);
+  s += ",\n";
+  jit_launch_init(s, G.fused[1]);
+  s += "},\n{";
+  for (int i = 0; i < RDDL_MAX_RED; ++i) s += jit_fmt("%lld,", G.red_off[i]);
+  s += "},{";
+  for (int i = 0; i < RDDL_MAX_RED; ++i) s += jit_fmt("%lld,", G.red_m[i]);
+  s += "},\n{";
+  for (int i = 0; i < G.nops; ++i) {
+    const PlaneOp& o = G.ops[i];
+    s += "{" + jit_fmt("%lld,", o.op) + jit_fmt("%lld,", o.dst) + jit_fmt("%lld,", o.a) + jit_fmt("%lld,", o.b) +
+         jit_fmt("%lld,", o.m) + jit_fmt("%lluu,", o.idx) + jit_fmt("%lld,", o.off) + jit_fmt("%lluu},\n", o.imm);
+  }
+  s += "},\n{";
+  int nw = 0;   // words in use: everything up to the last table
+  for (int i = 0; i < PLANE_WORDS; ++i) if (G.words[i]) nw = i + 1;
+  for (int i = 0; i < nw; ++i) s += jit_fmt("0x%llxu,", G.words[i]) + ((i & 15) == 15 ? "\n" : "");
+  s += "}};\n__device__ const RddlLaunch kL = ";
+  jit_launch_init(s, L);
+  s += ";\n__device__ const uint8_t kDT[RDDL_MAX_TENSORS] = {";
+  for (int i = 0; i < RDDL_MAX_TENSORS; ++i) s += jit_fmt("%lld,", dtype[i]);
+  s += "};\n";
+  return s;
+}
+
+// ---------------------------------------------------------------------------------------
+// NVRTC + driver entry points, bound lazily
+// ---------------------------------------------------------------------------------------
+#include <nvrtc.h>
+
+struct JitApi {
+  bool tried = false, ok = false;
+  std::string why;
+  void* h = nullptr;
+  nvrtcResult (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*);
+  nvrtcResult (*CompileProgram)(nvrtcProgram, int, const char* const*);
+  nvrtcResult (*GetCUBINSize)(nvrtcProgram, size_t*);
+  nvrtcResult (*GetCUBIN)(nvrtcProgram, char*);
+  nvrtcResult (*GetProgramLogSize)(nvrtcProgram, size_t*);
+  nvrtcResult (*GetProgramLog)(nvrtcProgram, char*);
+  nvrtcResult (*DestroyProgram)(nvrtcProgram*);
+  nvrtcResult (*Version)(int*, int*);
+  int major = 0, minor = 0;
+};
+
+static JitApi& jit_api() {
+  static JitApi api;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  if (api.tried) return api;
+  api.tried = true;
+  const char* names[] = {getenv("RDDL_B200_NVRTC"), "libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so"};
+  for (const char* n : names) {
+    if (!n || !*n) continue;
+    api.h = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+    if (api.h) break;
+  }
+  if (!api.h) { api.why = "libnvrtc.so.12 not found"; return api; }
+#define JIT_SYM(field, name)                                               \
+  *(void**)(&api.field) = dlsym(api.h, name);                               \
+  if (!api.field) { api.why = std::string("missing symbol ") + name; return api; }
+  JIT_SYM(CreateProgram, "nvrtcCreateProgram")
+  JIT_SYM(CompileProgram, "nvrtcCompileProgram")
+  JIT_SYM(GetCUBINSize, "nvrtcGetCUBINSize")
+  JIT_SYM(GetCUBIN, "nvrtcGetCUBIN")
+  JIT_SYM(GetProgramLogSize, "nvrtcGetProgramLogSize")
+  JIT_SYM(GetProgramLog, "nvrtcGetProgramLog")
+  JIT_SYM(DestroyProgram, "nvrtcDestroyProgram")
+  JIT_SYM(Version, "nvrtcVersion")
+#undef JIT_SYM
+  api.Version(&api.major, &api.minor);
+  api.ok = true;
+  return api;
+}
+
+// directory of this shared library: the kernel sources (*.cuh) and the cubin cache live next to it
+static std::string jit_lib_dir() {
+  Dl_info info;
+  if (dladdr((const void*)&jit_lib_dir, &info) && info.dli_fname) {
+    std::string p = info.dli_fname;
+    const size_t k = p.rfind('/');
+    return k == std::string::npos ? std::string(".") : p.substr(0, k);
+  }
+  return ".";
+}
+
+static bool jit_read_file(const std::string& path, std::string* out) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  char buf[1 << 16];
+  size_t n;
+  out->clear();
+  while ((n = fread(buf, 1, sizeof buf, f)) > 0) out->append(buf, n);
+  fclose(f);
+  return true;
+}
+
+static uint64_t jit_hash(uint64_t h, const std::string& s) {
+  for (unsigned char c : s) { h ^= c; h *= 0x100000001b3ull; }
+  return h;
+}
+
+static const char* const kJitHeaders[] = {"rddl_stdint.h", "philox.cuh", "rddl_plan.h", "rddl_samplers.cuh",
+                                          "rddl_device.cuh", "rddl_plane.cuh"};
+static const char* const kJitMain = "#define PLANE_STATIC 1\n#include \"rddl_device.cuh\"\n#include \"rddl_plane.cuh\"\n";
+
+// Compiles (or fetches from the disk cache) the specialised kernel for `data`; the cubin comes back in *cubin.
+static bool jit_compile_plane(const std::string& data, std::string* cubin, std::string* err, bool* cache_hit) {
+  const std::string dir = jit_lib_dir();
+  std::vector<std::string> texts;
+  uint64_t h = 0xcbf29ce484222325ull;
+  for (const char* name : kJitHeaders) {
+    std::string t;
+    if (!jit_read_file(dir + "/" + name, &t)) { *err = std::string("kernel source not found: ") + dir + "/" + name; return false; }
+    h = jit_hash(h, t);
+    texts.push_back(std::move(t));
+  }
+  h = jit_hash(h, data);
+  h = jit_hash(h, kJitMain);
+  JitApi& api = jit_api();
+  h = jit_hash(h, jit_fmt("nvrtc %lld.", api.major) + jit_fmt("%lld sm_100a O3 lineinfo", api.minor));
+  const char* cdir = getenv("RDDL_B200_JIT_CACHE");
+  const std::string cache_dir = cdir && *cdir ? std::string(cdir) : dir + "/jit_cache";
+  char name[64];
+  snprintf(name, sizeof name, "/plane_%016llx.cubin", (unsigned long long)h);
+  const std::string path = cache_dir + name;
+  if (cache_hit) *cache_hit = false;
+  if (jit_read_file(path, cubin) && cubin->size() > 64) {
+    if (cache_hit) *cache_hit = true;
+    return true;
+  }
+  if (!api.ok) { *err = "NVRTC unavailable: " + api.why; return false; }
+  std::vector<const char*> hdr_src, hdr_name;
+  for (size_t i = 0; i < texts.size(); ++i) { hdr_src.push_back(texts[i].c_str()); hdr_name.push_back(kJitHeaders[i]); }
+  hdr_src.push_back(data.c_str());
+  hdr_name.push_back("plane_static_data.inc");
+  nvrtcProgram prog;
+  if (api.CreateProgram(&prog, kJitMain, "rddl_plane_static.cu", (int)hdr_src.size(), hdr_src.data(), hdr_name.data()) !=
+      NVRTC_SUCCESS) {
+    *err = "nvrtcCreateProgram failed";
+    return false;
+  }
+  const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "--generate-line-info"};
+  const nvrtcResult rc = api.CompileProgram(prog, 3, opts);
+  if (rc != NVRTC_SUCCESS) {
+    size_t n = 0;
+    api.GetProgramLogSize(prog, &n);
+    std::string log(n, 0);
+    if (n) api.GetProgramLog(prog, &log[0]);
+    *err = "NVRTC compile failed:\n" + log.substr(0, 4000);
+    api.DestroyProgram(&prog);
+    return false;
+  }
+  size_t n = 0;
+  api.GetCUBINSize(prog, &n);
+  cubin->assign(n, 0);
+  if (n) api.GetCUBIN(prog, &(*cubin)[0]);
+  api.DestroyProgram(&prog);
+  if (n < 64) { *err = "NVRTC produced no cubin"; return false; }
+  // best-effort cache write (atomic rename; a read-only tree just recompiles next time)
+  mkdir(cache_dir.c_str(), 0777);
+  const std::string tmp = path + jit_fmt(".tmp%lld", (long long)getpid());
+  if (FILE* f = fopen(tmp.c_str(), "wb")) {
+    const bool okw = fwrite(cubin->data(), 1, cubin->size(), f) == cubin->size();
+    fclose(f);
+    if (!okw || rename(tmp.c_str(), path.c_str()) != 0) unlink(tmp.c_str());
+  }
+  return true;
+}
+
+// Driver entry points through the runtime (no link-time dependency on libcuda).
+struct JitDriver {
+  bool ok = false;
+  CUresult (*ModuleLoadData)(CUmodule*, const void*);
+  CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*);
+  CUresult (*ModuleUnload)(CUmodule);
+  CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int);
+  CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream,
+                           void**, void**);
+};
+
+static JitDriver& jit_driver() {
+  static JitDriver d;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  if (d.ok) return d;
+  bool ok = true;
+  auto get = [&](const char* name, void** fn) {
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !*fn)
+      ok = false;
+  };
+  get("cuModuleLoadData", (void**)&d.ModuleLoadData);
+  get("cuModuleGetFunction", (void**)&d.ModuleGetFunction);
+  get("cuModuleUnload", (void**)&d.ModuleUnload);
+  get("cuFuncSetAttribute", (void**)&d.FuncSetAttribute);
+  get("cuLaunchKernel", (void**)&d.LaunchKernel);
+  cudaGetLastError();
+  d.ok = ok;
+  return d;
+}
+
+// One specialised kernel of a program: (launch index, words per thread, tile geometry).
+struct JitKernel {
+  int launch = -1, wpt = 0, G = 0, ipt = 0;
+  CUmodule mod = nullptr;
+  CUfunction fn = nullptr;
+  bool failed = false;
+};

@@ -1,7 +1,7 @@
 // Op-table structs shared by host (C-ABI) and device (level interpreter).
 // Field-for-field mirror of pyrddlgym_b200/optable.py -- keep the two in sync.
 #pragma once
-#include <stdint.h>
+#include "rddl_stdint.h"
 
 #define RDDL_MAGIC 0x31304C444452ll
 #define RDDL_VERSION 9

@@ -44,6 +44,23 @@ struct PlaneProg {
   uint32_t words[PLANE_WORDS];
 };
 
+// Two build modes of this file. Ahead of time (nvcc, rddl_vm.cu): the program arrives in the kernel
+// parameter bank and the op loop below is an interpreter. Specialised (PLANE_STATIC, compiled at
+// program-create time with NVRTC, see rddl_jit.h): "plane_static_data.inc" defines the PlaneProg,
+// the launch geometry and the tensor dtypes of ONE launch as constants (kG, kL, kDT, PS_*), the op
+// loop unrolls, every switch folds, table masks become LOP3 immediates and the plane registers
+// become machine registers.
+#ifdef PLANE_STATIC
+#include "plane_static_data.inc"
+#define PLANE_OUTLINE __forceinline__
+#define PLANE_UNROLL_DYN _Pragma("unroll")
+#define PLANE_LAUNCH(A) kL
+#else
+#define PLANE_OUTLINE __noinline__
+#define PLANE_UNROLL_DYN _Pragma("unroll 1")
+#define PLANE_LAUNCH(A) (A).L
+#endif
+
 // 32 bool bytes (each 0/1) -> 32-bit word, cell i -> bit i
 __device__ __forceinline__ uint32_t plane_pack(const uint4 lo, const uint4 hi) {
   const uint32_t M = 0x01020408u;
@@ -127,13 +144,17 @@ template <int WPT, int BLOCK>
 struct PlaneCtx {
   // virtual plane registers live in shared memory, [reg][word][thread]: conflict-free, never
   // evicted (a local-memory register file of this size thrashes L1 at 3 CTAs per SM)
-  uint32_t* P;
+#ifdef PLANE_STATIC
+  uint32_t R[PS_NREGS][WPT];   // every index is a compile-time constant after unrolling: registers
+  __device__ __forceinline__ uint32_t& at(int r, int j) { return R[r][j]; }
+#else
   __device__ __forceinline__ uint32_t& at(int r, int j) {
     // the register file starts at offset 0 of the dynamic shared memory; naming the extern array
     // here keeps the accesses in the shared address space (LDS/STS instead of generic LD/ST)
     extern __shared__ uint32_t plane_smem_base[];
     return plane_smem_base[(r * WPT + j) * BLOCK + threadIdx.x];
   }
+#endif
   int env[WPT];       // local env index (relative to the launch's first env)
   int wi[WPT];        // word index inside the env
   uint32_t valid;     // bit j: word j is inside the batch
@@ -143,7 +164,7 @@ __device__ __forceinline__ int plane_reg(uint32_t idx, int i) { return (idx >> (
 
 // Bernoulli(table[idx]) for the thread's WPT words; M index planes
 template <int M, bool HC, int WPT, int BLOCK>
-__device__ __noinline__ void plane_bernoulli(PlaneCtx<WPT, BLOCK>& C, const VmArgs& A, const PlaneProg& G,
+__device__ PLANE_OUTLINE void plane_bernoulli(PlaneCtx<WPT, BLOCK>& C, const VmArgs& A, const PlaneProg& G,
                                              const PlaneOp& o, uint32_t* queue, int* qn, uint32_t* fix,
                                              int64_t env0, uint32_t step) {
   const int TT = 1 << M;
@@ -158,7 +179,7 @@ __device__ __noinline__ void plane_bernoulli(PlaneCtx<WPT, BLOCK>& C, const VmAr
   const bool has_bad = (o.b & 1) != 0, has_always = (o.b & 2) != 0;
   if (inj) {
     // parity mode: the reference's U <= p on the same float64 values (simulator.py:1053)
-#pragma unroll 1
+    PLANE_UNROLL_DYN
     for (int j = 0; j < WPT; ++j) {
       uint32_t res = 0;
       if ((C.valid >> j) & 1u) {
@@ -166,7 +187,7 @@ __device__ __noinline__ void plane_bernoulli(PlaneCtx<WPT, BLOCK>& C, const VmAr
 #pragma unroll
         for (int i = 0; i < M; ++i) x[i] = C.at(plane_reg(o.idx, i), j);
         if (has_bad && plane_mux<M>(bad, x)) atomicOr(A.status + env0 + C.env[j], 1u);
-        const double* u = inj + (env0 + C.env[j]) * A.L.E + ((int64_t)C.wi[j] << 5);
+        const double* u = inj + (env0 + C.env[j]) * PLANE_LAUNCH(A).E + ((int64_t)C.wi[j] << 5);
         for (int b = 0; b < 32; ++b) {
           int v = 0;
 #pragma unroll
@@ -180,12 +201,12 @@ __device__ __noinline__ void plane_bernoulli(PlaneCtx<WPT, BLOCK>& C, const VmAr
     return;
   }
   const uint2 key = make_uint2((uint32_t)A.seed, (uint32_t)(A.seed >> 32));
-  const uint32_t node = (uint32_t)A.variates[o.a].node & 0xffffu;
+  const uint32_t node = ((uint32_t)o.b >> 8) & 0xffffu;   // Philox node id, placed here by the host decoder
   const uint32_t e0 = (uint32_t)(A.env_offset + env0);
   if (lane == 0) qn[warp] = 0;
   __syncwarp();
   // two words at a time: bounds the live registers (index planes, random words, res/und)
-#pragma unroll 1
+  PLANE_UNROLL_DYN
   for (int j0 = 0; j0 < WPT; j0 += 2) {
     constexpr int NW = WPT >= 2 ? 2 : 1;
     uint32_t x[NW][M > 0 ? M : 1], res[NW], und[NW];
@@ -257,13 +278,13 @@ __device__ __noinline__ void plane_bernoulli(PlaneCtx<WPT, BLOCK>& C, const VmAr
       // the owner's word coordinates, recomputed from the tile geometry
       const int ow = oj * BLOCK + warp * 32 + ol;
       int env_l, wi_l;
-      if (A.L.chunks == 1) {
-        const int wpe = (int)(A.L.E >> 5);
+      if (PLANE_LAUNCH(A).chunks == 1) {
+        const int wpe = (int)(PLANE_LAUNCH(A).E >> 5);
         env_l = G.wpe_shift >= 0 ? (ow >> G.wpe_shift) : ow / wpe;
         wi_l = ow - env_l * wpe;
       } else {
         env_l = 0;
-        wi_l = (blockIdx.x % A.L.chunks) * A.L.ipt + ow;
+        wi_l = (blockIdx.x % PLANE_LAUNCH(A).chunks) * PLANE_LAUNCH(A).ipt + ow;
       }
       const uint4 r4 = rddl_philox4x32_10(
           make_uint4(((uint32_t)wi_l << 5) | b, e0 + (uint32_t)env_l, step, node | (0xC000u << 16)), key);
@@ -297,9 +318,9 @@ __device__ __forceinline__ void plane_lut(PlaneCtx<WPT, BLOCK>& C, const PlanePr
 // Partial tiles (last CTA of the batch / of an env): per-word validity and 64-bit addressing.
 // Kept out of line so that their address arithmetic is not hoisted into the dispatch loop.
 template <int WPT, int BLOCK>
-__device__ __noinline__ void plane_ld_partial(PlaneCtx<WPT, BLOCK>& C, const uint8_t* base, int64_t env0, int wpe,
+__device__ PLANE_OUTLINE void plane_ld_partial(PlaneCtx<WPT, BLOCK>& C, const uint8_t* base, int64_t env0, int wpe,
                                               int dst) {
-#pragma unroll 1
+  PLANE_UNROLL_DYN
   for (int j = 0; j < WPT; ++j) {
     uint32_t word = 0;
     if ((C.valid >> j) & 1u) {
@@ -311,8 +332,8 @@ __device__ __noinline__ void plane_ld_partial(PlaneCtx<WPT, BLOCK>& C, const uin
 }
 
 template <int WPT, int BLOCK>
-__device__ __noinline__ void plane_st_partial(PlaneCtx<WPT, BLOCK>& C, uint8_t* base, int64_t env0, int wpe, int src) {
-#pragma unroll 1
+__device__ PLANE_OUTLINE void plane_st_partial(PlaneCtx<WPT, BLOCK>& C, uint8_t* base, int64_t env0, int wpe, int src) {
+  PLANE_UNROLL_DYN
   for (int j = 0; j < WPT; ++j) {
     if ((C.valid >> j) & 1u) {
       uint4 lo, hi;
@@ -336,91 +357,59 @@ __device__ __forceinline__ int plane_spos(int row, int c, int env_l, int pitch) 
   return (row + 1 + env_l) * pitch + c + 1;
 }
 
+// Per-tile state shared by the op handlers (all of it lives in registers after inlining).
 template <int WPT, int BLOCK>
-__global__ void __launch_bounds__(BLOCK, WPT == 1 ? 4 : PLANE_MIN_BLOCKS) rddl_plane_interp(const __grid_constant__ VmArgs A,
-                                                                          const __grid_constant__ PlaneProg G) {
-  const RddlLaunch& L = A.L;
-  const int tid = threadIdx.x;
-  const int H = L.rank == 2 ? (int)L.extent[0] : 1;
-  const int W32 = (int)((L.rank == 2 ? L.extent[1] : L.extent[0]) >> 5);
-  const int wpe = (int)(L.E >> 5);              // words per env
-  const int envs_per_tile = L.G, tile_words = L.ipt, chunks = L.chunks;
-  const int chunk = blockIdx.x % chunks;
-  const int64_t env0 = (int64_t)(blockIdx.x / chunks) * envs_per_tile;   // first env of this tile
-  const int pitch = W32 + 2;
-  const int tile_rows = tile_words / W32;
-
-  // dynamic shared memory: plane registers [nregs][WPT][256] | [nshared] padded stencil planes |
-  // cnt | queue | qn | fix
-  extern __shared__ uint32_t smem[];
-  const int plane_stride = (tile_rows + envs_per_tile + 2) * pitch;
-  uint32_t* S = smem + L.nregs * WPT * BLOCK;
-  int32_t* cnt = reinterpret_cast<int32_t*>(S + G.nshared * plane_stride);      // [32][MAX_RED]
-  uint32_t* queue = reinterpret_cast<uint32_t*>(cnt + 32 * RDDL_MAX_RED);        // [8][PLANE_QUEUE]
-  int* qn = reinterpret_cast<int*>(queue + 8 * PLANE_QUEUE);                     // [8]
-  uint32_t* fix = reinterpret_cast<uint32_t*>(qn + 8);                           // [256][WPT]
-  if (L.nred > 0)
-    for (int i = tid; i < 32 * RDDL_MAX_RED; i += BLOCK) cnt[i] = 0;
-  for (int i = tid; i < G.nshared * plane_stride; i += BLOCK) S[i] = 0u;           // zero padding, once
-
+struct PlaneTile {
   PlaneCtx<WPT, BLOCK> C;
-  C.P = smem;
-  C.valid = 0;
-  int spos[WPT];      // shared-memory index of the word inside a staged plane
-#pragma unroll
-  for (int j = 0; j < WPT; ++j) {
-    const int w = j * BLOCK + tid;
-    bool ok = w < tile_words;
-    if (chunks == 1) {
-      C.env[j] = G.wpe_shift >= 0 ? (w >> G.wpe_shift) : w / wpe;
-      C.wi[j] = w - C.env[j] * wpe;
-    } else {
-      C.env[j] = 0;
-      C.wi[j] = chunk * tile_words + w;
-      ok = ok && C.wi[j] < wpe;
-    }
-    if (ok && env0 + C.env[j] < A.n_envs) C.valid |= 1u << j;
-    const int row = G.w32_shift >= 0 ? (w >> G.w32_shift) : w / W32;        // row inside the tile
-    spos[j] = plane_spos(row, w - row * W32, C.env[j], pitch);
-  }
-  // whole tile inside the batch (the common case): no per-word validity handling below
-  const bool full = __syncthreads_and(C.valid == ((1u << WPT) - 1u)) != 0;
-  // byte offset of this thread's first word (word j is 256 words further), valid when `full`
-  const int64_t tile_byte0 = ((env0 * wpe + (int64_t)chunk * tile_words + tid) << 5);
-  if (full) {
-    // issue the DRAM requests of every plane this tile reads up front (L2 prefetch): the loads of
-    // the later PLD ops then hit L2 and the compute of this CTA overlaps its own memory traffic
-    for (int pc = 0; pc < G.nops; ++pc) {
-      if (G.ops[pc].op != OP_PLD || A.dtype[G.ops[pc].imm] == DT_PACKED) continue;
-      const uint8_t* p = reinterpret_cast<const uint8_t*>(A.tensors[G.ops[pc].imm]) + tile_byte0;
-#pragma unroll
-      for (int j = 0; j < WPT; ++j)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(p + (int64_t)j * (BLOCK * 32)));
-    }
-  }
-  const bool single_env = envs_per_tile == 1;
+  int spos[WPT];        // shared-memory index of the word inside a staged plane
+  uint32_t* S;          // staged stencil planes
+  int32_t* cnt;         // [32][MAX_RED] per-env popcounts
+  uint32_t* queue;      // [8][PLANE_QUEUE]
+  int* qn;              // [8]
+  uint32_t* fix;        // [256][WPT]
+  int64_t env0, tile_byte0;
+  int W32, wpe, envs_per_tile, tile_words, chunks, chunk, pitch, tile_rows, plane_stride;
+  bool full, single_env;
+};
 
-  // per-env rollout state of the thread that runs env (env0 + tid)'s scalar epilogue
-  double ret_acc = 0.0, disc = 1.0;
-  bool alive = true;
-  const int T = A.n_steps > 1 ? A.n_steps : 1;
-#pragma unroll 1
-  for (int t = 0; t < T; ++t) {
-  const bool last_step = t == T - 1;
-  if (full && !last_step) {
-    // next step's action planes: start their DRAM reads now (L2 prefetch)
-    for (int pc = 0; pc < G.nops; ++pc) {
-      const PlaneOp& q = G.ops[pc];
-      if (q.op != OP_PLD || q.a > 0 || A.tstride[q.imm] == 0) continue;
-      const uint8_t* p = reinterpret_cast<const uint8_t*>(A.tensors[q.imm]) + (t + 1) * A.tstride[q.imm] + tile_byte0;
+// What plane_exec does with an op: run it, or only start the DRAM reads of the planes it loads
+// (all PLD planes of this step / the action planes of the next step of a fused rollout).
+enum { PLANE_RUN = 0, PLANE_PREFETCH = 1, PLANE_PREFETCH_NEXT = 2 };
+
+// One op of the program for this thread's WPT words. Interpreter: `pc` is a run-time index into the
+// parameter-bank program. Specialised build: PC is a template constant and the op a constant
+// expression, so only the selected case survives.
+template <int WPT, int BLOCK, int MODE, int PC>
+__device__ __forceinline__ void plane_exec(PlaneTile<WPT, BLOCK>& T, const VmArgs& A, const PlaneProg& G,
+                                           const RddlLaunch& L, const uint8_t* DT, int pc, int t, bool last_step) {
+#ifdef PLANE_STATIC
+  constexpr PlaneOp o = kG.ops[PC];
+#else
+  const PlaneOp& o = G.ops[pc];
+#endif
+  PlaneCtx<WPT, BLOCK>& C = T.C;
+  const int tid = threadIdx.x;
+  const int64_t env0 = T.env0, tile_byte0 = T.tile_byte0;
+  const bool full = T.full;
+  if (MODE != PLANE_RUN) {
+    if (o.op != OP_PLD || DT[o.imm] == DT_PACKED) return;
+    if (MODE == PLANE_PREFETCH_NEXT && (o.a > 0 || A.tstride[o.imm] == 0)) return;
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(A.tensors[o.imm]) + tile_byte0 +
+                       (MODE == PLANE_PREFETCH_NEXT ? (t + 1) * A.tstride[o.imm] : 0);
 #pragma unroll
-      for (int j = 0; j < WPT; ++j)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(p + (int64_t)j * (BLOCK * 32)));
-    }
+    for (int j = 0; j < WPT; ++j)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p + (int64_t)j * (BLOCK * 32)));
+    return;
   }
-#pragma unroll 1
-  for (int pc = 0; pc < G.nops; ++pc) {
-    const PlaneOp& o = G.ops[pc];
+  const int W32 = T.W32, wpe = T.wpe, tile_words = T.tile_words, chunks = T.chunks, chunk = T.chunk;
+  const int pitch = T.pitch, tile_rows = T.tile_rows, plane_stride = T.plane_stride;
+  const bool single_env = T.single_env;
+  uint32_t* S = T.S;
+  int32_t* cnt = T.cnt;
+  uint32_t* queue = T.queue;
+  int* qn = T.qn;
+  uint32_t* fix = T.fix;
+  const int* spos = T.spos;
     switch (o.op) {
       case OP_PLD: {
         if (t > 0 && o.a > 0) {   // state fluent: carried over from the value stored last step
@@ -429,7 +418,7 @@ __global__ void __launch_bounds__(BLOCK, WPT == 1 ? 4 : PLANE_MIN_BLOCKS) rddl_p
           break;
         }
         const uint8_t* base = reinterpret_cast<const uint8_t*>(A.tensors[o.imm]) + t * A.tstride[o.imm];
-        if (A.dtype[o.imm] == DT_PACKED) {   // state kept bit-packed in HBM: one word per 32 cells
+        if (DT[o.imm] == DT_PACKED) {   // state kept bit-packed in HBM: one word per 32 cells
           const uint32_t* wp = reinterpret_cast<const uint32_t*>(base) + (tile_byte0 >> 5);
 #pragma unroll
           for (int j = 0; j < WPT; ++j)
@@ -464,7 +453,7 @@ __global__ void __launch_bounds__(BLOCK, WPT == 1 ? 4 : PLANE_MIN_BLOCKS) rddl_p
       case OP_PST: {
         if (!last_step && o.b) break;   // carried state: only the final step reaches HBM
         uint8_t* base = reinterpret_cast<uint8_t*>(A.tensors[o.imm]);
-        if (A.dtype[o.imm] == DT_PACKED) {
+        if (DT[o.imm] == DT_PACKED) {
           uint32_t* wp = reinterpret_cast<uint32_t*>(base) + (tile_byte0 >> 5);
 #pragma unroll
           for (int j = 0; j < WPT; ++j)
@@ -520,7 +509,7 @@ __global__ void __launch_bounds__(BLOCK, WPT == 1 ? 4 : PLANE_MIN_BLOCKS) rddl_p
             const int wsrc = top ? chunk * tile_words - W32 + c : (chunk + 1) * tile_words + c;
             uint32_t word = 0;
             if (wsrc >= 0 && wsrc < wpe && env0 < A.n_envs) {
-              if (A.dtype[o.imm] == DT_PACKED) {
+              if (DT[o.imm] == DT_PACKED) {
                 word = __ldg(reinterpret_cast<const uint32_t*>(base) + env0 * wpe + wsrc);
               } else {
                 const uint4* p = reinterpret_cast<const uint4*>(base + ((env0 * wpe + wsrc) << 5));
@@ -617,7 +606,97 @@ __global__ void __launch_bounds__(BLOCK, WPT == 1 ? 4 : PLANE_MIN_BLOCKS) rddl_p
       }
       default: break;
     }
+}
+
+// All ops in program order: a loop in the interpreter, a compile-time sequence when specialised.
+template <int WPT, int BLOCK, int MODE, int PC>
+__device__ __forceinline__ void plane_run_ops(PlaneTile<WPT, BLOCK>& T, const VmArgs& A, const PlaneProg& G,
+                                              const RddlLaunch& L, const uint8_t* DT, int t, bool last_step) {
+#ifdef PLANE_STATIC
+  if constexpr (PC < PS_NOPS) {
+    plane_exec<WPT, BLOCK, MODE, PC>(T, A, G, L, DT, PC, t, last_step);
+    plane_run_ops<WPT, BLOCK, MODE, PC + 1>(T, A, G, L, DT, t, last_step);
   }
+#else
+#pragma unroll 1
+  for (int pc = 0; pc < G.nops; ++pc) plane_exec<WPT, BLOCK, MODE, 0>(T, A, G, L, DT, pc, t, last_step);
+#endif
+}
+
+// One tile of one launch: all ops of the program (for all steps of a fused rollout) by one CTA.
+// G / L / DT are kernel parameters (interpreter) or the constants of the specialised build.
+template <int WPT, int BLOCK>
+__device__ __forceinline__ void plane_tile(const VmArgs& A, const PlaneProg& G, const RddlLaunch& L,
+                                           const uint8_t* DT) {
+  const int tid = threadIdx.x;
+  const int W32 = (int)((L.rank == 2 ? L.extent[1] : L.extent[0]) >> 5);
+  const int wpe = (int)(L.E >> 5);              // words per env
+  const int envs_per_tile = L.G, tile_words = L.ipt, chunks = L.chunks;
+  const int chunk = blockIdx.x % chunks;
+  const int64_t env0 = (int64_t)(blockIdx.x / chunks) * envs_per_tile;   // first env of this tile
+  const int pitch = W32 + 2;
+  const int tile_rows = tile_words / W32;
+
+  // dynamic shared memory: (interpreter only: plane registers [nregs][WPT][256]) |
+  // [nshared] padded stencil planes | cnt | queue | qn | fix
+  extern __shared__ uint32_t smem[];
+  const int plane_stride = (tile_rows + envs_per_tile + 2) * pitch;
+  PlaneTile<WPT, BLOCK> T;
+#ifdef PLANE_STATIC
+  T.S = smem;                               // plane registers are machine registers
+#else
+  T.S = smem + L.nregs * WPT * BLOCK;
+#endif
+  uint32_t* S = T.S;
+  int32_t* cnt = T.cnt = reinterpret_cast<int32_t*>(S + G.nshared * plane_stride);
+  T.queue = reinterpret_cast<uint32_t*>(cnt + 32 * RDDL_MAX_RED);
+  T.qn = reinterpret_cast<int*>(T.queue + 8 * PLANE_QUEUE);
+  T.fix = reinterpret_cast<uint32_t*>(T.qn + 8);
+  if (L.nred > 0)
+    for (int i = tid; i < 32 * RDDL_MAX_RED; i += BLOCK) cnt[i] = 0;
+  for (int i = tid; i < G.nshared * plane_stride; i += BLOCK) S[i] = 0u;           // zero padding, once
+
+  PlaneCtx<WPT, BLOCK>& C = T.C;
+  C.valid = 0;
+#pragma unroll
+  for (int j = 0; j < WPT; ++j) {
+    const int w = j * BLOCK + tid;
+    bool ok = w < tile_words;
+    if (chunks == 1) {
+      C.env[j] = G.wpe_shift >= 0 ? (w >> G.wpe_shift) : w / wpe;
+      C.wi[j] = w - C.env[j] * wpe;
+    } else {
+      C.env[j] = 0;
+      C.wi[j] = chunk * tile_words + w;
+      ok = ok && C.wi[j] < wpe;
+    }
+    if (ok && env0 + C.env[j] < A.n_envs) C.valid |= 1u << j;
+    const int row = G.w32_shift >= 0 ? (w >> G.w32_shift) : w / W32;        // row inside the tile
+    T.spos[j] = plane_spos(row, w - row * W32, C.env[j], pitch);
+  }
+  // whole tile inside the batch (the common case): no per-word validity handling below
+  const bool full = __syncthreads_and(C.valid == ((1u << WPT) - 1u)) != 0;
+  T.full = full;
+  T.env0 = env0;
+  // byte offset of this thread's first word (word j is 256 words further), valid when `full`
+  T.tile_byte0 = ((env0 * wpe + (int64_t)chunk * tile_words + tid) << 5);
+  T.W32 = W32; T.wpe = wpe; T.envs_per_tile = envs_per_tile; T.tile_words = tile_words; T.chunks = chunks;
+  T.chunk = chunk; T.pitch = pitch; T.tile_rows = tile_rows; T.plane_stride = plane_stride;
+  T.single_env = envs_per_tile == 1;
+  // issue the DRAM requests of every plane this tile reads up front (L2 prefetch): the loads of
+  // the later PLD ops then hit L2 and the compute of this CTA overlaps its own memory traffic
+  if (full) plane_run_ops<WPT, BLOCK, PLANE_PREFETCH, 0>(T, A, G, L, DT, 0, false);
+
+  // per-env rollout state of the thread that runs env (env0 + tid)'s scalar epilogue
+  double ret_acc = 0.0, disc = 1.0;
+  bool alive = true;
+  const int NT = A.n_steps > 1 ? A.n_steps : 1;
+#pragma unroll 1
+  for (int t = 0; t < NT; ++t) {
+  const bool last_step = t == NT - 1;
+  // next step's action planes: start their DRAM reads now (L2 prefetch)
+  if (full && !last_step) plane_run_ops<WPT, BLOCK, PLANE_PREFETCH_NEXT, 0>(T, A, G, L, DT, t, last_step);
+  plane_run_ops<WPT, BLOCK, PLANE_RUN, 0>(T, A, G, L, DT, t, last_step);
 
   if (L.nred > 0) {
     __syncthreads();
@@ -654,7 +733,7 @@ __global__ void __launch_bounds__(BLOCK, WPT == 1 ? 4 : PLANE_MIN_BLOCKS) rddl_p
       int32_t idx0[RDDL_MAX_IDX];
       uint64_t rv[RDDL_MAX_RED];
       for (int f = 0; f < G.nfused; ++f) vm_exec_element<40>(A, G.fused[f], ge, A.step + t, idx0, rv);
-      if (T > 1) {
+      if (NT > 1) {
         // BaseAgent.evaluate (pyRDDLGym/core/policy.py:100-117): total += reward * gamma^t until done
         const double rwd = __ldcg(reinterpret_cast<const double*>(A.tensors[G.pad]) + ge);
         if (A.rewards) A.rewards[(int64_t)t * A.n_envs + ge] = rwd;
@@ -665,5 +744,17 @@ __global__ void __launch_bounds__(BLOCK, WPT == 1 ? 4 : PLANE_MIN_BLOCKS) rddl_p
     }
   }
   }   // step loop
-  if (T > 1 && A.returns && tid < envs_per_tile && env0 + tid < A.n_envs) A.returns[env0 + tid] += ret_acc;
+  if (NT > 1 && A.returns && tid < envs_per_tile && env0 + tid < A.n_envs) A.returns[env0 + tid] += ret_acc;
 }
+
+#ifdef PLANE_STATIC
+extern "C" __global__ void __launch_bounds__(256, PS_MINB) rddl_plane_static(const __grid_constant__ VmArgs A) {
+  plane_tile<PS_WPT, 256>(A, kG, kL, kDT);
+}
+#else
+template <int WPT, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, WPT == 1 ? 4 : PLANE_MIN_BLOCKS) rddl_plane_interp(const __grid_constant__ VmArgs A,
+                                                                          const __grid_constant__ PlaneProg G) {
+  plane_tile<WPT, BLOCK>(A, G, A.L, A.dtype);
+}
+#endif

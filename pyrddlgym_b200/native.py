@@ -46,12 +46,47 @@ def load():
     lib.rddl_profile.restype = ctypes.c_int
     lib.rddl_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64), ctypes.c_int]
     lib.rddl_profile_read.restype = ctypes.c_int
+    lib.rddl_program_option.argtypes = [vp, ctypes.c_int, i64]
+    lib.rddl_program_option.restype = ctypes.c_int
+    lib.rddl_jit_error.argtypes = [vp]
+    lib.rddl_jit_error.restype = ctypes.c_char_p
+    lib.rddl_plane_precompile.argtypes = [ctypes.c_char_p, ctypes.c_size_t, i64]
+    lib.rddl_plane_precompile.restype = ctypes.c_int
+    lib.rddl_plane_source.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, i64, ctypes.c_char_p,
+                                      ctypes.c_size_t]
+    lib.rddl_plane_source.restype = i64
     _lib = lib
     return lib
 
 
 EXPORTS = ['rddl_program_create', 'rddl_program_destroy', 'rddl_last_error', 'rddl_program_info',
-           'rddl_step', 'rddl_check', 'rddl_rollout', 'rddl_profile', 'rddl_profile_read']
+           'rddl_step', 'rddl_check', 'rddl_rollout', 'rddl_profile', 'rddl_profile_read',
+           'rddl_program_option', 'rddl_jit_error', 'rddl_plane_precompile', 'rddl_plane_source']
+
+OPTION_SPECIALIZE = 0
+INFO_JIT_BUILT, INFO_JIT_FAILED, INFO_JIT_CACHE_HITS = 5, 6, 7
+
+
+def precompile(blob, n_envs):
+    """Compiles the specialised plane kernels of an op table for batches of ``n_envs`` into the on-disk
+    cubin cache (host only: NVRTC needs no device). Returns the number of kernels."""
+    lib = load()
+    blob = bytes(blob)
+    rc = lib.rddl_plane_precompile(blob, len(blob), int(n_envs))
+    if rc < 0:
+        raise NativeError('rddl_plane_precompile failed (%d): %s' % (rc, lib.rddl_last_error(None).decode()))
+    return rc
+
+
+def plane_source(blob, launch, n_envs):
+    """The generated constants ("plane_static_data.inc") of one plane launch, for inspection."""
+    lib = load()
+    blob = bytes(blob)
+    buf = ctypes.create_string_buffer(1 << 20)
+    rc = lib.rddl_plane_source(blob, len(blob), int(launch), int(n_envs), buf, len(buf))
+    if rc < 0:
+        raise NativeError('rddl_plane_source failed (%d): %s' % (rc, lib.rddl_last_error(None).decode()))
+    return buf.value.decode()
 
 
 class NativeProgram:
@@ -73,6 +108,12 @@ class NativeProgram:
 
     def info(self, what):
         return int(self.lib.rddl_program_info(self.handle, what))
+
+    def option(self, what, value):
+        self._check(self.lib.rddl_program_option(self.handle, int(what), int(value)), 'rddl_program_option')
+
+    def jit_error(self):
+        return self.lib.rddl_jit_error(self.handle).decode()
 
     def step(self, ptrs, injected, status_ptr, n_envs, env_offset, seed, step, stream):
         self._check(self.lib.rddl_step(self.handle, ptrs, injected, status_ptr, n_envs, env_offset,

@@ -50,7 +50,9 @@ class BatchedSimulator:
     """N independent environments of one compiled RDDL problem, stepped in lock-step."""
 
     def __init__(self, program, n_envs=1, device='cuda:0', seed=0, env_offset=0, optable=None,
-                 use_planes=True, use_contract=True, use_packed=True):
+                 use_planes=True, use_contract=True, use_packed=True, specialize=None):
+        """``specialize``: build run-time specialised plane kernels (NVRTC, csrc/rddl_jit.h) for this
+        program; None = the library default (on, unless RDDL_B200_JIT=0), False = interpreter kernels."""
         self.program = program
         self.n_envs = int(n_envs)
         self.device = torch.device(device)
@@ -62,6 +64,9 @@ class BatchedSimulator:
             program, use_planes=use_planes, use_contract=use_contract, use_packed=use_packed)
         index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self.native = native.NativeProgram(self.table.blob, index)
+        if specialize is not None:
+            self.native.option(native.OPTION_SPECIALIZE, 1 if specialize else 0)
+        self._jit_warned = False
         self.names = list(self.table.tensor_names)
         self.packed = set(self.table.packed)
         self.tid = self.table.tensor_id
@@ -108,6 +113,20 @@ class BatchedSimulator:
     @property
     def launches_issued(self):
         return self.native.info(4)
+
+    @property
+    def specialised_kernels(self):
+        """Number of run-time specialised plane kernels this program runs (0 = interpreter kernels only)."""
+        return self.native.info(native.INFO_JIT_BUILT)
+
+    def _jit_check(self):
+        # a failed specialisation is not an error (the interpreter kernel ran, same results) but it is
+        # several times slower: say so once
+        if not self._jit_warned and self.native.info(native.INFO_JIT_FAILED) > 0:
+            self._jit_warned = True
+            import warnings
+            warnings.warn('pyrddlgym_b200: plane kernel specialisation failed, running the interpreter kernel: '
+                          + self.native.jit_error()[:500], RuntimeWarning)
 
     # ------------------------------------------------------------------ reference API
     def reset(self):
@@ -188,6 +207,8 @@ class BatchedSimulator:
         self._refresh_ptrs()
         self.native.step(self._ptrs, self._inj if variates else None, ctypes.c_void_p(self.status.data_ptr()),
                          self.n_envs, self.env_offset, self.seed_value, self.step_count, self._stream())
+        if not self._jit_warned:
+            self._jit_check()
         for s, ns in self.program.next_state.items():
             self.t[s], self.t[ns] = self.t[ns], self.t[s]
         self.step_count += 1
@@ -225,6 +246,8 @@ class BatchedSimulator:
             self._ptrs, ctypes.c_void_p(self.status.data_ptr()), self.n_envs, self.env_offset, self.seed_value,
             self.step_count, int(n_steps), strides, gamma, ctypes.c_void_p(returns.data_ptr()),
             ctypes.c_void_p(rewards.data_ptr()) if rewards is not None else None, self._stream())
+        if not self._jit_warned:
+            self._jit_check()
         if swapped:
             for s, ns in self.program.next_state.items():
                 self.t[s], self.t[ns] = self.t[ns], self.t[s]
