@@ -3,13 +3,14 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload wildfire32]
     python bench.py --impl reference ...        # CPU port of the reference algorithm (oracle)
 
-A "step" is one batched transition (RDDLSimulator.step for every env) of BASELINE.json
-config[1]: Wildfire 32x32, 4096 envs per GPU, random-policy actions (i.i.d. Bernoulli(0.05)
-put-out / cut-out per cell). `value` is timed with the action planes already resident in HBM
-(a rotating pool larger than L2); `e2e` goes through the host-facing call with pinned host
-action buffers copied H2D and the new state + reward + done copied D2H every step.
-Multi-GPU (torchrun): env batch sharded, 4096 envs per rank (weak scaling), one NCCL
-all-reduce of the return statistics at the end of the timed rollout.
+A bench "step" is one pass of the hot path over one batch of BASELINE.json config[1]: one 100-step
+random-policy rollout (i.i.d. Bernoulli(0.05) put-out / cut-out per cell) of Wildfire 32x32 for 4096
+envs per GPU -- BaseAgent.evaluate's episode for the whole batch: reset, 100 transitions with
+discounted return accumulation, return statistics. `value` = env-steps/s with the action sequence
+already resident in HBM (839 MB per rollout, larger than L2); `e2e` goes through the host-facing
+call with the pinned host action sequence copied H2D and per-step rewards, returns and the final
+state copied D2H every rollout. Multi-GPU (torchrun): env batch sharded, 4096 envs per rank (weak
+scaling), one NCCL all-gather of five numbers per rank for the return statistics of each rollout.
 """
 import argparse
 import json
@@ -28,11 +29,13 @@ UNIT = 'env-steps/s'
 
 WORKLOADS = {
     # BASELINE.json configs: [1] wildfire32 (the default), [2] reservoir1000, [3] wildfire1024, [4] pair512
-    'wildfire32': dict(kind='wildfire', n=32, separable=False, envs=4096),
-    'wildfire32_sep': dict(kind='wildfire', n=32, separable=True, envs=4096),
-    'wildfire1024': dict(kind='wildfire', n=1024, separable=True, envs=256),
-    'reservoir1000': dict(kind='reservoir', n=1000, envs=4096),
-    'pair512': dict(kind='pair', n=512, envs=1024),
+    # rollout = env-steps per bench step (BASELINE config[1]: 100-step rollouts; shorter where the
+    # action sequence of a rollout would not fit comfortably in HBM)
+    'wildfire32': dict(kind='wildfire', n=32, separable=False, envs=4096, rollout=100),
+    'wildfire32_sep': dict(kind='wildfire', n=32, separable=True, envs=4096, rollout=100),
+    'wildfire1024': dict(kind='wildfire', n=1024, separable=True, envs=256, rollout=10),
+    'reservoir1000': dict(kind='reservoir', n=1000, envs=4096, rollout=20),
+    'pair512': dict(kind='pair', n=512, envs=1024, rollout=40),
 }
 
 
@@ -60,9 +63,19 @@ def algorithmic_bytes_per_env_step(name):
 # DRAM traffic of the dominant kernel per env-step, from `ncu --set full` captures
 # (dram__bytes_read.sum + dram__bytes_write.sum; profiles/r01_ncu_full_*.csv). None = not captured.
 MEASURED_TRAFFIC_BYTES_PER_ENV_STEP = {
-    'wildfire32': (176.496128e6 + 7.141888e6) / (20 * 4096),      # fused 20-step rollout, plane_c2_v6
-    'wildfire1024': (537.102592e6 + 223.248384e6) / 128,          # one step, plane_1024_v5
 }
+
+
+def layout_bytes_per_env_step(name, sim, steps_per_launch):
+    """Bytes one env-step must move with the HBM layout this backend actually uses: action planes as
+    the caller's bool bytes; bool state fluents the op table packs (OpTable.packed) as bits, and --
+    when a launch fuses several steps -- read/written once per launch, not per step."""
+    w = WORKLOADS[name]
+    if w['kind'] != 'wildfire':
+        return algorithmic_bytes_per_env_step(name)
+    cells = w['n'] * w['n']
+    state = 4 * cells * (0.125 if sim.packed else 1.0) / steps_per_launch     # 2 read + 2 written
+    return 2 * cells + state + 9
 
 
 def workload_label(name):
@@ -189,23 +202,29 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    name = args.workload
+    w = WORKLOADS[name]
     cores = os.cpu_count() or 1
     use = max(1, min(cores, 32))
-    per_step_envs = 4
+    per_step_envs, per_step_len = 4, 4
     t0 = time.perf_counter()
-    # warm-up + K timed "steps": each step = every core advancing per_step_envs envs once
-    v, sample = cpu_baseline(args.workload, cores=use, envs_per_core=per_step_envs,
-                             steps=max(1, args.steps))
+    # K timed "steps": each a bounded sample of the GPU arm's step (a rollout of the batch) -- every
+    # core advances per_step_envs envs by per_step_len transitions of the same workload
+    v, sample = cpu_baseline(name, cores=use, envs_per_core=per_step_envs, steps=max(1, args.steps) * per_step_len)
     wall = time.perf_counter() - t0
     if v is None:
         print(json.dumps({'impl': 'reference', 'unavailable': sample}))
         return
+    N, R = args.envs or w['envs'], args.rollout or w['rollout']
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': 1e3 * use * per_step_envs / v, 'higher_is_better': True, 'scaling': 'weak',
+        'ms_per_step': 1e3 * use * per_step_envs * per_step_len / v, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'u8/f64', 'data': 'synthetic',
-        'config': {'workload': args.workload, 'envs_per_step': use * per_step_envs, 'wall_s': round(wall, 2)},
+        'config': {'workload': f'{workload_label(name)}, {N} envs/GPU, {R}-step random-policy rollouts',
+                   'step': f'bounded sample of one rollout of the batch: {use} cores x {per_step_envs} envs x '
+                           f'{per_step_len} transitions = {use * per_step_envs * per_step_len} env-steps',
+                   'wall_s': round(wall, 2)},
         'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': use, 'kind': 'port', 'sample': sample},
         'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -220,7 +239,7 @@ def run_reference(args):
 def run_gpu(args):
     import torch
     import torch.distributed as dist
-    from pyrddlgym_b200 import workloads
+    from pyrddlgym_b200 import parallel, workloads
     from pyrddlgym_b200.simulator import BatchedSimulator
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -233,24 +252,20 @@ def run_gpu(args):
     name = args.workload
     w = WORKLOADS[name]
     n, N = w['n'], args.envs or w['envs']
+    R = args.rollout or w['rollout']                 # env-steps per rollout = per bench step
     p = workloads.load_program(make_spec(name))
     sim = BatchedSimulator(p, n_envs=N, device=dev, seed=42, env_offset=rank * N)
     K, W = args.steps, args.warmup
     gamma = float(p.discount)
     act_bytes = sum(N * int(np.prod(p.tensor_shape(a), dtype=np.int64)) * (1 if p.tensors[a].dtype == 'b' else 8)
-                    for a in p.names_of_kind('action'))       # action bytes per step
+                    for a in p.names_of_kind('action'))       # action bytes per env-step of the batch
     state_bytes = sum(N * int(np.prod(p.tensor_shape(a), dtype=np.int64)) * (1 if p.tensors[a].dtype == 'b' else 8)
                       for a in p.next_state)
 
-    # random-policy action sequence for the timed rollout, resident in HBM: [K, N, n, n] x 2
-    # planes (larger than the 126 MB L2 unless K is tiny); the warm-up uses its own sequence
+    # random-policy action sequence of one rollout, resident in HBM: [R, N, ...] per action fluent
+    # (larger than the 126 MB L2, so every rollout streams it from DRAM again)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
-
-    def draw(k):
-        return draw_actions(name, p, k, N, dev, g)
-
-    seq = draw(K)
-    warm = draw(max(W, 1))
+    seq = draw_actions(name, p, R, N, dev, g)
 
     def barrier():
         if world > 1:
@@ -259,62 +274,65 @@ def run_gpu(args):
 
     returns = torch.zeros(N, dtype=torch.float64, device=dev)
 
-    def reduce_stats():
-        # statistics of BaseAgent.evaluate (pyRDDLGym/core/policy.py:120-126) over all ranks:
-        # two NCCL all-reduces of a few scalars (pyrddlgym_b200/parallel.py)
-        from pyrddlgym_b200 import parallel
-        return parallel.reduce_return_stats(returns)
+    def episode():
+        # one bench step = BaseAgent.evaluate's episode for every env of the batch
+        # (pyRDDLGym/core/policy.py:85-126): reset, R transitions with discounted return
+        # accumulation, return statistics over all ranks (one NCCL all-gather of 5 numbers per rank)
+        sim.reset()
+        returns.zero_()
+        sim.rollout(seq, R, gamma=gamma, returns=returns)
+        return parallel.return_stats_async(returns)
 
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, period=0.002)
     if rank == 0:
         sampler.start()
     # bring the clocks up before the W warm-up steps (an idle GPU needs ~100 ms to boost)
     t_spin = time.perf_counter()
     while time.perf_counter() - t_spin < 0.3:
-        sim.rollout(warm, max(W, 1), gamma=gamma)
+        episode()
         torch.cuda.synchronize()
-    sim.reset()
-    sim.rollout(warm, max(W, 1), gamma=gamma, returns=returns)     # W untimed warm-up steps
-    reduce_stats()                                                 # (loads torch's reduction kernels)
-    returns.zero_()
+    for _ in range(max(W, 1)):                                     # W untimed warm-up steps
+        parallel.finish_return_stats(episode())
     barrier()
     l0 = sim.launches_issued
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     sampler.timed = True
     e0.record()
-    sim.rollout(seq, K, gamma=gamma, returns=returns)              # exactly K timed steps
-    stats = reduce_stats()
+    for _ in range(K):                                             # exactly K timed steps
+        gathered = episode()
+    stats = parallel.finish_return_stats(gathered)
     e1.record()
     barrier()
+    sampler.timed = False
     ms = e0.elapsed_time(e1)
-    launches = sim.launches_issued - l0
+    launches = (sim.launches_issued - l0) + K                      # + rddl_return_stats per episode
     tms = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms = float(tms.item())
-    value = world * N * K / (ms * 1e-3)
+    value = world * N * R * K / (ms * 1e-3)
 
-    # the same K steps through the per-step call (rddl_step per transition), for comparison
+    # one episode through the per-transition call (rddl_step per env-step), for comparison
     sim.reset()
-    for t in range(min(W, K)):
+    for t in range(min(3, R)):
         sim.step({k: v[t] for k, v in seq.items()})
+    sim.reset()
     barrier()
     e0.record()
-    for t in range(K):
+    for t in range(R):
         sim.step({k: v[t] for k, v in seq.items()})
     e1.record()
     barrier()
-    step_api_value = N * K / (e0.elapsed_time(e1) * 1e-3)
+    step_api_value = N * R / (e0.elapsed_time(e1) * 1e-3)
 
-    # dominant kernel: per-launch CUDA events on the launch stream (second pass, same inputs)
+    # dominant kernel: per-launch CUDA events on the launch stream (one more episode, same inputs)
     sim.reset()
     sim.native.profile(True)
-    sim.rollout(seq, K, gamma=gamma)
+    sim.rollout(seq, R, gamma=gamma)
     torch.cuda.synchronize()
     prof = sim.native.profile_read(sim.table.launches)
     sim.native.profile(False)
-    sampler.timed = False
     top = max(prof, key=lambda r: r['ms']) if prof else None
     peaks = {}
     try:
@@ -325,54 +343,61 @@ def run_gpu(args):
     peak_src = 'measured' if 'hbm_gbs' in peaks else 'fallback'
     roofline = None
     if top:
-        steps_per_launch = K / top['count']
+        steps_per_launch = R / top['count']
         abytes = algorithmic_bytes_per_env_step(name) * N * steps_per_launch
+        lbytes = layout_bytes_per_env_step(name, sim, steps_per_launch) * N * steps_per_launch
         per_launch_ms = top['ms'] / top['count']
         ach = abytes / (per_launch_ms * 1e-3) / 1e9
         roofline = {'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
                     'traffic': (MEASURED_TRAFFIC_BYTES_PER_ENV_STEP[name] * N * steps_per_launch
                                 if name in MEASURED_TRAFFIC_BYTES_PER_ENV_STEP else None),
-                    'peak_source': peak_src, 'kernel': top['name'],
-                    'kernel_us': per_launch_ms * 1e3, 'steps_per_launch': steps_per_launch,
-                    'kernel_share_of_step': top['ms'] / max(1e-9, sum(r['ms'] for r in prof)),
+                    'peak_source': peak_src,
+                    'kernel': ('rddl_plane_static (NVRTC-specialised build of rddl_plane_interp)'
+                               if top['name'] == 'rddl_plane_interp' and sim.specialised_kernels else top['name']),
+                    'kernel_us': per_launch_ms * 1e3, 'env_steps_per_launch': steps_per_launch,
+                    'kernel_share_of_rollout': top['ms'] / max(1e-9, sum(r['ms'] for r in prof)),
                     'algorithmic_bytes_per_launch': abytes,
-                    'note': 'algorithmic bytes per env-step as in SURVEY 8(d) (state + action reads, next-state writes, reward, done); '
-                            'a fused multi-step launch keeps the state planes on chip, so its DRAM '
-                            'traffic is below this figure'}
+                    'layout_bytes_per_launch': lbytes,
+                    'frac_layout': lbytes / (per_launch_ms * 1e-3) / 1e9 / peak,
+                    'note': 'achieved/frac use the algorithmic bytes per env-step of SURVEY 8(d) (byte-per-bool state + action '
+                            'reads, next-state writes, reward, done). This backend keeps bool state bit-packed in HBM and, '
+                            'in a fused multi-step launch, on chip, so it has to move fewer bytes than that: '
+                            'layout_bytes_per_launch / frac_layout are the same figures for the bytes its own layout needs'}
 
-    # end-to-end through the host-facing call: pinned host action sequence -> H2D, rollout,
-    # per-step rewards + returns + final state -> D2H
+    # end-to-end through the host-facing call, per episode: pinned host action sequence -> H2D,
+    # reset + rollout, per-step rewards + returns + final state -> D2H
     h_seq = {k: v.cpu().pin_memory() for k, v in seq.items()}
     d_seq = {k: torch.empty_like(v) for k, v in seq.items()}
     h_state = {s: torch.empty_like(sim.fluent(s), device='cpu').pin_memory() for s in sim.state_names}
-    h_rew = torch.empty((K, N), dtype=torch.float64).pin_memory()
+    h_rew = torch.empty((R, N), dtype=torch.float64).pin_memory()
     h_ret = torch.empty(N, dtype=torch.float64).pin_memory()
 
-    def e2e_rollout():
+    def e2e_episode():
         for k in d_seq:
             d_seq[k].copy_(h_seq[k], non_blocking=True)
-        ret, rew = sim.rollout(d_seq, K, gamma=gamma, keep_rewards=True)
+        sim.reset()
+        ret, rew = sim.rollout(d_seq, R, gamma=gamma, keep_rewards=True)
         for s in sim.state_names:
             h_state[s].copy_(sim.fluent(s), non_blocking=True)
         h_rew.copy_(rew, non_blocking=True)
         h_ret.copy_(ret, non_blocking=True)
         torch.cuda.current_stream().synchronize()      # the caller owns the results after the call
 
-    sim.reset()
-    e2e_rollout()
-    sim.reset()
+    Ke = max(1, min(K, args.e2e_steps))
+    e2e_episode()
     barrier()
     e0.record()
-    e2e_rollout()
+    for _ in range(Ke):
+        e2e_episode()
     e1.record()
     barrier()
     ms_e2e = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
-    e2e_value = world * N * K / (float(ms_e2e.item()) * 1e-3)
+    e2e_value = world * N * R * Ke / (float(ms_e2e.item()) * 1e-3)
     clocks = sampler.stop() if rank == 0 else None
-    h2d = act_bytes
-    d2h = (state_bytes + 8 * N) // K + 8 * N
+    h2d = act_bytes * R
+    d2h = state_bytes + 8 * N * R + 8 * N
 
     if rank == 0:
         cpu_v, cpu_sample = cpu_baseline(name, cores=1, envs_per_core=4, steps=16) if world == 1 else (None, None)
@@ -380,19 +405,21 @@ def run_gpu(args):
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
             'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'u8/f64', 'data': 'synthetic',
-            'config': {'workload': f'{workload_label(name)}, '
-                                   f'{N} envs/GPU, {K}-step random-policy rollout',
-                       'envs_per_gpu': N, 'global_envs': N * world, 'grid': n,
-                       'api': 'rddl_rollout (K steps per call); per-step rddl_step loop reported as step_api_value',
+            'config': {'workload': f'{workload_label(name)}, {N} envs/GPU, {R}-step random-policy rollouts',
+                       'step': f'one bench step = one {R}-step rollout of the {N}-env batch (reset, {R} transitions, '
+                               f'return statistics) = {N * R} env-steps per GPU',
+                       'envs_per_gpu': N, 'global_envs': N * world, 'grid': n, 'rollout_len': R,
+                       'api': 'rddl_rollout (R transitions per call); the per-transition rddl_step loop is step_api_value',
                        'step_api_value': step_api_value,
-                       'l2': f'inputs larger than L2: the action sequence read by the timed rollout is '
-                             f'{K * act_bytes / 1e6:.0f} MB (L2 = 126 MB); state tensors {state_bytes / 1e6:.1f} MB',
-                       'parallelism': f'env-shard x{world}, return statistics all-reduced (NCCL) once per rollout',
+                       'l2': f'inputs larger than L2: the action sequence every rollout reads is '
+                             f'{R * act_bytes / 1e6:.0f} MB (L2 = 126 MB); state tensors {state_bytes / 1e6:.1f} MB',
+                       'parallelism': f'env-shard x{world}, return statistics all-gathered (NCCL) once per rollout',
                        'launches': [l['kernel'] for l in sim.table.launches if l['plan'] == 0],
+                       'specialised_kernels': sim.specialised_kernels,
                        'return_stats': stats},
             'roofline': roofline,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                    'ms_per_step': float(ms_e2e.item()) / K},
+                    'ms_per_step': float(ms_e2e.item()) / Ke, 'steps': Ke},
             'gpu_launches': launches,
             'clocks': clocks,
         }
@@ -406,11 +433,13 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=100)
+    ap.add_argument('--steps', type=int, default=50, help='timed bench steps; one step = one rollout of the batch')
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='wildfire32', choices=sorted(WORKLOADS))
     ap.add_argument('--envs', type=int, default=0)
+    ap.add_argument('--rollout', type=int, default=0, help='env-steps per rollout (default: per workload)')
+    ap.add_argument('--e2e-steps', type=int, default=10, help='rollouts timed for the end-to-end figure (<= --steps)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

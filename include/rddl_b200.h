@@ -79,6 +79,12 @@ int rddl_rollout(rddl_program_t* prog, void* const* tensors, uint32_t* status, i
                  const int64_t* step_stride_bytes, double gamma, double* returns, double* rewards,
                  int32_t* state_in_next, void* cuda_stream);
 
+/* Replaces the statistics of BaseAgent.evaluate (pyRDDLGym/core/policy.py:120-126: np.mean / std / min
+ * / max of the per-episode returns) for this rank's shard: out5 = {sum, sum of squares, count, min,
+ * max} of returns f64[n] (device pointers), one deterministic block reduction. Ranks combine their
+ * five numbers with one NCCL all-gather (pyrddlgym_b200/parallel.py). */
+int rddl_return_stats(const double* returns, int64_t n, double* out5, void* cuda_stream);
+
 /* Run-time specialisation of the bit-plane kernels (no reference counterpart; the closest analogue
  * is the reference's JAX backend jit-compiling a model once, pyRDDLGym-jax, docs/jax.rst). On the
  * first run of a plane launch the library recompiles its kernel source for sm_100a with NVRTC, with

@@ -109,6 +109,288 @@ __device__ __forceinline__ uint64_t red_combine(int op, uint64_t a, uint64_t b) 
   }
 }
 
+// The constant / address-descriptor / reduction-slot pools a program executes from: device copies
+// of the op table (interpreter) or the constants of a specialised build.
+struct VmPools {
+  const uint64_t* consts;
+  const RddlAddr* addrs;
+  const RddlRedSlot* redslots;
+  const int64_t* red_off;
+};
+
+// One instruction (raw = its four 32-bit words) of the program of launch L for one (env, element):
+// idx[] holds the element's scope coordinates, r[] the virtual registers. `pc` is advanced by
+// control-flow ops (prog = the launch's instruction stream; null for straight-line specialised
+// programs, which contain none). cap (optional): values stored to tensors cap_tensor, cap_tensor + 1.
+template <int NREG>
+__device__ __forceinline__ void vm_exec_one(const VmArgs& A, const VmPools& P, const RddlLaunch& L, const int64_t env,
+                                            const uint64_t step, int32_t* idx, uint64_t* redval, uint64_t* r,
+                                            int32_t* jcur, int32_t* jend, const RddlInsn* prog, int& pc,
+                                            const uint4 raw, uint64_t* cap, const int cap_tensor) {
+  const uint32_t op = raw.x & 0xff;
+  const uint32_t dst = raw.x >> 16;
+  const uint32_t ra = raw.y & 0xffff, rb = raw.y >> 16;
+  const uint32_t rc = raw.z & 0xffff;
+  const uint32_t imm = raw.w;
+#define RA r[ra]
+#define RB r[rb]
+#define FA as_f(r[ra])
+#define FB as_f(r[rb])
+#define IA ((int64_t)r[ra])
+#define IB ((int64_t)r[rb])
+#define SETF(v) r[dst] = from_f(v)
+#define SETI(v) r[dst] = (uint64_t)(int64_t)(v)
+  switch (op) {
+    case OP_NOP: break;
+    case OP_CONST: r[dst] = P.consts[imm]; break;
+    case OP_AXIS: SETI(idx[ra]); break;
+    case OP_MOV: r[dst] = RA; break;
+    case OP_I2F: SETF((double)IA); break;
+    case OP_F2I: SETI(__double2ll_rz(FA)); break;
+    case OP_LOAD:
+    case OP_STORE:
+    case OP_RANDU:
+    case OP_RANDN:
+    case OP_RANDE:
+    case OP_RANDC: {
+      const RddlAddr* ad = P.addrs + imm;
+      int64_t off = ad->c0;
+      const int na = ad->naxis;
+      for (int i = 0; i < na; ++i) off += ad->coef[i] * (int64_t)idx[ad->axis[i]];
+      const int nr = ad->nreg;
+      for (int i = 0; i < nr; ++i) {
+        int64_t v = (int64_t)r[ad->reg[i]];
+        const int64_t ext = ad->rextent[i];
+        if (v < 0 || v >= ext) {
+          atomicOr(A.status + env, 8u);
+          v = v < 0 ? 0 : ext - 1;
+        }
+        off += v * ad->rstride[i];
+      }
+      const int t = ad->tensor;
+      if (op == OP_LOAD) {
+        off += env * ad->env_stride;
+        const void* base = A.tensors[t];
+        const int dt = A.dtype[t];
+        if (dt == DT_BOOL) r[dst] = reinterpret_cast<const uint8_t*>(base)[off] != 0;
+        else if (dt == DT_PACKED) r[dst] = (reinterpret_cast<const uint32_t*>(base)[off >> 5] >> (off & 31)) & 1u;
+        else r[dst] = reinterpret_cast<const uint64_t*>(base)[off];
+      } else if (op == OP_STORE) {
+        off += env * ad->env_stride;
+        void* base = A.tensors[t];
+        const int dt = A.dtype[t];
+        if (dt == DT_BOOL) reinterpret_cast<uint8_t*>(base)[off] = RA != 0;
+        else reinterpret_cast<uint64_t*>(base)[off] = RA;
+        if (cap && (t == cap_tensor || t == cap_tensor + 1)) cap[t - cap_tensor] = RA;
+      } else {
+        const int slot = (int)ra;
+        const double* inj = A.inj[slot];
+        double v;
+        if (inj) {
+          v = inj[env * ad->env_stride + off];
+        } else {
+          const uint32_t node = (uint32_t)A.variates[slot].node;
+          uint4 x = rddl_philox_draw(A.seed, (uint64_t)(A.env_offset + env), step, node, (uint64_t)off);
+          const double u = rddl_u53(x.x, x.y);
+          if (op == OP_RANDU) v = u;
+          else if (op == OP_RANDN) v = sqrt(-2.0 * log(1.0 - u)) * cos(2.0 * 3.141592653589793 * rddl_u53(x.z, x.w));
+          else if (op == OP_RANDE) v = -log1p(-u);
+          else v = tan(3.141592653589793 * (u - 0.5));
+        }
+        SETF(v);
+      }
+      break;
+    }
+    case OP_FADD: SETF(FA + FB); break;
+    case OP_FSUB: SETF(FA - FB); break;
+    case OP_FMUL: SETF(FA * FB); break;
+    case OP_FDIV: SETF(FA / FB); break;
+    case OP_FNEG: SETF(-FA); break;
+    case OP_FABS: SETF(fabs(FA)); break;
+    case OP_FMIN: SETF(np_fmin(FA, FB)); break;
+    case OP_FMAX: SETF(np_fmax(FA, FB)); break;
+    case OP_FPOW: SETF(pow(FA, FB)); break;
+    case OP_FMOD: {  // np.mod (sign of the divisor), simulator.py:117-118
+      const double a = FA, b = FB;
+      double m = fmod(a, b);
+      if (b != 0.0) {
+        if (m != 0.0) { if ((b < 0) != (m < 0)) m += b; }
+        else m = copysign(0.0, b);
+      }
+      SETF(m);
+      break;
+    }
+    case OP_FLOGB: SETF(log(FA) / log(FB)); break;
+    case OP_FHYPOT: SETF(hypot(FA, FB)); break;
+    case OP_COS: SETF(cos(FA)); break;
+    case OP_SIN: SETF(sin(FA)); break;
+    case OP_TAN: SETF(tan(FA)); break;
+    case OP_ACOS: SETF(acos(FA)); break;
+    case OP_ASIN: SETF(asin(FA)); break;
+    case OP_ATAN: SETF(atan(FA)); break;
+    case OP_COSH: SETF(cosh(FA)); break;
+    case OP_SINH: SETF(sinh(FA)); break;
+    case OP_TANH: SETF(tanh(FA)); break;
+    case OP_EXP: SETF(exp(FA)); break;
+    case OP_LN: SETF(log(FA)); break;
+    case OP_SQRT: SETF(sqrt(FA)); break;
+    case OP_EXPM1: SETF(expm1(FA)); break;
+    case OP_LOG1P: SETF(log1p(FA)); break;
+    case OP_LNGAMMA: SETF(rddl_lngamma(FA)); break;
+    case OP_GAMMA: SETF(exp(rddl_lngamma(FA))); break;
+    case OP_FSGN: { const double a = FA; SETI((a > 0) - (a < 0)); break; }
+    case OP_FROUND: SETI(__double2ll_rn(FA)); break;
+    case OP_FFLOOR: SETI(__double2ll_rd(FA)); break;
+    case OP_FCEIL: SETI(__double2ll_ru(FA)); break;
+    case OP_IADD: SETI(IA + IB); break;
+    case OP_ISUB: SETI(IA - IB); break;
+    case OP_IMUL: SETI(IA * IB); break;
+    case OP_INEG: SETI(-IA); break;
+    case OP_IABS: SETI(llabs(IA)); break;
+    case OP_IMIN: SETI(min((long long)IA, (long long)IB)); break;
+    case OP_IMAX: SETI(max((long long)IA, (long long)IB)); break;
+    case OP_IPOW: SETI(ipow64(IA, IB)); break;
+    case OP_IFLOORDIV: {
+      const int64_t a = IA, b = IB;
+      int64_t q = 0;
+      if (b != 0) { q = a / b; if ((a % b != 0) && ((a < 0) != (b < 0))) --q; }
+      SETI(q);
+      break;
+    }
+    case OP_IMOD: {
+      const int64_t a = IA, b = IB;
+      int64_t m = 0;
+      if (b != 0) { m = a % b; if (m != 0 && ((m < 0) != (b < 0))) m += b; }
+      SETI(m);
+      break;
+    }
+    case OP_ISGN: { const int64_t a = IA; SETI((a > 0) - (a < 0)); break; }
+    case OP_FLT: SETI(FA < FB); break;
+    case OP_FLE: SETI(FA <= FB); break;
+    case OP_FGT: SETI(FA > FB); break;
+    case OP_FGE: SETI(FA >= FB); break;
+    case OP_FEQ: SETI(FA == FB); break;
+    case OP_FNE: SETI(FA != FB); break;
+    case OP_ILT: SETI(IA < IB); break;
+    case OP_ILE: SETI(IA <= IB); break;
+    case OP_IGT: SETI(IA > IB); break;
+    case OP_IGE: SETI(IA >= IB); break;
+    case OP_IEQ: SETI(IA == IB); break;
+    case OP_INE: SETI(IA != IB); break;
+    case OP_AND: r[dst] = (RA & RB) & 1; break;
+    case OP_OR: r[dst] = (RA | RB) & 1; break;
+    case OP_XOR: r[dst] = (RA ^ RB) & 1; break;
+    case OP_NOT: r[dst] = RA == 0; break;
+    case OP_IMPLY: r[dst] = ((RA == 0) | RB) & 1; break;
+    case OP_SEL: r[dst] = RA ? RB : r[rc]; break;
+    case OP_LOOP:
+      idx[ra] = 0;
+      if (imm == 0) pc = (int)rb;
+      break;
+    case OP_ENDLOOP:
+      if ((uint32_t)(++idx[ra]) < imm) pc = (int)rb;
+      break;
+    case OP_CSRLOOP:
+    case OP_CSREND: {
+      const RddlCsr* cs = A.csrs + imm;
+      int32_t j;
+      if (op == OP_CSRLOOP) {
+        int64_t row = cs->row_c0;
+        for (int i = 0; i < cs->row_naxis; ++i) row += cs->row_coef[i] * (int64_t)idx[cs->row_axis[i]];
+        j = __ldg(A.pool + cs->rowptr_off + row);
+        jend[ra] = __ldg(A.pool + cs->rowptr_off + row + 1);
+        jcur[ra] = j;
+        if (j >= jend[ra]) { pc = (int)rb; break; }
+      } else {
+        j = ++jcur[ra];
+        if (j >= jend[ra]) break;
+        pc = (int)rb;
+      }
+      for (int c = 0; c < cs->ncols; ++c) idx[cs->slot[c]] = __ldg(A.pool + cs->col_off[c] + j);
+      break;
+    }
+    case OP_REDOUT: redval[rb] = red_combine(L.red_op[rb], redval[rb], RA); break;
+    case OP_REDIN: {
+      const RddlRedSlot s = P.redslots[imm];
+      const uint64_t* base = A.red + (P.red_off[imm] * A.n_envs + env * s.chunks);
+      uint64_t acc = __ldcg(base);
+      for (int c = 1; c < s.chunks; ++c) acc = red_combine(s.op, acc, __ldcg(base + c));
+      r[dst] = acc;
+      break;
+    }
+    case OP_STATUS:
+      if (RA) atomicOr(A.status + env, imm);
+      break;
+    case OP_SAMPLE: {
+      // rejection / search samplers: one private Philox stream per (env, step, node, element)
+      const RddlAddr* ad = P.addrs + imm;
+      int64_t off = ad->c0;
+      for (int i = 0; i < ad->naxis; ++i) off += ad->coef[i] * (int64_t)idx[ad->axis[i]];
+      const uint32_t node = (uint32_t)A.variates[rc].node;
+      r[dst] = rddl_sample((int)((raw.x >> 8) & 0xff), RA, RB, A.seed, (uint64_t)(A.env_offset + env), step,
+                           node, (uint64_t)off);
+      break;
+    }
+    case OP_SUMLOOP: {
+      // sum over one loop variable of t1 [* t2], t = plain tensor reads: native MAC loop.
+      // data word (next instruction): dst | a << 16 = extent or CSR id, imm = address of t2
+      const uint4 raw2 = __ldg(reinterpret_cast<const uint4*>(prog + pc));
+      ++pc;
+      const uint32_t arg = (raw2.x >> 16) | ((raw2.y & 0xffff) << 16);
+      const bool is_csr = rb & 1u, two = rb & 2u, flt = rb & 4u;
+      const int slot = (int)ra;
+      int64_t base[2], stride[2];
+      const void* ptr[2];
+      int dts[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const RddlAddr* ad = P.addrs + (k == 0 ? imm : raw2.w);
+        int64_t off = ad->c0 + env * ad->env_stride, st = 0;
+        for (int i = 0; i < ad->naxis; ++i) {
+          if (ad->axis[i] == slot) st = ad->coef[i];
+          else off += ad->coef[i] * (int64_t)idx[ad->axis[i]];
+        }
+        base[k] = off; stride[k] = st;
+        ptr[k] = A.tensors[ad->tensor];
+        dts[k] = A.dtype[ad->tensor];
+      }
+      int32_t j0 = 0, j1 = (int32_t)arg;
+      const int32_t* cols = nullptr;
+      if (is_csr) {
+        const RddlCsr* cs = A.csrs + arg;
+        int64_t row = cs->row_c0;
+        for (int i = 0; i < cs->row_naxis; ++i) row += cs->row_coef[i] * (int64_t)idx[cs->row_axis[i]];
+        j0 = __ldg(A.pool + cs->rowptr_off + row);
+        j1 = __ldg(A.pool + cs->rowptr_off + row + 1);
+        cols = A.pool + cs->col_off[0];
+      }
+      double facc = 0.0;
+      int64_t iacc = 0;
+      for (int32_t j = j0; j < j1; ++j) {
+        const int64_t k = is_csr ? (int64_t)__ldg(cols + j) : (int64_t)j;
+        double fv[2] = {1.0, 1.0};
+        int64_t iv[2] = {1, 1};
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          if (q == 1 && !two) break;
+          const int64_t o = base[q] + stride[q] * k;
+          if (dts[q] == DT_REAL) fv[q] = reinterpret_cast<const double*>(ptr[q])[o];
+          else {
+            iv[q] = dts[q] == DT_BOOL ? (int64_t)(reinterpret_cast<const uint8_t*>(ptr[q])[o] != 0)
+                                      : reinterpret_cast<const int64_t*>(ptr[q])[o];
+            fv[q] = (double)iv[q];
+          }
+        }
+        if (flt) facc = __dadd_rn(facc, two ? __dmul_rn(fv[0], fv[1]) : fv[0]);
+        else iacc += two ? iv[0] * iv[1] : iv[0];
+      }
+      r[dst] = flt ? from_f(facc) : (uint64_t)iacc;
+      break;
+    }
+    default: break;
+  }
+}
+
 // Interprets the program of launch L for one (env, element); idx[] holds the element's scope
 // coordinates. Shared by the scalar kernel below and by the plane kernel's fused epilogue.
 template <int NREG>
@@ -118,272 +400,11 @@ __device__ __noinline__ void vm_exec_element(const VmArgs& A, const RddlLaunch& 
   int32_t jcur[4], jend[4];
   const int npc = L.pc_end - L.pc_begin;
   const RddlInsn* prog = A.insns + L.pc_begin;
-  {
-    int pc = 0;
-    while (pc < npc) {
-      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(prog + pc));
-      const uint32_t op = raw.x & 0xff;
-      const uint32_t dst = raw.x >> 16;
-      const uint32_t ra = raw.y & 0xffff, rb = raw.y >> 16;
-      const uint32_t rc = raw.z & 0xffff;
-      const uint32_t imm = raw.w;
-      ++pc;
-#define RA r[ra]
-#define RB r[rb]
-#define FA as_f(r[ra])
-#define FB as_f(r[rb])
-#define IA ((int64_t)r[ra])
-#define IB ((int64_t)r[rb])
-#define SETF(v) r[dst] = from_f(v)
-#define SETI(v) r[dst] = (uint64_t)(int64_t)(v)
-      switch (op) {
-        case OP_NOP: break;
-        case OP_CONST: r[dst] = __ldg(A.consts + imm); break;
-        case OP_AXIS: SETI(idx[ra]); break;
-        case OP_MOV: r[dst] = RA; break;
-        case OP_I2F: SETF((double)IA); break;
-        case OP_F2I: SETI(__double2ll_rz(FA)); break;
-        case OP_LOAD:
-        case OP_STORE:
-        case OP_RANDU:
-        case OP_RANDN:
-        case OP_RANDE:
-        case OP_RANDC: {
-          const RddlAddr* ad = A.addrs + imm;
-          int64_t off = ad->c0;
-          const int na = ad->naxis;
-          for (int i = 0; i < na; ++i) off += ad->coef[i] * (int64_t)idx[ad->axis[i]];
-          const int nr = ad->nreg;
-          for (int i = 0; i < nr; ++i) {
-            int64_t v = (int64_t)r[ad->reg[i]];
-            const int64_t ext = ad->rextent[i];
-            if (v < 0 || v >= ext) {
-              atomicOr(A.status + env, 8u);
-              v = v < 0 ? 0 : ext - 1;
-            }
-            off += v * ad->rstride[i];
-          }
-          const int t = ad->tensor;
-          if (op == OP_LOAD) {
-            off += env * ad->env_stride;
-            const void* base = A.tensors[t];
-            const int dt = A.dtype[t];
-            if (dt == DT_BOOL) r[dst] = reinterpret_cast<const uint8_t*>(base)[off] != 0;
-            else if (dt == DT_PACKED) r[dst] = (reinterpret_cast<const uint32_t*>(base)[off >> 5] >> (off & 31)) & 1u;
-            else r[dst] = reinterpret_cast<const uint64_t*>(base)[off];
-          } else if (op == OP_STORE) {
-            off += env * ad->env_stride;
-            void* base = A.tensors[t];
-            const int dt = A.dtype[t];
-            if (dt == DT_BOOL) reinterpret_cast<uint8_t*>(base)[off] = RA != 0;
-            else reinterpret_cast<uint64_t*>(base)[off] = RA;
-          } else {
-            const int slot = (int)ra;
-            const double* inj = A.inj[slot];
-            double v;
-            if (inj) {
-              v = inj[env * ad->env_stride + off];
-            } else {
-              const uint32_t node = (uint32_t)A.variates[slot].node;
-              uint4 x = rddl_philox_draw(A.seed, (uint64_t)(A.env_offset + env), step, node, (uint64_t)off);
-              const double u = rddl_u53(x.x, x.y);
-              if (op == OP_RANDU) v = u;
-              else if (op == OP_RANDN) v = sqrt(-2.0 * log(1.0 - u)) * cos(2.0 * 3.141592653589793 * rddl_u53(x.z, x.w));
-              else if (op == OP_RANDE) v = -log1p(-u);
-              else v = tan(3.141592653589793 * (u - 0.5));
-            }
-            SETF(v);
-          }
-          break;
-        }
-        case OP_FADD: SETF(FA + FB); break;
-        case OP_FSUB: SETF(FA - FB); break;
-        case OP_FMUL: SETF(FA * FB); break;
-        case OP_FDIV: SETF(FA / FB); break;
-        case OP_FNEG: SETF(-FA); break;
-        case OP_FABS: SETF(fabs(FA)); break;
-        case OP_FMIN: SETF(np_fmin(FA, FB)); break;
-        case OP_FMAX: SETF(np_fmax(FA, FB)); break;
-        case OP_FPOW: SETF(pow(FA, FB)); break;
-        case OP_FMOD: {  // np.mod (sign of the divisor), simulator.py:117-118
-          const double a = FA, b = FB;
-          double m = fmod(a, b);
-          if (b != 0.0) {
-            if (m != 0.0) { if ((b < 0) != (m < 0)) m += b; }
-            else m = copysign(0.0, b);
-          }
-          SETF(m);
-          break;
-        }
-        case OP_FLOGB: SETF(log(FA) / log(FB)); break;
-        case OP_FHYPOT: SETF(hypot(FA, FB)); break;
-        case OP_COS: SETF(cos(FA)); break;
-        case OP_SIN: SETF(sin(FA)); break;
-        case OP_TAN: SETF(tan(FA)); break;
-        case OP_ACOS: SETF(acos(FA)); break;
-        case OP_ASIN: SETF(asin(FA)); break;
-        case OP_ATAN: SETF(atan(FA)); break;
-        case OP_COSH: SETF(cosh(FA)); break;
-        case OP_SINH: SETF(sinh(FA)); break;
-        case OP_TANH: SETF(tanh(FA)); break;
-        case OP_EXP: SETF(exp(FA)); break;
-        case OP_LN: SETF(log(FA)); break;
-        case OP_SQRT: SETF(sqrt(FA)); break;
-        case OP_EXPM1: SETF(expm1(FA)); break;
-        case OP_LOG1P: SETF(log1p(FA)); break;
-        case OP_LNGAMMA: SETF(rddl_lngamma(FA)); break;
-        case OP_GAMMA: SETF(exp(rddl_lngamma(FA))); break;
-        case OP_FSGN: { const double a = FA; SETI((a > 0) - (a < 0)); break; }
-        case OP_FROUND: SETI(__double2ll_rn(FA)); break;
-        case OP_FFLOOR: SETI(__double2ll_rd(FA)); break;
-        case OP_FCEIL: SETI(__double2ll_ru(FA)); break;
-        case OP_IADD: SETI(IA + IB); break;
-        case OP_ISUB: SETI(IA - IB); break;
-        case OP_IMUL: SETI(IA * IB); break;
-        case OP_INEG: SETI(-IA); break;
-        case OP_IABS: SETI(llabs(IA)); break;
-        case OP_IMIN: SETI(min((long long)IA, (long long)IB)); break;
-        case OP_IMAX: SETI(max((long long)IA, (long long)IB)); break;
-        case OP_IPOW: SETI(ipow64(IA, IB)); break;
-        case OP_IFLOORDIV: {
-          const int64_t a = IA, b = IB;
-          int64_t q = 0;
-          if (b != 0) { q = a / b; if ((a % b != 0) && ((a < 0) != (b < 0))) --q; }
-          SETI(q);
-          break;
-        }
-        case OP_IMOD: {
-          const int64_t a = IA, b = IB;
-          int64_t m = 0;
-          if (b != 0) { m = a % b; if (m != 0 && ((m < 0) != (b < 0))) m += b; }
-          SETI(m);
-          break;
-        }
-        case OP_ISGN: { const int64_t a = IA; SETI((a > 0) - (a < 0)); break; }
-        case OP_FLT: SETI(FA < FB); break;
-        case OP_FLE: SETI(FA <= FB); break;
-        case OP_FGT: SETI(FA > FB); break;
-        case OP_FGE: SETI(FA >= FB); break;
-        case OP_FEQ: SETI(FA == FB); break;
-        case OP_FNE: SETI(FA != FB); break;
-        case OP_ILT: SETI(IA < IB); break;
-        case OP_ILE: SETI(IA <= IB); break;
-        case OP_IGT: SETI(IA > IB); break;
-        case OP_IGE: SETI(IA >= IB); break;
-        case OP_IEQ: SETI(IA == IB); break;
-        case OP_INE: SETI(IA != IB); break;
-        case OP_AND: r[dst] = (RA & RB) & 1; break;
-        case OP_OR: r[dst] = (RA | RB) & 1; break;
-        case OP_XOR: r[dst] = (RA ^ RB) & 1; break;
-        case OP_NOT: r[dst] = RA == 0; break;
-        case OP_IMPLY: r[dst] = ((RA == 0) | RB) & 1; break;
-        case OP_SEL: r[dst] = RA ? RB : r[rc]; break;
-        case OP_LOOP:
-          idx[ra] = 0;
-          if (imm == 0) pc = (int)rb;
-          break;
-        case OP_ENDLOOP:
-          if ((uint32_t)(++idx[ra]) < imm) pc = (int)rb;
-          break;
-        case OP_CSRLOOP:
-        case OP_CSREND: {
-          const RddlCsr* cs = A.csrs + imm;
-          int32_t j;
-          if (op == OP_CSRLOOP) {
-            int64_t row = cs->row_c0;
-            for (int i = 0; i < cs->row_naxis; ++i) row += cs->row_coef[i] * (int64_t)idx[cs->row_axis[i]];
-            j = __ldg(A.pool + cs->rowptr_off + row);
-            jend[ra] = __ldg(A.pool + cs->rowptr_off + row + 1);
-            jcur[ra] = j;
-            if (j >= jend[ra]) { pc = (int)rb; break; }
-          } else {
-            j = ++jcur[ra];
-            if (j >= jend[ra]) break;
-            pc = (int)rb;
-          }
-          for (int c = 0; c < cs->ncols; ++c) idx[cs->slot[c]] = __ldg(A.pool + cs->col_off[c] + j);
-          break;
-        }
-        case OP_REDOUT: redval[rb] = red_combine(L.red_op[rb], redval[rb], RA); break;
-        case OP_REDIN: {
-          const RddlRedSlot s = A.redslots[imm];
-          const uint64_t* base = A.red + (A.red_off[imm] * A.n_envs + env * s.chunks);
-          uint64_t acc = __ldcg(base);
-          for (int c = 1; c < s.chunks; ++c) acc = red_combine(s.op, acc, __ldcg(base + c));
-          r[dst] = acc;
-          break;
-        }
-        case OP_STATUS:
-          if (RA) atomicOr(A.status + env, imm);
-          break;
-        case OP_SAMPLE: {
-          // rejection / search samplers: one private Philox stream per (env, step, node, element)
-          const RddlAddr* ad = A.addrs + imm;
-          int64_t off = ad->c0;
-          for (int i = 0; i < ad->naxis; ++i) off += ad->coef[i] * (int64_t)idx[ad->axis[i]];
-          const uint32_t node = (uint32_t)A.variates[rc].node;
-          r[dst] = rddl_sample((int)((raw.x >> 8) & 0xff), RA, RB, A.seed, (uint64_t)(A.env_offset + env), step,
-                               node, (uint64_t)off);
-          break;
-        }
-        case OP_SUMLOOP: {
-          // sum over one loop variable of t1 [* t2], t = plain tensor reads: native MAC loop.
-          // data word (next instruction): dst | a << 16 = extent or CSR id, imm = address of t2
-          const uint4 raw2 = __ldg(reinterpret_cast<const uint4*>(prog + pc));
-          ++pc;
-          const uint32_t arg = (raw2.x >> 16) | ((raw2.y & 0xffff) << 16);
-          const bool is_csr = rb & 1u, two = rb & 2u, flt = rb & 4u;
-          const int slot = (int)ra;
-          int64_t base[2], stride[2];
-          const void* ptr[2];
-          int dts[2];
-#pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            const RddlAddr* ad = A.addrs + (k == 0 ? imm : raw2.w);
-            int64_t off = ad->c0 + env * ad->env_stride, st = 0;
-            for (int i = 0; i < ad->naxis; ++i) {
-              if (ad->axis[i] == slot) st = ad->coef[i];
-              else off += ad->coef[i] * (int64_t)idx[ad->axis[i]];
-            }
-            base[k] = off; stride[k] = st;
-            ptr[k] = A.tensors[ad->tensor];
-            dts[k] = A.dtype[ad->tensor];
-          }
-          int32_t j0 = 0, j1 = (int32_t)arg;
-          const int32_t* cols = nullptr;
-          if (is_csr) {
-            const RddlCsr* cs = A.csrs + arg;
-            int64_t row = cs->row_c0;
-            for (int i = 0; i < cs->row_naxis; ++i) row += cs->row_coef[i] * (int64_t)idx[cs->row_axis[i]];
-            j0 = __ldg(A.pool + cs->rowptr_off + row);
-            j1 = __ldg(A.pool + cs->rowptr_off + row + 1);
-            cols = A.pool + cs->col_off[0];
-          }
-          double facc = 0.0;
-          int64_t iacc = 0;
-          for (int32_t j = j0; j < j1; ++j) {
-            const int64_t k = is_csr ? (int64_t)__ldg(cols + j) : (int64_t)j;
-            double fv[2] = {1.0, 1.0};
-            int64_t iv[2] = {1, 1};
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              if (q == 1 && !two) break;
-              const int64_t o = base[q] + stride[q] * k;
-              if (dts[q] == DT_REAL) fv[q] = reinterpret_cast<const double*>(ptr[q])[o];
-              else {
-                iv[q] = dts[q] == DT_BOOL ? (int64_t)(reinterpret_cast<const uint8_t*>(ptr[q])[o] != 0)
-                                          : reinterpret_cast<const int64_t*>(ptr[q])[o];
-                fv[q] = (double)iv[q];
-              }
-            }
-            if (flt) facc = __dadd_rn(facc, two ? __dmul_rn(fv[0], fv[1]) : fv[0]);
-            else iacc += two ? iv[0] * iv[1] : iv[0];
-          }
-          r[dst] = flt ? from_f(facc) : (uint64_t)iacc;
-          break;
-        }
-        default: break;
-      }
-    }
+  const VmPools P = {A.consts, A.addrs, A.redslots, A.red_off};
+  int pc = 0;
+  while (pc < npc) {
+    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(prog + pc));
+    ++pc;
+    vm_exec_one<NREG>(A, P, L, env, step, idx, redval, r, jcur, jend, prog, pc, raw, nullptr, 0);
   }
 }

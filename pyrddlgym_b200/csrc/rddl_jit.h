@@ -45,9 +45,75 @@ static void jit_launch_init(std::string& s, const RddlLaunch& L) {
 }
 
 // The constants of one (plane launch, words per thread) pair, as C++ source.
+// Host copies of the op-table pools the fused scalar epilogue of a plane launch executes from.
+struct JitPools {
+  const RddlInsn* insns; int64_t n_insns;
+  const uint64_t* consts; int64_t n_consts;
+  const RddlAddr* addrs; int64_t n_addrs;
+  const RddlRedSlot* redslots; int64_t n_redslots;
+  const int64_t* red_off;
+};
+
+// The scalar programs fused into a plane launch's epilogue (reward / termination from the
+// reductions) as constants: instruction words, const pool, address descriptors, reduction slots.
+// Only straight-line programs qualify (no loop ops); otherwise the epilogue calls the interpreter.
+static bool jit_fused_static(const PlaneProg& G, const JitPools& P, std::string& s) {
+  if (G.nfused <= 0 || P.n_consts > 4096 || P.n_addrs > 512 || P.n_redslots > 64) return false;
+  int lo = 1 << 30, hi = 0;
+  for (int f = 0; f < G.nfused; ++f) {
+    const RddlLaunch& F = G.fused[f];
+    if (F.rank != 0 || F.nred != 0 || F.pc_end - F.pc_begin > 256) return false;
+    for (int pc = F.pc_begin; pc < F.pc_end; ++pc) {
+      const int op = P.insns[pc].op;
+      if (op == OP_LOOP || op == OP_ENDLOOP || op == OP_CSRLOOP || op == OP_CSREND || op == OP_SUMLOOP ||
+          op == OP_REDOUT || op == OP_AXIS)
+        return false;
+    }
+    if (F.pc_begin < lo) lo = F.pc_begin;
+    if (F.pc_end > hi) hi = F.pc_end;
+  }
+  if (hi - lo > 512) return false;
+  s += jit_fmt("#define PS_INSN_BASE %lld\n", lo);
+  s += "__device__ constexpr uint32_t kInsnWords[][4] = {";
+  for (int pc = lo; pc < hi; ++pc) {
+    uint32_t w[4];
+    memcpy(w, &P.insns[pc], 16);
+    s += "{" + jit_fmt("0x%llxu,", w[0]) + jit_fmt("0x%llxu,", w[1]) + jit_fmt("0x%llxu,", w[2]) + jit_fmt("0x%llxu},", w[3]);
+  }
+  s += "};\n__device__ constexpr uint64_t kConsts[] = {";
+  for (int64_t i = 0; i < P.n_consts; ++i) s += jit_fmt("0x%llxull,", (long long)P.consts[i]);
+  s += "0};\n__device__ constexpr RddlAddr kAddrs[] = {";
+  for (int64_t i = 0; i < P.n_addrs; ++i) {
+    const RddlAddr& a = P.addrs[i];
+    s += "{" + jit_fmt("%lld,", a.tensor) + jit_fmt("%lld,", a.naxis) + jit_fmt("%lldll,", (long long)a.env_stride) +
+         jit_fmt("%lldll,{", (long long)a.c0);
+    for (int k = 0; k < 8; ++k) s += jit_fmt("%lld,", a.axis[k]);
+    s += "},{";
+    for (int k = 0; k < 8; ++k) s += jit_fmt("%lldll,", (long long)a.coef[k]);
+    s += "}," + jit_fmt("%lld,", a.nreg) + jit_fmt("%lld,{", a.pad);
+    for (int k = 0; k < 4; ++k) s += jit_fmt("%lld,", a.reg[k]);
+    s += "},{";
+    for (int k = 0; k < 4; ++k) s += jit_fmt("%lldll,", (long long)a.rstride[k]);
+    s += "},{";
+    for (int k = 0; k < 4; ++k) s += jit_fmt("%lldll,", (long long)a.rextent[k]);
+    s += "}},\n";
+  }
+  s += "{}};\n__device__ constexpr RddlRedSlot kRedSlots[] = {";
+  for (int64_t i = 0; i < P.n_redslots; ++i) s += "{" + jit_fmt("%lld,", P.redslots[i].op) + jit_fmt("%lld},", P.redslots[i].chunks);
+  s += "{}};\n__device__ constexpr int64_t kRedOff[] = {";
+  for (int64_t i = 0; i < P.n_redslots; ++i) s += jit_fmt("%lldll,", (long long)P.red_off[i]);
+  s += "0};\n";
+  return true;
+}
+
 static std::string plane_static_data(const PlaneProg& G, const RddlLaunch& L, const uint8_t* dtype, int wpt,
-                                     int min_blocks) {
+                                     int min_blocks, const JitPools& P) {
   std::string s;
+  {
+    std::string f;
+    if (jit_fused_static(G, P, f)) s += "#define PS_FUSED_STATIC 1\n" + f;
+    else s += "#define PS_FUSED_STATIC 0\n";
+  }
   s += jit_fmt("#define PS_WPT %lld\n", wpt) + jit_fmt("#define PS_NREGS %lld\n", L.nregs > 0 ? L.nregs : 1) +
        jit_fmt("#define PS_NOPS %lld\n", G.nops) + jit_fmt("#define PS_MINB %lld\n", min_blocks);
   s += "__device__ constexpr PlaneProg kG = {" + jit_fmt("%lld,", G.nops) + jit_fmt("%lld,", G.nshared) +

@@ -55,6 +55,22 @@ struct PlaneProg {
 #define PLANE_OUTLINE __forceinline__
 #define PLANE_UNROLL_DYN _Pragma("unroll")
 #define PLANE_LAUNCH(A) kL
+#if PS_FUSED_STATIC
+// The fused scalar programs as a compile-time instruction sequence: every operand field is a
+// constant, the register file r[] becomes machine registers, loads of the pools fold.
+template <int PC, int END>
+__device__ __forceinline__ void vm_exec_static(const VmArgs& A, const VmPools& P, const RddlLaunch& L, const int64_t env,
+                                               const uint64_t step, int32_t* idx, uint64_t* redval, uint64_t* r,
+                                               uint64_t* cap, const int cap_tensor) {
+  if constexpr (PC < END) {
+    constexpr uint4 raw = {kInsnWords[PC - PS_INSN_BASE][0], kInsnWords[PC - PS_INSN_BASE][1],
+                           kInsnWords[PC - PS_INSN_BASE][2], kInsnWords[PC - PS_INSN_BASE][3]};
+    int pc = 0;
+    vm_exec_one<40>(A, P, L, env, step, idx, redval, r, nullptr, nullptr, nullptr, pc, raw, cap, cap_tensor);
+    vm_exec_static<PC + 1, END>(A, P, L, env, step, idx, redval, r, cap, cap_tensor);
+  }
+}
+#endif
 #else
 #define PLANE_OUTLINE __noinline__
 #define PLANE_UNROLL_DYN _Pragma("unroll 1")
@@ -732,14 +748,32 @@ __device__ __forceinline__ void plane_tile(const VmArgs& A, const PlaneProg& G, 
       const int64_t ge = env0 + tid;
       int32_t idx0[RDDL_MAX_IDX];
       uint64_t rv[RDDL_MAX_RED];
+#if defined(PLANE_STATIC) && PS_FUSED_STATIC
+      // specialised epilogue: straight-line code, reward / done taken from the stores themselves
+      uint64_t cap[2] = {0, 0};
+      const VmPools P = {kConsts, kAddrs, kRedSlots, kRedOff};
+      {
+        uint64_t r0[40];
+        vm_exec_static<kG.fused[0].pc_begin, kG.fused[0].pc_end>(A, P, kG.fused[0], ge, A.step + t, idx0, rv, r0, cap, G.pad);
+      }
+      if constexpr (kG.nfused > 1) {
+        uint64_t r1[40];
+        vm_exec_static<kG.fused[1].pc_begin, kG.fused[1].pc_end>(A, P, kG.fused[1], ge, A.step + t, idx0, rv, r1, cap, G.pad);
+      }
+      if (NT > 1) {
+        const double rwd = as_f(cap[0]);
+        const bool done_now = cap[1] != 0;
+#else
       for (int f = 0; f < G.nfused; ++f) vm_exec_element<40>(A, G.fused[f], ge, A.step + t, idx0, rv);
       if (NT > 1) {
         // BaseAgent.evaluate (pyRDDLGym/core/policy.py:100-117): total += reward * gamma^t until done
         const double rwd = __ldcg(reinterpret_cast<const double*>(A.tensors[G.pad]) + ge);
+        const bool done_now = __ldcg(reinterpret_cast<const uint8_t*>(A.tensors[G.pad + 1]) + ge) != 0;
+#endif
         if (A.rewards) A.rewards[(int64_t)t * A.n_envs + ge] = rwd;
         if (alive) ret_acc += rwd * disc;
         disc *= A.gamma;
-        if (__ldcg(reinterpret_cast<const uint8_t*>(A.tensors[G.pad + 1]) + ge)) alive = false;
+        if (done_now) alive = false;
       }
     }
   }

@@ -124,10 +124,28 @@ struct rddl_program {
   int64_t alive_capacity = 0;
   // run-time specialised plane kernels (rddl_jit.h), built on first use per (launch, tile geometry)
   bool specialize = true;
+  std::vector<RddlInsn> h_insns;          // host copies for the specialised epilogue (rddl_jit.h)
+  std::vector<uint64_t> h_consts;
+  std::vector<RddlAddr> h_addrs;
+  JitPools pools() const {
+    return JitPools{h_insns.data(), (int64_t)h_insns.size(), h_consts.data(), (int64_t)h_consts.size(),
+                    h_addrs.data(), (int64_t)h_addrs.size(), redslots.data(), (int64_t)redslots.size(), red_off.data()};
+  }
   std::vector<JitKernel> jit;
   int64_t jit_built = 0, jit_cache_hits = 0, jit_failed = 0;
   std::string jit_err;
 };
+
+// Resident CTAs per SM the specialised kernel is compiled for (its register budget): the plane
+// registers are machine registers there, and programs of Wildfire's size fit 3 CTAs x 256 threads
+// (<= 85 registers) without spilling. RDDL_PLANE_MINB overrides (tuning knob).
+static int plane_static_min_blocks(int wpt) {
+  if (const char* e = getenv("RDDL_PLANE_MINB")) {
+    const int v = atoi(e);
+    if (v >= 1 && v <= 8) return v;
+  }
+  return wpt == 1 ? 4 : PLANE_MIN_BLOCKS;
+}
 
 // The specialised kernel of plane launch `li` for the tile geometry `adj` / wpt, or nullptr (then the
 // interpreter kernel runs): compiled with NVRTC on first use, cubins cached on disk.
@@ -139,7 +157,7 @@ static JitKernel* jit_get(rddl_program* g, int li, int wpt, const RddlLaunch& ad
   k.launch = li; k.wpt = wpt; k.G = adj.G; k.ipt = adj.ipt;
   uint8_t dt[RDDL_MAX_TENSORS] = {0};
   for (size_t i = 0; i < g->tensors.size(); ++i) dt[i] = (uint8_t)g->tensors[i].dtype;
-  const std::string data = plane_static_data(g->plane_progs[li], adj, dt, wpt, wpt == 1 ? 4 : PLANE_MIN_BLOCKS);
+  const std::string data = plane_static_data(g->plane_progs[li], adj, dt, wpt, plane_static_min_blocks(wpt), g->pools());
   std::string cubin, err;
   bool hit = false;
   JitDriver& drv = jit_driver();
@@ -298,6 +316,9 @@ static int parse_program(const void* optable, size_t nbytes, int device, rddl_pr
   g->redslots.assign((const RddlRedSlot*)sec[7], (const RddlRedSlot*)sec[7] + hdr[9]);
   g->variates.assign((const RddlVariate*)sec[8], (const RddlVariate*)sec[8] + hdr[10]);
   g->n_insns = hdr[4];
+  g->h_insns.assign((const RddlInsn*)sec[2], (const RddlInsn*)sec[2] + hdr[4]);
+  g->h_consts.assign((const uint64_t*)sec[3], (const uint64_t*)sec[3] + hdr[5]);
+  g->h_addrs.assign((const RddlAddr*)sec[4], (const RddlAddr*)sec[4] + hdr[6]);
   g->plane_progs.resize(g->launches.size());
   const int reward_tensor = (int)g->tensors.size() - 3;   // specials: __reward, __done, __chk
   for (size_t i = 0; i < g->launches.size(); ++i) {
@@ -414,7 +435,7 @@ extern "C" int64_t rddl_plane_source(const void* optable, size_t nbytes, int lau
   const int wpt = plane_geometry(g->launches[launch], n_envs, &adj);
   uint8_t dt[RDDL_MAX_TENSORS] = {0};
   for (size_t i = 0; i < g->tensors.size(); ++i) dt[i] = (uint8_t)g->tensors[i].dtype;
-  const std::string s = plane_static_data(g->plane_progs[launch], adj, dt, wpt, wpt == 1 ? 4 : PLANE_MIN_BLOCKS);
+  const std::string s = plane_static_data(g->plane_progs[launch], adj, dt, wpt, plane_static_min_blocks(wpt), g->pools());
   delete g;
   if (out && cap > 0) {
     const size_t n = s.size() < cap - 1 ? s.size() : cap - 1;
@@ -440,7 +461,7 @@ extern "C" int rddl_plane_precompile(const void* optable, size_t nbytes, int64_t
     RddlLaunch adj;
     const int wpt = plane_geometry(g->launches[i], n_envs, &adj);
     std::string cubin, err;
-    if (!jit_compile_plane(plane_static_data(g->plane_progs[i], adj, dt, wpt, wpt == 1 ? 4 : PLANE_MIN_BLOCKS), &cubin,
+    if (!jit_compile_plane(plane_static_data(g->plane_progs[i], adj, dt, wpt, plane_static_min_blocks(wpt), g->pools()), &cubin,
                            &err, nullptr)) {
       g_create_error = err;
       delete g;
@@ -479,6 +500,7 @@ extern "C" int64_t rddl_program_info(const rddl_program_t* g, int what) {
     case 5: return g->jit_built;        // specialised plane kernels in use
     case 6: return g->jit_failed;       // plane launches that fell back to the interpreter kernel (rddl_jit_error)
     case 7: return g->jit_cache_hits;
+    case 8: { JitApi& a = jit_api(); return a.ok ? a.major * 100 + a.minor : 0; }   // NVRTC version in use
     default: return -1;
   }
 }
@@ -645,6 +667,44 @@ extern "C" int rddl_rollout(rddl_program_t* g, void* const* tensors, uint32_t* s
   }
   *state_in_next = n_steps & 1;
   return RDDL_OK;
+}
+
+// Local part of the return statistics of BaseAgent.evaluate (pyRDDLGym/core/policy.py:120-126): one
+// CTA, fixed summation order (deterministic): out = {sum, sum of squares, count, min, max}.
+__global__ void __launch_bounds__(1024) rddl_return_stats_kernel(const double* __restrict__ r, int64_t n, double* out) {
+  double s = 0.0, q = 0.0, mn = INFINITY, mx = -INFINITY;
+  for (int64_t i = threadIdx.x; i < n; i += 1024) {
+    const double v = r[i];
+    s += v; q += v * v; mn = fmin(mn, v); mx = fmax(mx, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_down_sync(0xffffffffu, s, o);
+    q += __shfl_down_sync(0xffffffffu, q, o);
+    mn = fmin(mn, __shfl_down_sync(0xffffffffu, mn, o));
+    mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, o));
+  }
+  __shared__ double sh[4][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { sh[0][warp] = s; sh[1][warp] = q; sh[2][warp] = mn; sh[3][warp] = mx; }
+  __syncthreads();
+  if (warp == 0) {
+    s = sh[0][lane]; q = sh[1][lane]; mn = sh[2][lane]; mx = sh[3][lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_down_sync(0xffffffffu, s, o);
+      q += __shfl_down_sync(0xffffffffu, q, o);
+      mn = fmin(mn, __shfl_down_sync(0xffffffffu, mn, o));
+      mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, o));
+    }
+    if (lane == 0) { out[0] = s; out[1] = q; out[2] = (double)n; out[3] = mn; out[4] = mx; }
+  }
+}
+
+extern "C" int rddl_return_stats(const double* returns, int64_t n, double* out5, void* cuda_stream) {
+  if (!returns || !out5 || n < 0) return RDDL_ERR_ARG;
+  rddl_return_stats_kernel<<<1, 1024, 0, (cudaStream_t)cuda_stream>>>(returns, n, out5);
+  return cudaGetLastError() == cudaSuccess ? RDDL_OK : RDDL_ERR_CUDA;
 }
 
 extern "C" int rddl_check(rddl_program_t* g, int which, void* const* tensors, uint32_t* status,

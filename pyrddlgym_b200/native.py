@@ -46,6 +46,8 @@ def load():
     lib.rddl_profile.restype = ctypes.c_int
     lib.rddl_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64), ctypes.c_int]
     lib.rddl_profile_read.restype = ctypes.c_int
+    lib.rddl_return_stats.argtypes = [vp, i64, vp, vp]
+    lib.rddl_return_stats.restype = ctypes.c_int
     lib.rddl_program_option.argtypes = [vp, ctypes.c_int, i64]
     lib.rddl_program_option.restype = ctypes.c_int
     lib.rddl_jit_error.argtypes = [vp]
@@ -61,10 +63,18 @@ def load():
 
 EXPORTS = ['rddl_program_create', 'rddl_program_destroy', 'rddl_last_error', 'rddl_program_info',
            'rddl_step', 'rddl_check', 'rddl_rollout', 'rddl_profile', 'rddl_profile_read',
-           'rddl_program_option', 'rddl_jit_error', 'rddl_plane_precompile', 'rddl_plane_source']
+           'rddl_return_stats', 'rddl_program_option', 'rddl_jit_error', 'rddl_plane_precompile', 'rddl_plane_source']
 
 OPTION_SPECIALIZE = 0
 INFO_JIT_BUILT, INFO_JIT_FAILED, INFO_JIT_CACHE_HITS = 5, 6, 7
+
+
+def return_stats(returns, out5, stream):
+    """out5 (f64[5], device) <- {sum, sum of squares, count, min, max} of returns (f64[n], device)."""
+    rc = load().rddl_return_stats(ctypes.c_void_p(returns.data_ptr()), int(returns.numel()),
+                                  ctypes.c_void_p(out5.data_ptr()), ctypes.c_void_p(stream))
+    if rc != 0:
+        raise NativeError('rddl_return_stats failed (%d)' % rc)
 
 
 def precompile(blob, n_envs):

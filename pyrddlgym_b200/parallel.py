@@ -21,20 +21,51 @@ def shard_envs(global_envs, world_size, rank):
     return n_local, offset
 
 
+def local_return_stats(returns):
+    """f64[5] = {sum, sum of squares, count, min, max} of this rank's per-env returns, on the tensor's
+    device. CUDA tensors: one launch of the library's block reduction (rddl_return_stats); CPU tensors
+    (the gloo tests of this plumbing) use torch."""
+    r = returns.to(torch.float64).contiguous()
+    if r.is_cuda:
+        from . import native
+        out = torch.empty(5, dtype=torch.float64, device=r.device)
+        native.return_stats(r, out, torch.cuda.current_stream(r.device).cuda_stream)
+        return out
+    inf = float('inf')
+    return torch.tensor([float(r.sum()), float((r * r).sum()), float(r.numel()),
+                         float(r.min()) if r.numel() else inf, float(r.max()) if r.numel() else -inf],
+                        dtype=torch.float64)
+
+
+def return_stats_async(returns, group=None):
+    """Per-rank statistics of every rank, f64[world, 5], without synchronising the host: the one
+    collective of the path (an all-gather of five numbers per rank)."""
+    local = local_return_stats(returns)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        world = dist.get_world_size(group)
+        out = torch.empty(world * 5, dtype=torch.float64, device=local.device)
+        dist.all_gather_into_tensor(out, local, group=group)
+        return out.view(world, 5)
+    return local[None]
+
+
+def finish_return_stats(gathered):
+    """The dict of BaseAgent.evaluate (mean, population std, min, max) + count from return_stats_async's
+    tensor (this is where the host waits for the device)."""
+    g = gathered.cpu().tolist()
+    total = sum(x[0] for x in g)
+    sq = sum(x[1] for x in g)
+    n = sum(x[2] for x in g)
+    mean = total / n
+    var = max(0.0, sq / n - mean * mean)
+    return {'mean': mean, 'std': math.sqrt(var), 'min': min(x[3] for x in g), 'max': max(x[4] for x in g),
+            'count': int(n)}
+
+
 def reduce_return_stats(returns, group=None):
     """returns: f64[n_local] per-env (discounted) returns of this rank's shard. Gives the dict of
     BaseAgent.evaluate -- mean, std (population), min, max -- over ALL ranks, plus the count."""
-    r = returns.to(torch.float64)
-    s = torch.stack([r.sum(), (r * r).sum(), torch.tensor(float(r.numel()), dtype=torch.float64, device=r.device)])
-    big = torch.tensor(float('inf'), dtype=torch.float64, device=r.device)
-    mm = torch.stack([r.min() if r.numel() else big, -r.max() if r.numel() else big])
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(s, op=dist.ReduceOp.SUM, group=group)
-        dist.all_reduce(mm, op=dist.ReduceOp.MIN, group=group)
-    total, sq, n = [float(x) for x in s.tolist()]
-    mean = total / n
-    var = max(0.0, sq / n - mean * mean)
-    return {'mean': mean, 'std': math.sqrt(var), 'min': float(mm[0]), 'max': -float(mm[1]), 'count': int(n)}
+    return finish_return_stats(return_stats_async(returns, group))
 
 
 def gather_median(returns, group=None):

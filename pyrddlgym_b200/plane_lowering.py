@@ -178,7 +178,10 @@ class PlaneBuilder:
     def finalize(self):
         """Liveness-based register allocation (the virtual register file lives in shared
         memory: fewer registers = more resident CTAs), then emission of the instructions."""
-        ops = self.ops
+        # every plane load first: they have no inputs, and issued back to back their DRAM / L2
+        # latencies overlap instead of each stalling the ops behind it
+        ops = self.ops = ([o for o in self.ops if o['op'] in ('PLD', 'PLDC')] +
+                          [o for o in self.ops if o['op'] not in ('PLD', 'PLDC')])
         nxt = set(self.lw.p.next_state.values())
         INF = len(ops) + 1
         defs, uses = [], []

@@ -93,6 +93,7 @@ class BatchedSimulator:
             self.device, dtype=_TORCH_DT[program.tensors[name].dtype])
             for name in program.tensors if program.tensors[name].kind != 'nonfluent'}
         self._owned_actions = {name: self.t[name] for name in self.action_names}
+        self._init_packed = {}
         self._ptrs = (ctypes.c_void_p * len(self.names))()
         self._inj = (ctypes.c_void_p * max(1, len(self.table.variates)))()
         self._external = {}
@@ -135,7 +136,9 @@ class BatchedSimulator:
             self.t[name] = own          # never write into caller-owned action tensors
         for name, v in self._init.items():
             if name in self.packed:
-                self.t[name].copy_(self._pack(v.reshape(1, -1)).expand_as(self.t[name]))
+                if name not in self._init_packed:
+                    self._init_packed[name] = self._pack(v.reshape(1, -1))
+                self.t[name].copy_(self._init_packed[name].expand_as(self.t[name]))
             else:
                 self.t[name].copy_(v.expand_as(self.t[name]))
         self.status.zero_()
@@ -252,11 +255,11 @@ class BatchedSimulator:
             for s, ns in self.program.next_state.items():
                 self.t[s], self.t[ns] = self.t[ns], self.t[s]
         self.step_count += int(n_steps)
-        # action fluents go back to owned [N, ...] storage holding the last step's actions
+        # the action fluents now hold the last step's actions: a read-only view of the caller's
+        # sequence (zero-copy, like set_actions; reset / set_actions go back to owned storage)
         for name in actions:
             last = self.t[name]
-            self.t[name] = self._owned_actions[name]
-            self.t[name].copy_(last[-1] if last.dim() == self.t[name].dim() + 1 else last, non_blocking=True)
+            self.t[name] = last[-1] if last.dim() == self._owned_actions[name].dim() + 1 else last
         self._keep = keep
         return returns, rewards
 

@@ -71,3 +71,27 @@ def test_every_workload_optable_decodes_on_the_host():
         buf = ctypes.create_string_buffer(blob, len(blob))
         rc = lib.rddl_program_create(ctypes.cast(buf, ctypes.c_void_p), len(blob), 0, ctypes.byref(h))
         assert rc == -2, (spec['name'], rc, lib.rddl_last_error(None))
+
+
+def test_specialised_plane_kernel_compiles_without_a_gpu(tmp_path, monkeypatch):
+    """rddl_plane_precompile: the generated constants + csrc/rddl_plane.cuh compile for sm_100a with
+    NVRTC on a machine without a device, land in the cubin cache, and the second call is a cache hit."""
+    import time
+    from pyrddlgym_b200 import lowering, native, workloads
+    monkeypatch.setenv('RDDL_B200_JIT_CACHE', str(tmp_path))
+    tab = lowering.lower(workloads.load_program(workloads.wildfire(64, separable=True)))
+    li = [i for i, L in enumerate(tab.launches) if L['kind'] == 1]
+    assert li
+    src = native.plane_source(tab.blob, li[0], 4096)
+    assert '#define PS_NOPS %d' % tab.launches[li[0]]['n_insns'] in src and 'constexpr PlaneProg kG' in src
+    assert native.precompile(tab.blob, 4096) == len(li)
+    cubins = [f for f in os.listdir(tmp_path) if f.endswith('.cubin')]
+    assert len(cubins) == len(li) and os.path.getsize(os.path.join(tmp_path, cubins[0])) > 10000
+    t0 = time.time()
+    assert native.precompile(tab.blob, 4096) == len(li)
+    assert time.time() - t0 < 0.5                      # served from the cache
+    # a different batch geometry (one word per thread for tiny batches) is a different kernel
+    assert native.precompile(tab.blob, 3) == len(li)
+    assert len([f for f in os.listdir(tmp_path) if f.endswith('.cubin')]) == 2 * len(li)
+    # programs without plane launches need nothing
+    assert native.precompile(lowering.lower(workloads.load_program(workloads.cartpole())).blob, 64) == 0

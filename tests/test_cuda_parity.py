@@ -214,6 +214,36 @@ def test_plane_interpreter_equals_scalar_interpreter(n, N):
     assert bool(a.fluent('burning').any())
 
 
+@pytest.mark.parametrize('n,sep,N', [(32, False, 70), (32, False, 4099), (32, True, 33), (64, True, 9), (256, True, 3),
+                                     (1024, True, 2)])
+def test_specialised_plane_kernel_equals_interpreter_kernel(n, sep, N):
+    """The NVRTC-specialised build of rddl_plane.cuh (program as constants, csrc/rddl_jit.h) and the
+    ahead-of-time interpreter build are the same source: bit-identical states, rewards and
+    terminations under the native Philox streams, for steps and fused rollouts, full and partial tiles."""
+    import torch
+    p = workloads.load_program(workloads.wildfire(n, separable=sep))
+    a = _make(p, N, seed=5)
+    b = _make(p, N, seed=5, specialize=False)
+    g = torch.Generator(device='cuda').manual_seed(n + N)
+    T = 3
+    seq = {k: torch.rand((T, N, n, n), device='cuda', generator=g) < 0.05 for k in ('put-out', 'cut-out')}
+    for t in range(2):
+        _, ra, da = a.step({k: v[t] for k, v in seq.items()})
+        _, rb, db = b.step({k: v[t] for k, v in seq.items()})
+        assert torch.equal(ra, rb) and torch.equal(da, db)
+        for s_ in p.next_state:
+            assert torch.equal(a.fluent(s_), b.fluent(s_)), (s_, t)
+    reta, rewa = a.rollout(seq, T, gamma=0.95, keep_rewards=True)
+    retb, rewb = b.rollout(seq, T, gamma=0.95, keep_rewards=True)
+    assert torch.equal(reta, retb) and torch.equal(rewa, rewb)
+    for s_ in p.next_state:
+        assert torch.equal(a.fluent(s_), b.fluent(s_)), s_
+    assert bool(a.fluent('burning').any())
+    assert a.specialised_kernels >= 1, a.native.jit_error()
+    assert b.specialised_kernels == 0
+    assert int(a.status.max()) == 0 and int(b.status.max()) == 0
+
+
 def test_wildfire1024_vs_independent_stencil_restatement():
     """BASELINE config 4 grid size (1024x1024), which the reference cannot build: compared
     with an independent NumPy stencil restatement of the Wildfire CPFs (oracle/wildfire_stencil.py)
@@ -376,3 +406,17 @@ def test_fp64_tensor_core_contraction_vs_scalar_path_and_oracle(X, N):
         np.testing.assert_allclose(_np(a.fluent('x')), ora.subs['x'], rtol=1e-9, atol=1e-12)
         np.testing.assert_allclose(_np(ra), ro, rtol=1e-9)
         assert np.array_equal(_np(a.check_state_invariants()), ora.check_state_invariants())
+
+
+def test_return_statistics_kernel_matches_numpy():
+    """rddl_return_stats (policy.py:120-126 for one shard) vs NumPy, including tiny and odd sizes."""
+    import torch
+    from pyrddlgym_b200 import parallel
+    rng = np.random.default_rng(3)
+    for n in (1, 31, 4096, 100003):
+        r = rng.normal(-5e5, 1e5, size=n)
+        st = parallel.reduce_return_stats(torch.from_numpy(r).cuda())
+        assert st['count'] == n
+        np.testing.assert_allclose(st['mean'], r.mean(), rtol=1e-12)
+        np.testing.assert_allclose(st['std'], r.std(), rtol=1e-6, atol=1e-6)
+        assert st['min'] == r.min() and st['max'] == r.max()

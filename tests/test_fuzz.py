@@ -125,3 +125,14 @@ def test_fuzz_grid_cuda_plane_vs_scalar_vs_oracle(seed):
         for k in range(3):
             assert torch.equal(a.fluent(f's{k}'), b.fluent(f's{k}'))
         np.testing.assert_allclose(ra.cpu().numpy(), rb.cpu().numpy(), rtol=1e-9)
+    # specialised (NVRTC) vs interpreter build of the plane kernel, native Philox: bit-identical
+    c = BatchedSimulator(p, n_envs=N, seed=3)
+    d = BatchedSimulator(p, n_envs=N, seed=3, specialize=False)
+    for t in range(3):
+        acts = harness.random_actions(p, N, rng, p_bool=0.2)
+        _, rc, dc = c.step(acts)
+        _, rd, dd = d.step(acts)
+        for k in range(3):
+            assert torch.equal(c.fluent(f's{k}'), d.fluent(f's{k}'))
+        assert torch.equal(rc, rd) and torch.equal(dc, dd)
+    assert c.specialised_kernels >= 1 and d.specialised_kernels == 0, c.native.jit_error()

@@ -8,16 +8,22 @@ root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = os.path.join(root, 'pyrddlgym_b200', 'csrc', 'librddl_b200.so')
 tmp = tempfile.mkdtemp()
 subprocess.run(['cuobjdump', '-xelf', 'all', so], cwd=tmp, check=True, capture_output=True)
-cubin = [f for f in os.listdir(tmp) if f.endswith('.cubin')][0]
-dis = subprocess.run(['nvdisasm', '-g', '-c', os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
-fn = None; line = None; seq = collections.defaultdict(list)
-for l in dis.splitlines():
-    m = re.match(r'\s*\.section\s+\.text\.(\S+),', l)
-    if m: fn = m.group(1); line = None; continue
-    m = re.search(r'//## File "([^"]+)", line (\d+)', l)
-    if m: line = (m.group(1).split('/')[-1], int(m.group(2))); continue
-    m = re.match(r'\s*/\*([0-9a-f]{4,})\*/\s+(.*?);', l)
-    if m and fn: seq[fn].append((line, m.group(2)))
+# the ahead-of-time library plus every run-time specialised kernel in the cubin cache
+cubins = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith('.cubin')]
+cache = os.path.join(os.path.dirname(so), 'jit_cache')
+if os.path.isdir(cache):
+    cubins += [os.path.join(cache, f) for f in sorted(os.listdir(cache)) if f.endswith('.cubin')]
+seq = collections.defaultdict(list)
+for cubin in cubins:
+    dis = subprocess.run(['nvdisasm', '-g', '-c', cubin], capture_output=True, text=True).stdout
+    fn = None; line = None
+    for l in dis.splitlines():
+        m = re.match(r'\s*\.section\s+\.text\.(\S+),', l)
+        if m: fn = m.group(1) + '@' + os.path.basename(cubin); line = None; continue
+        m = re.search(r'//## File "([^"]+)", line (\d+)', l)
+        if m: line = (m.group(1).split('/')[-1], int(m.group(2))); continue
+        m = re.match(r'\s*/\*([0-9a-f]{4,})\*/\s+(.*?);', l)
+        if m and fn: seq[fn].append((line, m.group(2)))
 out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'sass'], capture_output=True, text=True).stdout
 # split per kernel
 blocks = out.split('"Kernel Name",')
@@ -38,7 +44,9 @@ for blk in blocks[1:]:
     stot = sum(bys.values()) or 1
     print(name[:90], '| total warp inst', tot, '| thread-instr per cell %.1f' % (tot * 32 / cells))
     src = {}
-    for ln, c in by.most_common(int(os.environ.get('TOP', '45'))):
+    order = bys if os.environ.get('SORT') == 'stall' else by
+    for ln, _c in order.most_common(int(os.environ.get('TOP', '45'))):
+        c = by[ln]
         t = ''
         if ln:
             path = os.path.join(root, 'pyrddlgym_b200', 'csrc', ln[0])

@@ -1,6 +1,7 @@
 """Fills the specialised-kernel cubin cache (pyrddlgym_b200/csrc/jit_cache) on a machine without a GPU:
 NVRTC compiles for sm_100a anywhere. usage: python tools/prewarm_jit.py [n:N ...]  (wildfire n x n, N envs)"""
 import os, sys, time
+import torch  # noqa: F401  (first: the process then binds the same NVRTC as the simulator does -> same cache keys)
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pyrddlgym_b200 import workloads, lowering, native
 

@@ -21,4 +21,5 @@ prof = sim.native.profile_read(sim.table.launches)
 top = max(prof, key=lambda r: r['ms'])
 us_per_step = 1e3 * top['ms'] / K
 gbs = (6 * n * n + 9) * N / (us_per_step * 1e-6) / 1e9
+print(f"jit built={sim.native.info(5)} failed={sim.native.info(6)} cache_hits={sim.native.info(7)} nvrtc={sim.native.info(8)}", end=' ')
 print(f"{os.environ.get('RDDL_B200_LIB', 'default'):>28s} n={n} N={N}: {us_per_step:8.1f} us/step  {gbs:7.0f} GB/s  {gbs / 6541.1:.3f} of peak", flush=True)
