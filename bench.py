@@ -291,22 +291,40 @@ def run_gpu(args):
     while time.perf_counter() - t_spin < 0.3:
         episode()
         torch.cuda.synchronize()
+    launches_per_episode = 0
     for _ in range(max(W, 1)):                                     # W untimed warm-up steps
+        la = sim.launches_issued
         parallel.finish_return_stats(episode())
+        launches_per_episode = sim.launches_issued - la
+    # The episode is a fixed launch sequence (reset copies, one rollout kernel, the statistics
+    # kernel, the NCCL all-gather): captured once into a CUDA graph and replayed per step, so the
+    # host's per-launch latency is not part of the step.
+    graph = None
+    if not args.no_graph:
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            gathered = episode()
+        graph.replay()
+        torch.cuda.synchronize()
     barrier()
-    l0 = sim.launches_issued
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    l0 = sim.launches_issued
     sampler.timed = True
     e0.record()
     for _ in range(K):                                             # exactly K timed steps
-        gathered = episode()
+        if graph is not None:
+            graph.replay()
+        else:
+            gathered = episode()
     stats = parallel.finish_return_stats(gathered)
     e1.record()
     barrier()
     sampler.timed = False
     ms = e0.elapsed_time(e1)
-    launches = (sim.launches_issued - l0) + K                      # + rddl_return_stats per episode
+    # kernels of this library per episode (one graph replay issues what one eager episode does) + rddl_return_stats
+    launches = K * launches_per_episode + K
     tms = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -416,6 +434,7 @@ def run_gpu(args):
                        'parallelism': f'env-shard x{world}, return statistics all-gathered (NCCL) once per rollout',
                        'launches': [l['kernel'] for l in sim.table.launches if l['plan'] == 0],
                        'specialised_kernels': sim.specialised_kernels,
+                       'cuda_graph': graph is not None,
                        'return_stats': stats},
             'roofline': roofline,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
@@ -438,6 +457,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='wildfire32', choices=sorted(WORKLOADS))
     ap.add_argument('--envs', type=int, default=0)
+    ap.add_argument('--no-graph', action='store_true', help='issue every episode eagerly instead of replaying a CUDA graph')
     ap.add_argument('--rollout', type=int, default=0, help='env-steps per rollout (default: per workload)')
     ap.add_argument('--e2e-steps', type=int, default=10, help='rollouts timed for the end-to-end figure (<= --steps)')
     args = ap.parse_args()

@@ -107,7 +107,7 @@ static bool jit_fused_static(const PlaneProg& G, const JitPools& P, std::string&
 }
 
 static std::string plane_static_data(const PlaneProg& G, const RddlLaunch& L, const uint8_t* dtype, int wpt,
-                                     int min_blocks, const JitPools& P) {
+                                     int min_blocks, int block, const JitPools& P) {
   std::string s;
   {
     std::string f;
@@ -115,7 +115,8 @@ static std::string plane_static_data(const PlaneProg& G, const RddlLaunch& L, co
     else s += "#define PS_FUSED_STATIC 0\n";
   }
   s += jit_fmt("#define PS_WPT %lld\n", wpt) + jit_fmt("#define PS_NREGS %lld\n", L.nregs > 0 ? L.nregs : 1) +
-       jit_fmt("#define PS_NOPS %lld\n", G.nops) + jit_fmt("#define PS_MINB %lld\n", min_blocks);
+       jit_fmt("#define PS_NOPS %lld\n", G.nops) + jit_fmt("#define PS_MINB %lld\n", min_blocks) +
+       jit_fmt("#define PS_BLOCK %lld\n", block);
   s += "__device__ constexpr PlaneProg kG = {" + jit_fmt("%lld,", G.nops) + jit_fmt("%lld,", G.nshared) +
        jit_fmt("%lld,", G.w32_shift) + jit_fmt("%lld,", G.wpe_shift) + jit_fmt("%lld,", G.nfused) +
        jit_fmt("%lld,", G.fused_nregs) + jit_fmt("%lld,", G.rollout_ok) + jit_fmt("%lld,\n{", G.pad);

@@ -782,8 +782,8 @@ __device__ __forceinline__ void plane_tile(const VmArgs& A, const PlaneProg& G, 
 }
 
 #ifdef PLANE_STATIC
-extern "C" __global__ void __launch_bounds__(256, PS_MINB) rddl_plane_static(const __grid_constant__ VmArgs A) {
-  plane_tile<PS_WPT, 256>(A, kG, kL, kDT);
+extern "C" __global__ void __launch_bounds__(PS_BLOCK, PS_MINB) rddl_plane_static(const __grid_constant__ VmArgs A) {
+  plane_tile<PS_WPT, PS_BLOCK>(A, kG, kL, kDT);
 }
 #else
 template <int WPT, int BLOCK>

@@ -149,7 +149,7 @@ static int plane_static_min_blocks(int wpt) {
 
 // The specialised kernel of plane launch `li` for the tile geometry `adj` / wpt, or nullptr (then the
 // interpreter kernel runs): compiled with NVRTC on first use, cubins cached on disk.
-static JitKernel* jit_get(rddl_program* g, int li, int wpt, const RddlLaunch& adj) {
+static JitKernel* jit_get(rddl_program* g, int li, int wpt, int blk, const RddlLaunch& adj) {
   if (!g->specialize) return nullptr;
   for (JitKernel& k : g->jit)
     if (k.launch == li && k.wpt == wpt && k.G == adj.G && k.ipt == adj.ipt) return k.failed ? nullptr : &k;
@@ -157,7 +157,7 @@ static JitKernel* jit_get(rddl_program* g, int li, int wpt, const RddlLaunch& ad
   k.launch = li; k.wpt = wpt; k.G = adj.G; k.ipt = adj.ipt;
   uint8_t dt[RDDL_MAX_TENSORS] = {0};
   for (size_t i = 0; i < g->tensors.size(); ++i) dt[i] = (uint8_t)g->tensors[i].dtype;
-  const std::string data = plane_static_data(g->plane_progs[li], adj, dt, wpt, plane_static_min_blocks(wpt), g->pools());
+  const std::string data = plane_static_data(g->plane_progs[li], adj, dt, wpt, plane_static_min_blocks(wpt), blk, g->pools());
   std::string cubin, err;
   bool hit = false;
   JitDriver& drv = jit_driver();
@@ -245,26 +245,72 @@ static bool decode_plane(const RddlLaunch& L, const RddlInsn* insns, const uint6
   return true;
 }
 
-// Words per thread and tile geometry of a plane launch for a batch of n_envs: the op table's tile is
-// 4 words per thread (32768 cells per CTA: big tiles amortise the per-tile overhead); very small
-// batches of small grids take one word per thread so that the grid still spans the SMs.
-// RDDL_PLANE_FORCE_WPT overrides. Returns wpt and the adjusted launch (G = envs per tile, ipt = words per tile).
-static int plane_geometry(const RddlLaunch& L, int64_t n_envs, RddlLaunch* adj) {
+// Words per thread and tile geometry of a plane launch for a batch of n_envs. The op table's tile is
+// 4 words per thread x 256 threads (32768 cells per CTA: big tiles amortise the per-tile overhead),
+// which is what large batches and multi-tile grids use. When the whole batch fits one wave of
+// resident CTAs (small grids, a few thousand envs -- the fused-rollout case, where a CTA keeps
+// its envs for every step), the envs per tile are chosen so that the busiest SM holds as few envs
+// as possible, preferring more, smaller CTAs per SM (more warps to hide latency behind).
+// RDDL_PLANE_FORCE_WPT overrides. Returns wpt and the adjusted launch (G = envs per tile,
+// ipt = words per tile); *block = threads of the specialised kernel (the tile's words / wpt,
+// rounded up to a warp: the interpreter kernels always run 256 threads and mask the rest).
+static int plane_geometry(const RddlLaunch& L, int64_t n_envs, RddlLaunch* adj, int* block, bool balanced = true) {
   *adj = L;
+  *block = 256;
   int wpt = L.ipt <= 256 ? 1 : (L.ipt <= 512 ? 2 : 4);
-  if (L.chunks == 1 && wpt > 1) {
-    const char* force = getenv("RDDL_PLANE_FORCE_WPT");
-    int want = force ? atoi(force) : ((n_envs + L.G - 1) / L.G < 74 ? 1 : wpt);
-    if (want != 1 && want != 2 && want != 4) want = wpt;
-    if (want < wpt && L.E <= 8192 * want) {
-      int ept = (int)((8192 * want) / L.E);
-      if (ept > 32) ept = 32;
-      wpt = want;
-      adj->G = ept;
-      adj->ipt = (int)(ept * (L.E >> 5));
+  if (L.chunks != 1 || wpt == 1) return wpt;
+  const int64_t wpe = L.E >> 5;
+  auto set = [&](int w, int ept) {
+    adj->G = ept;
+    adj->ipt = (int)(ept * wpe);
+    *block = (int)(((adj->ipt + w - 1) / w + 31) / 32 * 32);
+    if (*block > 256) *block = 256;
+    return w;
+  };
+  if (const char* force = getenv("RDDL_PLANE_FORCE_WPT")) {
+    const int want = atoi(force);
+    if ((want == 1 || want == 2 || want == 4) && want <= wpt && wpe <= 256 * want) {
+      int ept = (int)((256 * want) / wpe);
+      return set(want, ept > 32 ? 32 : ept);
+    }
+    return wpt;
+  }
+  const int sms = 148;
+  const int64_t tiles_full = (n_envs + L.G - 1) / L.G;
+  if (!balanced) {
+    // interpreter kernels (fixed 256 threads, masked partial tiles are slow): full tiles only; one
+    // word per thread when the batch would otherwise leave half of the SMs idle
+    if (tiles_full < 74 && wpe <= 256) {
+      int ept = (int)(256 / wpe);
+      return set(1, ept > 32 ? 32 : ept);
+    }
+    return wpt;
+  }
+  if (tiles_full >= (int64_t)sms * 2 * 3) return wpt;     // several waves anyway: keep the big tiles
+  int best_w = 0, best_ept = 0;
+  int64_t best_score = -1;
+  const int order[3] = {2, 1, 4};                          // tie-break: preference order
+  // first pass: tile sizes that divide the batch (a partial last tile takes the slower masked
+  // path, and in a fused rollout the slowest CTA sets the kernel time); second pass: any
+  for (int pass = 0; pass < 2 && best_w == 0; ++pass) {
+    for (int k = 0; k < 3; ++k) {
+      const int w = order[k];
+      if (w > wpt || wpe > 256 * w) continue;
+      int cap = (int)((256 * w) / wpe);
+      if (cap > 32) cap = 32;
+      const int resident = w == 1 ? 4 : 2;
+      for (int ept = cap; ept >= 1 && ept * 2 > cap; --ept) {
+        if (pass == 0 && n_envs % ept != 0) continue;
+        const int64_t tiles = (n_envs + ept - 1) / ept;
+        const int64_t per_sm = (tiles + sms - 1) / sms;
+        if (per_sm > resident) continue;
+        const int64_t score = per_sm * ept * 8 + k;        // envs on the busiest SM, then preference
+        if (best_score < 0 || score < best_score) { best_score = score; best_w = w; best_ept = ept; }
+      }
     }
   }
-  return wpt;
+  if (best_w == 0) return wpt;
+  return set(best_w, best_ept);
 }
 
 #define CK(call)                                                                      \
@@ -432,10 +478,11 @@ extern "C" int64_t rddl_plane_source(const void* optable, size_t nbytes, int lau
     return RDDL_ERR_ARG;
   }
   RddlLaunch adj;
-  const int wpt = plane_geometry(g->launches[launch], n_envs, &adj);
+  int blk = 256;
+  const int wpt = plane_geometry(g->launches[launch], n_envs, &adj, &blk);
   uint8_t dt[RDDL_MAX_TENSORS] = {0};
   for (size_t i = 0; i < g->tensors.size(); ++i) dt[i] = (uint8_t)g->tensors[i].dtype;
-  const std::string s = plane_static_data(g->plane_progs[launch], adj, dt, wpt, plane_static_min_blocks(wpt), g->pools());
+  const std::string s = plane_static_data(g->plane_progs[launch], adj, dt, wpt, plane_static_min_blocks(wpt), blk, g->pools());
   delete g;
   if (out && cap > 0) {
     const size_t n = s.size() < cap - 1 ? s.size() : cap - 1;
@@ -459,9 +506,10 @@ extern "C" int rddl_plane_precompile(const void* optable, size_t nbytes, int64_t
   for (size_t i = 0; i < g->launches.size(); ++i) {
     if (g->launches[i].kind != 1) continue;
     RddlLaunch adj;
-    const int wpt = plane_geometry(g->launches[i], n_envs, &adj);
+    int blk = 256;
+    const int wpt = plane_geometry(g->launches[i], n_envs, &adj, &blk);
     std::string cubin, err;
-    if (!jit_compile_plane(plane_static_data(g->plane_progs[i], adj, dt, wpt, plane_static_min_blocks(wpt), g->pools()), &cubin,
+    if (!jit_compile_plane(plane_static_data(g->plane_progs[i], adj, dt, wpt, plane_static_min_blocks(wpt), blk, g->pools()), &cubin,
                            &err, nullptr)) {
       g_create_error = err;
       delete g;
@@ -544,7 +592,15 @@ static int run_plan(rddl_program* g, int plan, void* const* tensors, const doubl
     if (L.plan != plan || L.kind == 2) continue;   // kind 2 runs inside the preceding plane launch
     A.L = L;
     const int block = 256;
-    const int wpt = L.kind == 1 ? plane_geometry(L, n_envs, &A.L) : 1;
+    int jit_block = 256;
+    int wpt = 1;
+    JitKernel* jk = nullptr;
+    if (L.kind == 1) {
+      const int li = (int)(&L - g->launches.data());
+      wpt = plane_geometry(L, n_envs, &A.L, &jit_block, g->specialize);
+      jk = jit_get(g, li, wpt, jit_block, A.L);
+      if (!jk && g->specialize) wpt = plane_geometry(L, n_envs, &A.L, &jit_block, false);   // interpreter kernel
+    }
     const int envs_per_cta = L.kind == 1 ? A.L.G : 256 / L.G;
     const int64_t groups = (n_envs + envs_per_cta - 1) / envs_per_cta;
     const int64_t blocks = groups * L.chunks;
@@ -570,11 +626,10 @@ static int run_plan(rddl_program* g, int plan, void* const* tensors, const doubl
                                               (size_t)G.nshared * ((A.L.ipt / W32 + A.L.G + 2) * (W32 + 2)) +
                                               32 * RDDL_MAX_RED +
                                               8 * PLANE_QUEUE + 8 + block * wpt);
-      const size_t smem_static = smem - sizeof(uint32_t) * (size_t)L.nregs * wpt * block;
-      JitKernel* jk = jit_get(g, (int)(&L - g->launches.data()), wpt, A.L);
+      const size_t smem_static = smem - sizeof(uint32_t) * ((size_t)L.nregs * wpt * block + (size_t)(block - jit_block) * wpt);
       if (jk) {
         void* params[] = {(void*)&A};
-        if (jit_driver().LaunchKernel(jk->fn, (unsigned)blocks, 1, 1, 256, 1, 1, (unsigned)smem_static, (CUstream)stream,
+        if (jit_driver().LaunchKernel(jk->fn, (unsigned)blocks, 1, 1, (unsigned)jit_block, 1, 1, (unsigned)smem_static, (CUstream)stream,
                                       params, nullptr) != CUDA_SUCCESS) {
           g->err = "cuLaunchKernel failed (specialised plane kernel)";
           return RDDL_ERR_CUDA;
