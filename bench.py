@@ -39,6 +39,19 @@ WORKLOADS = {
 }
 
 
+_RESULT_FD = None
+
+
+def emit(line):
+    """The one JSON line of the run, on the real stdout."""
+    data = (json.dumps(line) + '\n').encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def make_spec(name):
     from pyrddlgym_b200 import workloads
     w = WORKLOADS[name]
@@ -213,7 +226,7 @@ def run_reference(args):
     v, sample = cpu_baseline(name, cores=use, envs_per_core=per_step_envs, steps=max(1, args.steps) * per_step_len)
     wall = time.perf_counter() - t0
     if v is None:
-        print(json.dumps({'impl': 'reference', 'unavailable': sample}))
+        emit({'impl': 'reference', 'unavailable': sample})
         return
     N, R = args.envs or w['envs'], args.rollout or w['rollout']
     line = {
@@ -229,7 +242,7 @@ def run_reference(args):
         'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------
@@ -274,14 +287,24 @@ def run_gpu(args):
 
     returns = torch.zeros(N, dtype=torch.float64, device=dev)
 
-    def episode():
+    local_stats = torch.empty(5, dtype=torch.float64, device=dev)
+
+    def episode_local():
         # one bench step = BaseAgent.evaluate's episode for every env of the batch
         # (pyRDDLGym/core/policy.py:85-126): reset, R transitions with discounted return
-        # accumulation, return statistics over all ranks (one NCCL all-gather of 5 numbers per rank)
+        # accumulation, this rank's part of the return statistics
         sim.reset()
         returns.zero_()
         sim.rollout(seq, R, gamma=gamma, returns=returns)
-        return parallel.return_stats_async(returns)
+        local_stats.copy_(parallel.local_return_stats(returns))
+
+    def episode(graph=None):
+        if graph is not None:
+            graph.replay()
+        else:
+            episode_local()
+        # ... and the statistics over all ranks: one NCCL all-gather of 5 numbers per rank
+        return parallel.gather_return_stats(local_stats)
 
     sampler = ClockSampler(local, period=0.002)
     if rank == 0:
@@ -289,24 +312,23 @@ def run_gpu(args):
     # bring the clocks up before the W warm-up steps (an idle GPU needs ~100 ms to boost)
     t_spin = time.perf_counter()
     while time.perf_counter() - t_spin < 0.3:
-        episode()
+        episode_local()            # (local work only: a time-based loop must not issue collectives)
         torch.cuda.synchronize()
     launches_per_episode = 0
     for _ in range(max(W, 1)):                                     # W untimed warm-up steps
         la = sim.launches_issued
         parallel.finish_return_stats(episode())
         launches_per_episode = sim.launches_issued - la
-    # The episode is a fixed launch sequence (reset copies, one rollout kernel, the statistics
-    # kernel, the NCCL all-gather): captured once into a CUDA graph and replayed per step, so the
-    # host's per-launch latency is not part of the step.
+    # The local part of the episode is a fixed launch sequence (reset copies, one rollout kernel,
+    # the statistics kernel): captured once into a CUDA graph and replayed per step, so the host's
+    # per-launch latency is not part of the step.
     graph = None
     if not args.no_graph:
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            gathered = episode()
-        graph.replay()
-        torch.cuda.synchronize()
+            episode_local()                  # (the collective stays outside the graph)
+        parallel.finish_return_stats(episode(graph))
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -314,10 +336,7 @@ def run_gpu(args):
     sampler.timed = True
     e0.record()
     for _ in range(K):                                             # exactly K timed steps
-        if graph is not None:
-            graph.replay()
-        else:
-            gathered = episode()
+        gathered = episode(graph)
     stats = parallel.finish_return_stats(gathered)
     e1.record()
     barrier()
@@ -444,8 +463,14 @@ def run_gpu(args):
         }
         if cpu_v is not None:
             line['cpu_baseline'] = {'value': cpu_v, 'unit': UNIT, 'cores': 1, 'kind': 'port', 'sample': cpu_sample}
-        print(json.dumps(line))
+        emit(line)
+    del graph
     if world > 1:
+        # the result is out: never let a stuck NCCL teardown hold the job
+        watchdog = threading.Timer(30.0, lambda: os._exit(0))
+        watchdog.daemon = True
+        watchdog.start()
+        barrier()
         dist.destroy_process_group()
 
 
@@ -461,6 +486,12 @@ def main():
     ap.add_argument('--rollout', type=int, default=0, help='env-steps per rollout (default: per workload)')
     ap.add_argument('--e2e-steps', type=int, default=10, help='rollouts timed for the end-to-end figure (<= --steps)')
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: anything a library writes to fd 1 meanwhile (NCCL's
+    # version banner, ...) goes to stderr instead
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == 'reference':
         run_reference(args)
     else:

@@ -40,7 +40,11 @@ def local_return_stats(returns):
 def return_stats_async(returns, group=None):
     """Per-rank statistics of every rank, f64[world, 5], without synchronising the host: the one
     collective of the path (an all-gather of five numbers per rank)."""
-    local = local_return_stats(returns)
+    return gather_return_stats(local_return_stats(returns), group)
+
+
+def gather_return_stats(local, group=None):
+    """All-gather of the ranks' f64[5] local statistics -> f64[world, 5]."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         world = dist.get_world_size(group)
         out = torch.empty(world * 5, dtype=torch.float64, device=local.device)
