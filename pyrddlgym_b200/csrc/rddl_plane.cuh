@@ -388,6 +388,21 @@ struct PlaneTile {
   bool full, single_env;
 };
 
+#ifdef PLANE_STATIC
+// Consecutive byte-plane loads (the action planes) are issued as one batch: all their 128-bit loads
+// are in flight before the first is consumed, so the tile pays one memory latency instead of one
+// per plane. plane_group_len(pc) = planes in the batch starting at op pc (0: pc is inside a batch).
+__host__ __device__ constexpr bool plane_is_byte_load(int pc) {
+  return pc >= 0 && pc < PS_NOPS && kG.ops[pc].op == OP_PLD && kG.ops[pc].a == 0 && kDT[kG.ops[pc].imm] != DT_PACKED;
+}
+__host__ __device__ constexpr int plane_group_len(int pc) {
+  if (!plane_is_byte_load(pc) || plane_is_byte_load(pc - 1)) return 0;
+  int n = 1;
+  while (n < 4 && plane_is_byte_load(pc + n)) ++n;
+  return n;
+}
+#endif
+
 // What plane_exec does with an op: run it, or only start the DRAM reads of the planes it loads
 // (all PLD planes of this step / the action planes of the next step of a fused rollout).
 enum { PLANE_RUN = 0, PLANE_PREFETCH = 1, PLANE_PREFETCH_NEXT = 2 };
@@ -445,6 +460,38 @@ __device__ __forceinline__ void plane_exec(PlaneTile<WPT, BLOCK>& T, const VmArg
           plane_ld_partial<WPT, BLOCK>(C, base, env0, wpe, o.dst);
           break;
         }
+#ifdef PLANE_STATIC
+        if constexpr (plane_is_byte_load(PC) && plane_group_len(PC) != 1) {
+          constexpr int GL = plane_group_len(PC);
+          if constexpr (GL >= 2) {
+            constexpr int CHG = (4 / GL < 1 ? 1 : 4 / GL) < WPT ? (4 / GL < 1 ? 1 : 4 / GL) : WPT;   // words per batch
+#pragma unroll
+            for (int j0 = 0; j0 < WPT; j0 += CHG) {
+              uint4 lo[GL][CHG], hi[GL][CHG];
+#pragma unroll
+              for (int q = 0; q < GL; ++q) {
+                const uint32_t ten = kG.ops[PC + q].imm;
+                const uint4* pq = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(A.tensors[ten]) +
+                                                                 t * A.tstride[ten] + tile_byte0);
+#pragma unroll
+                for (int j = 0; j < CHG; ++j) {
+                  if (j0 + j < WPT) {
+                    lo[q][j] = __ldcs(pq + (j0 + j) * (BLOCK * 2));
+                    hi[q][j] = __ldcs(pq + (j0 + j) * (BLOCK * 2) + 1);
+                  }
+                }
+              }
+#pragma unroll
+              for (int q = 0; q < GL; ++q) {
+#pragma unroll
+                for (int j = 0; j < CHG; ++j)
+                  if (j0 + j < WPT) C.at(kG.ops[PC + q].dst, j0 + j) = plane_pack(lo[q][j], hi[q][j]);
+              }
+            }
+          }
+          break;   // GL == 0: this plane was loaded with the batch of an earlier op
+        }
+#endif
         const uint4* p = reinterpret_cast<const uint4*>(base + tile_byte0);
         constexpr int CH = WPT < 4 ? WPT : 4;     // loads in flight per thread: 2 * CH x 16 B
 #pragma unroll

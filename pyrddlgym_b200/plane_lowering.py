@@ -180,7 +180,12 @@ class PlaneBuilder:
         memory: fewer registers = more resident CTAs), then emission of the instructions."""
         # every plane load first: they have no inputs, and issued back to back their DRAM / L2
         # latencies overlap instead of each stalling the ops behind it
-        ops = self.ops = ([o for o in self.ops if o['op'] in ('PLD', 'PLDC')] +
+        # (non-fluent planes, then fluent planes: the kernel batches consecutive fluent byte planes)
+        state = set(self.lw.p.next_state)
+        is_state = lambda o: self.lw.tensor_names_by_id[o['imm']] in state
+        ops = self.ops = ([o for o in self.ops if o['op'] == 'PLDC'] +
+                          [o for o in self.ops if o['op'] == 'PLD' and is_state(o)] +
+                          [o for o in self.ops if o['op'] == 'PLD' and not is_state(o)] +
                           [o for o in self.ops if o['op'] not in ('PLD', 'PLDC')])
         nxt = set(self.lw.p.next_state.values())
         INF = len(ops) + 1
