@@ -240,7 +240,7 @@ static bool jit_compile_plane(const std::string& data, std::string* cubin, std::
   h = jit_hash(h, data);
   h = jit_hash(h, kJitMain);
   JitApi& api = jit_api();
-  h = jit_hash(h, jit_fmt("nvrtc %lld.", api.major) + jit_fmt("%lld sm_100a O3 lineinfo", api.minor));
+  h = jit_hash(h, jit_fmt("nvrtc %lld.", api.major) + jit_fmt("%lld sm_100a O3 lineinfo default-device", api.minor));
   const char* cdir = getenv("RDDL_B200_JIT_CACHE");
   const std::string cache_dir = cdir && *cdir ? std::string(cdir) : dir + "/jit_cache";
   char name[64];
@@ -262,8 +262,9 @@ static bool jit_compile_plane(const std::string& data, std::string* cubin, std::
     *err = "nvrtcCreateProgram failed";
     return false;
   }
-  const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "--generate-line-info"};
-  const nvrtcResult rc = api.CompileProgram(prog, 3, opts);
+  const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "--generate-line-info",
+                        "--device-as-default-execution-space"};
+  const nvrtcResult rc = api.CompileProgram(prog, 4, opts);
   if (rc != NVRTC_SUCCESS) {
     size_t n = 0;
     api.GetProgramLogSize(prog, &n);
@@ -324,7 +325,7 @@ static JitDriver& jit_driver() {
 
 // One specialised kernel of a program: (launch index, words per thread, tile geometry).
 struct JitKernel {
-  int launch = -1, wpt = 0, G = 0, ipt = 0;
+  int launch = -1, wpt = 0, G = 0, ipt = 0, minb = 0;
   CUmodule mod = nullptr;
   CUfunction fn = nullptr;
   bool failed = false;

@@ -374,6 +374,9 @@ __device__ __forceinline__ int plane_spos(int row, int c, int env_l, int pitch) 
 }
 
 // Per-tile state shared by the op handlers (all of it lives in registers after inlining).
+template <bool B>
+struct PlaneBool { static constexpr bool value = B; };
+
 template <int WPT, int BLOCK>
 struct PlaneTile {
   PlaneCtx<WPT, BLOCK> C;
@@ -384,6 +387,7 @@ struct PlaneTile {
   int* qn;              // [8]
   uint32_t* fix;        // [256][WPT]
   int64_t env0, tile_byte0;
+  int64_t gw_limit;     // last valid global word index this tile may touch (ragged tiles clamp loads to it)
   int W32, wpe, envs_per_tile, tile_words, chunks, chunk, pitch, tile_rows, plane_stride;
   bool full, single_env;
 };
@@ -425,11 +429,14 @@ __device__ __forceinline__ void plane_exec(PlaneTile<WPT, BLOCK>& T, const VmArg
   if (MODE != PLANE_RUN) {
     if (o.op != OP_PLD || DT[o.imm] == DT_PACKED) return;
     if (MODE == PLANE_PREFETCH_NEXT && (o.a > 0 || A.tstride[o.imm] == 0)) return;
-    const uint8_t* p = reinterpret_cast<const uint8_t*>(A.tensors[o.imm]) + tile_byte0 +
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(A.tensors[o.imm]) +
                        (MODE == PLANE_PREFETCH_NEXT ? (t + 1) * A.tstride[o.imm] : 0);
 #pragma unroll
-    for (int j = 0; j < WPT; ++j)
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(p + (int64_t)j * (BLOCK * 32)));
+    for (int j = 0; j < WPT; ++j) {
+      int64_t gw = (tile_byte0 >> 5) + j * BLOCK;
+      if (!full) gw = gw < T.gw_limit ? gw : T.gw_limit;      // ragged tile: stay inside the tensor
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p + (gw << 5)));
+    }
     return;
   }
   const int W32 = T.W32, wpe = T.wpe, tile_words = T.tile_words, chunks = T.chunks, chunk = T.chunk;
@@ -456,42 +463,61 @@ __device__ __forceinline__ void plane_exec(PlaneTile<WPT, BLOCK>& T, const VmArg
             C.at(o.dst, j) = (full || ((C.valid >> j) & 1u)) ? __ldcs(wp + j * BLOCK) : 0u;
           break;
         }
-        if (!full) {
-          plane_ld_partial<WPT, BLOCK>(C, base, env0, wpe, o.dst);
-          break;
-        }
 #ifdef PLANE_STATIC
-        if constexpr (plane_is_byte_load(PC) && plane_group_len(PC) != 1) {
+        if constexpr (plane_is_byte_load(PC)) {
           constexpr int GL = plane_group_len(PC);
-          if constexpr (GL >= 2) {
-            constexpr int CHG = (4 / GL < 1 ? 1 : 4 / GL) < WPT ? (4 / GL < 1 ? 1 : 4 / GL) : WPT;   // words per batch
+          if constexpr (GL >= 1) {
+            // the whole batch of consecutive byte planes: loads first, then the packing. Ragged tiles
+            // (RG: the last tile of the batch / of an env) clamp the word address to the last valid
+            // word and zero the words outside the batch instead of taking a separate slow path.
+            auto load_batch = [&](auto rg) {
+              constexpr bool RG = decltype(rg)::value;
+              constexpr int CHG = (4 / GL < 1 ? 1 : 4 / GL) < WPT ? (4 / GL < 1 ? 1 : 4 / GL) : WPT;   // words per batch
 #pragma unroll
-            for (int j0 = 0; j0 < WPT; j0 += CHG) {
-              uint4 lo[GL][CHG], hi[GL][CHG];
+              for (int j0 = 0; j0 < WPT; j0 += CHG) {
+                uint4 lo[GL][CHG], hi[GL][CHG];
 #pragma unroll
-              for (int q = 0; q < GL; ++q) {
-                const uint32_t ten = kG.ops[PC + q].imm;
-                const uint4* pq = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(A.tensors[ten]) +
-                                                                 t * A.tstride[ten] + tile_byte0);
+                for (int q = 0; q < GL; ++q) {
+                  const uint32_t ten = kG.ops[PC + q].imm;
+                  const uint8_t* bq = reinterpret_cast<const uint8_t*>(A.tensors[ten]) + t * A.tstride[ten];
 #pragma unroll
-                for (int j = 0; j < CHG; ++j) {
-                  if (j0 + j < WPT) {
-                    lo[q][j] = __ldcs(pq + (j0 + j) * (BLOCK * 2));
-                    hi[q][j] = __ldcs(pq + (j0 + j) * (BLOCK * 2) + 1);
+                  for (int j = 0; j < CHG; ++j) {
+                    if (j0 + j < WPT) {
+                      const uint4* pq;
+                      if constexpr (RG) {
+                        int64_t gw = (tile_byte0 >> 5) + (j0 + j) * BLOCK;
+                        gw = gw < T.gw_limit ? gw : T.gw_limit;
+                        pq = reinterpret_cast<const uint4*>(bq + (gw << 5));
+                      } else {
+                        pq = reinterpret_cast<const uint4*>(bq + tile_byte0) + (j0 + j) * (BLOCK * 2);
+                      }
+                      lo[q][j] = __ldcs(pq);
+                      hi[q][j] = __ldcs(pq + 1);
+                    }
+                  }
+                }
+#pragma unroll
+                for (int q = 0; q < GL; ++q) {
+#pragma unroll
+                  for (int j = 0; j < CHG; ++j) {
+                    if (j0 + j < WPT) {
+                      const uint32_t w = plane_pack(lo[q][j], hi[q][j]);
+                      C.at(kG.ops[PC + q].dst, j0 + j) = (!RG || ((C.valid >> (j0 + j)) & 1u)) ? w : 0u;
+                    }
                   }
                 }
               }
-#pragma unroll
-              for (int q = 0; q < GL; ++q) {
-#pragma unroll
-                for (int j = 0; j < CHG; ++j)
-                  if (j0 + j < WPT) C.at(kG.ops[PC + q].dst, j0 + j) = plane_pack(lo[q][j], hi[q][j]);
-              }
-            }
+            };
+            if (full) load_batch(PlaneBool<false>{});
+            else load_batch(PlaneBool<true>{});
           }
           break;   // GL == 0: this plane was loaded with the batch of an earlier op
         }
 #endif
+        if (!full) {
+          plane_ld_partial<WPT, BLOCK>(C, base, env0, wpe, o.dst);
+          break;
+        }
         const uint4* p = reinterpret_cast<const uint4*>(base + tile_byte0);
         constexpr int CH = WPT < 4 ? WPT : 4;     // loads in flight per thread: 2 * CH x 16 B
 #pragma unroll
@@ -743,12 +769,17 @@ __device__ __forceinline__ void plane_tile(const VmArgs& A, const PlaneProg& G, 
   T.env0 = env0;
   // byte offset of this thread's first word (word j is 256 words further), valid when `full`
   T.tile_byte0 = ((env0 * wpe + (int64_t)chunk * tile_words + tid) << 5);
+  T.gw_limit = (chunks == 1 ? A.n_envs * (int64_t)wpe : (env0 + 1) * (int64_t)wpe) - 1;
   T.W32 = W32; T.wpe = wpe; T.envs_per_tile = envs_per_tile; T.tile_words = tile_words; T.chunks = chunks;
   T.chunk = chunk; T.pitch = pitch; T.tile_rows = tile_rows; T.plane_stride = plane_stride;
   T.single_env = envs_per_tile == 1;
   // issue the DRAM requests of every plane this tile reads up front (L2 prefetch): the loads of
   // the later PLD ops then hit L2 and the compute of this CTA overlaps its own memory traffic
+#ifdef PLANE_STATIC
+  plane_run_ops<WPT, BLOCK, PLANE_PREFETCH, 0>(T, A, G, L, DT, 0, false);
+#else
   if (full) plane_run_ops<WPT, BLOCK, PLANE_PREFETCH, 0>(T, A, G, L, DT, 0, false);
+#endif
 
   // per-env rollout state of the thread that runs env (env0 + tid)'s scalar epilogue
   double ret_acc = 0.0, disc = 1.0;
@@ -758,7 +789,11 @@ __device__ __forceinline__ void plane_tile(const VmArgs& A, const PlaneProg& G, 
   for (int t = 0; t < NT; ++t) {
   const bool last_step = t == NT - 1;
   // next step's action planes: start their DRAM reads now (L2 prefetch)
+#ifdef PLANE_STATIC
+  if (!last_step) plane_run_ops<WPT, BLOCK, PLANE_PREFETCH_NEXT, 0>(T, A, G, L, DT, t, last_step);
+#else
   if (full && !last_step) plane_run_ops<WPT, BLOCK, PLANE_PREFETCH_NEXT, 0>(T, A, G, L, DT, t, last_step);
+#endif
   plane_run_ops<WPT, BLOCK, PLANE_RUN, 0>(T, A, G, L, DT, t, last_step);
 
   if (L.nred > 0) {

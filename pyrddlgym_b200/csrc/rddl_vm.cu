@@ -137,27 +137,33 @@ struct rddl_program {
 };
 
 // Resident CTAs per SM the specialised kernel is compiled for (its register budget): the plane
-// registers are machine registers there, and programs of Wildfire's size fit 3 CTAs x 256 threads
-// (<= 85 registers) without spilling. RDDL_PLANE_MINB overrides (tuning knob).
-static int plane_static_min_blocks(int wpt) {
+// registers are machine registers there. Launches of many waves (big grids / big batches) run best
+// at 3 CTAs x 256 threads (<= 85 registers: Wildfire-sized programs still do not spill) -- more
+// warps to hide the DRAM latency of each new tile; single-wave launches (fused rollouts of a few
+// thousand envs) keep 2 CTAs with the full register budget, one-word-per-thread tiles 4.
+// RDDL_PLANE_MINB overrides (tuning knob).
+static int plane_static_min_blocks(int wpt, const RddlLaunch& adj, int64_t n_envs) {
   if (const char* e = getenv("RDDL_PLANE_MINB")) {
     const int v = atoi(e);
     if (v >= 1 && v <= 8) return v;
   }
+  const int64_t tiles = (n_envs + adj.G - 1) / adj.G * adj.chunks;
+  if (tiles >= 148 * 2 * 3) return 3;
   return wpt == 1 ? 4 : PLANE_MIN_BLOCKS;
 }
 
 // The specialised kernel of plane launch `li` for the tile geometry `adj` / wpt, or nullptr (then the
 // interpreter kernel runs): compiled with NVRTC on first use, cubins cached on disk.
-static JitKernel* jit_get(rddl_program* g, int li, int wpt, int blk, const RddlLaunch& adj) {
+static JitKernel* jit_get(rddl_program* g, int li, int wpt, int blk, const RddlLaunch& adj, int64_t n_envs) {
   if (!g->specialize) return nullptr;
+  const int minb = plane_static_min_blocks(wpt, adj, n_envs);
   for (JitKernel& k : g->jit)
-    if (k.launch == li && k.wpt == wpt && k.G == adj.G && k.ipt == adj.ipt) return k.failed ? nullptr : &k;
+    if (k.launch == li && k.wpt == wpt && k.G == adj.G && k.ipt == adj.ipt && k.minb == minb) return k.failed ? nullptr : &k;
   JitKernel k;
-  k.launch = li; k.wpt = wpt; k.G = adj.G; k.ipt = adj.ipt;
+  k.launch = li; k.wpt = wpt; k.G = adj.G; k.ipt = adj.ipt; k.minb = minb;
   uint8_t dt[RDDL_MAX_TENSORS] = {0};
   for (size_t i = 0; i < g->tensors.size(); ++i) dt[i] = (uint8_t)g->tensors[i].dtype;
-  const std::string data = plane_static_data(g->plane_progs[li], adj, dt, wpt, plane_static_min_blocks(wpt), blk, g->pools());
+  const std::string data = plane_static_data(g->plane_progs[li], adj, dt, wpt, minb, blk, g->pools());
   std::string cubin, err;
   bool hit = false;
   JitDriver& drv = jit_driver();
@@ -290,23 +296,18 @@ static int plane_geometry(const RddlLaunch& L, int64_t n_envs, RddlLaunch* adj, 
   int best_w = 0, best_ept = 0;
   int64_t best_score = -1;
   const int order[3] = {2, 1, 4};                          // tie-break: preference order
-  // first pass: tile sizes that divide the batch (a partial last tile takes the slower masked
-  // path, and in a fused rollout the slowest CTA sets the kernel time); second pass: any
-  for (int pass = 0; pass < 2 && best_w == 0; ++pass) {
-    for (int k = 0; k < 3; ++k) {
-      const int w = order[k];
-      if (w > wpt || wpe > 256 * w) continue;
-      int cap = (int)((256 * w) / wpe);
-      if (cap > 32) cap = 32;
-      const int resident = w == 1 ? 4 : 2;
-      for (int ept = cap; ept >= 1 && ept * 2 > cap; --ept) {
-        if (pass == 0 && n_envs % ept != 0) continue;
-        const int64_t tiles = (n_envs + ept - 1) / ept;
-        const int64_t per_sm = (tiles + sms - 1) / sms;
-        if (per_sm > resident) continue;
-        const int64_t score = per_sm * ept * 8 + k;        // envs on the busiest SM, then preference
-        if (best_score < 0 || score < best_score) { best_score = score; best_w = w; best_ept = ept; }
-      }
+  for (int k = 0; k < 3; ++k) {
+    const int w = order[k];
+    if (w > wpt || wpe > 256 * w) continue;
+    int cap = (int)((256 * w) / wpe);
+    if (cap > 32) cap = 32;
+    const int resident = w == 1 ? 4 : 2;
+    for (int ept = cap; ept >= 1 && ept * 2 > cap; --ept) {
+      const int64_t tiles = (n_envs + ept - 1) / ept;
+      const int64_t per_sm = (tiles + sms - 1) / sms;
+      if (per_sm > resident) continue;
+      const int64_t score = per_sm * ept * 8 + k;          // envs on the busiest SM, then preference
+      if (best_score < 0 || score < best_score) { best_score = score; best_w = w; best_ept = ept; }
     }
   }
   if (best_w == 0) return wpt;
@@ -482,7 +483,7 @@ extern "C" int64_t rddl_plane_source(const void* optable, size_t nbytes, int lau
   const int wpt = plane_geometry(g->launches[launch], n_envs, &adj, &blk);
   uint8_t dt[RDDL_MAX_TENSORS] = {0};
   for (size_t i = 0; i < g->tensors.size(); ++i) dt[i] = (uint8_t)g->tensors[i].dtype;
-  const std::string s = plane_static_data(g->plane_progs[launch], adj, dt, wpt, plane_static_min_blocks(wpt), blk, g->pools());
+  const std::string s = plane_static_data(g->plane_progs[launch], adj, dt, wpt, plane_static_min_blocks(wpt, adj, n_envs), blk, g->pools());
   delete g;
   if (out && cap > 0) {
     const size_t n = s.size() < cap - 1 ? s.size() : cap - 1;
@@ -509,7 +510,7 @@ extern "C" int rddl_plane_precompile(const void* optable, size_t nbytes, int64_t
     int blk = 256;
     const int wpt = plane_geometry(g->launches[i], n_envs, &adj, &blk);
     std::string cubin, err;
-    if (!jit_compile_plane(plane_static_data(g->plane_progs[i], adj, dt, wpt, plane_static_min_blocks(wpt), blk, g->pools()), &cubin,
+    if (!jit_compile_plane(plane_static_data(g->plane_progs[i], adj, dt, wpt, plane_static_min_blocks(wpt, adj, n_envs), blk, g->pools()), &cubin,
                            &err, nullptr)) {
       g_create_error = err;
       delete g;
@@ -598,7 +599,7 @@ static int run_plan(rddl_program* g, int plan, void* const* tensors, const doubl
     if (L.kind == 1) {
       const int li = (int)(&L - g->launches.data());
       wpt = plane_geometry(L, n_envs, &A.L, &jit_block, g->specialize);
-      jk = jit_get(g, li, wpt, jit_block, A.L);
+      jk = jit_get(g, li, wpt, jit_block, A.L, n_envs);
       if (!jk && g->specialize) wpt = plane_geometry(L, n_envs, &A.L, &jit_block, false);   // interpreter kernel
     }
     const int envs_per_cta = L.kind == 1 ? A.L.G : 256 / L.G;
