@@ -85,20 +85,24 @@ int rddl_rollout(rddl_program_t* prog, void* const* tensors, uint32_t* status, i
  * five numbers with one NCCL all-gather (pyrddlgym_b200/parallel.py). */
 int rddl_return_stats(const double* returns, int64_t n, double* out5, void* cuda_stream);
 
-/* Run-time specialisation of the bit-plane kernels (no reference counterpart; the closest analogue
- * is the reference's JAX backend jit-compiling a model once, pyRDDLGym-jax, docs/jax.rst). On the
- * first run of a plane launch the library recompiles its kernel source for sm_100a with NVRTC, with
- * the launch's program and geometry as constants (pyrddlgym_b200/csrc/rddl_jit.h); results are
- * bit-identical to the interpreter kernel's, which runs instead whenever NVRTC is unavailable.
+/* Run-time specialisation of the kernels (no reference counterpart; the closest analogue is the
+ * reference's JAX backend jit-compiling a model once, pyRDDLGym-jax, docs/jax.rst). The library
+ * recompiles its own kernel sources for sm_100a with NVRTC with a launch's program, pools and
+ * geometry as constants (pyrddlgym_b200/csrc/rddl_jit.h): plane launches on their first run, the
+ * scalar launches of a program (one module) once it has issued a number of scalar launches. Results
+ * are bit-identical to the interpreter kernels', which run instead whenever NVRTC is unavailable.
  *   rddl_program_option(prog, 0, v)  v = 0: interpreter kernels only; 1 (default unless the
  *                                    environment has RDDL_B200_JIT=0): specialise
+ *   rddl_program_option(prog, 1, n)  scalar kernels are specialised after n scalar launches
+ *                                    (default 24, $RDDL_B200_JIT_HOT; 0 = on first use)
  *   rddl_program_info(prog, 5 | 6 | 7)  specialised kernels in use | launches that fell back to the
  *                                    interpreter (rddl_jit_error has the compiler log) | cubins
  *                                    taken from the disk cache (<library dir>/jit_cache or
  *                                    $RDDL_B200_JIT_CACHE)
  *   rddl_plane_precompile            host only (no device needed): fills the disk cache with the
- *                                    kernels an op table needs for batches of n_envs; returns the
- *                                    number of kernels, < 0 on error (rddl_last_error(NULL))
+ *                                    modules an op table needs for batches of n_envs (one per plane
+ *                                    launch + one for all scalar launches); returns their number,
+ *                                    < 0 on error (rddl_last_error(NULL))
  *   rddl_plane_source                inspection aid: the generated constants of plane launch `launch`;
  *                                    returns the text length, writes at most cap - 1 bytes + NUL */
 int rddl_program_option(rddl_program_t* prog, int what, int64_t value);

@@ -9,7 +9,7 @@ SOURCES = ['rddl_vm.cu']
 HEADERS = ['rddl_plan.h', 'philox.cuh', os.path.join('..', '..', 'include', 'rddl_b200.h')]
 LIB = os.path.join(CSRC, 'librddl_b200.so')
 
-NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-fmad=false',
               '-shared', '-Xcompiler', '-fPIC']
 
 

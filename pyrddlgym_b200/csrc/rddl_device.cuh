@@ -116,18 +116,21 @@ struct VmPools {
   const RddlAddr* addrs;
   const RddlRedSlot* redslots;
   const int64_t* red_off;
+  const RddlCsr* csrs;
 };
 
 // One instruction (raw = its four 32-bit words) of the program of launch L for one (env, element):
 // idx[] holds the element's scope coordinates, r[] the virtual registers. `pc` is advanced by
 // control-flow ops (prog = the launch's instruction stream; null for straight-line specialised
 // programs, which contain none). cap (optional): values stored to tensors cap_tensor, cap_tensor + 1.
-template <int NREG>
+// OPC >= 0: the opcode as a template constant (specialised builds: only that case is compiled in).
+template <int NREG, int OPC = -1>
 __device__ __forceinline__ void vm_exec_one(const VmArgs& A, const VmPools& P, const RddlLaunch& L, const int64_t env,
                                             const uint64_t step, int32_t* idx, uint64_t* redval, uint64_t* r,
                                             int32_t* jcur, int32_t* jend, const RddlInsn* prog, int& pc,
-                                            const uint4 raw, uint64_t* cap, const int cap_tensor) {
-  const uint32_t op = raw.x & 0xff;
+                                            const uint4 raw, uint64_t* cap, const int cap_tensor,
+                                            const uint4 raw2_static = uint4{0u, 0u, 0u, 0u}) {
+  const uint32_t op = OPC >= 0 ? (uint32_t)OPC : (raw.x & 0xff);
   const uint32_t dst = raw.x >> 16;
   const uint32_t ra = raw.y & 0xffff, rb = raw.y >> 16;
   const uint32_t rc = raw.z & 0xffff;
@@ -292,7 +295,7 @@ __device__ __forceinline__ void vm_exec_one(const VmArgs& A, const VmPools& P, c
       break;
     case OP_CSRLOOP:
     case OP_CSREND: {
-      const RddlCsr* cs = A.csrs + imm;
+      const RddlCsr* cs = P.csrs + imm;
       int32_t j;
       if (op == OP_CSRLOOP) {
         int64_t row = cs->row_c0;
@@ -334,8 +337,9 @@ __device__ __forceinline__ void vm_exec_one(const VmArgs& A, const VmPools& P, c
     case OP_SUMLOOP: {
       // sum over one loop variable of t1 [* t2], t = plain tensor reads: native MAC loop.
       // data word (next instruction): dst | a << 16 = extent or CSR id, imm = address of t2
-      const uint4 raw2 = __ldg(reinterpret_cast<const uint4*>(prog + pc));
-      ++pc;
+      // (specialised programs pass the data word; the interpreter fetches it and skips over it)
+      const uint4 raw2 = prog ? __ldg(reinterpret_cast<const uint4*>(prog + pc)) : raw2_static;
+      if (prog) ++pc;
       const uint32_t arg = (raw2.x >> 16) | ((raw2.y & 0xffff) << 16);
       const bool is_csr = rb & 1u, two = rb & 2u, flt = rb & 4u;
       const int slot = (int)ra;
@@ -357,7 +361,7 @@ __device__ __forceinline__ void vm_exec_one(const VmArgs& A, const VmPools& P, c
       int32_t j0 = 0, j1 = (int32_t)arg;
       const int32_t* cols = nullptr;
       if (is_csr) {
-        const RddlCsr* cs = A.csrs + arg;
+        const RddlCsr* cs = P.csrs + arg;
         int64_t row = cs->row_c0;
         for (int i = 0; i < cs->row_naxis; ++i) row += cs->row_coef[i] * (int64_t)idx[cs->row_axis[i]];
         j0 = __ldg(A.pool + cs->rowptr_off + row);
@@ -400,11 +404,78 @@ __device__ __noinline__ void vm_exec_element(const VmArgs& A, const RddlLaunch& 
   int32_t jcur[4], jend[4];
   const int npc = L.pc_end - L.pc_begin;
   const RddlInsn* prog = A.insns + L.pc_begin;
-  const VmPools P = {A.consts, A.addrs, A.redslots, A.red_off};
+  const VmPools P = {A.consts, A.addrs, A.redslots, A.red_off, A.csrs};
   int pc = 0;
   while (pc < npc) {
     const uint4 raw = __ldg(reinterpret_cast<const uint4*>(prog + pc));
     ++pc;
     vm_exec_one<NREG>(A, P, L, env, step, idx, redval, r, jcur, jend, prog, pc, raw, nullptr, 0);
+  }
+}
+
+// One CTA of a scalar launch: a group of G consecutive threads works on one env, each thread visits
+// `ipt` elements strided by G, then the per-env reductions are combined (shuffle within the group,
+// shared memory across warps when G = 256). `exec(env, idx, redval)` runs the launch's program for
+// one element: the bytecode interpreter (rddl_level_interp) or a specialised instruction sequence
+// (rddl_level_static, rddl_level_static.cuh).
+template <typename Exec>
+__device__ __forceinline__ void level_tile(const VmArgs& A, const RddlLaunch& L, const int64_t* red_off, Exec exec) {
+  const int G = L.G;
+  const int tid = threadIdx.x;
+  const int lane = tid & (G - 1);
+  const int envs_per_cta = 256 / G;
+  const int64_t chunk = blockIdx.x % L.chunks;
+  const int64_t env = (int64_t)(blockIdx.x / L.chunks) * envs_per_cta + tid / G;
+  const bool env_ok = env < A.n_envs;
+
+  int32_t idx[RDDL_MAX_IDX];
+  uint64_t redval[RDDL_MAX_RED];
+#pragma unroll
+  for (int j = 0; j < RDDL_MAX_RED; ++j) redval[j] = j < L.nred ? red_identity(L.red_op[j]) : 0;
+
+  for (int it = 0; it < L.ipt; ++it) {
+    const int64_t elem = chunk * ((int64_t)G * L.ipt) + (int64_t)it * G + lane;
+    if (!env_ok || elem >= L.E) continue;
+    {  // decode the element index into scope coordinates (C order)
+      int64_t rem = elem;
+#pragma unroll
+      for (int k = RDDL_MAX_IDX - 1; k >= 0; --k) {
+        if (k < L.rank) {
+          int64_t e = L.extent[k];
+          idx[k] = (int32_t)(rem % e);
+          rem /= e;
+        }
+      }
+    }
+    exec(env, idx, redval);
+  }
+
+  // per-env reductions: shuffle within the group, shared memory across warps when G = 256
+  if (L.nred > 0) {
+    __shared__ uint64_t sm[RDDL_MAX_RED][8];
+    for (int j = 0; j < L.nred; ++j) {
+      const int op = L.red_op[j];
+      uint64_t v = redval[j];
+      const int w = G < 32 ? G : 32;
+      for (int o = w >> 1; o > 0; o >>= 1) v = red_combine(op, v, __shfl_xor_sync(0xffffffffu, v, o, 32));
+      if (G > 32) {
+        if ((tid & 31) == 0) sm[j][tid >> 5] = v;
+      } else if (lane == 0 && env_ok) {
+        A.red[red_off[L.red_slot[j]] * A.n_envs + env * L.chunks + chunk] = v;
+      }
+    }
+    if (G > 32) {
+      __syncthreads();
+      const int nw = G / 32;  // warps per group
+      if (lane == 0 && env_ok) {
+        const int w0 = (tid / G) * nw;
+        for (int j = 0; j < L.nred; ++j) {
+          const int op = L.red_op[j];
+          uint64_t v = sm[j][w0];
+          for (int w = 1; w < nw; ++w) v = red_combine(op, v, sm[j][w0 + w]);
+          A.red[red_off[L.red_slot[j]] * A.n_envs + env * L.chunks + chunk] = v;
+        }
+      }
+    }
   }
 }

@@ -52,6 +52,7 @@ struct JitPools {
   const RddlAddr* addrs; int64_t n_addrs;
   const RddlRedSlot* redslots; int64_t n_redslots;
   const int64_t* red_off;
+  const RddlCsr* csrs; int64_t n_csrs;
 };
 
 // The scalar programs fused into a plane launch's epilogue (reward / termination from the
@@ -104,6 +105,65 @@ static bool jit_fused_static(const PlaneProg& G, const JitPools& P, std::string&
   for (int64_t i = 0; i < P.n_redslots; ++i) s += jit_fmt("%lldll,", (long long)P.red_off[i]);
   s += "0};\n";
   return true;
+}
+
+// The constants of the specialised scalar kernels of a whole program ("level_static_data.inc"): every
+// instruction word, the pools, the launches, and the list of scalar launches (PS_LEVELS) that get a
+// kernel each (rddl_level_static_<launch index>, rddl_level_static.cuh). Empty string: program too
+// large to embed (the interpreter kernels run).
+static std::string level_static_data(const JitPools& P, const RddlLaunch* launches, int n_launches) {
+  if (P.n_insns > 4096 || P.n_consts > 8192 || P.n_addrs > 1024 || P.n_csrs > 64 || P.n_redslots > 256) return "";
+  std::string s, list;
+  for (int i = 0; i < n_launches; ++i)
+    if (launches[i].kind == 0) list += jit_fmt(" X(%lld)", i);
+  if (list.empty()) return "";
+  s += "#define PS_LEVELS(X)" + list + "\n";
+  s += "__device__ constexpr uint32_t kInsnWords[][4] = {";
+  for (int64_t pc = 0; pc < P.n_insns; ++pc) {
+    uint32_t w[4];
+    memcpy(w, &P.insns[pc], 16);
+    s += "{" + jit_fmt("0x%llxu,", w[0]) + jit_fmt("0x%llxu,", w[1]) + jit_fmt("0x%llxu,", w[2]) + jit_fmt("0x%llxu},", w[3]);
+    if ((pc & 7) == 7) s += "\n";
+  }
+  s += "{0,0,0,0}};\n__device__ constexpr uint64_t kConsts[] = {";
+  for (int64_t i = 0; i < P.n_consts; ++i) s += jit_fmt("0x%llxull,", (long long)P.consts[i]) + ((i & 7) == 7 ? "\n" : "");
+  s += "0};\n__device__ constexpr RddlAddr kAddrs[] = {";
+  for (int64_t i = 0; i < P.n_addrs; ++i) {
+    const RddlAddr& a = P.addrs[i];
+    s += "{" + jit_fmt("%lld,", a.tensor) + jit_fmt("%lld,", a.naxis) + jit_fmt("%lldll,", (long long)a.env_stride) +
+         jit_fmt("%lldll,{", (long long)a.c0);
+    for (int k = 0; k < 8; ++k) s += jit_fmt("%lld,", a.axis[k]);
+    s += "},{";
+    for (int k = 0; k < 8; ++k) s += jit_fmt("%lldll,", (long long)a.coef[k]);
+    s += "}," + jit_fmt("%lld,", a.nreg) + jit_fmt("%lld,{", a.pad);
+    for (int k = 0; k < 4; ++k) s += jit_fmt("%lld,", a.reg[k]);
+    s += "},{";
+    for (int k = 0; k < 4; ++k) s += jit_fmt("%lldll,", (long long)a.rstride[k]);
+    s += "},{";
+    for (int k = 0; k < 4; ++k) s += jit_fmt("%lldll,", (long long)a.rextent[k]);
+    s += "}},\n";
+  }
+  s += "{}};\n__device__ constexpr RddlRedSlot kRedSlots[] = {";
+  for (int64_t i = 0; i < P.n_redslots; ++i) s += "{" + jit_fmt("%lld,", P.redslots[i].op) + jit_fmt("%lld},", P.redslots[i].chunks);
+  s += "{}};\n__device__ constexpr int64_t kRedOff[] = {";
+  for (int64_t i = 0; i < P.n_redslots; ++i) s += jit_fmt("%lldll,", (long long)P.red_off[i]);
+  s += "0};\n__device__ constexpr RddlCsr kCsrs[] = {";
+  for (int64_t i = 0; i < P.n_csrs; ++i) {
+    const RddlCsr& c = P.csrs[i];
+    s += "{" + jit_fmt("%lldll,", (long long)c.rowptr_off) + jit_fmt("%lld,", c.ncols) + jit_fmt("%lld,{", c.pad);
+    for (int k = 0; k < 4; ++k) s += jit_fmt("%lldll,", (long long)c.col_off[k]);
+    s += "},{";
+    for (int k = 0; k < 4; ++k) s += jit_fmt("%lld,", c.slot[k]);
+    s += "}," + jit_fmt("%lldll,", (long long)c.row_c0) + jit_fmt("%lld,", c.row_naxis) + jit_fmt("%lld,{", c.pad2);
+    for (int k = 0; k < 8; ++k) s += jit_fmt("%lld,", c.row_axis[k]);
+    s += "},{";
+    for (int k = 0; k < 8; ++k) s += jit_fmt("%lldll,", (long long)c.row_coef[k]);
+    s += "}},\n";
+  }
+  s += "{}};\n__device__ constexpr RddlLaunch kLaunches[] = {";
+  for (int i = 0; i < n_launches; ++i) { jit_launch_init(s, launches[i]); s += ",\n"; }
+  s += "};\n";
+  return s;
 }
 
 static std::string plane_static_data(const PlaneProg& G, const RddlLaunch& L, const uint8_t* dtype, int wpt,
@@ -223,11 +283,24 @@ static uint64_t jit_hash(uint64_t h, const std::string& s) {
 }
 
 static const char* const kJitHeaders[] = {"rddl_stdint.h", "philox.cuh", "rddl_plan.h", "rddl_samplers.cuh",
-                                          "rddl_device.cuh", "rddl_plane.cuh"};
+                                          "rddl_device.cuh", "rddl_plane.cuh", "rddl_level_static.cuh"};
 static const char* const kJitMain = "#define PLANE_STATIC 1\n#include \"rddl_device.cuh\"\n#include \"rddl_plane.cuh\"\n";
+static const char* const kJitMainLevel = "#include \"rddl_level_static.cuh\"\n";
 
 // Compiles (or fetches from the disk cache) the specialised kernel for `data`; the cubin comes back in *cubin.
+static bool jit_compile(const std::string& data, const char* data_name, const char* main_src, const char* prefix,
+                        std::string* cubin, std::string* err, bool* cache_hit);
+
 static bool jit_compile_plane(const std::string& data, std::string* cubin, std::string* err, bool* cache_hit) {
+  return jit_compile(data, "plane_static_data.inc", kJitMain, "plane", cubin, err, cache_hit);
+}
+
+static bool jit_compile_level(const std::string& data, std::string* cubin, std::string* err, bool* cache_hit) {
+  return jit_compile(data, "level_static_data.inc", kJitMainLevel, "level", cubin, err, cache_hit);
+}
+
+static bool jit_compile(const std::string& data, const char* data_name, const char* main_src, const char* prefix,
+                        std::string* cubin, std::string* err, bool* cache_hit) {
   const std::string dir = jit_lib_dir();
   std::vector<std::string> texts;
   uint64_t h = 0xcbf29ce484222325ull;
@@ -238,13 +311,13 @@ static bool jit_compile_plane(const std::string& data, std::string* cubin, std::
     texts.push_back(std::move(t));
   }
   h = jit_hash(h, data);
-  h = jit_hash(h, kJitMain);
+  h = jit_hash(h, main_src);
   JitApi& api = jit_api();
-  h = jit_hash(h, jit_fmt("nvrtc %lld.", api.major) + jit_fmt("%lld sm_100a O3 lineinfo default-device", api.minor));
+  h = jit_hash(h, jit_fmt("nvrtc %lld.", api.major) + jit_fmt("%lld sm_100a O3 lineinfo default-device fmad=false", api.minor));
   const char* cdir = getenv("RDDL_B200_JIT_CACHE");
   const std::string cache_dir = cdir && *cdir ? std::string(cdir) : dir + "/jit_cache";
   char name[64];
-  snprintf(name, sizeof name, "/plane_%016llx.cubin", (unsigned long long)h);
+  snprintf(name, sizeof name, "/%s_%016llx.cubin", prefix, (unsigned long long)h);
   const std::string path = cache_dir + name;
   if (cache_hit) *cache_hit = false;
   if (jit_read_file(path, cubin) && cubin->size() > 64) {
@@ -255,16 +328,18 @@ static bool jit_compile_plane(const std::string& data, std::string* cubin, std::
   std::vector<const char*> hdr_src, hdr_name;
   for (size_t i = 0; i < texts.size(); ++i) { hdr_src.push_back(texts[i].c_str()); hdr_name.push_back(kJitHeaders[i]); }
   hdr_src.push_back(data.c_str());
-  hdr_name.push_back("plane_static_data.inc");
+  hdr_name.push_back(data_name);
   nvrtcProgram prog;
-  if (api.CreateProgram(&prog, kJitMain, "rddl_plane_static.cu", (int)hdr_src.size(), hdr_src.data(), hdr_name.data()) !=
+  if (api.CreateProgram(&prog, main_src, "rddl_static.cu", (int)hdr_src.size(), hdr_src.data(), hdr_name.data()) !=
       NVRTC_SUCCESS) {
     *err = "nvrtcCreateProgram failed";
     return false;
   }
+  // --fmad=false: no contraction across what the interpreter executes as separate multiply / add
+  // instructions (the ahead-of-time build uses the same flag), so both builds round identically
   const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "--generate-line-info",
-                        "--device-as-default-execution-space"};
-  const nvrtcResult rc = api.CompileProgram(prog, 4, opts);
+                        "--device-as-default-execution-space", "--fmad=false"};
+  const nvrtcResult rc = api.CompileProgram(prog, 5, opts);
   if (rc != NVRTC_SUCCESS) {
     size_t n = 0;
     api.GetProgramLogSize(prog, &n);

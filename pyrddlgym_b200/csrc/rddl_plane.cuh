@@ -66,7 +66,7 @@ __device__ __forceinline__ void vm_exec_static(const VmArgs& A, const VmPools& P
     constexpr uint4 raw = {kInsnWords[PC - PS_INSN_BASE][0], kInsnWords[PC - PS_INSN_BASE][1],
                            kInsnWords[PC - PS_INSN_BASE][2], kInsnWords[PC - PS_INSN_BASE][3]};
     int pc = 0;
-    vm_exec_one<40>(A, P, L, env, step, idx, redval, r, nullptr, nullptr, nullptr, pc, raw, cap, cap_tensor);
+    vm_exec_one<40, (int)(raw.x & 0xff)>(A, P, L, env, step, idx, redval, r, nullptr, nullptr, nullptr, pc, raw, cap, cap_tensor);
     vm_exec_static<PC + 1, END>(A, P, L, env, step, idx, redval, r, cap, cap_tensor);
   }
 }
@@ -833,7 +833,7 @@ __device__ __forceinline__ void plane_tile(const VmArgs& A, const PlaneProg& G, 
 #if defined(PLANE_STATIC) && PS_FUSED_STATIC
       // specialised epilogue: straight-line code, reward / done taken from the stores themselves
       uint64_t cap[2] = {0, 0};
-      const VmPools P = {kConsts, kAddrs, kRedSlots, kRedOff};
+      const VmPools P = {kConsts, kAddrs, kRedSlots, kRedOff, nullptr};
       {
         uint64_t r0[40];
         vm_exec_static<kG.fused[0].pc_begin, kG.fused[0].pc_end>(A, P, kG.fused[0], ge, A.step + t, idx0, rv, r0, cap, G.pad);

@@ -25,64 +25,18 @@
 
 #include "rddl_plane.cuh"
 
+// Functor form of the interpreter (a named type instead of a lambda: this kernel is built ahead of time).
+template <int NREG>
+struct LevelInterpExec {
+  const VmArgs& A;
+  __device__ __forceinline__ void operator()(int64_t env, int32_t* idx, uint64_t* redval) const {
+    vm_exec_element<NREG>(A, A.L, env, A.step, idx, redval);
+  }
+};
+
 template <int NREG>
 __global__ void __launch_bounds__(256) rddl_level_interp(const __grid_constant__ VmArgs A) {
-  const RddlLaunch& L = A.L;
-  const int G = L.G;
-  const int tid = threadIdx.x;
-  const int lane = tid & (G - 1);
-  const int envs_per_cta = 256 / G;
-  const int64_t chunk = blockIdx.x % L.chunks;
-  const int64_t env = (int64_t)(blockIdx.x / L.chunks) * envs_per_cta + tid / G;
-  const bool env_ok = env < A.n_envs;
-
-  int32_t idx[RDDL_MAX_IDX];
-  uint64_t redval[RDDL_MAX_RED];
-#pragma unroll
-  for (int j = 0; j < RDDL_MAX_RED; ++j) redval[j] = j < L.nred ? red_identity(L.red_op[j]) : 0;
-
-  for (int it = 0; it < L.ipt; ++it) {
-    const int64_t elem = chunk * ((int64_t)G * L.ipt) + (int64_t)it * G + lane;
-    if (!env_ok || elem >= L.E) continue;
-    {  // decode the element index into scope coordinates (C order)
-      int64_t rem = elem;
-      for (int k = L.rank - 1; k >= 0; --k) {
-        int64_t e = L.extent[k];
-        idx[k] = (int32_t)(rem % e);
-        rem /= e;
-      }
-    }
-    vm_exec_element<NREG>(A, L, env, A.step, idx, redval);
-  }
-
-  // per-env reductions: shuffle within the group, shared memory across warps when G = 256
-  if (L.nred > 0) {
-    __shared__ uint64_t sm[RDDL_MAX_RED][8];
-    for (int j = 0; j < L.nred; ++j) {
-      const int op = L.red_op[j];
-      uint64_t v = redval[j];
-      const int w = G < 32 ? G : 32;
-      for (int o = w >> 1; o > 0; o >>= 1) v = red_combine(op, v, __shfl_xor_sync(0xffffffffu, v, o, 32));
-      if (G > 32) {
-        if ((tid & 31) == 0) sm[j][tid >> 5] = v;
-      } else if (lane == 0 && env_ok) {
-        A.red[A.red_off[L.red_slot[j]] * A.n_envs + env * L.chunks + chunk] = v;
-      }
-    }
-    if (G > 32) {
-      __syncthreads();
-      const int nw = G / 32;  // warps per group
-      if (lane == 0 && env_ok) {
-        const int w0 = (tid / G) * nw;
-        for (int j = 0; j < L.nred; ++j) {
-          const int op = L.red_op[j];
-          uint64_t v = sm[j][w0];
-          for (int w = 1; w < nw; ++w) v = red_combine(op, v, sm[j][w0 + w]);
-          A.red[A.red_off[L.red_slot[j]] * A.n_envs + env * L.chunks + chunk] = v;
-        }
-      }
-    }
-  }
+  level_tile(A, A.L, A.red_off, LevelInterpExec<NREG>{A});
 }
 
 // ---------------------------------------------------------------------------------------
@@ -127,10 +81,18 @@ struct rddl_program {
   std::vector<RddlInsn> h_insns;          // host copies for the specialised epilogue (rddl_jit.h)
   std::vector<uint64_t> h_consts;
   std::vector<RddlAddr> h_addrs;
+  std::vector<RddlCsr> h_csrs;
   JitPools pools() const {
     return JitPools{h_insns.data(), (int64_t)h_insns.size(), h_consts.data(), (int64_t)h_consts.size(),
-                    h_addrs.data(), (int64_t)h_addrs.size(), redslots.data(), (int64_t)redslots.size(), red_off.data()};
+                    h_addrs.data(), (int64_t)h_addrs.size(), redslots.data(), (int64_t)redslots.size(), red_off.data(),
+                    h_csrs.data(), (int64_t)h_csrs.size()};
   }
+  // specialised scalar kernels (rddl_level_static.cuh): one module per program, built once the
+  // program has issued `level_hot` scalar launches (tiered: short-lived programs never pay for it)
+  int64_t scalar_launches = 0, level_hot = 24;
+  bool level_tried = false;
+  CUmodule level_mod = nullptr;
+  std::vector<CUfunction> level_fn;       // per launch index, nullptr = interpreter kernel
   std::vector<JitKernel> jit;
   int64_t jit_built = 0, jit_cache_hits = 0, jit_failed = 0;
   std::string jit_err;
@@ -251,6 +213,40 @@ static bool decode_plane(const RddlLaunch& L, const RddlInsn* insns, const uint6
   return true;
 }
 
+// Builds (or fetches from the cubin cache) the specialised scalar kernels of the whole program.
+static void jit_levels(rddl_program* g) {
+  g->level_tried = true;
+  g->level_fn.assign(g->launches.size(), nullptr);
+  const std::string data = level_static_data(g->pools(), g->launches.data(), (int)g->launches.size());
+  if (data.empty()) return;
+  std::string cubin, err;
+  bool hit = false;
+  JitDriver& drv = jit_driver();
+  if (!drv.ok) err = "driver entry points unavailable";
+  else if (jit_compile_level(data, &cubin, &err, &hit)) {
+    if (drv.ModuleLoadData(&g->level_mod, cubin.data()) != CUDA_SUCCESS) err = "cuModuleLoadData failed";
+    else {
+      for (size_t i = 0; i < g->launches.size(); ++i) {
+        if (g->launches[i].kind != 0) continue;
+        char name[64];
+        snprintf(name, sizeof name, "rddl_level_static_%d", (int)i);
+        if (drv.ModuleGetFunction(&g->level_fn[i], g->level_mod, name) != CUDA_SUCCESS) {
+          g->level_fn[i] = nullptr;
+          err = std::string("cuModuleGetFunction failed: ") + name;
+        } else {
+          ++g->jit_built;
+        }
+      }
+    }
+  }
+  if (!err.empty()) {
+    ++g->jit_failed;
+    g->jit_err = err;
+  } else {
+    g->jit_cache_hits += hit;
+  }
+}
+
 // Words per thread and tile geometry of a plane launch for a batch of n_envs. The op table's tile is
 // 4 words per thread x 256 threads (32768 cells per CTA: big tiles amortise the per-tile overhead),
 // which is what large batches and multi-tile grids use. When the whole batch fits one wave of
@@ -366,6 +362,8 @@ static int parse_program(const void* optable, size_t nbytes, int device, rddl_pr
   g->h_insns.assign((const RddlInsn*)sec[2], (const RddlInsn*)sec[2] + hdr[4]);
   g->h_consts.assign((const uint64_t*)sec[3], (const uint64_t*)sec[3] + hdr[5]);
   g->h_addrs.assign((const RddlAddr*)sec[4], (const RddlAddr*)sec[4] + hdr[6]);
+  g->h_csrs.assign((const RddlCsr*)sec[5], (const RddlCsr*)sec[5] + hdr[7]);
+  if (const char* e = getenv("RDDL_B200_JIT_HOT")) g->level_hot = atoll(e);
   g->plane_progs.resize(g->launches.size());
   const int reward_tensor = (int)g->tensors.size() - 3;   // specials: __reward, __done, __chk
   for (size_t i = 0; i < g->launches.size(); ++i) {
@@ -518,6 +516,18 @@ extern "C" int rddl_plane_precompile(const void* optable, size_t nbytes, int64_t
     }
     ++n;
   }
+  {
+    const std::string data = level_static_data(g->pools(), g->launches.data(), (int)g->launches.size());
+    std::string cubin, err;
+    if (!data.empty()) {
+      if (!jit_compile_level(data, &cubin, &err, nullptr)) {
+        g_create_error = err;
+        delete g;
+        return RDDL_ERR_FORMAT;
+      }
+      ++n;
+    }
+  }
   delete g;
   return n;
 }
@@ -531,6 +541,7 @@ extern "C" void rddl_program_destroy(rddl_program_t* g) {
   cudaFree(g->d_alive);
   for (JitKernel& k : g->jit)
     if (k.mod) jit_driver().ModuleUnload(k.mod);
+  if (g->level_mod) jit_driver().ModuleUnload(g->level_mod);
   delete g;
 }
 
@@ -638,6 +649,14 @@ static int run_plan(rddl_program* g, int plan, void* const* tensors, const doubl
       } else if (wpt == 1) rddl_plane_interp<1, 256><<<(unsigned)blocks, 256, smem, stream>>>(A, G);
       else if (wpt == 2) rddl_plane_interp<2, 256><<<(unsigned)blocks, 256, smem, stream>>>(A, G);
       else rddl_plane_interp<4, 256><<<(unsigned)blocks, 256, smem, stream>>>(A, G);
+    } else if (L.kind == 0 && g->specialize && (g->level_tried || ++g->scalar_launches > g->level_hot) &&
+               (g->level_tried || (jit_levels(g), true)) && g->level_fn[(size_t)(&L - g->launches.data())]) {
+      void* params[] = {(void*)&A};
+      if (jit_driver().LaunchKernel(g->level_fn[(size_t)(&L - g->launches.data())], (unsigned)blocks, 1, 1, 256, 1, 1, 0,
+                                    (CUstream)stream, params, nullptr) != CUDA_SUCCESS) {
+        g->err = "cuLaunchKernel failed (specialised scalar kernel)";
+        return RDDL_ERR_CUDA;
+      }
     } else if (L.nregs <= 16) rddl_level_interp<16><<<(unsigned)blocks, 256, 0, stream>>>(A);
     else if (L.nregs <= 40) rddl_level_interp<40><<<(unsigned)blocks, 256, 0, stream>>>(A);
     else rddl_level_interp<RDDL_MAX_REGS><<<(unsigned)blocks, 256, 0, stream>>>(A);
@@ -776,6 +795,7 @@ extern "C" int rddl_check(rddl_program_t* g, int which, void* const* tensors, ui
 extern "C" int rddl_program_option(rddl_program_t* g, int what, int64_t value) {
   if (!g) return RDDL_ERR_ARG;
   if (what == 0) { g->specialize = value != 0; return RDDL_OK; }
+  if (what == 1) { g->level_hot = value; return RDDL_OK; }
   g->err = "rddl_program_option: unknown option";
   return RDDL_ERR_ARG;
 }

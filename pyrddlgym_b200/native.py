@@ -66,6 +66,7 @@ EXPORTS = ['rddl_program_create', 'rddl_program_destroy', 'rddl_last_error', 'rd
            'rddl_return_stats', 'rddl_program_option', 'rddl_jit_error', 'rddl_plane_precompile', 'rddl_plane_source']
 
 OPTION_SPECIALIZE = 0
+OPTION_SCALAR_HOT = 1       # scalar launches a program issues before its scalar kernels are specialised
 INFO_JIT_BUILT, INFO_JIT_FAILED, INFO_JIT_CACHE_HITS = 5, 6, 7
 
 

@@ -51,8 +51,9 @@ class BatchedSimulator:
 
     def __init__(self, program, n_envs=1, device='cuda:0', seed=0, env_offset=0, optable=None,
                  use_planes=True, use_contract=True, use_packed=True, specialize=None):
-        """``specialize``: build run-time specialised plane kernels (NVRTC, csrc/rddl_jit.h) for this
-        program; None = the library default (on, unless RDDL_B200_JIT=0), False = interpreter kernels."""
+        """``specialize``: run-time specialised kernels (NVRTC, csrc/rddl_jit.h) for this program.
+        None = the library default (on unless RDDL_B200_JIT=0: plane kernels on first use, scalar
+        kernels once the program is hot); True = everything on first use; False = interpreter kernels."""
         self.program = program
         self.n_envs = int(n_envs)
         self.device = torch.device(device)
@@ -66,6 +67,8 @@ class BatchedSimulator:
         self.native = native.NativeProgram(self.table.blob, index)
         if specialize is not None:
             self.native.option(native.OPTION_SPECIALIZE, 1 if specialize else 0)
+            if specialize:
+                self.native.option(native.OPTION_SCALAR_HOT, 0)
         self._jit_warned = False
         self.names = list(self.table.tensor_names)
         self.packed = set(self.table.packed)

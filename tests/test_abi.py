@@ -73,25 +73,30 @@ def test_every_workload_optable_decodes_on_the_host():
         assert rc == -2, (spec['name'], rc, lib.rddl_last_error(None))
 
 
-def test_specialised_plane_kernel_compiles_without_a_gpu(tmp_path, monkeypatch):
-    """rddl_plane_precompile: the generated constants + csrc/rddl_plane.cuh compile for sm_100a with
-    NVRTC on a machine without a device, land in the cubin cache, and the second call is a cache hit."""
+def test_specialised_kernels_compile_without_a_gpu(tmp_path, monkeypatch):
+    """rddl_plane_precompile: the generated constants + the kernel sources (csrc/rddl_plane.cuh,
+    csrc/rddl_level_static.cuh) compile for sm_100a with NVRTC on a machine without a device, land in
+    the cubin cache, and the second call is a cache hit."""
     import time
     from pyrddlgym_b200 import lowering, native, workloads
     monkeypatch.setenv('RDDL_B200_JIT_CACHE', str(tmp_path))
     tab = lowering.lower(workloads.load_program(workloads.wildfire(64, separable=True)))
     li = [i for i, L in enumerate(tab.launches) if L['kind'] == 1]
+    n_scalar = 1 if any(L['kind'] == 0 for L in tab.launches) else 0      # one module for all scalar launches
     assert li
     src = native.plane_source(tab.blob, li[0], 4096)
     assert '#define PS_NOPS %d' % tab.launches[li[0]]['n_insns'] in src and 'constexpr PlaneProg kG' in src
-    assert native.precompile(tab.blob, 4096) == len(li)
-    cubins = [f for f in os.listdir(tmp_path) if f.endswith('.cubin')]
-    assert len(cubins) == len(li) and os.path.getsize(os.path.join(tmp_path, cubins[0])) > 10000
+    assert native.precompile(tab.blob, 4096) == len(li) + n_scalar
+    planes = [f for f in os.listdir(tmp_path) if f.startswith('plane_') and f.endswith('.cubin')]
+    levels = [f for f in os.listdir(tmp_path) if f.startswith('level_') and f.endswith('.cubin')]
+    assert len(planes) == len(li) and len(levels) == n_scalar
+    assert os.path.getsize(os.path.join(tmp_path, planes[0])) > 10000
     t0 = time.time()
-    assert native.precompile(tab.blob, 4096) == len(li)
+    assert native.precompile(tab.blob, 4096) == len(li) + n_scalar
     assert time.time() - t0 < 0.5                      # served from the cache
-    # a different batch geometry (one word per thread for tiny batches) is a different kernel
-    assert native.precompile(tab.blob, 3) == len(li)
-    assert len([f for f in os.listdir(tmp_path) if f.endswith('.cubin')]) == 2 * len(li)
-    # programs without plane launches need nothing
-    assert native.precompile(lowering.lower(workloads.load_program(workloads.cartpole())).blob, 64) == 0
+    # a different batch geometry (smaller tiles for tiny batches) is a different plane kernel
+    assert native.precompile(tab.blob, 3) == len(li) + n_scalar
+    assert len([f for f in os.listdir(tmp_path) if f.startswith('plane_')]) == 2 * len(li)
+    # a scalar-only program: one module holding a kernel per scalar launch
+    cart = lowering.lower(workloads.load_program(workloads.cartpole()))
+    assert native.precompile(cart.blob, 64) == 1

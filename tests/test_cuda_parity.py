@@ -420,3 +420,39 @@ def test_return_statistics_kernel_matches_numpy():
         np.testing.assert_allclose(st['mean'], r.mean(), rtol=1e-12)
         np.testing.assert_allclose(st['std'], r.std(), rtol=1e-6, atol=1e-6)
         assert st['min'] == r.min() and st['max'] == r.max()
+
+
+@pytest.mark.parametrize('name,spec,N', [
+    ('cartpole', lambda: workloads.cartpole(), 300),
+    ('opzoo', lambda: workloads.opzoo(), 40),
+    ('distzoo', lambda: workloads.distzoo(), 64),
+    ('reservoir', lambda: workloads.reservoir(64), 33),
+    ('reservoir_exp', lambda: workloads.reservoir(30, rain='exponential'), 17),
+    ('pair', lambda: workloads.pair_contraction(40), 9),
+])
+def test_specialised_scalar_kernels_equal_interpreter_kernels(name, spec, N):
+    """rddl_level_static_<i> (the scalar launches of a program unrolled at compile time through the
+    same vm_exec_one as the interpreter, csrc/rddl_level_static.cuh) vs rddl_level_interp: identical
+    bits for every fluent, reward, termination, check and status word under the native Philox streams."""
+    import torch
+    p = workloads.load_program(spec())
+    a = _make(p, N, seed=9, specialize=True)
+    b = _make(p, N, seed=9, specialize=False)
+    rng = np.random.default_rng(4)
+    for t in range(4):
+        acts = harness.random_actions(p, N, rng, p_bool=0.3)
+        _, ra, da = a.step(acts)
+        _, rb, db = b.step(acts)
+        assert torch.equal(ra.view(torch.int64), rb.view(torch.int64)), t
+        assert torch.equal(da, db)
+        for nm in p.tensors:
+            if p.tensors[nm].kind != 'nonfluent':
+                fa, fb = a.fluent(nm), b.fluent(nm)
+                if fa.dtype == torch.float64:
+                    fa, fb = fa.view(torch.int64), fb.view(torch.int64)
+                assert torch.equal(fa, fb), (nm, t)
+        assert torch.equal(a.check_state_invariants(), b.check_state_invariants())
+        assert torch.equal(a.check_action_preconditions(), b.check_action_preconditions())
+        assert torch.equal(a.status, b.status)
+    assert a.specialised_kernels >= 1, a.native.jit_error()
+    assert b.specialised_kernels == 0

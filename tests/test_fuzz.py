@@ -47,7 +47,8 @@ def test_fuzz_cuda_vs_oracle(seed):
     from pyrddlgym_b200.simulator import BatchedSimulator
     p = random_program(seed, depth=4)
     N = 6
-    sim = BatchedSimulator(p, n_envs=N, device='cuda:0', seed=1)
+    # every third program runs through the run-time specialised scalar kernels from its first launch
+    sim = BatchedSimulator(p, n_envs=N, device='cuda:0', seed=1, specialize=True if seed % 3 == 0 else None)
     ora = OracleSimulator(p, n_envs=N, seed=1)
     to_np = lambda x: x.detach().cpu().numpy()
 
@@ -59,6 +60,8 @@ def test_fuzz_cuda_vs_oracle(seed):
            (lambda a: to_np(sim.check_action_preconditions(a)), lambda: to_np(sim.check_state_invariants())),
            ora, N, 3, np.random.default_rng(seed))
     assert np.array_equal(to_np(sim.status).astype(np.uint32), ora.status)
+    if seed % 3 == 0:
+        assert sim.specialised_kernels >= 1, sim.native.jit_error()
 
 
 def _grid_drive(p, table, make, N, steps, seed, inject):
