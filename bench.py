@@ -271,7 +271,8 @@ def run_gpu(args):
     n, N = w['n'], args.envs or w['envs']
     R = args.rollout or w['rollout']                 # env-steps per rollout = per bench step
     p = workloads.load_program(make_spec(name))
-    sim = BatchedSimulator(p, n_envs=N, device=dev, seed=42, env_offset=rank * N)
+    # specialize=True: every kernel of the program is specialised on its first launch (during the warm-up)
+    sim = BatchedSimulator(p, n_envs=N, device=dev, seed=42, env_offset=rank * N, specialize=True)
     K, W = args.steps, args.warmup
     gamma = float(p.discount)
     act_bytes = sum(N * int(np.prod(p.tensor_shape(a), dtype=np.int64)) * (1 if p.tensors[a].dtype == 'b' else 8)
@@ -393,8 +394,9 @@ def run_gpu(args):
                     'traffic': (MEASURED_TRAFFIC_BYTES_PER_ENV_STEP[name] * N * steps_per_launch
                                 if name in MEASURED_TRAFFIC_BYTES_PER_ENV_STEP else None),
                     'peak_source': peak_src,
-                    'kernel': ('rddl_plane_static (NVRTC-specialised build of rddl_plane_interp)'
-                               if top['name'] == 'rddl_plane_interp' and sim.specialised_kernels else top['name']),
+                    'kernel': ({'rddl_plane_interp': 'rddl_plane_static (NVRTC-specialised build of rddl_plane_interp)',
+                                'rddl_level_interp': 'rddl_level_static_%d (NVRTC-specialised build of rddl_level_interp)' % top['launch']
+                                }.get(top['name'], top['name']) if sim.specialised_kernels else top['name']),
                     'kernel_us': per_launch_ms * 1e3, 'env_steps_per_launch': steps_per_launch,
                     'kernel_share_of_rollout': top['ms'] / max(1e-9, sum(r['ms'] for r in prof)),
                     'algorithmic_bytes_per_launch': abytes,

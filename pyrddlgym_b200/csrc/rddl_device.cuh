@@ -370,23 +370,38 @@ __device__ __forceinline__ void vm_exec_one(const VmArgs& A, const VmPools& P, c
       }
       double facc = 0.0;
       int64_t iacc = 0;
-      for (int32_t j = j0; j < j1; ++j) {
-        const int64_t k = is_csr ? (int64_t)__ldg(cols + j) : (int64_t)j;
-        double fv[2] = {1.0, 1.0};
-        int64_t iv[2] = {1, 1};
+      // four terms at a time: their (dependent) index and value loads are issued together, the
+      // accumulation stays in index order (same rounding as the reference's left-to-right sum)
+      for (int32_t j = j0; j < j1; j += 4) {
+        int64_t k[4];
+        double fv[4][2];
+        int64_t iv[4][2];
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          if (q == 1 && !two) break;
-          const int64_t o = base[q] + stride[q] * k;
-          if (dts[q] == DT_REAL) fv[q] = reinterpret_cast<const double*>(ptr[q])[o];
-          else {
-            iv[q] = dts[q] == DT_BOOL ? (int64_t)(reinterpret_cast<const uint8_t*>(ptr[q])[o] != 0)
-                                      : reinterpret_cast<const int64_t*>(ptr[q])[o];
-            fv[q] = (double)iv[q];
+        for (int u = 0; u < 4; ++u)
+          k[u] = j + u < j1 ? (is_csr ? (int64_t)__ldg(cols + j + u) : (int64_t)(j + u)) : -1;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          fv[u][0] = fv[u][1] = 1.0;
+          iv[u][0] = iv[u][1] = 1;
+          if (k[u] < 0) continue;
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            if (q == 1 && !two) break;
+            const int64_t o = base[q] + stride[q] * k[u];
+            if (dts[q] == DT_REAL) fv[u][q] = reinterpret_cast<const double*>(ptr[q])[o];
+            else {
+              iv[u][q] = dts[q] == DT_BOOL ? (int64_t)(reinterpret_cast<const uint8_t*>(ptr[q])[o] != 0)
+                                           : reinterpret_cast<const int64_t*>(ptr[q])[o];
+              fv[u][q] = (double)iv[u][q];
+            }
           }
         }
-        if (flt) facc = __dadd_rn(facc, two ? __dmul_rn(fv[0], fv[1]) : fv[0]);
-        else iacc += two ? iv[0] * iv[1] : iv[0];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (k[u] < 0) continue;
+          if (flt) facc = __dadd_rn(facc, two ? __dmul_rn(fv[u][0], fv[u][1]) : fv[u][0]);
+          else iacc += two ? iv[u][0] * iv[u][1] : iv[u][0];
+        }
       }
       r[dst] = flt ? from_f(facc) : (uint64_t)iacc;
       break;
