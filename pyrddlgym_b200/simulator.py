@@ -149,6 +149,28 @@ class BatchedSimulator:
         done = self.check_terminal_states()
         return self.states, done
 
+    def reset_envs(self, mask):
+        """Re-initialises the environments selected by ``mask`` (bool[N]) in place -- the rows of every
+        fluent tensor go back to their initial values, status words are cleared -- while the others
+        keep running (vector-env auto-reset). The Philox step index stays global: draws remain
+        unique per (env, step)."""
+        mask = mask.to(self.device, dtype=torch.bool)
+        for name, own in self._owned_actions.items():
+            if self.t[name] is not own:
+                own.copy_(self.t[name])       # keep the live values of the other envs, in owned storage
+                self.t[name] = own
+        for name, v in self._init.items():
+            t = self.t[name]
+            if name in self.packed:
+                if name not in self._init_packed:
+                    self._init_packed[name] = self._pack(v.reshape(1, -1))
+                init = self._init_packed[name].expand_as(t)
+            else:
+                init = v.expand_as(t)
+            m = mask.reshape((self.n_envs,) + (1,) * (t.dim() - 1))
+            t.copy_(torch.where(m, init, t))
+        self.status.masked_fill_(mask, 0)
+
     @staticmethod
     def _pack(x):
         """bool [n, cells] -> int32 [n, cells / 32], cell i -> bit (i % 32) of word i / 32."""

@@ -1,0 +1,75 @@
+"""Vector-environment adapter over ``BatchedSimulator``: the batched counterpart of
+/root/reference/pyRDDLGym/core/env.py (RDDLEnv.reset :282-310, RDDLEnv.step :226-280) with the
+calling convention of ``gymnasium.vector.VectorEnv`` (duck-typed: gymnasium is not a dependency).
+
+N environments advance in lock-step on the device. ``step`` returns ``(obs, reward, terminated,
+truncated, info)`` with tensors of leading dimension N: ``terminated`` is the RDDL termination of
+the new state (env.py:262-264), ``truncated`` the horizon (env.py:265-266: an episode ends after
+``horizon`` steps). With ``auto_reset`` (default) the environments whose episode ended are reset in
+place after the step -- only their rows of the state tensors are re-initialised, the others keep
+running -- and ``info['episode_return']`` / ``info['episode_length']`` carry the finished episodes'
+discounted return and length (NaN / 0 elsewhere). Observations are the state fluents (MDP) or the
+observ-fluents (POMDP, env.py:270-273).
+"""
+import torch
+
+from pyrddlgym_b200.simulator import BatchedSimulator
+
+
+class BatchedRDDLEnv:
+    def __init__(self, program, n_envs, device='cuda:0', seed=0, horizon=None, auto_reset=True, **sim_kwargs):
+        self.sim = program if isinstance(program, BatchedSimulator) else BatchedSimulator(
+            program, n_envs=n_envs, device=device, seed=seed, **sim_kwargs)
+        self.program = self.sim.program
+        self.num_envs = self.sim.n_envs
+        self.device = self.sim.device
+        self.horizon = int(self.program.horizon if horizon is None else horizon)
+        self.discount = float(self.program.discount)
+        self.auto_reset = bool(auto_reset)
+        observ = self.program.names_of_kind('observ')
+        self.observation_names = list(observ) if observ else list(self.sim.state_names)
+        self.action_names = list(self.sim.action_names)
+        N, dev = self.num_envs, self.device
+        self.episode_step = torch.zeros(N, dtype=torch.int64, device=dev)
+        self.episode_return = torch.zeros(N, dtype=torch.float64, device=dev)
+        self._disc = torch.ones(N, dtype=torch.float64, device=dev)
+
+    # ---------------------------------------------------------------------------------
+    def _obs(self):
+        return {name: self.sim.fluent(name) for name in self.observation_names}
+
+    def reset(self, seed=None):
+        """All environments back to the initial state -> (obs, info)."""
+        if seed is not None:
+            self.sim.seed(seed)
+        self.sim.reset()
+        self.episode_step.zero_()
+        self.episode_return.zero_()
+        self._disc.fill_(1.0)
+        return self._obs(), {}
+
+    def step(self, actions):
+        """actions: name -> tensor / array [N, *shape] (missing action-fluents keep their defaults,
+        like RDDLEnv.step's partial action dicts)."""
+        full = {name: self.sim._init[name].expand_as(self.sim._owned_actions[name]) for name in self.action_names}
+        full.update(actions or {})
+        _, reward, terminated = self.sim.step(full)
+        reward = reward.clone()
+        terminated = terminated.to(torch.bool).clone()
+        self.episode_return += reward * self._disc
+        self._disc *= self.discount
+        self.episode_step += 1
+        truncated = (self.episode_step >= self.horizon) & ~terminated
+        ended = terminated | truncated
+        info = {'episode_return': torch.where(ended, self.episode_return, torch.full_like(self.episode_return, float('nan'))),
+                'episode_length': torch.where(ended, self.episode_step, torch.zeros_like(self.episode_step))}
+        if self.auto_reset:
+            self.sim.reset_envs(ended)
+            keep = (~ended).to(torch.float64)
+            self.episode_return *= keep
+            self._disc = torch.where(ended, torch.ones_like(self._disc), self._disc)
+            self.episode_step *= (~ended).to(torch.int64)
+        return self._obs(), reward, terminated, truncated, info
+
+    def close(self):
+        self.sim.close()

@@ -456,3 +456,41 @@ def test_specialised_scalar_kernels_equal_interpreter_kernels(name, spec, N):
         assert torch.equal(a.status, b.status)
     assert a.specialised_kernels >= 1, a.native.jit_error()
     assert b.specialised_kernels == 0
+
+
+def test_vector_env_auto_reset_and_truncation():
+    """BatchedRDDLEnv (env.py:226-310 for N envs): terminated / truncated flags, in-place reset of the
+    finished environments only, episode statistics; running environments are untouched by their
+    neighbours' resets (same rewards as a plain BatchedSimulator under the same actions and seed)."""
+    import torch
+    from pyrddlgym_b200.vector_env import BatchedRDDLEnv
+    p = workloads.load_program(workloads.cartpole())
+    N, H = 64, 25
+    env = BatchedRDDLEnv(p, N, seed=5, horizon=H)
+    ref = _make(p, N, seed=5)
+    obs, _ = env.reset()
+    g = torch.Generator(device='cuda').manual_seed(2)
+    (an,) = env.action_names
+    init = {s: env.sim._init[s].clone() for s in env.sim.state_names}
+    ever_reset = torch.zeros(N, dtype=torch.bool, device='cuda')
+    n_term = 0
+    for t in range(H):
+        # strong pushes on a third of the envs: they leave the track / tip over and terminate early
+        force = (torch.rand((N,) + tuple(p.tensor_shape(an)), device='cuda', generator=g, dtype=torch.float64) - 0.5) * 4.0
+        force[: N // 3] = 10.0
+        obs, r, term, trunc, info = env.step({an: force})
+        _, r_ref, d_ref = ref.step({an: force})
+        live = ~ever_reset
+        assert torch.equal(r[live], r_ref[live]) and torch.equal(term[live], d_ref[live].to(torch.bool))
+        ended = term | trunc
+        n_term += int(term.sum())
+        for s in env.sim.state_names:      # finished envs are back at the initial state, the others are not touched
+            assert torch.equal(obs[s][ended], init[s].expand_as(obs[s])[ended]), s
+            assert torch.equal(obs[s][live & ~ended], ref.fluent(s)[live & ~ended]), s
+        assert bool((info['episode_length'][ended] > 0).all())
+        assert bool((info['episode_length'][~ended] == 0).all()) and bool(torch.isnan(info['episode_return'][~ended]).all())
+        ever_reset |= ended
+        if t < H - 1:
+            assert not bool(trunc.any())
+    assert n_term > 0 and bool(trunc.any())       # early terminations and horizon truncations both seen
+    assert bool((env.episode_step[trunc] == 0).all())
