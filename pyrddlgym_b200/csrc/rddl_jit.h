@@ -114,8 +114,14 @@ static bool jit_fused_static(const PlaneProg& G, const JitPools& P, std::string&
 static std::string level_static_data(const JitPools& P, const RddlLaunch* launches, int n_launches) {
   if (P.n_insns > 4096 || P.n_consts > 8192 || P.n_addrs > 1024 || P.n_csrs > 64 || P.n_redslots > 256) return "";
   std::string s, list;
-  for (int i = 0; i < n_launches; ++i)
-    if (launches[i].kind == 0) list += jit_fmt(" X(%lld)", i);
+  // a launch's program is one template recursion per instruction: very long programs stay interpreted
+  int64_t total = 0;
+  for (int i = 0; i < n_launches; ++i) {
+    const int len = launches[i].pc_end - launches[i].pc_begin;
+    if (launches[i].kind != 0 || len > 200 || total + len > 2000) continue;
+    total += len;
+    list += jit_fmt(" X(%lld)", i);
+  }
   if (list.empty()) return "";
   s += "#define PS_LEVELS(X)" + list + "\n";
   s += "__device__ constexpr uint32_t kInsnWords[][4] = {";

@@ -230,12 +230,9 @@ static void jit_levels(rddl_program* g) {
         if (g->launches[i].kind != 0) continue;
         char name[64];
         snprintf(name, sizeof name, "rddl_level_static_%d", (int)i);
-        if (drv.ModuleGetFunction(&g->level_fn[i], g->level_mod, name) != CUDA_SUCCESS) {
-          g->level_fn[i] = nullptr;
-          err = std::string("cuModuleGetFunction failed: ") + name;
-        } else {
-          ++g->jit_built;
-        }
+        // (launches too long to unroll are not in the module: they keep the interpreter kernel)
+        if (drv.ModuleGetFunction(&g->level_fn[i], g->level_mod, name) != CUDA_SUCCESS) g->level_fn[i] = nullptr;
+        else ++g->jit_built;
       }
     }
   }
@@ -273,6 +270,7 @@ static int plane_geometry(const RddlLaunch& L, int64_t n_envs, RddlLaunch* adj, 
     const int want = atoi(force);
     if ((want == 1 || want == 2 || want == 4) && want <= wpt && wpe <= 256 * want) {
       int ept = (int)((256 * want) / wpe);
+      if (const char* fe = getenv("RDDL_PLANE_FORCE_EPT")) { const int v = atoi(fe); if (v >= 1 && v <= ept) ept = v; }
       return set(want, ept > 32 ? 32 : ept);
     }
     return wpt;
