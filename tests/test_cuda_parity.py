@@ -187,7 +187,7 @@ def test_plane_path_is_taken_for_wildfire():
     assert kinds[0] == 'rddl_plane_interp', (kinds, sim.table.plane_rejects)
 
 
-@pytest.mark.parametrize('n,N', [(32, 70), (64, 9), (256, 3), (1024, 2)])
+@pytest.mark.parametrize('n,N', [(32, 70), (64, 9), (192, 5), (256, 3), (1024, 2)])
 def test_plane_interpreter_equals_scalar_interpreter(n, N):
     """Two independent CUDA implementations of the same op-table semantics (bit-plane ops vs
     one thread per cell through CSR neighbour lists) agree bit for bit under injected uniforms,
@@ -214,8 +214,8 @@ def test_plane_interpreter_equals_scalar_interpreter(n, N):
     assert bool(a.fluent('burning').any())
 
 
-@pytest.mark.parametrize('n,sep,N', [(32, False, 70), (32, False, 4099), (32, True, 33), (64, True, 9), (256, True, 3),
-                                     (1024, True, 2)])
+@pytest.mark.parametrize('n,sep,N', [(32, False, 70), (32, False, 4099), (32, True, 33), (64, True, 9), (96, True, 301),
+                                     (192, True, 5), (256, True, 3), (1024, True, 2)])
 def test_specialised_plane_kernel_equals_interpreter_kernel(n, sep, N):
     """The NVRTC-specialised build of rddl_plane.cuh (program as constants, csrc/rddl_jit.h) and the
     ahead-of-time interpreter build are the same source: bit-identical states, rewards and
