@@ -303,13 +303,40 @@ def run_gpu(args):
         sim.rollout(seq, R, gamma=gamma, returns=returns)
         local_stats.copy_(parallel.local_return_stats(returns))
 
+    # The collective of episode k runs on a side stream and overlaps the rollout of episode k + 1
+    # (two result slots; the main stream only waits before it reuses a slot); everything is
+    # joined before the timed region ends.
+    side = torch.cuda.Stream(device=dev) if world > 1 else None
+    slots = [torch.empty(5, dtype=torch.float64, device=dev) for _ in range(2)]
+    slot_free = [None, None]
+    counter = [0]
+
     def episode(graph=None):
         if graph is not None:
             graph.replay()
         else:
             episode_local()
         # ... and the statistics over all ranks: one NCCL all-gather of 5 numbers per rank
-        return parallel.gather_return_stats(local_stats)
+        if world == 1 or args.sync_collective:
+            return parallel.gather_return_stats(local_stats)
+        k = counter[0] & 1
+        counter[0] += 1
+        main = torch.cuda.current_stream()
+        if slot_free[k] is not None:
+            main.wait_event(slot_free[k])
+        slots[k].copy_(local_stats)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        side.wait_event(ready)
+        with torch.cuda.stream(side):
+            out = parallel.gather_return_stats(slots[k])
+            slot_free[k] = torch.cuda.Event()
+            slot_free[k].record(side)
+        return out
+
+    def join_collectives():
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
 
     sampler = ClockSampler(local, period=0.002)
     if rank == 0:
@@ -322,7 +349,9 @@ def run_gpu(args):
     launches_per_episode = 0
     for _ in range(max(W, 1)):                                     # W untimed warm-up steps
         la = sim.launches_issued
-        parallel.finish_return_stats(episode())
+        g_ = episode()
+        join_collectives()
+        parallel.finish_return_stats(g_)
         launches_per_episode = sim.launches_issued - la
     # The local part of the episode is a fixed launch sequence (reset copies, one rollout kernel,
     # the statistics kernel): captured once into a CUDA graph and replayed per step, so the host's
@@ -333,7 +362,9 @@ def run_gpu(args):
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             episode_local()                  # (the collective stays outside the graph)
-        parallel.finish_return_stats(episode(graph))
+        g_ = episode(graph)
+        join_collectives()
+        parallel.finish_return_stats(g_)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -342,6 +373,7 @@ def run_gpu(args):
     e0.record()
     for _ in range(K):                                             # exactly K timed steps
         gathered = episode(graph)
+    join_collectives()
     stats = parallel.finish_return_stats(gathered)
     e1.record()
     barrier()
@@ -456,7 +488,8 @@ def run_gpu(args):
                        'step_api_value': step_api_value,
                        'l2': f'inputs larger than L2: the action sequence every rollout reads is '
                              f'{R * act_bytes / 1e6:.0f} MB (L2 = 126 MB); state tensors {state_bytes / 1e6:.1f} MB',
-                       'parallelism': f'env-shard x{world}, return statistics all-gathered (NCCL) once per rollout',
+                       'parallelism': f'env-shard x{world}, return statistics all-gathered (NCCL) once per rollout, '
+                                      f'on a side stream overlapping the next rollout',
                        'launches': [l['kernel'] for l in sim.table.launches if l['plan'] == 0],
                        'specialised_kernels': sim.specialised_kernels,
                        'cuda_graph': graph is not None,
@@ -488,6 +521,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='wildfire32', choices=sorted(WORKLOADS))
     ap.add_argument('--envs', type=int, default=0)
+    ap.add_argument('--sync-collective', action='store_true', help='run the statistics all-gather on the main stream')
     ap.add_argument('--no-graph', action='store_true', help='issue every episode eagerly instead of replaying a CUDA graph')
     ap.add_argument('--rollout', type=int, default=0, help='env-steps per rollout (default: per workload)')
     ap.add_argument('--e2e-steps', type=int, default=10, help='rollouts timed for the end-to-end figure (<= --steps)')
