@@ -1,17 +1,23 @@
-// Run-time specialisation of the bit-plane kernel (host side).
+// Run-time specialisation of the kernels (host side).
 //
-// rddl_plane.cuh is written once and built twice: ahead of time as an interpreter whose program
-// arrives in the kernel parameter bank, and -- here -- per plane launch of a created program, with
-// the pre-decoded PlaneProg, the launch geometry and the tensor dtypes emitted as constants
-// ("plane_static_data.inc") and the file recompiled for sm_100a by NVRTC. The op loop then unrolls,
-// the dispatch switches fold, truth-table masks turn into LOP3 immediates and the plane registers
-// into machine registers. Same source, same Philox counters: results are bit-identical to the
-// interpreter's (tests/test_cuda_parity.py::test_specialised_*).
+// The kernel sources are written once and built twice: ahead of time (nvcc, rddl_vm.cu) as
+// interpreters whose program arrives at run time, and -- here -- per created program with the op
+// table emitted as compile-time constants and the same files recompiled for sm_100a by NVRTC:
+//   * rddl_plane.cuh + "plane_static_data.inc" (the pre-decoded PlaneProg of one plane launch, its
+//     tile geometry, the tensor dtypes, the fused scalar programs): the op sequence unrolls, the
+//     dispatch switches fold, truth-table masks turn into LOP3 immediates, the plane registers
+//     into machine registers  -> rddl_plane_static, one module per (launch, geometry);
+//   * rddl_level_static.cuh + "level_static_data.inc" (every instruction word, the pools, the
+//     launches): each scalar launch becomes straight-line code over machine registers with real
+//     loops for its dense / CSR loops  -> rddl_level_static_<launch>, one module per program.
+// Same source, same Philox counters, no FMA contraction in either build: results are bit-identical
+// to the interpreters' (tests/test_cuda_parity.py::test_specialised_*).
 //
 // NVRTC and the driver entry points are bound lazily (dlopen / cudaGetDriverEntryPoint): the
 // library keeps loading on machines without a driver, and when NVRTC is missing the interpreter
-// kernels run instead (rddl_program_info(prog, 5) reports how many launches are specialised).
-// Compiled cubins are cached on disk, keyed by a hash of every source byte and option.
+// kernels run instead (rddl_program_info(prog, 5 | 6) report specialised / fallen-back launches).
+// Compiled cubins are cached on disk, keyed by a hash of every source byte, the generated
+// constants, the options and the NVRTC version.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
