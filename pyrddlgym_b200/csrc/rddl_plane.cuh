@@ -431,9 +431,11 @@ __device__ __forceinline__ void plane_exec(PlaneTile<WPT, BLOCK>& T, const VmArg
     if (MODE == PLANE_PREFETCH_NEXT && (o.a > 0 || A.tstride[o.imm] == 0)) return;
     const uint8_t* p = reinterpret_cast<const uint8_t*>(A.tensors[o.imm]) +
                        (MODE == PLANE_PREFETCH_NEXT ? (t + 1) * A.tstride[o.imm] : 0);
-#pragma unroll
-    for (int j = 0; j < WPT; ++j) {
-      int64_t gw = (tile_byte0 >> 5) + j * BLOCK;
+    // a warp's words of one plane are WPT runs of 1 KiB = WPT * 8 lines of 128 B: one line per lane,
+    // one prefetch instruction per plane
+    const int lane = tid & 31;
+    if (lane < WPT * 8) {
+      int64_t gw = (tile_byte0 >> 5) - lane + (lane >> 3) * BLOCK + (lane & 7) * 4;
       if (!full) gw = gw < T.gw_limit ? gw : T.gw_limit;      // ragged tile: stay inside the tensor
       asm volatile("prefetch.global.L2 [%0];" ::"l"(p + (gw << 5)));
     }
