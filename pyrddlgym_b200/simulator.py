@@ -96,6 +96,7 @@ class BatchedSimulator:
             self.device, dtype=_TORCH_DT[program.tensors[name].dtype])
             for name in program.tensors if program.tensors[name].kind != 'nonfluent'}
         self._owned_actions = {name: self.t[name] for name in self.action_names}
+        self._owned_is_default = set()        # action fluents whose owned storage holds the defaults
         self._init_packed = {}
         self._ptrs = (ctypes.c_void_p * len(self.names))()
         self._inj = (ctypes.c_void_p * max(1, len(self.table.variates)))()
@@ -138,12 +139,15 @@ class BatchedSimulator:
         for name, own in self._owned_actions.items():
             self.t[name] = own          # never write into caller-owned action tensors
         for name, v in self._init.items():
+            if name in self._owned_is_default:
+                continue                # untouched since the last reset (zero-copy actions): nothing to rewrite
             if name in self.packed:
                 if name not in self._init_packed:
                     self._init_packed[name] = self._pack(v.reshape(1, -1))
                 self.t[name].copy_(self._init_packed[name].expand_as(self.t[name]))
             else:
                 self.t[name].copy_(v.expand_as(self.t[name]))
+        self._owned_is_default = set(self.action_names)
         self.status.zero_()
         self.step_count = 0
         done = self.check_terminal_states()
@@ -159,6 +163,7 @@ class BatchedSimulator:
             if self.t[name] is not own:
                 own.copy_(self.t[name])       # keep the live values of the other envs, in owned storage
                 self.t[name] = own
+                self._owned_is_default.discard(name)
         for name, v in self._init.items():
             t = self.t[name]
             if name in self.packed:
@@ -212,6 +217,7 @@ class BatchedSimulator:
             else:
                 a = torch.from_numpy(np.array(np.broadcast_to(np.asarray(v), tuple(dst.shape)), order='C'))
                 dst.copy_(a, non_blocking=True)
+            self._owned_is_default.discard(name)
             self.t[name] = dst
 
     def step(self, actions=None, variates=None):
