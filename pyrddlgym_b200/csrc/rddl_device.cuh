@@ -117,6 +117,7 @@ struct VmPools {
   const RddlRedSlot* redslots;
   const int64_t* red_off;
   const RddlCsr* csrs;
+  const uint8_t* dtype;      // per tensor id
 };
 
 // One instruction (raw = its four 32-bit words) of the program of launch L for one (env, element):
@@ -174,14 +175,14 @@ __device__ __forceinline__ void vm_exec_one(const VmArgs& A, const VmPools& P, c
       if (op == OP_LOAD) {
         off += env * ad->env_stride;
         const void* base = A.tensors[t];
-        const int dt = A.dtype[t];
+        const int dt = P.dtype[t];
         if (dt == DT_BOOL) r[dst] = reinterpret_cast<const uint8_t*>(base)[off] != 0;
         else if (dt == DT_PACKED) r[dst] = (reinterpret_cast<const uint32_t*>(base)[off >> 5] >> (off & 31)) & 1u;
         else r[dst] = reinterpret_cast<const uint64_t*>(base)[off];
       } else if (op == OP_STORE) {
         off += env * ad->env_stride;
         void* base = A.tensors[t];
-        const int dt = A.dtype[t];
+        const int dt = P.dtype[t];
         if (dt == DT_BOOL) reinterpret_cast<uint8_t*>(base)[off] = RA != 0;
         else reinterpret_cast<uint64_t*>(base)[off] = RA;
         if (cap && (t == cap_tensor || t == cap_tensor + 1)) cap[t - cap_tensor] = RA;
@@ -356,7 +357,7 @@ __device__ __forceinline__ void vm_exec_one(const VmArgs& A, const VmPools& P, c
         }
         base[k] = off; stride[k] = st;
         ptr[k] = A.tensors[ad->tensor];
-        dts[k] = A.dtype[ad->tensor];
+        dts[k] = P.dtype[ad->tensor];
       }
       int32_t j0 = 0, j1 = (int32_t)arg;
       const int32_t* cols = nullptr;
@@ -419,7 +420,7 @@ __device__ __noinline__ void vm_exec_element(const VmArgs& A, const RddlLaunch& 
   int32_t jcur[4], jend[4];
   const int npc = L.pc_end - L.pc_begin;
   const RddlInsn* prog = A.insns + L.pc_begin;
-  const VmPools P = {A.consts, A.addrs, A.redslots, A.red_off, A.csrs};
+  const VmPools P = {A.consts, A.addrs, A.redslots, A.red_off, A.csrs, A.dtype};
   int pc = 0;
   while (pc < npc) {
     const uint4 raw = __ldg(reinterpret_cast<const uint4*>(prog + pc));

@@ -117,7 +117,8 @@ static bool jit_fused_static(const PlaneProg& G, const JitPools& P, std::string&
 // instruction word, the pools, the launches, and the list of scalar launches (PS_LEVELS) that get a
 // kernel each (rddl_level_static_<launch index>, rddl_level_static.cuh). Empty string: program too
 // large to embed (the interpreter kernels run).
-static std::string level_static_data(const JitPools& P, const RddlLaunch* launches, int n_launches) {
+static std::string level_static_data(const JitPools& P, const RddlLaunch* launches, int n_launches,
+                                     const uint8_t* dtype) {
   if (P.n_insns > 4096 || P.n_consts > 8192 || P.n_addrs > 1024 || P.n_csrs > 64 || P.n_redslots > 256) return "";
   std::string s, list;
   // a launch's program is one template recursion per instruction: very long programs stay interpreted
@@ -174,6 +175,8 @@ static std::string level_static_data(const JitPools& P, const RddlLaunch* launch
   }
   s += "{}};\n__device__ constexpr RddlLaunch kLaunches[] = {";
   for (int i = 0; i < n_launches; ++i) { jit_launch_init(s, launches[i]); s += ",\n"; }
+  s += "};\n__device__ constexpr uint8_t kDT[RDDL_MAX_TENSORS] = {";
+  for (int i = 0; i < RDDL_MAX_TENSORS; ++i) s += jit_fmt("%lld,", dtype[i]);
   s += "};\n";
   return s;
 }

@@ -25,7 +25,7 @@ __device__ __forceinline__ void vm_seq(VmStaticCtx& c) {
   if constexpr (PC < END) {
     constexpr uint4 raw = {kInsnWords[PC][0], kInsnWords[PC][1], kInsnWords[PC][2], kInsnWords[PC][3]};
     constexpr uint32_t op = raw.x & 0xff, ra = raw.y & 0xffff, rb = raw.y >> 16, imm = raw.w;
-    const VmPools P = {kConsts, kAddrs, kRedSlots, kRedOff, kCsrs};
+    const VmPools P = {kConsts, kAddrs, kRedSlots, kRedOff, kCsrs, kDT};
     if constexpr (op == OP_LOOP) {
       // dense loop over axis slot ra, extent imm; rb = pc after the matching ENDLOOP
       constexpr int AFTER = BASE + (int)rb;

@@ -835,7 +835,7 @@ __device__ __forceinline__ void plane_tile(const VmArgs& A, const PlaneProg& G, 
 #if defined(PLANE_STATIC) && PS_FUSED_STATIC
       // specialised epilogue: straight-line code, reward / done taken from the stores themselves
       uint64_t cap[2] = {0, 0};
-      const VmPools P = {kConsts, kAddrs, kRedSlots, kRedOff, nullptr};
+      const VmPools P = {kConsts, kAddrs, kRedSlots, kRedOff, nullptr, kDT};
       {
         uint64_t r0[40];
         vm_exec_static<kG.fused[0].pc_begin, kG.fused[0].pc_end>(A, P, kG.fused[0], ge, A.step + t, idx0, rv, r0, cap, G.pad);

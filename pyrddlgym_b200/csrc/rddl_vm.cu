@@ -82,6 +82,11 @@ struct rddl_program {
   std::vector<uint64_t> h_consts;
   std::vector<RddlAddr> h_addrs;
   std::vector<RddlCsr> h_csrs;
+  std::vector<uint8_t> dtypes() const {
+    std::vector<uint8_t> d(RDDL_MAX_TENSORS, 0);
+    for (size_t i = 0; i < tensors.size(); ++i) d[i] = (uint8_t)tensors[i].dtype;
+    return d;
+  }
   JitPools pools() const {
     return JitPools{h_insns.data(), (int64_t)h_insns.size(), h_consts.data(), (int64_t)h_consts.size(),
                     h_addrs.data(), (int64_t)h_addrs.size(), redslots.data(), (int64_t)redslots.size(), red_off.data(),
@@ -217,7 +222,7 @@ static bool decode_plane(const RddlLaunch& L, const RddlInsn* insns, const uint6
 static void jit_levels(rddl_program* g) {
   g->level_tried = true;
   g->level_fn.assign(g->launches.size(), nullptr);
-  const std::string data = level_static_data(g->pools(), g->launches.data(), (int)g->launches.size());
+  const std::string data = level_static_data(g->pools(), g->launches.data(), (int)g->launches.size(), g->dtypes().data());
   if (data.empty()) return;
   std::string cubin, err;
   bool hit = false;
@@ -515,7 +520,7 @@ extern "C" int rddl_plane_precompile(const void* optable, size_t nbytes, int64_t
     ++n;
   }
   {
-    const std::string data = level_static_data(g->pools(), g->launches.data(), (int)g->launches.size());
+    const std::string data = level_static_data(g->pools(), g->launches.data(), (int)g->launches.size(), g->dtypes().data());
     std::string cubin, err;
     if (!data.empty()) {
       if (!jit_compile_level(data, &cubin, &err, nullptr)) {
