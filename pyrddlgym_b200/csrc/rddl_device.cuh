@@ -130,7 +130,8 @@ __device__ __forceinline__ void vm_exec_one(const VmArgs& A, const VmPools& P, c
                                             const uint64_t step, int32_t* idx, uint64_t* redval, uint64_t* r,
                                             int32_t* jcur, int32_t* jend, const RddlInsn* prog, int& pc,
                                             const uint4 raw, uint64_t* cap, const int cap_tensor,
-                                            const uint4 raw2_static = uint4{0u, 0u, 0u, 0u}) {
+                                            const uint4 raw2_static = uint4{0u, 0u, 0u, 0u},
+                                            const uint64_t* red_local = nullptr, const RddlLaunch* red_src = nullptr) {
   const uint32_t op = OPC >= 0 ? (uint32_t)OPC : (raw.x & 0xff);
   const uint32_t dst = raw.x >> 16;
   const uint32_t ra = raw.y & 0xffff, rb = raw.y >> 16;
@@ -315,6 +316,13 @@ __device__ __forceinline__ void vm_exec_one(const VmArgs& A, const VmPools& P, c
     }
     case OP_REDOUT: redval[rb] = red_combine(L.red_op[rb], redval[rb], RA); break;
     case OP_REDIN: {
+      if (red_local) {
+        // reductions of the producing launch (red_src) handed over in registers: slot imm -> its index there
+#pragma unroll
+        for (int j = 0; j < RDDL_MAX_RED; ++j)
+          if (j < red_src->nred && (uint32_t)red_src->red_slot[j] == imm) r[dst] = red_local[j];
+        break;
+      }
       const RddlRedSlot s = P.redslots[imm];
       const uint64_t* base = A.red + (P.red_off[imm] * A.n_envs + env * s.chunks);
       uint64_t acc = __ldcg(base);

@@ -212,7 +212,7 @@ static std::string plane_static_data(const PlaneProg& G, const RddlLaunch& L, co
   int nw = 0;   // words in use: everything up to the last table
   for (int i = 0; i < PLANE_WORDS; ++i) if (G.words[i]) nw = i + 1;
   for (int i = 0; i < nw; ++i) s += jit_fmt("0x%llxu,", G.words[i]) + ((i & 15) == 15 ? "\n" : "");
-  s += "}};\n__device__ const RddlLaunch kL = ";
+  s += "}};\n__device__ constexpr RddlLaunch kL = ";
   jit_launch_init(s, L);
   s += ";\n__device__ constexpr uint8_t kDT[RDDL_MAX_TENSORS] = {";
   for (int i = 0; i < RDDL_MAX_TENSORS; ++i) s += jit_fmt("%lld,", dtype[i]);

@@ -61,13 +61,14 @@ struct PlaneProg {
 template <int PC, int END>
 __device__ __forceinline__ void vm_exec_static(const VmArgs& A, const VmPools& P, const RddlLaunch& L, const int64_t env,
                                                const uint64_t step, int32_t* idx, uint64_t* redval, uint64_t* r,
-                                               uint64_t* cap, const int cap_tensor) {
+                                               uint64_t* cap, const int cap_tensor, const uint64_t* red_local) {
   if constexpr (PC < END) {
     constexpr uint4 raw = {kInsnWords[PC - PS_INSN_BASE][0], kInsnWords[PC - PS_INSN_BASE][1],
                            kInsnWords[PC - PS_INSN_BASE][2], kInsnWords[PC - PS_INSN_BASE][3]};
     int pc = 0;
-    vm_exec_one<40, (int)(raw.x & 0xff)>(A, P, L, env, step, idx, redval, r, nullptr, nullptr, nullptr, pc, raw, cap, cap_tensor);
-    vm_exec_static<PC + 1, END>(A, P, L, env, step, idx, redval, r, cap, cap_tensor);
+    vm_exec_one<40, (int)(raw.x & 0xff)>(A, P, L, env, step, idx, redval, r, nullptr, nullptr, nullptr, pc, raw, cap, cap_tensor,
+                                         uint4{0u, 0u, 0u, 0u}, red_local, &kL);
+    vm_exec_static<PC + 1, END>(A, P, L, env, step, idx, redval, r, cap, cap_tensor, red_local);
   }
 }
 #endif
@@ -798,35 +799,44 @@ __device__ __forceinline__ void plane_tile(const VmArgs& A, const PlaneProg& G, 
 #endif
   plane_run_ops<WPT, BLOCK, PLANE_RUN, 0>(T, A, G, L, DT, t, last_step);
 
-  if (L.nred > 0) {
+  // Specialised single-tile launches with a fused scalar program: the thread that runs env e's
+  // epilogue finishes e's reductions itself and hands them over in registers (one barrier, no
+  // round trip through the reduction scratch in L2).
+#if defined(PLANE_STATIC) && PS_FUSED_STATIC
+  constexpr bool kRedLocal = kL.chunks == 1 && kL.nred > 0 && kG.nfused > 0;
+#else
+  constexpr bool kRedLocal = false;
+#endif
+  const int64_t cells = chunks == 1 ? L.E : (int64_t)min(tile_words, wpe - chunk * tile_words) * 32;
+  // value of reduction jr of local env e from its popcount (the PRED op carries the per-cell values
+  // at 0 and at 1 as raw 64-bit words); clears the counter for the next step of a fused rollout
+  auto finish_red = [&](int e, int jr) -> uint64_t {
+    const int off = G.red_off[jr], m = G.red_m[jr];
+    const uint64_t v0 = ((uint64_t)G.words[off + 1] << 32) | G.words[off];
+    const uint64_t v1 = ((uint64_t)G.words[off + 3] << 32) | G.words[off + 2];
+    const int64_t ones = cnt[e * RDDL_MAX_RED + jr];
+    cnt[e * RDDL_MAX_RED + jr] = 0;
+    const int64_t n1 = m ? ones : 0, n0 = m ? cells - ones : cells;
+    if (L.red_op[jr] == RED_SUM_F) {
+      double acc = __dmul_rn(__longlong_as_double((long long)v0), (double)n0);
+      acc = __dadd_rn(acc, __dmul_rn(__longlong_as_double((long long)v1), (double)n1));
+      return (uint64_t)__double_as_longlong(acc);
+    }
+    return (uint64_t)((int64_t)v0 * n0 + (int64_t)v1 * n1);
+  };
+  if (L.nred > 0 && !kRedLocal) {
     __syncthreads();
-    const int64_t cells = chunks == 1 ? L.E : (int64_t)min(tile_words, wpe - chunk * tile_words) * 32;
     for (int i = tid; i < envs_per_tile * L.nred; i += BLOCK) {
       const int e = i / L.nred, jr = i - e * L.nred;
       const int64_t ge = env0 + e;
       if (ge >= A.n_envs) continue;
-      // the PRED op of reduction jr carries (value at 0, value at 1) as raw 64-bit words
-      const int off = G.red_off[jr], m = G.red_m[jr];
-      const uint64_t v0 = ((uint64_t)G.words[off + 1] << 32) | G.words[off];
-      const uint64_t v1 = ((uint64_t)G.words[off + 3] << 32) | G.words[off + 2];
-      const int64_t ones = cnt[e * RDDL_MAX_RED + jr];
-      cnt[e * RDDL_MAX_RED + jr] = 0;      // ready for the next step of a fused rollout
-      const int64_t n1 = m ? ones : 0, n0 = m ? cells - ones : cells;
-      uint64_t out;
-      if (L.red_op[jr] == RED_SUM_F) {
-        double acc = __dmul_rn(__longlong_as_double((long long)v0), (double)n0);
-        acc = __dadd_rn(acc, __dmul_rn(__longlong_as_double((long long)v1), (double)n1));
-        out = (uint64_t)__double_as_longlong(acc);
-      } else {
-        out = (uint64_t)((int64_t)v0 * n0 + (int64_t)v1 * n1);
-      }
-      A.red[A.red_off[L.red_slot[jr]] * A.n_envs + ge * chunks + chunk] = out;
+      A.red[A.red_off[L.red_slot[jr]] * A.n_envs + ge * chunks + chunk] = finish_red(e, jr);
     }
   }
   if (G.nfused > 0) {
     // scope-free programs fused into this launch (reward / termination from the reductions):
     // one thread per env of the tile runs them through the scalar interpreter
-    __threadfence_block();
+    if (!kRedLocal) __threadfence_block();
     __syncthreads();
     if (tid < envs_per_tile && env0 + tid < A.n_envs) {
       const int64_t ge = env0 + tid;
@@ -836,13 +846,25 @@ __device__ __forceinline__ void plane_tile(const VmArgs& A, const PlaneProg& G, 
       // specialised epilogue: straight-line code, reward / done taken from the stores themselves
       uint64_t cap[2] = {0, 0};
       const VmPools P = {kConsts, kAddrs, kRedSlots, kRedOff, nullptr, kDT};
+      uint64_t redv[RDDL_MAX_RED];
+      const uint64_t* red_local = nullptr;
+      if constexpr (kRedLocal) {
+#pragma unroll
+        for (int jr = 0; jr < RDDL_MAX_RED; ++jr) {
+          if (jr < kL.nred) {
+            redv[jr] = finish_red(tid, jr);
+            A.red[A.red_off[L.red_slot[jr]] * A.n_envs + ge] = redv[jr];     // (kept for launches outside this kernel)
+          }
+        }
+        red_local = redv;
+      }
       {
         uint64_t r0[40];
-        vm_exec_static<kG.fused[0].pc_begin, kG.fused[0].pc_end>(A, P, kG.fused[0], ge, A.step + t, idx0, rv, r0, cap, G.pad);
+        vm_exec_static<kG.fused[0].pc_begin, kG.fused[0].pc_end>(A, P, kG.fused[0], ge, A.step + t, idx0, rv, r0, cap, G.pad, red_local);
       }
       if constexpr (kG.nfused > 1) {
         uint64_t r1[40];
-        vm_exec_static<kG.fused[1].pc_begin, kG.fused[1].pc_end>(A, P, kG.fused[1], ge, A.step + t, idx0, rv, r1, cap, G.pad);
+        vm_exec_static<kG.fused[1].pc_begin, kG.fused[1].pc_end>(A, P, kG.fused[1], ge, A.step + t, idx0, rv, r1, cap, G.pad, red_local);
       }
       if (NT > 1) {
         const double rwd = as_f(cap[0]);
