@@ -77,9 +77,9 @@ def algorithmic_bytes_per_env_step(name):
 # (dram__bytes_read.sum + dram__bytes_write.sum; profiles/r01_ncu_full_*.csv). None = not captured.
 MEASURED_TRAFFIC_BYTES_PER_ENV_STEP = {
     # rddl_plane_static, fused 20-step rollout of 4096 envs (r01_ncu_full_plane_static_rollout20_32x32_4096env.csv)
-    'wildfire32': (168.914944e6 + 5.043456e6) / (20 * 4096),
+    'wildfire32': (168.882688e6 + 4.095232e6) / (20 * 4096),
     # rddl_plane_static, one step of 128 envs (r01_ncu_full_plane_static_1024x1024_128env.csv)
-    'wildfire1024': (302.375936e6 + 8.758784e6) / 128,
+    'wildfire1024': (302.261760e6 + 9.407744e6) / 128,
 }
 
 
