@@ -246,7 +246,9 @@ static JitApi& jit_api() {
   std::lock_guard<std::mutex> lock(mu);
   if (api.tried) return api;
   api.tried = true;
-  const char* names[] = {getenv("RDDL_B200_NVRTC"), "libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so"};
+  const char* want = getenv("RDDL_B200_NVRTC");
+  if (want && !strcmp(want, "none")) { api.why = "disabled (RDDL_B200_NVRTC=none)"; return api; }   // fallback tests
+  const char* names[] = {want, "libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so"};
   for (const char* n : names) {
     if (!n || !*n) continue;
     api.h = dlopen(n, RTLD_NOW | RTLD_LOCAL);
