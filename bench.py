@@ -149,19 +149,25 @@ class ClockSampler:
         self.thread = threading.Thread(target=self._run, daemon=True)
         self.thread.start()
 
-    def _run(self):
+    def sample(self):
+        """One NVML query; recorded when inside the timed region."""
+        if self.nv is None:
+            return
         nv = self.nv
+        try:
+            mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            if self.timed:
+                self.sm.append(mhz)
+                for name, bit in self.REASONS:
+                    if bits & bit:
+                        self.reasons.add(name)
+        except Exception:
+            pass
+
+    def _run(self):
         while not self._stop.is_set():
-            try:
-                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
-                if self.timed:
-                    self.sm.append(mhz)
-                    for name, bit in self.REASONS:
-                        if bits & bit:
-                            self.reasons.add(name)
-            except Exception:
-                pass
+            self.sample()
             time.sleep(self.period)
 
     def stop(self):
@@ -338,7 +344,7 @@ def run_gpu(args):
         if side is not None:
             torch.cuda.current_stream().wait_stream(side)
 
-    sampler = ClockSampler(local, period=0.002)
+    sampler = ClockSampler(local, period=0.001)
     if rank == 0:
         sampler.start()
     # bring the clocks up before the W warm-up steps (an idle GPU needs ~100 ms to boost)
@@ -373,6 +379,8 @@ def run_gpu(args):
     e0.record()
     for _ in range(K):                                             # exactly K timed steps
         gathered = episode(graph)
+    if rank == 0:
+        sampler.sample()        # the queue is still draining: at least one sample under load even for tiny K
     join_collectives()
     stats = parallel.finish_return_stats(gathered)
     e1.record()
