@@ -120,6 +120,14 @@ struct VmPools {
   const uint8_t* dtype;      // per tensor id
 };
 
+// A per-env tensor slice staged in shared memory by the CTA (specialised scalar kernels whose CTA
+// works on a single env): SUMLOOP gathers from `tensor` read ptr[offset - base] instead of global memory.
+struct VmStage {
+  const double* ptr;
+  int tensor;
+  int64_t base;
+};
+
 // One instruction (raw = its four 32-bit words) of the program of launch L for one (env, element):
 // idx[] holds the element's scope coordinates, r[] the virtual registers. `pc` is advanced by
 // control-flow ops (prog = the launch's instruction stream; null for straight-line specialised
@@ -131,7 +139,8 @@ __device__ __forceinline__ void vm_exec_one(const VmArgs& A, const VmPools& P, c
                                             int32_t* jcur, int32_t* jend, const RddlInsn* prog, int& pc,
                                             const uint4 raw, uint64_t* cap, const int cap_tensor,
                                             const uint4 raw2_static = uint4{0u, 0u, 0u, 0u},
-                                            const uint64_t* red_local = nullptr, const RddlLaunch* red_src = nullptr) {
+                                            const uint64_t* red_local = nullptr, const RddlLaunch* red_src = nullptr,
+                                            const VmStage* stage = nullptr) {
   const uint32_t op = OPC >= 0 ? (uint32_t)OPC : (raw.x & 0xff);
   const uint32_t dst = raw.x >> 16;
   const uint32_t ra = raw.y & 0xffff, rb = raw.y >> 16;
@@ -366,6 +375,10 @@ __device__ __forceinline__ void vm_exec_one(const VmArgs& A, const VmPools& P, c
         base[k] = off; stride[k] = st;
         ptr[k] = A.tensors[ad->tensor];
         dts[k] = P.dtype[ad->tensor];
+        if (stage && ad->tensor == stage->tensor && dts[k] == DT_REAL) {   // gather from the staged slice
+          ptr[k] = stage->ptr;
+          base[k] = off - stage->base;
+        }
       }
       int32_t j0 = 0, j1 = (int32_t)arg;
       const int32_t* cols = nullptr;
@@ -442,8 +455,13 @@ __device__ __noinline__ void vm_exec_element(const VmArgs& A, const RddlLaunch& 
 // shared memory across warps when G = 256). `exec(env, idx, redval)` runs the launch's program for
 // one element: the bytecode interpreter (rddl_level_interp) or a specialised instruction sequence
 // (rddl_level_static, rddl_level_static.cuh).
-template <typename Exec>
-__device__ __forceinline__ void level_tile(const VmArgs& A, const RddlLaunch& L, const int64_t* red_off, Exec exec) {
+struct LevelNoPrologue {
+  __device__ __forceinline__ void operator()(int64_t, bool) const {}
+};
+
+template <typename Exec, typename Pre = LevelNoPrologue>
+__device__ __forceinline__ void level_tile(const VmArgs& A, const RddlLaunch& L, const int64_t* red_off, Exec exec,
+                                           Pre prologue = Pre()) {
   const int G = L.G;
   const int tid = threadIdx.x;
   const int lane = tid & (G - 1);
@@ -456,6 +474,7 @@ __device__ __forceinline__ void level_tile(const VmArgs& A, const RddlLaunch& L,
   uint64_t redval[RDDL_MAX_RED];
 #pragma unroll
   for (int j = 0; j < RDDL_MAX_RED; ++j) redval[j] = j < L.nred ? red_identity(L.red_op[j]) : 0;
+  prologue(env, env_ok);      // (all threads of the CTA: may stage data in shared memory and synchronise)
 
   for (int it = 0; it < L.ipt; ++it) {
     const int64_t elem = chunk * ((int64_t)G * L.ipt) + (int64_t)it * G + lane;
