@@ -364,13 +364,19 @@ def run_gpu(args):
     # per-launch latency is not part of the step.
     graph = None
     if not args.no_graph:
-        torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            episode_local()                  # (the collective stays outside the graph)
-        g_ = episode(graph)
-        join_collectives()
-        parallel.finish_return_stats(g_)
+        try:
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                episode_local()              # (the collective stays outside the graph)
+            g_ = episode(graph)
+            join_collectives()
+            parallel.finish_return_stats(g_)
+        except Exception as e:               # capture not possible here: issue the episodes eagerly
+            sys.stderr.write('bench: CUDA graph capture failed (%s); running eagerly\n' % e)
+            graph = None
+            torch.cuda.synchronize()
+            sim.reset()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
