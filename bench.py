@@ -376,7 +376,9 @@ def run_gpu(args):
             sys.stderr.write('bench: CUDA graph capture failed (%s); running eagerly\n' % e)
             graph = None
             torch.cuda.synchronize()
-            sim.reset()
+            g_ = episode(None)               # (same number of collectives as the ranks whose capture worked)
+            join_collectives()
+            parallel.finish_return_stats(g_)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
