@@ -100,3 +100,29 @@ def test_specialised_kernels_compile_without_a_gpu(tmp_path, monkeypatch):
     # a scalar-only program: one module holding a kernel per scalar launch
     cart = lowering.lower(workloads.load_program(workloads.cartpole()))
     assert native.precompile(cart.blob, 64) == 1
+
+
+def test_tile_geometry_of_the_specialised_plane_kernel():
+    """plane_geometry (csrc/rddl_vm.cu), read back through the generated constants: the tile always holds
+    whole envs and fits the thread block; a batch that fits one wave of resident CTAs is spread so that
+    no SM holds more than ceil(N / 148) + a tile of envs; big batches keep the 32768-cell tiles at 3 CTAs/SM."""
+    import re
+    from pyrddlgym_b200 import lowering, native, workloads
+    tab = lowering.lower(workloads.load_program(workloads.wildfire(32)))
+    wpe = 32 * 32 // 32
+    seen = {}
+    for n_envs in (1, 16, 37, 4096, 5000, 8192, 65536):
+        src = native.plane_source(tab.blob, 0, n_envs)
+        d = {k: int(v) for k, v in re.findall(r'#define (PS_\w+) (\d+)', src)}
+        f = [x for x in re.split(r'[{},]+', src.split('kL = ')[1].split(';')[0]) if x.strip()]
+        ept, ipt, chunks = int(f[14]), int(f[15]), int(f[16])
+        assert chunks == 1 and ipt == ept * wpe and 1 <= ept <= 32
+        assert d['PS_BLOCK'] % 32 == 0 and d['PS_BLOCK'] <= 256 and d['PS_BLOCK'] * d['PS_WPT'] >= ipt
+        assert (d['PS_BLOCK'] - 32) * d['PS_WPT'] < ipt                      # no idle warp
+        tiles = -(-n_envs // ept)
+        if tiles <= 148 * d['PS_MINB']:                                       # one wave: balanced over the SMs
+            per_sm = -(-tiles // 148)
+            assert per_sm * ept <= -(-n_envs // 148) + ept
+        seen[n_envs] = (d['PS_WPT'], ept, d['PS_BLOCK'], d['PS_MINB'])
+    assert seen[4096] == (2, 14, 224, 2)          # BASELINE config 2: 293 CTAs of 14 envs, 2 per SM
+    assert seen[65536] == (4, 32, 256, 3)         # many waves: full tiles, 3 resident CTAs
