@@ -18,7 +18,6 @@
 #include <stdint.h>
 
 #define CT_BM 64
-#define CT_BN 64
 #define CT_BK 16
 #define CT_PAD 4
 
@@ -31,6 +30,7 @@ __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, do
 // Global -> register part of one K step's operand tiles (8 + 8 doubles per thread), and the
 // register -> shared part. Splitting the two lets the loads of step k + 1 fly while the DMMAs of
 // step k run (register double buffering; the shared tiles are double buffered too, one barrier per step).
+template <int CT_BN>
 __device__ __forceinline__ void contract_fetch(const double* __restrict__ X, const double* __restrict__ W, int64_t M, int N,
                                                int K, int64_t w_stride_k, int64_t w_stride_n, int64_t m0, int n0, int k0,
                                                int tid, double* xa, double* wb) {
@@ -52,6 +52,7 @@ __device__ __forceinline__ void contract_fetch(const double* __restrict__ X, con
   }
 }
 
+template <int CT_BN>
 __device__ __forceinline__ void contract_stage(double (*As)[CT_BK + CT_PAD], double (*Bs)[CT_BK + CT_PAD],
                                                int64_t w_stride_n, int tid, const double* xa, const double* wb) {
 #pragma unroll
@@ -69,43 +70,45 @@ __device__ __forceinline__ void contract_stage(double (*As)[CT_BK + CT_PAD], dou
   }
 }
 
+template <int CT_BN>
 __global__ void __launch_bounds__(128) rddl_contract_f64(const double* __restrict__ X, const double* __restrict__ W,
                                                          double* __restrict__ Out, int64_t M, int N, int K,
                                                          int64_t w_stride_k, int64_t w_stride_n) {
   __shared__ double As[2][CT_BM][CT_BK + CT_PAD];   // x tile: [env][k], double buffered
   __shared__ double Bs[2][CT_BN][CT_BK + CT_PAD];   // W tile, n-major: [n][k]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;    // warp origin inside the CTA tile
+  constexpr int TN = CT_BN / 16;                             // mma tiles per warp along n
+  const int wm = (warp >> 1) * 32, wn = (warp & 1) * (CT_BN / 2);    // warp origin inside the CTA tile
   const int64_t m0 = (int64_t)blockIdx.y * CT_BM;
   const int n0 = blockIdx.x * CT_BN;
-  double acc[4][4][2];
+  double acc[4][TN][2];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < TN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   double xa[CT_BM * CT_BK / 128], wb[CT_BK * CT_BN / 128];
-  contract_fetch(X, W, M, N, K, w_stride_k, w_stride_n, m0, n0, 0, tid, xa, wb);
-  contract_stage(As[0], Bs[0], w_stride_n, tid, xa, wb);
+  contract_fetch<CT_BN>(X, W, M, N, K, w_stride_k, w_stride_n, m0, n0, 0, tid, xa, wb);
+  contract_stage<CT_BN>(As[0], Bs[0], w_stride_n, tid, xa, wb);
   __syncthreads();
   int cur = 0;
   for (int k0 = 0; k0 < K; k0 += CT_BK) {
     const bool more = k0 + CT_BK < K;
-    if (more) contract_fetch(X, W, M, N, K, w_stride_k, w_stride_n, m0, n0, k0 + CT_BK, tid, xa, wb);   // in flight during the DMMAs
+    if (more) contract_fetch<CT_BN>(X, W, M, N, K, w_stride_k, w_stride_n, m0, n0, k0 + CT_BK, tid, xa, wb);   // in flight during the DMMAs
 #pragma unroll
     for (int kk = 0; kk < CT_BK; kk += 4) {
-      double a[4], b[4];
+      double a[4], b[TN];
       // fragments (PTX ISA m8n8k4): A[row = lane/4][col = lane%4], B[row = lane%4][col = lane/4]
 #pragma unroll
       for (int i = 0; i < 4; ++i) a[i] = As[cur][wm + 8 * i + (lane >> 2)][kk + (lane & 3)];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[cur][wn + 8 * j + (lane >> 2)][kk + (lane & 3)];
+      for (int j = 0; j < TN; ++j) b[j] = Bs[cur][wn + 8 * j + (lane >> 2)][kk + (lane & 3)];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        for (int j = 0; j < TN; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
-    if (more) contract_stage(As[cur ^ 1], Bs[cur ^ 1], w_stride_n, tid, xa, wb);
+    if (more) contract_stage<CT_BN>(As[cur ^ 1], Bs[cur ^ 1], w_stride_n, tid, xa, wb);
     __syncthreads();
     cur ^= 1;
   }
@@ -115,7 +118,7 @@ __global__ void __launch_bounds__(128) rddl_contract_f64(const double* __restric
     const int64_t m = m0 + wm + 8 * i + (lane >> 2);
     if (m >= M) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < TN; ++j) {
       const int n = n0 + wn + 8 * j + (lane & 3) * 2;
       if (n < N) Out[m * N + n] = acc[i][j][0];
       if (n + 1 < N) Out[m * N + n + 1] = acc[i][j][1];

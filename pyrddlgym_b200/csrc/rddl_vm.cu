@@ -629,11 +629,18 @@ static int run_plan(rddl_program* g, int plan, void* const* tensors, const doubl
     }
     if (L.kind == 3) {
       const int N = (int)L.extent[0], K = (int)L.extent[1];
-      dim3 grid((unsigned)((N + CT_BN - 1) / CT_BN), (unsigned)((n_envs + CT_BM - 1) / CT_BM));
-      rddl_contract_f64<<<grid, 128, 0, stream>>>((const double*)tensors[L.red_slot[1]],
-                                                  (const double*)tensors[L.red_slot[0]],
-                                                  (double*)tensors[L.red_slot[2]], n_envs, N, K,
-                                                  (int64_t)L.red_op[0], (int64_t)L.red_op[1]);
+      // 64 x 64 CTA tiles; 64 x 32 when that grid would not give every SM two CTAs (RDDL_CONTRACT_BN overrides)
+      int bn = ((int64_t)((N + 63) / 64) * ((n_envs + CT_BM - 1) / CT_BM) < 2 * 148) ? 32 : 64;
+      if (const char* e = getenv("RDDL_CONTRACT_BN")) bn = atoi(e) == 32 ? 32 : 64;
+      dim3 grid((unsigned)((N + bn - 1) / bn), (unsigned)((n_envs + CT_BM - 1) / CT_BM));
+      if (bn == 64)
+        rddl_contract_f64<64><<<grid, 128, 0, stream>>>((const double*)tensors[L.red_slot[1]], (const double*)tensors[L.red_slot[0]],
+                                                        (double*)tensors[L.red_slot[2]], n_envs, N, K,
+                                                        (int64_t)L.red_op[0], (int64_t)L.red_op[1]);
+      else
+        rddl_contract_f64<32><<<grid, 128, 0, stream>>>((const double*)tensors[L.red_slot[1]], (const double*)tensors[L.red_slot[0]],
+                                                        (double*)tensors[L.red_slot[2]], n_envs, N, K,
+                                                        (int64_t)L.red_op[0], (int64_t)L.red_op[1]);
     } else if (L.kind == 1) {
       const PlaneProg& G = g->plane_progs[(size_t)(&L - g->launches.data())];
       const int W32 = (int)((L.rank == 2 ? L.extent[1] : L.extent[0]) >> 5);
