@@ -23,6 +23,9 @@ SPECS = {
 RTOL = 1e-5
 ATOL = 1e-9
 
+FUZZSPEC_CASES = sorted(f[:-len('.program.npz')] for f in os.listdir(os.path.join(GOLDEN_DIR, 'fuzzspec'))
+                        if f.endswith('.program.npz')) if os.path.isdir(os.path.join(GOLDEN_DIR, 'fuzzspec')) else []
+
 
 def load_golden(case):
     with np.load(os.path.join(GOLDEN_DIR, case + '.npz')) as z:
@@ -57,8 +60,16 @@ def replay(case, make_sim, to_np=np.asarray, steps=None):
     """Replays a golden trajectory through ``make_sim(program, n_envs)``; the simulator must
     offer reset() -> (.., done), step(actions, variates) -> (.., reward, done),
     check_state_invariants(), check_action_preconditions(actions), fluent(name)."""
-    g = load_golden(case)
-    p = workloads.load_program(SPECS[case]())
+    if case.startswith('fuzzspec'):
+        # random domains (tests/fuzz_specs.py): program + trajectory generated from the reference by
+        # oracle/gen_fuzz_fixtures.py
+        from pyrddlgym_b200 import hir
+        p = hir.Program.load(os.path.join(GOLDEN_DIR, 'fuzzspec', case + '.program.npz'))
+        with np.load(os.path.join(GOLDEN_DIR, 'fuzzspec', case + '.npz')) as z:
+            g = {k: z[k] for k in z.files}
+    else:
+        g = load_golden(case)
+        p = workloads.load_program(SPECS[case]())
     N, T = int(g['n_envs']), int(g['steps'])
     sim = make_sim(p, N)
     _, done0 = sim.reset()

@@ -1,0 +1,176 @@
+"""TEST INFRASTRUCTURE ONLY -- random RDDL domains in the neutral spec form of
+pyrddlgym_b200/workloads.py (tuples shaped like the reference parser's AST), so that the SAME random
+program can be given to the unmodified reference RDDLSimulator (oracle/ast_builders.py) and -- through
+the front end -- to the oracle, the lowering and the kernels. Expressions are typed (real / int / bool)
+and scoped over ?a : ta, ?b : tb; arguments of partial functions are made safe by construction."""
+import numpy as np
+
+from pyrddlgym_b200.workloads import (add, agg, div, eq, equiv, func, ge, gt, implies, ite, land, le, lnot, lor, lt,
+                                      mul, ne, neg, num, pv, rand, sub, xor, boolean)
+
+VARS = {'?a': 'ta', '?b': 'tb'}
+
+
+class SpecGen:
+    def __init__(self, seed, n=4, m=3):
+        self.rng = np.random.default_rng(seed)
+        self.n, self.m = n, m
+        self.allow_rand = True
+        # name -> (dtype, params)
+        self.readable = {
+            'K': ('f', ['?a']), 'M': ('f', ['?a', '?b']), 'IK': ('i', ['?a']), 'FLAG': ('b', ['?a']),
+            'fa': ('f', ['?a']), 'ia': ('i', ['?a']), 'ba': ('b', ['?a']), 'fab': ('f', ['?a', '?b']), 's0': ('f', []),
+            'act': ('f', ['?a']), 'bact': ('b', ['?a']),
+        }
+
+    def pick(self, xs):
+        return xs[int(self.rng.integers(0, len(xs)))]
+
+    def leaf(self, dt, scope):
+        rng = self.rng
+        cands = [k for k, (d, ps) in self.readable.items() if d == dt and all(p in scope for p in ps)]
+        if cands and rng.random() < 0.75:
+            k = self.pick(cands)
+            return pv(k, *self.readable[k][1])
+        if dt == 'f':
+            return num(float(np.round(rng.uniform(-2, 2), 3)))
+        if dt == 'i':
+            return num(int(rng.integers(-3, 5)))
+        return boolean(rng.random() < 0.5)
+
+    def gen(self, dt, scope, depth):
+        rng = self.rng
+        if depth <= 0 or rng.random() < 0.12:
+            return self.leaf(dt, scope)
+        g = lambda d, s=scope, k=depth - 1: self.gen(d, s, k)
+        free = [v for v in VARS if v not in scope]
+        if dt == 'f':
+            c = int(rng.integers(0, 12))
+            if c == 0:
+                return self.pick([add, sub, mul])(g('f'), g(self.pick(['f', 'i'])))
+            if c == 1:
+                return div(g('f'), add(func('abs', g('f')), num(0.5)))
+            if c == 2:
+                return func(self.pick(['abs', 'cos', 'sin', 'tanh', 'atan']), g('f'))
+            if c == 3:
+                return self.pick([lambda x: func('exp', mul(func('tanh', x), num(0.5))),
+                                  lambda x: func('sqrt', add(func('abs', x), num(0.1))),
+                                  lambda x: func('ln', add(func('abs', x), num(1.0)))])(g('f'))
+            if c == 4:
+                return func(self.pick(['min', 'max', 'hypot']), g('f'), g('f'))
+            if c == 5:
+                return func('pow', add(func('abs', g('f')), num(0.1)), num(float(np.round(rng.uniform(0.5, 2.0), 2))))
+            if c == 6:
+                return ite(g('b'), g('f'), g('f'))
+            if c == 7 and free:
+                v = self.pick(free)
+                return agg(self.pick(['sum', 'avg', 'max', 'min']), [(v, VARS[v])], self.gen('f', scope + [v], depth - 1))
+            if c == 8 and self.allow_rand:
+                # (x appears twice below: it must not contain a random node itself -- two occurrences are two draws)
+                self.allow_rand = False
+                x = func('tanh', g('f'))
+                self.allow_rand = True
+                return self.pick([lambda: rand('Uniform', x, add(x, num(1.0))),
+                                  lambda: rand('Normal', x, add(func('abs', x), num(0.1))),
+                                  lambda: rand('Exponential', add(func('abs', x), num(0.2)))])()
+            if c == 9:
+                return mul(num(1.0), g('i'))
+            if c == 10:
+                return neg(g('f'))
+            return mul(num(0.5), add(g('f'), g('f')))
+        if dt == 'i':
+            c = int(rng.integers(0, 8))
+            if c == 0:
+                return self.pick([add, sub])(g('i'), g('i'))
+            if c == 1:
+                return mul(g('i'), num(int(rng.integers(-2, 3))))
+            if c == 2:
+                return func(self.pick(['abs', 'sgn']), g('i'))
+            if c == 3:
+                return func(self.pick(['round', 'floor', 'ceil', 'sgn']), mul(func('tanh', g('f')), num(3.0)))
+            if c == 4:
+                return func(self.pick(['div', 'mod']), g('i'), num(int(self.pick([2, 3, 5]))))
+            if c == 5:
+                return func(self.pick(['min', 'max']), g('i'), g('i'))
+            if c == 6:
+                return ite(g('b'), g('i'), g('i'))
+            if free:
+                v = self.pick(free)
+                return agg('sum', [(v, VARS[v])], self.gen('b', scope + [v], depth - 1))
+            return add(g('i'), g('b'))
+        c = int(rng.integers(0, 8))
+        if c == 0:
+            return self.pick([lt, le, gt, ge])(g('f'), g('f'))
+        if c == 1:
+            return self.pick([eq, ne, lt, ge])(g('i'), g('i'))
+        if c == 2:
+            return self.pick([land, lor, xor, implies, equiv])(g('b'), g('b'))
+        if c == 3:
+            return lnot(g('b'))
+        if c == 4 and free:
+            v = self.pick(free)
+            return agg(self.pick(['forall', 'exists']), [(v, VARS[v])], self.gen('b', scope + [v], depth - 1))
+        if c == 5 and self.allow_rand:
+            return rand('Bernoulli', mul(num(0.5), add(num(1.0), func('tanh', g('f')))))
+        if c == 6:
+            return ite(g('b'), g('b'), g('b'))
+        return gt(g('f'), num(0.0))
+
+
+def random_spec(seed, depth=3, n=4, m=3):
+    G = SpecGen(seed, n, m)
+    rng = G.rng
+    As = [f'a{i + 1}' for i in range(n)]
+    Bs = [f'b{i + 1}' for i in range(m)]
+    a, b = '?a', '?b'
+    pvars = [
+        ('K', 'non-fluent', 'real', ['ta'], 1.0), ('M', 'non-fluent', 'real', ['ta', 'tb'], 0.0),
+        ('IK', 'non-fluent', 'int', ['ta'], 1), ('FLAG', 'non-fluent', 'bool', ['ta'], False),
+        ('fa', 'state-fluent', 'real', ['ta'], 0.5), ('ia', 'state-fluent', 'int', ['ta'], 2),
+        ('ba', 'state-fluent', 'bool', ['ta'], False), ('fab', 'state-fluent', 'real', ['ta', 'tb'], 0.25),
+        ('s0', 'state-fluent', 'real', None, 1.5),
+        ('act', 'action-fluent', 'real', ['ta'], 0.0), ('bact', 'action-fluent', 'bool', ['ta'], False),
+        ('t0', 'interm-fluent', 'real', ['ta'], 0.0), ('t1', 'interm-fluent', 'real', ['ta', 'tb'], 0.0),
+        ('t2', 'interm-fluent', 'real', None, 0.0), ('tb0', 'interm-fluent', 'bool', ['ta'], False),
+        ('ti0', 'interm-fluent', 'int', ['ta'], 0),
+    ]
+    cpfs = [(('t0', [a]), G.gen('f', [a], depth)), (('t1', [a, b]), G.gen('f', [a, b], depth)),
+            (('tb0', [a]), G.gen('b', [a], depth)), (('ti0', [a]), G.gen('i', [a], depth))]
+    G.readable.update({'t0': ('f', ['?a']), 't1': ('f', ['?a', '?b']), 'tb0': ('b', ['?a']), 'ti0': ('i', ['?a'])})
+    cpfs.append((('t2', None), G.gen('f', [], depth)))
+    G.readable['t2'] = ('f', [])
+    cpfs += [
+        (("fa'", [a]), func('tanh', G.gen('f', [a], depth))),
+        (("ia'", [a]), func('max', num(-5), func('min', num(9), G.gen('i', [a], depth)))),
+        (("ba'", [a]), G.gen('b', [a], depth)),
+        (("fab'", [a, b]), func('tanh', G.gen('f', [a, b], depth))),
+        (("s0'", None), func('tanh', G.gen('f', [], depth))),
+    ]
+    G.readable.update({"fa'": ('f', ['?a']), "ba'": ('b', ['?a'])})
+    reward = add(G.gen('f', [], depth), agg('sum', [(a, 'ta')], mul(num(-0.1), func('abs', pv('act', a)))))
+    # terminations may only read state fluents and non-fluents (levels.py VALID_DEPENDENCIES)
+    full = dict(G.readable)
+    G.readable = {k: v for k, v in full.items() if k in ('K', 'M', 'IK', 'FLAG', 'fa', 'ia', 'ba', 'fab', 's0')}
+    G.allow_rand = False     # (the harness resets the reference before any variates exist)
+    terminal = G.gen('b', [], 2)
+    G.allow_rand = True
+    G.readable = full
+    init_nf, init_state = [], []
+    for i in range(n):
+        init_nf.append((('K', [As[i]]), float(np.round(rng.random() + 0.5, 3))))
+        init_nf.append((('IK', [As[i]]), int(rng.integers(0, 4))))
+        init_nf.append((('FLAG', [As[i]]), bool(rng.random() < 0.5)))
+        init_state.append((('fa', [As[i]]), float(np.round(rng.standard_normal() * 0.5, 3))))
+        init_state.append((('ia', [As[i]]), int(rng.integers(-3, 8))))
+        init_state.append((('ba', [As[i]]), bool(rng.random() < 0.5)))
+        for j in range(m):
+            init_nf.append((('M', [As[i], Bs[j]]), float(np.round(rng.standard_normal(), 3))))
+            init_state.append((('fab', [As[i], Bs[j]]), float(np.round(rng.random() - 0.5, 3))))
+    return dict(
+        name=f'fuzzspec{seed}', types=[('ta', 'object'), ('tb', 'object')], pvariables=pvars, cpfs=cpfs, reward=reward,
+        preconds=[agg('forall', [(a, 'ta')], le(func('abs', pv('act', a)), num(5.0)))],
+        invariants=[agg('forall', [(a, 'ta')], le(func('abs', pv('fa', a)), num(1.0)))],
+        terminals=[terminal],
+        objects=[('ta', As), ('tb', Bs)], init_non_fluent=init_nf, init_state=init_state,
+        max_nondef_actions='pos-inf', horizon=10, discount=0.9,
+    )

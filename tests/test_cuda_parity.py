@@ -31,6 +31,17 @@ def test_cuda_matches_reference_golden(case):
     sim.raise_for_status()
 
 
+@pytest.mark.parametrize('case', cases.FUZZSPEC_CASES)
+@pytest.mark.parametrize('specialize', [None, True])
+def test_cuda_matches_reference_on_random_domains(case, specialize):
+    """Random domains (tests/fuzz_specs.py) with trajectories generated from the unmodified reference
+    simulator (oracle/gen_fuzz_fixtures.py): interpreter kernels and specialised kernels."""
+    sim = cases.replay(case, lambda p, n: _make(p, n, specialize=specialize), to_np=_np)
+    sim.raise_for_status()
+    if specialize:
+        assert sim.specialised_kernels >= 1, sim.native.jit_error()
+
+
 def _lockstep(spec, N, T, inject, seed=11, akw=None, rtol=cases.RTOL):
     p = workloads.load_program(spec)
     sim = _make(p, N, seed=seed)

@@ -1,0 +1,49 @@
+"""Random RDDL domains through the UNMODIFIED reference simulator and through this repo's front end +
+oracle + lowering (op-table emulator): pins the oracle -- the checker of every GPU parity test -- to the
+reference on programs nobody wrote by hand. Needs the reference checkout (build container only)."""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+from fuzz_specs import random_spec
+from oracle import harness
+from oracle.oracle_sim import OracleSimulator
+from optable_emulator import EmulatedSimulator
+from pyrddlgym_b200 import lowering
+
+pytestmark = pytest.mark.skipif(not os.path.isdir('/root/reference/pyRDDLGym'), reason='reference checkout not present')
+
+
+@pytest.mark.parametrize('seed', range(80))
+def test_random_domain_reference_vs_oracle_vs_emulated_optable(seed):
+    from oracle.gen_fixtures import reference_program
+    spec = random_spec(seed, depth=3 + seed % 3)
+    p = reference_program(spec)
+    N, T = 3, 3
+    ref = harness.ReferenceBatch(spec, N)
+    ora = OracleSimulator(p, n_envs=N, seed=1)
+    emu = EmulatedSimulator(p, lowering.lower(p), N, seed=1)
+    d0 = ref.reset()
+    assert np.array_equal(d0, ora.reset()[1]) and np.array_equal(d0, emu.reset())
+    rng = np.random.default_rng(seed)
+    fluents = [n for n in p.tensors if p.tensors[n].kind not in ('nonfluent', 'next', 'action')]
+    for t in range(T):
+        acts = harness.random_actions(p, N, rng, p_bool=0.4)
+        var = harness.random_variates(p, N, rng)
+        r0, dn0 = ref.step(acts, var)
+        _, r1, dn1 = ora.step(acts, var)
+        r2, dn2 = emu.step(acts, var)
+        np.testing.assert_allclose(r1, r0, rtol=cases.RTOL, atol=1e-12)
+        np.testing.assert_allclose(r2, r0, rtol=cases.RTOL, atol=1e-12)
+        assert np.array_equal(dn0, dn1) and np.array_equal(dn0, dn2)
+        for f in fluents:
+            want = ref.fluent(f)
+            for name, got in (('oracle', ora.subs[f]), ('emulator', emu.fluent(f))):
+                got = np.asarray(got).reshape(want.shape)
+                if want.dtype.kind == 'f':
+                    np.testing.assert_allclose(got, want, rtol=cases.RTOL, atol=1e-12, err_msg=f'{name} {f} step {t}')
+                else:
+                    assert np.array_equal(got.astype(want.dtype), want), (name, f, t)
+        assert np.array_equal(ref.invariants(), ora.check_state_invariants())

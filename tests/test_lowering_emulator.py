@@ -34,6 +34,11 @@ def test_emulated_optable_matches_reference_golden(case, steps):
     assert not sim.status.any()
 
 
+@pytest.mark.parametrize('case', cases.FUZZSPEC_CASES)
+def test_emulated_optable_matches_reference_on_random_domains(case):
+    cases.replay(case, lambda p, n: _Adapter(p, n))
+
+
 def test_wildfire_neighbour_mask_becomes_csr():
     from pyrddlgym_b200 import workloads
     for sep in (False, True):

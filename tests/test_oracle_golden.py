@@ -17,6 +17,12 @@ def test_oracle_matches_reference_golden(case):
     assert not sim.status.any()
 
 
+@pytest.mark.parametrize('case', cases.FUZZSPEC_CASES)
+def test_oracle_matches_reference_on_random_domains(case):
+    """Random domains (tests/fuzz_specs.py), trajectories from the reference (oracle/gen_fuzz_fixtures.py)."""
+    cases.replay(case, lambda p, n: _Adapter(p, n))
+
+
 @pytest.mark.parametrize('case', ['wildfire8', 'wildfire8_sep', 'wildfire32'])
 def test_stencil_restatement_matches_reference_golden(case):
     """Pins oracle/wildfire_stencil.py (used at grid sizes the reference cannot build)."""
