@@ -5,8 +5,8 @@ the front end -- to the oracle, the lowering and the kernels. Expressions are ty
 and scoped over ?a : ta, ?b : tb; arguments of partial functions are made safe by construction."""
 import numpy as np
 
-from pyrddlgym_b200.workloads import (add, agg, div, eq, equiv, func, ge, gt, implies, ite, land, le, lnot, lor, lt,
-                                      mul, ne, neg, num, pv, rand, sub, xor, boolean)
+from pyrddlgym_b200.workloads import (add, agg, discrete, div, eq, equiv, func, ge, gt, implies, ite, land, le, lnot,
+                                      lor, lt, mul, ne, neg, num, pv, rand, sub, switch, xor, boolean)
 
 VARS = {'?a': 'ta', '?b': 'tb'}
 
@@ -57,23 +57,53 @@ class SpecGen:
                                   lambda x: func('sqrt', add(func('abs', x), num(0.1))),
                                   lambda x: func('ln', add(func('abs', x), num(1.0)))])(g('f'))
             if c == 4:
-                return func(self.pick(['min', 'max', 'hypot']), g('f'), g('f'))
+                k = self.pick(['min', 'max', 'hypot', 'fmod', 'log'])
+                if k == 'fmod':
+                    return func('fmod', g('f'), num(float(self.pick([0.7, -0.7, 1.3]))))
+                if k == 'log':
+                    return func('log', add(func('abs', g('f')), num(1.1)), num(2.0))
+                return func(k, g('f'), g(self.pick(['f', 'i'])))
             if c == 5:
                 return func('pow', add(func('abs', g('f')), num(0.1)), num(float(np.round(rng.uniform(0.5, 2.0), 2))))
             if c == 6:
                 return ite(g('b'), g('f'), g('f'))
             if c == 7 and free:
                 v = self.pick(free)
-                return agg(self.pick(['sum', 'avg', 'max', 'min']), [(v, VARS[v])], self.gen('f', scope + [v], depth - 1))
+                op = self.pick(['sum', 'avg', 'max', 'min', 'prod'])
+                body = self.gen('f', scope + [v], depth - 1)
+                if op == 'prod':
+                    body = add(num(1.0), mul(num(0.1), func('tanh', body)))
+                return agg(op, [(v, VARS[v])], body)
             if c == 8 and self.allow_rand:
                 # (x appears twice below: it must not contain a random node itself -- two occurrences are two draws)
                 self.allow_rand = False
                 x = func('tanh', g('f'))
                 self.allow_rand = True
+                pos = add(func('abs', x), num(0.2))
                 return self.pick([lambda: rand('Uniform', x, add(x, num(1.0))),
                                   lambda: rand('Normal', x, add(func('abs', x), num(0.1))),
-                                  lambda: rand('Exponential', add(func('abs', x), num(0.2)))])()
+                                  lambda: rand('Exponential', pos),
+                                  lambda: rand('Weibull', num(1.5), pos),
+                                  lambda: rand('Gumbel', x, num(0.5)),
+                                  lambda: rand('Laplace', x, pos),
+                                  lambda: rand('Cauchy', x, num(0.01)),
+                                  lambda: rand('Gompertz', num(1.2), pos),
+                                  lambda: rand('Kumaraswamy', num(2.0), add(pos, num(1.0))),
+                                  lambda: rand('Pareto', num(3.0), pos),
+                                  lambda: rand('DiracDelta', x)])()
             if c == 9:
+                k = int(rng.integers(0, 5))
+                if k == 0 and '?a' in scope:        # nested object index (non-fluent and state pointers)
+                    return pv('fa', pv(self.pick(['NEXT', 'ptr']), '?a'))
+                if k == 1 and '?a' in scope:        # enum-valued fluent: switch with / without default
+                    if rng.random() < 0.5:
+                        return switch(pv('col', '?a'), [('@red', g('f')), ('@blue', g('f'))], default=pv('CW', '@green'))
+                    return switch(pv('col', '?a'), [('@red', g('f')), ('@green', g('f')), ('@blue', g('f'))])
+                if k == 2 and '?a' in scope and '?b' not in scope:     # argmax / argmin as an index
+                    body = self.gen('f', scope + ['?b'], depth - 1)
+                    return pv('fab', '?a', agg(self.pick(['argmax', 'argmin']), [('?b', 'tb')], body))
+                if k == 3 and '?a' in scope:
+                    return pv('CW', pv('col', '?a'))
                 return mul(num(1.0), g('i'))
             if c == 10:
                 return neg(g('f'))
@@ -91,6 +121,11 @@ class SpecGen:
             if c == 4:
                 return func(self.pick(['div', 'mod']), g('i'), num(int(self.pick([2, 3, 5]))))
             if c == 5:
+                k = self.pick(['min', 'max', 'pow', 'kron'])
+                if k == 'pow':
+                    return func('pow', func('max', num(-3), func('min', num(3), g('i'))), num(2))
+                if k == 'kron' and self.allow_rand:
+                    return rand('KronDelta', g('i'))
                 return func(self.pick(['min', 'max']), g('i'), g('i'))
             if c == 6:
                 return ite(g('b'), g('i'), g('i'))
@@ -98,7 +133,11 @@ class SpecGen:
                 v = self.pick(free)
                 return agg('sum', [(v, VARS[v])], self.gen('b', scope + [v], depth - 1))
             return add(g('i'), g('b'))
-        c = int(rng.integers(0, 8))
+        c = int(rng.integers(0, 9))
+        if c == 8 and '?a' in scope:
+            return self.pick([lambda: eq(pv('col', '?a'), pv(self.pick(['@red', '@green', '@blue']))),
+                              lambda: eq(pv('ptr', '?a'), pv('NEXT', '?a')),
+                              lambda: ne(pv('ptr', '?a'), pv('?a'))])()
         if c == 0:
             return self.pick([lt, le, gt, ge])(g('f'), g('f'))
         if c == 1:
@@ -123,12 +162,15 @@ def random_spec(seed, depth=3, n=4, m=3):
     As = [f'a{i + 1}' for i in range(n)]
     Bs = [f'b{i + 1}' for i in range(m)]
     a, b = '?a', '?b'
+    colors = ['@red', '@green', '@blue']
     pvars = [
         ('K', 'non-fluent', 'real', ['ta'], 1.0), ('M', 'non-fluent', 'real', ['ta', 'tb'], 0.0),
         ('IK', 'non-fluent', 'int', ['ta'], 1), ('FLAG', 'non-fluent', 'bool', ['ta'], False),
         ('fa', 'state-fluent', 'real', ['ta'], 0.5), ('ia', 'state-fluent', 'int', ['ta'], 2),
         ('ba', 'state-fluent', 'bool', ['ta'], False), ('fab', 'state-fluent', 'real', ['ta', 'tb'], 0.25),
         ('s0', 'state-fluent', 'real', None, 1.5),
+        ('NEXT', 'non-fluent', 'ta', ['ta'], None), ('CW', 'non-fluent', 'real', ['color'], 1.0),
+        ('ptr', 'state-fluent', 'ta', ['ta'], None), ('col', 'state-fluent', 'color', ['ta'], '@red'),
         ('act', 'action-fluent', 'real', ['ta'], 0.0), ('bact', 'action-fluent', 'bool', ['ta'], False),
         ('t0', 'interm-fluent', 'real', ['ta'], 0.0), ('t1', 'interm-fluent', 'real', ['ta', 'tb'], 0.0),
         ('t2', 'interm-fluent', 'real', None, 0.0), ('tb0', 'interm-fluent', 'bool', ['ta'], False),
@@ -145,6 +187,12 @@ def random_spec(seed, depth=3, n=4, m=3):
         (("ba'", [a]), G.gen('b', [a], depth)),
         (("fab'", [a, b]), func('tanh', G.gen('f', [a, b], depth))),
         (("s0'", None), func('tanh', G.gen('f', [], depth))),
+        (("ptr'", [a]), ite(G.gen('b', [a], 2), pv('NEXT', a), pv('ptr', pv('NEXT', a)))),
+        (("col'", [a]), G.pick([
+            lambda: discrete('color', [('@red', num(0.2)), ('@green', num(0.3)), ('@blue', num(0.5))]),
+            lambda: discrete('color', [('@red', mul(num(0.5), add(num(1.0), func('tanh', G.gen('f', [a], 2))))),
+                                       ('@green', num(1.0)), ('@blue', num(0.5))], unnorm=True),
+            lambda: ite(G.gen('b', [a], 2), pv('col', a), pv('@blue'))])()),
     ]
     G.readable.update({"fa'": ('f', ['?a']), "ba'": ('b', ['?a'])})
     reward = add(G.gen('f', [], depth), agg('sum', [(a, 'ta')], mul(num(-0.1), func('abs', pv('act', a)))))
@@ -163,11 +211,16 @@ def random_spec(seed, depth=3, n=4, m=3):
         init_state.append((('fa', [As[i]]), float(np.round(rng.standard_normal() * 0.5, 3))))
         init_state.append((('ia', [As[i]]), int(rng.integers(-3, 8))))
         init_state.append((('ba', [As[i]]), bool(rng.random() < 0.5)))
+        init_nf.append((('NEXT', [As[i]]), As[(i + 1) % n]))
+        init_state.append((('ptr', [As[i]]), As[int(rng.integers(0, n))]))
+        init_state.append((('col', [As[i]]), colors[int(rng.integers(0, 3))]))
         for j in range(m):
             init_nf.append((('M', [As[i], Bs[j]]), float(np.round(rng.standard_normal(), 3))))
             init_state.append((('fab', [As[i], Bs[j]]), float(np.round(rng.random() - 0.5, 3))))
+    for (c_, w_) in zip(colors, (0.7, 1.3, 2.1)):
+        init_nf.append((('CW', [c_]), w_))
     return dict(
-        name=f'fuzzspec{seed}', types=[('ta', 'object'), ('tb', 'object')], pvariables=pvars, cpfs=cpfs, reward=reward,
+        name=f'fuzzspec{seed}', types=[('ta', 'object'), ('tb', 'object'), ('color', colors)], pvariables=pvars, cpfs=cpfs, reward=reward,
         preconds=[agg('forall', [(a, 'ta')], le(func('abs', pv('act', a)), num(5.0)))],
         invariants=[agg('forall', [(a, 'ta')], le(func('abs', pv('fa', a)), num(1.0)))],
         terminals=[terminal],
