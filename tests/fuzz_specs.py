@@ -92,7 +92,7 @@ class SpecGen:
                                   lambda: rand('Pareto', num(3.0), pos),
                                   lambda: rand('DiracDelta', x)])()
             if c == 9:
-                k = int(rng.integers(0, 5))
+                k = int(rng.integers(0, 6))
                 if k == 0 and '?a' in scope:        # nested object index (non-fluent and state pointers)
                     return pv('fa', pv(self.pick(['NEXT', 'ptr']), '?a'))
                 if k == 1 and '?a' in scope:        # enum-valued fluent: switch with / without default
@@ -104,6 +104,8 @@ class SpecGen:
                     return pv('fab', '?a', agg(self.pick(['argmax', 'argmin']), [('?b', 'tb')], body))
                 if k == 3 and '?a' in scope:
                     return pv('CW', pv('col', '?a'))
+                if k == 4 and '?a' in scope:        # object-valued state fluent as an index
+                    return pv('fab', '?a', pv('pick', '?a'))
                 return mul(num(1.0), g('i'))
             if c == 10:
                 return neg(g('f'))
@@ -174,11 +176,15 @@ def random_spec(seed, depth=3, n=4, m=3):
         ('act', 'action-fluent', 'real', ['ta'], 0.0), ('bact', 'action-fluent', 'bool', ['ta'], False),
         ('t0', 'interm-fluent', 'real', ['ta'], 0.0), ('t1', 'interm-fluent', 'real', ['ta', 'tb'], 0.0),
         ('t2', 'interm-fluent', 'real', None, 0.0), ('tb0', 'interm-fluent', 'bool', ['ta'], False),
-        ('ti0', 'interm-fluent', 'int', ['ta'], 0),
+        ('ti0', 'interm-fluent', 'int', ['ta'], 0), ('t3', 'interm-fluent', 'real', ['ta'], 0.0),
+        ('iact', 'action-fluent', 'int', None, 0), ('pick', 'state-fluent', 'tb', ['ta'], None),
     ]
     cpfs = [(('t0', [a]), G.gen('f', [a], depth)), (('t1', [a, b]), G.gen('f', [a, b], depth)),
             (('tb0', [a]), G.gen('b', [a], depth)), (('ti0', [a]), G.gen('i', [a], depth))]
     G.readable.update({'t0': ('f', ['?a']), 't1': ('f', ['?a', '?b']), 'tb0': ('b', ['?a']), 'ti0': ('i', ['?a'])})
+    G.readable['iact'] = ('i', [])
+    cpfs.append((('t3', [a]), G.gen('f', [a], depth)))          # second interm level: may read t0 / t1 / tb0 / ti0
+    G.readable['t3'] = ('f', ['?a'])
     cpfs.append((('t2', None), G.gen('f', [], depth)))
     G.readable['t2'] = ('f', [])
     cpfs += [
@@ -188,6 +194,12 @@ def random_spec(seed, depth=3, n=4, m=3):
         (("fab'", [a, b]), func('tanh', G.gen('f', [a, b], depth))),
         (("s0'", None), func('tanh', G.gen('f', [], depth))),
         (("ptr'", [a]), ite(G.gen('b', [a], 2), pv('NEXT', a), pv('ptr', pv('NEXT', a)))),
+        # object-valued sample from a normalised / unnormalised probability vector over tb
+        (("pick'", [a]), G.pick([
+            lambda: ('randomvar', ('UnnormDiscrete(p)', (('typed_var', (b, 'tb')),
+                                   (add(num(0.1), func('abs', func('tanh', G.gen('f', [a, b], 2)))),)))),
+            lambda: ('randomvar', ('Discrete(p)', (('typed_var', (b, 'tb')), (num(1.0 / m),)))),
+            lambda: agg('argmax', [(b, 'tb')], G.gen('f', [a, b], 2))])()),
         (("col'", [a]), G.pick([
             lambda: discrete('color', [('@red', num(0.2)), ('@green', num(0.3)), ('@blue', num(0.5))]),
             lambda: discrete('color', [('@red', mul(num(0.5), add(num(1.0), func('tanh', G.gen('f', [a], 2))))),
@@ -214,6 +226,7 @@ def random_spec(seed, depth=3, n=4, m=3):
         init_nf.append((('NEXT', [As[i]]), As[(i + 1) % n]))
         init_state.append((('ptr', [As[i]]), As[int(rng.integers(0, n))]))
         init_state.append((('col', [As[i]]), colors[int(rng.integers(0, 3))]))
+        init_state.append((('pick', [As[i]]), Bs[int(rng.integers(0, m))]))
         for j in range(m):
             init_nf.append((('M', [As[i], Bs[j]]), float(np.round(rng.standard_normal(), 3))))
             init_state.append((('fab', [As[i], Bs[j]]), float(np.round(rng.random() - 0.5, 3))))

@@ -19,7 +19,7 @@ pytestmark = pytest.mark.skipif(not os.path.isdir('/root/reference/pyRDDLGym'), 
 @pytest.mark.parametrize('seed', range(80))
 def test_random_domain_reference_vs_oracle_vs_emulated_optable(seed):
     from oracle.gen_fixtures import reference_program
-    spec = random_spec(seed, depth=3 + seed % 3)
+    spec = random_spec(seed, depth=3 + seed % 3, n=3 + seed % 4, m=2 + (seed // 4) % 3)
     p = reference_program(spec)
     N, T = 3, 3
     ref = harness.ReferenceBatch(spec, N)
