@@ -78,7 +78,7 @@ class SpecGen:
                 # (x appears twice below: it must not contain a random node itself -- two occurrences are two draws)
                 self.allow_rand = False
                 x = func('tanh', g('f'))
-                self.allow_rand = True
+                self.allow_rand = not getattr(self, 'deterministic', False)
                 pos = add(func('abs', x), num(0.2))
                 return self.pick([lambda: rand('Uniform', x, add(x, num(1.0))),
                                   lambda: rand('Normal', x, add(func('abs', x), num(0.1))),
@@ -158,8 +158,11 @@ class SpecGen:
         return gt(g('f'), num(0.0))
 
 
-def random_spec(seed, depth=3, n=4, m=3):
+def random_spec(seed, depth=3, n=4, m=3, deterministic=False):
+    """deterministic=True: no random variables anywhere (the drop-in tests compare native runs)."""
     G = SpecGen(seed, n, m)
+    G.deterministic = deterministic
+    G.allow_rand = not deterministic
     rng = G.rng
     As = [f'a{i + 1}' for i in range(n)]
     Bs = [f'b{i + 1}' for i in range(m)]
@@ -195,12 +198,12 @@ def random_spec(seed, depth=3, n=4, m=3):
         (("s0'", None), func('tanh', G.gen('f', [], depth))),
         (("ptr'", [a]), ite(G.gen('b', [a], 2), pv('NEXT', a), pv('ptr', pv('NEXT', a)))),
         # object-valued sample from a normalised / unnormalised probability vector over tb
-        (("pick'", [a]), G.pick([
+        (("pick'", [a]), agg('argmin', [(b, 'tb')], G.gen('f', [a, b], 2)) if deterministic else G.pick([
             lambda: ('randomvar', ('UnnormDiscrete(p)', (('typed_var', (b, 'tb')),
                                    (add(num(0.1), func('abs', func('tanh', G.gen('f', [a, b], 2)))),)))),
             lambda: ('randomvar', ('Discrete(p)', (('typed_var', (b, 'tb')), (num(1.0 / m),)))),
             lambda: agg('argmax', [(b, 'tb')], G.gen('f', [a, b], 2))])()),
-        (("col'", [a]), G.pick([
+        (("col'", [a]), ite(G.gen('b', [a], 2), pv('col', a), pv('@green')) if deterministic else G.pick([
             lambda: discrete('color', [('@red', num(0.2)), ('@green', num(0.3)), ('@blue', num(0.5))]),
             lambda: discrete('color', [('@red', mul(num(0.5), add(num(1.0), func('tanh', G.gen('f', [a], 2))))),
                                        ('@green', num(1.0)), ('@blue', num(0.5))], unnorm=True),
@@ -213,7 +216,7 @@ def random_spec(seed, depth=3, n=4, m=3):
     G.readable = {k: v for k, v in full.items() if k in ('K', 'M', 'IK', 'FLAG', 'fa', 'ia', 'ba', 'fab', 's0')}
     G.allow_rand = False     # (the harness resets the reference before any variates exist)
     terminal = G.gen('b', [], 2)
-    G.allow_rand = True
+    G.allow_rand = not deterministic
     G.readable = full
     init_nf, init_state = [], []
     for i in range(n):

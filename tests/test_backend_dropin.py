@@ -101,3 +101,37 @@ def test_invalid_distribution_parameter_maps_to_value_out_of_range_error():
     b.reset()
     with pytest.raises(ref.exc.RDDLValueOutOfRangeError):
         b.step(b.prepare_actions_for_sim({}))
+
+
+@pytest.mark.parametrize('seed', range(300, 312))
+def test_random_deterministic_domains_dropin_matches_reference(seed):
+    """Random deterministic domains (tests/fuzz_specs.py): the drop-in subclass returns what the reference
+    returns -- observation dicts (grounded names / tensors, object values as strings or indices), float
+    reward, bool done, check results -- step after step under the same grounded action dicts."""
+    from fuzz_specs import random_spec
+    kw = dict(keep_tensors=bool(seed % 2), objects_as_strings=bool((seed // 2) % 2))
+    spec_fn = lambda: random_spec(seed, depth=3, n=3 + seed % 3, m=2 + seed % 2, deterministic=True)
+    ref, a, b = _pair(spec_fn, **kw)
+    oa, da = a.reset()
+    ob, db = b.reset()
+    assert da == db and set(oa) == set(ob)
+    rng = np.random.default_rng(seed)
+    n = 3 + seed % 3
+    for t in range(4):
+        act = {f'act___a{i + 1}': float(np.round(rng.uniform(-2, 2), 3)) for i in range(n) if rng.random() < 0.7}
+        act.update({f'bact___a{i + 1}': True for i in range(n) if rng.random() < 0.4})
+        if rng.random() < 0.5:
+            act['iact'] = int(rng.integers(0, 4))
+        sa, sb = a.prepare_actions_for_sim(act), b.prepare_actions_for_sim(act)
+        assert a.check_action_preconditions(sa, silent=True) == b.check_action_preconditions(sb, silent=True)
+        oa, ra, da = a.step(sa)
+        ob, rb, db = b.step(sb)
+        assert isinstance(rb, float) and isinstance(db, bool)
+        np.testing.assert_allclose(rb, ra, rtol=1e-9, atol=1e-12)
+        assert da == db and set(oa) == set(ob)
+        for k in oa:
+            if isinstance(oa[k], str) or (isinstance(oa[k], np.ndarray) and oa[k].dtype.kind in 'UO'):
+                assert np.array_equal(np.asarray(oa[k]), np.asarray(ob[k])), k
+            else:
+                _same(oa[k], ob[k])
+        assert a.check_state_invariants(silent=True) == b.check_state_invariants(silent=True)
