@@ -15,16 +15,21 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
-from fuzz_specs import random_spec          # noqa: E402
+from fuzz_specs import random_grid_spec, random_spec          # noqa: E402
 from oracle import harness                  # noqa: E402
 from oracle.gen_fixtures import reference_program   # noqa: E402
 
 SEEDS = list(range(100, 116))
+GRID_SEEDS = list(range(500, 508))       # Wildfire-like grid domains (bit-plane path)
 OUT = os.path.join(ROOT, 'tests', 'golden', 'fuzzspec')
 
 
-def gen(seed, N=5, T=4):
-    spec = random_spec(seed, depth=3 + seed % 3)
+def gen(seed, N=5, T=4, grid=False):
+    if grid:
+        H, W = [(3, 32), (2, 64), (5, 32), (1, 96)][seed % 4]
+        spec = random_grid_spec(seed, H, W)
+    else:
+        spec = random_spec(seed, depth=3 + seed % 3)
     p = reference_program(spec)
     rb = harness.ReferenceBatch(spec, N)
     rng = np.random.default_rng(seed)
@@ -48,8 +53,8 @@ def gen(seed, N=5, T=4):
 
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
-    for seed in SEEDS:
-        p, out = gen(seed)
+    for seed, grid in [(s_, False) for s_ in SEEDS] + [(s_, True) for s_ in GRID_SEEDS]:
+        p, out = gen(seed, grid=grid)
         p.save(os.path.join(OUT, p.name + '.program.npz'))
         np.savez_compressed(os.path.join(OUT, p.name + '.npz'), **out)
         print(p.name, os.path.getsize(os.path.join(OUT, p.name + '.program.npz')), os.path.getsize(os.path.join(OUT, p.name + '.npz')))

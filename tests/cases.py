@@ -60,7 +60,7 @@ def replay(case, make_sim, to_np=np.asarray, steps=None):
     """Replays a golden trajectory through ``make_sim(program, n_envs)``; the simulator must
     offer reset() -> (.., done), step(actions, variates) -> (.., reward, done),
     check_state_invariants(), check_action_preconditions(actions), fluent(name)."""
-    if case.startswith('fuzzspec'):
+    if case.startswith(('fuzzspec', 'gridspec')):
         # random domains (tests/fuzz_specs.py): program + trajectory generated from the reference by
         # oracle/gen_fuzz_fixtures.py
         from pyrddlgym_b200 import hir

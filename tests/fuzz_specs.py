@@ -243,3 +243,101 @@ def random_spec(seed, depth=3, n=4, m=3, deterministic=False):
         objects=[('ta', As), ('tb', Bs)], init_non_fluent=init_nf, init_state=init_state,
         max_nondef_actions='pos-inf', horizon=10, discount=0.9,
     )
+
+
+# ---------------------------------------------------------------------------------------------
+# Wildfire-like boolean grid domains (the bit-plane path of the lowering) in spec form
+# ---------------------------------------------------------------------------------------------
+
+class GridSpecGen:
+    """Random domains over an H x W grid: bool planes, 3x3-stencil neighbour counts through separable
+    band masks XN(x,x2) ^ YN(y,y2), Bernoulli of a logistic function of the count, reward sums of
+    coefficient * boolean expression (the spec-form twin of tests/fuzz_programs.py:GridGen)."""
+
+    def __init__(self, seed, H, W):
+        self.rng = np.random.default_rng(seed)
+        self.H, self.W = H, W
+
+    def plane(self, name, x='?x', y='?y'):
+        return pv(name, x, y)
+
+    def nb(self, src):
+        return land(land(pv('XN', '?x', '?x2'), pv('YN', '?y', '?y2')), pv(src, '?x2', '?y2'))
+
+    def boolean(self, depth, avail):
+        rng = self.rng
+        r = rng.random()
+        if depth <= 0 or r < 0.2:
+            return self.plane(avail[int(rng.integers(len(avail)))])
+        B = lambda: self.boolean(depth - 1, avail)
+        if r < 0.5:
+            return [land, lor, xor, implies, equiv][int(rng.integers(5))](B(), B())
+        if r < 0.6:
+            return lnot(B())
+        if r < 0.7:
+            return ite(B(), B(), B())
+        tv = [('?x2', 'x_pos'), ('?y2', 'y_pos')]
+        src = [s for s in avail if s.startswith('s')] or ['s0']
+        body = self.nb(src[int(rng.integers(len(src)))])
+        if r < 0.8:
+            return agg('exists', tv, body)
+        cnt = agg('sum', tv, body)
+        if r < 0.9:
+            return [gt, ge, eq, lt][int(rng.integers(4))](cnt, num(int(rng.integers(0, 4))))
+        w = float(np.round(rng.uniform(0.3, 1.5), 2))
+        pr = div(num(1.0), add(num(1.0), func('exp', sub(pv('C1'), mul(cnt, num(w))))))
+        if rng.random() < 0.4:
+            pr = ite(self.plane(avail[int(rng.integers(len(avail)))]), pr, num(float(np.round(rng.uniform(0, 1), 2))))
+        return rand('Bernoulli', pr)
+
+
+def random_grid_spec(seed, H=3, W=32, depth=3):
+    G = GridSpecGen(seed, H, W)
+    rng = G.rng
+    xs = [f'x{i + 1}' for i in range(H)]
+    ys = [f'y{i + 1}' for i in range(W)]
+    offx = [d for d in (-1, 0, 1) if rng.random() < 0.8] or [0]
+    offy = [d for d in (-1, 0, 1) if rng.random() < 0.8] or [1]
+    pvars = [
+        ('XN', 'non-fluent', 'bool', ['x_pos', 'x_pos'], False), ('YN', 'non-fluent', 'bool', ['y_pos', 'y_pos'], False),
+        ('NA', 'non-fluent', 'bool', ['x_pos', 'y_pos'], False),
+        ('C0', 'non-fluent', 'real', None, float(np.round(rng.uniform(-9, -1), 1))),
+        ('C1', 'non-fluent', 'real', None, float(np.round(rng.uniform(0.5, 4), 2))),
+    ]
+    for k in range(3):
+        pvars.append((f's{k}', 'state-fluent', 'bool', ['x_pos', 'y_pos'], False))
+    for k in range(2):
+        pvars.append((f'a{k}', 'action-fluent', 'bool', ['x_pos', 'y_pos'], False))
+    init_nf, init_state = [], []
+    for i in range(H):
+        for d in offx:
+            if 0 <= i + d < H:
+                init_nf.append((('XN', [xs[i], xs[i + d]]), True))
+    for j in range(W):
+        for d in offy:
+            if 0 <= j + d < W:
+                init_nf.append((('YN', [ys[j], ys[j + d]]), True))
+    for i in range(H):
+        for j in range(W):
+            if rng.random() < 0.3:
+                init_nf.append((('NA', [xs[i], ys[j]]), True))
+            for k in range(3):
+                if rng.random() < 0.25:
+                    init_state.append(((f's{k}', [xs[i], ys[j]]), True))
+    avail = ['s0', 's1', 's2', 'a0', 'a1', 'NA']
+    xy = ['?x', '?y']
+    cpfs = [((f"s{k}'", xy), G.boolean(depth, avail)) for k in range(3)]
+    axy = [('?x', 'x_pos'), ('?y', 'y_pos')]
+    terms = []
+    for k in range(int(rng.integers(1, 4))):
+        coef = pv('C0') if k == 0 else num(float(np.round(rng.uniform(-5, 5), 1)))
+        terms.append(agg('sum', axy, mul(coef, G.boolean(1, avail))))
+    reward = terms[0]
+    for t_ in terms[1:]:
+        reward = add(reward, t_)
+    return dict(
+        name=f'gridspec{seed}', types=[('x_pos', 'object'), ('y_pos', 'object')], pvariables=pvars, cpfs=cpfs,
+        reward=reward, preconds=[], invariants=[], terminals=[],
+        objects=[('x_pos', xs), ('y_pos', ys)], init_non_fluent=init_nf, init_state=init_state,
+        max_nondef_actions='pos-inf', horizon=10, discount=1.0,
+    )

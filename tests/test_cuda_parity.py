@@ -40,6 +40,8 @@ def test_cuda_matches_reference_on_random_domains(case, specialize):
     sim.raise_for_status()
     if specialize:
         assert sim.specialised_kernels >= 1, sim.native.jit_error()
+    if case.startswith('gridspec'):
+        assert sim.table.launches[0]['kernel'] == 'rddl_plane_interp', sim.table.plane_rejects
 
 
 def _lockstep(spec, N, T, inject, seed=11, akw=None, rtol=cases.RTOL):
