@@ -64,17 +64,31 @@ class RandomPolicy:
         return out
 
 
-def evaluate(sim, policy, n_steps=None, gamma=None, seed=None, group=None):
-    """BaseAgent.evaluate (policy.py:45-126) with one episode per env: returns
-    {'mean', 'median', 'min', 'max', 'std'} of the discounted returns over all envs (and ranks)."""
+def evaluate(sim, policy, n_steps=None, gamma=None, seed=None, group=None, episodes=None):
+    """BaseAgent.evaluate (policy.py:45-126) with one episode per env and rollout: returns
+    {'mean', 'median', 'min', 'max', 'std'} of the discounted returns over all episodes (and ranks).
+    ``episodes`` (per rank; default = n_envs, one rollout): more episodes than envs run as successive
+    rollouts of the whole batch -- the reference's ``episodes`` loop, n_envs at a time."""
     p = sim.program
     n_steps = int(p.horizon if n_steps is None else n_steps)
+    episodes = sim.n_envs if episodes is None else int(episodes)
+    if episodes < 1:
+        raise ValueError('episodes must be >= 1')
     gen = None
     if seed is not None:
         gen = torch.Generator(device=sim.device).manual_seed(int(seed) + sim.env_offset)
-    sim.reset()
-    actions = policy.sample(sim, n_steps, generator=gen)
-    returns, _ = sim.rollout(actions, n_steps, gamma=gamma)
+    chunks, seed0, k = [], sim.seed_value, 0
+    while sum(int(c.numel()) for c in chunks) < episodes:
+        # reset() restarts the Philox step index, so every further rollout of the same envs runs under a
+        # seed of its own (restored afterwards): no rollout repeats another's random numbers
+        sim.seed((seed0 + k * 0x9E3779B97F4A7C15) & 0x7FFFFFFFFFFFFFFF)
+        sim.reset()
+        actions = policy.sample(sim, n_steps, generator=gen)
+        returns, _ = sim.rollout(actions, n_steps, gamma=gamma)
+        chunks.append(returns.clone())
+        k += 1
+    sim.seed(seed0)
+    returns = torch.cat(chunks)[:episodes]
     stats = parallel.reduce_return_stats(returns, group=group)
     stats['median'] = parallel.gather_median(returns, group=group)
     return {k: stats[k] for k in ('mean', 'median', 'min', 'max', 'std')}
