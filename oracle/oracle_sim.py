@@ -75,6 +75,7 @@ class OracleSimulator:
         self.env_offset = int(env_offset)
         self.step_count = 0
         self._nf_cache = {}
+        self._guard = None        # per-env mask of the scalar if-branches being evaluated (status reporting)
         self.status = np.zeros(self.N, dtype=np.uint32)
         self.reset()
 
@@ -165,6 +166,8 @@ class OracleSimulator:
         if bad.shape[0] == 1:
             bad = np.broadcast_to(bad, (self.N,) + bad.shape[1:])
         per_env = bad.reshape(self.N, -1).any(axis=1)
+        if self._guard is not None:
+            per_env = per_env & self._guard      # inside a branch the reference does not evaluate for this env
         self.status[per_env] |= np.uint32(bit)
 
     def ev(self, n):
@@ -197,6 +200,20 @@ class OracleSimulator:
         if k == 'agg':
             return self._agg(n)
         if k == 'if':                                     # simulator.py:903-923
+            if len(n.args[0].scope) == 0:
+                # a predicate that is one value per env: the reference short-circuits (all elements of the
+                # predicate tensor are equal, :912-919) and never evaluates the other branch, so parameter
+                # errors there are not errors. (Tensor predicates: both branches are evaluated whenever
+                # the predicate is mixed; their errors are reported unconditionally here.)
+                c = self.ev(n.args[0])
+                cg = np.broadcast_to(np.asarray(c, dtype=bool).reshape(-1), (self.N,))
+                g = self._guard
+                self._guard = cg if g is None else (g & cg)
+                a = self.ev(n.args[1])
+                self._guard = ~cg if g is None else (g & ~cg)
+                b = self.ev(n.args[2])
+                self._guard = g
+                return np.where(c, a, b)
             c, a, b = [self.ev(x) for x in n.args]
             return np.where(c, a, b)
         if k == 'switch':                                 # simulator.py:925-952

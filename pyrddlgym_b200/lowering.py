@@ -182,6 +182,7 @@ class _LaunchBuilder:
         self.free = []
         self.nregs = 0
         self.pinned = {}            # reg -> pin count
+        self.guard = None           # register: the enclosing scalar-`if` branches are taken for this env
         self.depth = 0
         self.loop_id = 0
         self.produced_slots = set()
@@ -256,6 +257,12 @@ class _LaunchBuilder:
 
     def flag_unless(self, ok, bit):
         bad = self.op1('NOT', ok)
+        if self.guard is not None:
+            # inside a branch of an `if` whose predicate is one value per env: the reference short-circuits
+            # such an `if` (simulator.py:912-919), so a parameter error in the branch it does not take is
+            # not an error
+            g = self.keep(self.guard)
+            bad = self.op2('AND', bad, g)
         self.ins('STATUS', a=bad, imm=bit)
         self.release(bad)
 
@@ -294,8 +301,27 @@ class _LaunchBuilder:
             return r, cls
         if k == 'if':
             c, _ = self.emit(n.args[0])
-            a, ca = self.emit(n.args[1])
-            b, cb = self.emit(n.args[2])
+            if len(n.args[0].scope) == 0:
+                outer = self.guard
+                self.pin(c)                      # live across both branches
+                gt = self.keep(c) if outer is None else self.op2('AND', self.keep(c), self.keep(outer))
+                self.pin(gt)
+                self.guard = gt
+                a, ca = self.emit(n.args[1])
+                self.unpin(gt)
+                self.release(gt)
+                nc = self.op1('NOT', self.keep(c))
+                ge = nc if outer is None else self.op2('AND', nc, self.keep(outer))
+                self.pin(ge)
+                self.guard = ge
+                b, cb = self.emit(n.args[2])
+                self.unpin(ge)
+                self.release(ge)
+                self.guard = outer
+                self.unpin(c)
+            else:
+                a, ca = self.emit(n.args[1])
+                b, cb = self.emit(n.args[2])
             t = _promote(ca, cb)
             a = self.conv(a, ca, t)
             b = self.conv(b, cb, t)

@@ -79,3 +79,48 @@ def test_random_grid_domain_reference_vs_oracle_vs_plane_optable(seed):
             want = ref.fluent(f's{k}')
             assert np.array_equal(np.asarray(ora.subs[f's{k}']).reshape(want.shape), want), (k, t)
             assert np.array_equal(np.asarray(emu.fluent(f's{k}')).reshape(want.shape).astype(bool), want), (k, t)
+
+
+def test_parameter_errors_behind_scalar_guards_match_the_reference_exceptions():
+    """`if (c) then Normal(m, v) else ...` with one value of c per env: the reference short-circuits the `if`
+    (simulator.py:912-919), so an invalid v only raises when its branch is taken. Per env: reference raised
+    RDDLValueOutOfRangeError <=> status word set (oracle and emulated op table), also under nested guards."""
+    from pyrddlgym_b200.workloads import add, gt, ite, lt, mul, num, pv, rand
+    from oracle.gen_fixtures import reference_program
+    from oracle.ref_import import load_reference
+    inner = ite(lt(pv('u'), num(1.0)), rand('Normal', num(0.0), pv('act')), rand('Exponential', pv('act')))
+    spec = dict(
+        name='guards', types=[('ta', 'object')],
+        pvariables=[('f0', 'state-fluent', 'real', None, 0.5), ('act', 'action-fluent', 'real', None, 0.0),
+                    ('u', 'action-fluent', 'real', None, 0.0)],
+        cpfs=[(("f0'", None), ite(gt(pv('u'), num(0.0)), inner, mul(pv('f0'), num(0.5))))],
+        reward=pv('f0'), preconds=[], invariants=[], terminals=[],
+        objects=[('ta', ['a1'])], init_non_fluent=[], init_state=[],
+        max_nondef_actions='pos-inf', horizon=5, discount=1.0)
+    p = reference_program(spec)
+    ref_err = load_reference().RDDLValueOutOfRangeError if hasattr(load_reference(), 'RDDLValueOutOfRangeError') else Exception
+    #        u: outer guard / which inner branch     act: variance (Normal, >= 0 required) or scale (Exponential, > 0)
+    u = np.array([-1.0, 0.5, 0.5, 2.0, 2.0, -3.0])
+    act = np.array([-2.0, 1.0, -1.0, 1.0, -1.0, 0.0])
+    N = len(u)
+    want = np.array([False, False, True, False, True, False])      # raised by the reference
+    ora = OracleSimulator(p, n_envs=N, seed=1)
+    emu = EmulatedSimulator(p, lowering.lower(p), N, seed=1)
+    ora.reset(); emu.reset()
+    var = harness.random_variates(p, N, np.random.default_rng(0))
+    acts = {'act': act, 'u': u}
+    raised = []
+    for e in range(N):
+        rb = harness.ReferenceBatch(spec, 1)
+        rb.reset()
+        try:
+            rb.step({k: v[e:e + 1] for k, v in acts.items()}, {k: v[e:e + 1] for k, v in var.items()})
+            raised.append(False)
+        except Exception as ex:
+            assert 'OutOfRange' in type(ex).__name__, ex
+            raised.append(True)
+    assert np.array_equal(np.array(raised), want)
+    ora.step(acts, var)
+    emu.step(acts, var)
+    assert np.array_equal(ora.status != 0, want), ora.status
+    assert np.array_equal(emu.status != 0, want), emu.status
