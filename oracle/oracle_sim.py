@@ -218,8 +218,30 @@ class OracleSimulator:
             return np.where(c, a, b)
         if k == 'switch':                                 # simulator.py:925-952
             pred = self.ev(n.args[0])
-            df = None if n.default is None else self.ev(n.default)
-            cases = [(df if c is None else self.ev(c)) for c in n.cases]
+            if len(n.args[0].scope) == 0:
+                # one predicate value per env: the reference short-circuits only when the predicate equals
+                # bool(predicate) (:933-943), i.e. for the first two cases, and then evaluates just that case;
+                # otherwise every case and the default
+                pg = np.broadcast_to(np.asarray(pred).reshape(-1), (self.N,))
+                g = self._guard
+                general = (pg != 0) & (pg != 1)
+
+                def guarded(mask, node):
+                    mask = mask | general
+                    self._guard = mask if g is None else (g & mask)
+                    out = self.ev(node)
+                    self._guard = g
+                    return out
+
+                dmask = np.zeros(self.N, dtype=bool)
+                for i in (0, 1):
+                    if i >= len(n.cases) or n.cases[i] is None:
+                        dmask = dmask | (pg == i)
+                df = None if n.default is None else guarded(dmask, n.default)
+                cases = [(df if c is None else guarded(pg == i, c)) for i, c in enumerate(n.cases)]
+            else:
+                df = None if n.default is None else self.ev(n.default)
+                cases = [(df if c is None else self.ev(c)) for c in n.cases]
             full = (self.N,) + self._shape(n.scope)
             stack = np.stack([np.broadcast_to(c, full) for c in cases], axis=0)
             idx = np.broadcast_to(pred, full)[np.newaxis, ...]

@@ -475,16 +475,54 @@ class _LaunchBuilder:
         self.pin(pred)
         t = n.dtype
         present = [(k, c) for (k, c) in enumerate(n.cases) if c is not None]
+        # A predicate that is one value per env: the reference short-circuits the switch only when the
+        # predicate equals bool(predicate), i.e. for the first two cases (simulator.py:933-943:
+        # `first_elem = bool(...)`, `all_equal = np.all(sample_pred == first_elem)`); then it evaluates
+        # just that case, otherwise every case and the default. Parameter errors are reported for what
+        # the reference evaluates (see flag_unless).
+        scalar = len(n.args[0].scope) == 0
+        outer = self.guard
+
+        def eq_const(k):
+            kk = self.const(k, 'i')
+            hit = self.alloc()
+            self.ins('IEQ', dst=hit, a=pred, b=kk)
+            self.release(kk)
+            return hit
+
+        def case_guard(keys):
+            """guard register: (pred in keys) OR (pred not in {0, 1}), AND the enclosing guard."""
+            g = self.op1('NOT', self.op2('OR', eq_const(0), eq_const(1)))
+            for k in keys:
+                g = self.op2('OR', g, eq_const(k))
+            if outer is not None:
+                g = self.op2('AND', g, self.keep(outer))
+            self.pin(g)
+            return g
+
+        def guarded(keys, negate, node):
+            if not scalar:
+                return self.emit(node)
+            if negate:      # the default: selected by the short-circuit when case 0 / 1 has no expression
+                keys = [k for k in (0, 1) if k >= len(n.cases) or n.cases[k] is None]
+            g = case_guard(keys)
+            self.guard = g
+            out = self.emit(node)
+            self.guard = outer
+            self.unpin(g)
+            self.release(g)
+            return out
+
         if n.default is not None:
-            acc, ca = self.emit(n.default)
+            acc, ca = guarded([k for (k, _) in present], True, n.default)
             acc = self.conv(acc, ca, t)
             rest = present
         else:
-            acc, ca = self.emit(present[-1][1])
+            acc, ca = guarded([present[-1][0]], False, present[-1][1])
             acc = self.conv(acc, ca, t)
             rest = present[:-1]
         for (k, c) in rest:
-            v, cv = self.emit(c)
+            v, cv = guarded([k], False, c)
             v = self.conv(v, cv, t)
             kk = self.const(k, 'i')
             hit = self.alloc()

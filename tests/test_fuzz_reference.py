@@ -124,3 +124,51 @@ def test_parameter_errors_behind_scalar_guards_match_the_reference_exceptions():
     emu.step(acts, var)
     assert np.array_equal(ora.status != 0, want), ora.status
     assert np.array_equal(emu.status != 0, want), emu.status
+
+
+def test_parameter_errors_behind_a_scalar_switch_match_the_reference_exceptions():
+    """switch on an enum-valued scalar fluent (one value per env): the reference evaluates only the selected
+    case when it short-circuits (simulator.py:933-943); per env, raised <=> status word set."""
+    from pyrddlgym_b200.workloads import mul, num, pv, rand, switch
+    from oracle.gen_fixtures import reference_program
+    modes = ['@normal', '@expo', '@idle', '@other']
+    body = switch(pv('mode'), [('@normal', rand('Normal', num(0.0), num(1.0))),
+                               ('@expo', rand('Exponential', pv('act')))], default=mul(pv('f0'), num(0.5)))
+    spec = dict(
+        name='switchguard', types=[('ta', 'object'), ('mode_t', modes)],
+        pvariables=[('f0', 'state-fluent', 'real', None, 0.5), ('mode', 'state-fluent', 'mode_t', None, '@idle'),
+                    ('act', 'action-fluent', 'real', None, 0.0)],
+        cpfs=[(("f0'", None), body), (("mode'", None), pv('mode'))],
+        reward=pv('f0'), preconds=[], invariants=[], terminals=[],
+        objects=[('ta', ['a1'])], init_non_fluent=[], init_state=[],
+        max_nondef_actions='pos-inf', horizon=5, discount=1.0)
+    act_values = [-1.0, 2.0]
+    for mi, mode in enumerate(modes):
+        spec_m = dict(spec, init_state=[(('mode', None), mode)])
+        p = reference_program(spec_m)
+        N = len(act_values)
+        acts = {'act': np.array(act_values)}
+        var = harness.random_variates(p, N, np.random.default_rng(mi))
+        raised = []
+        for e in range(N):
+            rb = harness.ReferenceBatch(spec_m, 1)
+            rb.reset()
+            try:
+                rb.step({k: v[e:e + 1] for k, v in acts.items()}, {k: v[e:e + 1] for k, v in var.items()})
+                raised.append(False)
+            except Exception as ex:
+                assert 'OutOfRange' in type(ex).__name__, ex
+                raised.append(True)
+        want = np.array(raised)
+        # act = -1 is an invalid Exponential scale. @normal (enum value 0): short-circuit, only the Normal case
+        # is evaluated -> no error. @expo (1): short-circuit into the Exponential -> error. @idle / @other (2, 3):
+        # the reference short-circuits only for the first two enum values (`first_elem = bool(pred)`), so it
+        # evaluates every case -> error.
+        assert want.tolist() == [mode != '@normal', False], (mode, raised)
+        ora = OracleSimulator(p, n_envs=N, seed=1)
+        emu = EmulatedSimulator(p, lowering.lower(p), N, seed=1)
+        ora.reset(); emu.reset()
+        ora.step(acts, var)
+        emu.step(acts, var)
+        assert np.array_equal(ora.status != 0, want), (mode, ora.status)
+        assert np.array_equal(emu.status != 0, want), (mode, emu.status)
