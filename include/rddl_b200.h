@@ -79,6 +79,46 @@ int rddl_rollout(rddl_program_t* prog, void* const* tensors, uint32_t* status, i
                  const int64_t* step_stride_bytes, double gamma, double* returns, double* rewards,
                  int32_t* state_in_next, void* cuda_stream);
 
+/* Device-side random policy: the batched counterpart of RandomAgent / NoOpAgent
+ * (pyRDDLGym/core/policy.py:129-195). RandomAgent.sample_action draws every action grounding uniformly
+ * from its range and then keeps `num_actions` randomly chosen groundings (policy.py:166-178); here the
+ * draws happen inside the kernels (no action tensor crosses PCIe or HBM):
+ *   kind RDDL_POLICY_BERNOULLI     bool fluent, 1 with probability lo (1/2 = the agent's Discrete(2))
+ *        RDDL_POLICY_UNIFORM_REAL  real fluent, lo + (hi - lo) * U,  U in [0, 1)
+ *        RDDL_POLICY_UNIFORM_INT   int fluent, uniform on {lo, ..., hi}
+ *        RDDL_POLICY_DEFAULT       the fluent keeps its default (NoOpAgent)
+ *   dflt        the fluent's default (noop) value
+ *   max_nondef  < 0 or >= #groundings: every grounding keeps its draw; otherwise only max_nondef
+ *               groundings per (env, step), chosen uniformly without replacement over the groundings of
+ *               all entries in entry order (at most 32), keep theirs and the rest take the default --
+ *               the max-nondef-actions rule of check_default_action_count (simulator.py:329-360).
+ * Every draw is a function of (seed, global env id, step, fluent, grounding) only; the mapping is
+ * restated in oracle/philox_np.py (policy_actions). Action fluents not listed are read from `tensors`. */
+enum { RDDL_POLICY_BERNOULLI = 1, RDDL_POLICY_UNIFORM_REAL = 2, RDDL_POLICY_UNIFORM_INT = 3, RDDL_POLICY_DEFAULT = 4 };
+typedef struct { int32_t tensor, kind; double lo, hi, dflt; } rddl_policy_entry_t;
+typedef struct { int32_t n_entries, max_nondef; rddl_policy_entry_t entries[8]; } rddl_policy_t;
+
+/* rddl_rollout with the actions of `policy` drawn on the device (the loop of BaseAgent.evaluate with a
+ * RandomAgent, policy.py:85-117): same arguments and results as rddl_rollout minus the action
+ * sequences; n_steps = 1 is one policy-driven transition. Identical to materialising every step's
+ * actions with rddl_policy_sample and calling rddl_rollout with them. */
+int rddl_rollout_policy(rddl_program_t* prog, const rddl_policy_t* policy, void* const* tensors, uint32_t* status,
+                        int64_t n_envs, int64_t env_offset, uint64_t seed, uint64_t step0, int32_t n_steps,
+                        double gamma, double* returns, double* rewards, int32_t* state_in_next, void* cuda_stream);
+
+/* Writes the actions the policy takes at `step` into the action tensors (tensors[entry.tensor],
+ * [n_envs, ...]): RandomAgent.sample_action for every env (policy.py:166-178). */
+int rddl_policy_sample(rddl_program_t* prog, const rddl_policy_t* policy, void* const* tensors, int64_t n_envs,
+                       int64_t env_offset, uint64_t seed, uint64_t step, void* cuda_stream);
+
+/* Replaces the counting part of check_default_action_count (simulator.py:329-360) as a device
+ * reduction: counts[e] (int32[n_envs], device) = number of groundings of the n_actions action tensors
+ * action_tensors[i] whose value differs from default_values[i]; the caller compares the maximum with
+ * max_allowed_actions and raises RDDLInvalidActionError. */
+int rddl_action_count(rddl_program_t* prog, void* const* tensors, const int32_t* action_tensors,
+                      const double* default_values, int32_t n_actions, int32_t* counts, int64_t n_envs,
+                      void* cuda_stream);
+
 /* Replaces the statistics of BaseAgent.evaluate (pyRDDLGym/core/policy.py:120-126: np.mean / std / min
  * / max of the per-episode returns) for this rank's shard: out5 = {sum, sum of squares, count, min,
  * max} of returns f64[n] (device pointers), one deterministic block reduction. Ranks combine their
@@ -108,6 +148,7 @@ int rddl_return_stats(const double* returns, int64_t n, double* out5, void* cuda
 int rddl_program_option(rddl_program_t* prog, int what, int64_t value);
 const char* rddl_jit_error(const rddl_program_t* prog);
 int rddl_plane_precompile(const void* optable, size_t nbytes, int64_t n_envs);
+int rddl_policy_precompile(const void* optable, size_t nbytes, int64_t n_envs, const rddl_policy_t* policy);
 int64_t rddl_plane_source(const void* optable, size_t nbytes, int launch, int64_t n_envs, char* out, size_t cap);
 
 /* Measurement aid (no reference counterpart): when enabled, every kernel launch of this

@@ -8,9 +8,9 @@ one extra leading axis: N independent environments (the reference has no batch a
 
 Parity status: the reference ships no tests or golden vectors for this path (SURVEY.md
 section 4), so the oracle is pinned against *outputs of the reference itself* generated in
-the build container by ``oracle/gen_golden.py`` and committed under ``tests/golden/``
-(tests/test_oracle_golden.py replays them; tests/test_oracle_vs_reference.py compares
-live against the imported reference when it is present).
+the build container by ``oracle/gen_fixtures.py`` / ``oracle/gen_fuzz_fixtures.py`` and committed
+under ``tests/golden/`` (tests/test_oracle_golden.py replays them; tests/test_fuzz_reference.py
+compares live against the imported reference when it is present).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu-baseline leg may import this
 module; the product package never does.
@@ -90,9 +90,14 @@ class OracleSimulator:
                 self.subs[name] = v
             else:
                 self.subs[name] = np.broadcast_to(v, (self.N,) + v.shape).copy()
-        self.step_count = 0
+        # (the Philox step index is not rewound: episodes after a reset draw fresh noise, like the
+        # reference's generator stream, simulator.py:129-134; set_seed restarts it)
         self.status[:] = 0
         return self.states(), self.check_terminal_states()
+
+    def set_seed(self, seed):
+        self.seed = int(seed)
+        self.step_count = 0
 
     def states(self):
         return {s: self.subs[s] for s in self.p.next_state}

@@ -135,3 +135,81 @@ def bernoulli_bitsliced(seed, env_ids, step, node_id, p):
     tail = u64 < (T << np.uint64(BERN_LEVELS))
     out = np.where(und.reshape(N, n_cells), tail, res.reshape(N, n_cells))
     return out | always
+
+
+# ---------------------------------------------------------------------------------------
+# Device-side random policy (pyrddlgym_b200/csrc/rddl_device.cuh: rddl_policy_value,
+# rddl_policy_pick, rddl_policy_floyd; include/rddl_b200.h: rddl_policy_t) -- the batched
+# counterpart of RandomAgent.sample_action (/root/reference/pyRDDLGym/core/policy.py:166-178):
+# every action grounding is drawn from its range, then -- under a max-nondef rule -- only k
+# groundings chosen uniformly without replacement keep their draw.
+# ---------------------------------------------------------------------------------------
+
+POLICY_NODE = 0xF000
+POLICY_SELECT_NODE = 0xFF00
+POL_BERNOULLI, POL_UNIFORM_REAL, POL_UNIFORM_INT, POL_DEFAULT = 1, 2, 3, 4
+
+
+def policy_select(seed, env_ids, step, k, total):
+    """int64 [len(env_ids), k]: the groundings of [0, total) that keep their draw. Candidate i is
+    umulhi64((x << 32) | y, total - k + i + 1) of Philox(counter = (i, env, step, POLICY_SELECT_NODE));
+    Floyd's rule: a candidate already chosen is replaced by total - k + i."""
+    env = (np.asarray(env_ids, dtype=np.uint64) & MASK).astype(np.uint32)[:, None]
+    i = np.arange(k, dtype=np.uint32)[None, :]
+    x, y, _, _ = philox4x32_10(i, env, np.uint32(step & 0xFFFFFFFF), np.uint32(POLICY_SELECT_NODE),
+                               seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    sel = np.zeros((len(env_ids), k), dtype=np.int64)
+    for e in range(len(env_ids)):
+        chosen = []
+        for q in range(k):
+            j = total - k + q
+            u64 = (int(x[e, q]) << 32) | int(y[e, q])
+            t = (u64 * (j + 1)) >> 64
+            if t in chosen:
+                t = j
+            chosen.append(t)
+        sel[e] = chosen
+    return sel
+
+
+def policy_actions(entries, max_nondef, seed, env_ids, step):
+    """entries: list of dicts {tensor (id), kind, lo, hi, dflt, shape, dtype ('b' | 'i' | 'f')} in
+    policy order. Returns {tensor id: array [len(env_ids), *shape]} -- what rddl_policy_sample writes
+    and what the kernels draw in registers under rddl_rollout_policy."""
+    N = len(env_ids)
+    sizes = [int(np.prod(e['shape'], dtype=np.int64)) if len(e['shape']) else 1 for e in entries]
+    total = sum(sizes)
+    k = 0
+    kinds = [e['kind'] for e in entries]
+    if max_nondef is not None and 0 <= max_nondef < total:
+        if max_nondef == 0:
+            kinds = [POL_DEFAULT] * len(entries)
+        else:
+            k = int(max_nondef)
+    sel = policy_select(seed, env_ids, step, k, total) if k else None
+    out = {}
+    base = 0
+    for e, kind, n in zip(entries, kinds, sizes):
+        npdt = {'b': np.bool_, 'i': np.int64, 'f': np.float64}[e['dtype']]
+        dflt = np.asarray(e['dflt']).astype(npdt)
+        node = POLICY_NODE + int(e['tensor'])
+        if kind == POL_DEFAULT:
+            v = np.full((N, n), dflt, dtype=npdt)
+        elif kind == POL_BERNOULLI:
+            pad = (-n) % 32      # the bit-sliced mapping is defined per 32-cell word; a ragged last word is cut
+            p = np.full((N, n + pad), float(e['lo']), dtype=np.float64)
+            v = bernoulli_bitsliced(seed, env_ids, step, node, p)[:, :n]
+        else:
+            u = base_variates('U', seed, env_ids, step, node, (n,))
+            if kind == POL_UNIFORM_REAL:
+                v = float(e['lo']) + (float(e['hi']) - float(e['lo'])) * u
+            else:
+                lo, hi = int(e['lo']), int(e['hi'])
+                v = np.minimum(lo + np.floor(u * float(hi - lo + 1)).astype(np.int64), hi)
+        if k and kind != POL_DEFAULT:
+            g = base + np.arange(n, dtype=np.int64)[None, :]
+            keep = (sel[:, :, None] == g[:, None, :]).any(axis=1)
+            v = np.where(keep, v, dflt)
+        out[e['tensor']] = np.asarray(v, dtype=npdt).reshape((N,) + tuple(e['shape']))
+        base += n
+    return out

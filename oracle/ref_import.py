@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY -- imports the unmodified reference (pyRDDLGym) read-only.
 
-Only ``tests/``, ``oracle/gen_golden.py`` (fixture generation, run in the build
-container) and ``bench.py --impl reference`` may import this module. The product
+Only ``tests/``, ``oracle/gen_fixtures.py`` / ``gen_fuzz_fixtures.py`` (fixture generation, run in
+the build container) and ``bench.py --impl reference`` may import this module. The product
 package ``pyrddlgym_b200`` never does (its drop-in backend imports ``pyRDDLGym``
 directly and only when the user already has it installed).
 
@@ -18,7 +18,20 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get('RDDL_REFERENCE_ROOT', '/root/reference')
+# Where the unmodified reference lives: $RDDL_REFERENCE_ROOT, else the read-only checkout of the build
+# container, else the copy `pip install --target baseline/_ref` made from it (oracle/install_reference.py;
+# git-ignored, but it travels to the GPU box with the tree -- there it is the only one present).
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_root():
+    for cand in (os.environ.get('RDDL_REFERENCE_ROOT'), '/root/reference', os.path.join(_REPO, 'baseline', '_ref')):
+        if cand and os.path.isdir(os.path.join(cand, 'pyRDDLGym')):
+            return cand
+    return os.environ.get('RDDL_REFERENCE_ROOT', '/root/reference')
+
+
+REFERENCE_ROOT = _find_root()
 
 _STUBS = ['gymnasium', 'gymnasium.spaces', 'pygame', 'matplotlib',
           'matplotlib.pyplot', 'ply', 'ply.lex', 'ply.yacc']

@@ -1,5 +1,7 @@
 """Drop-in backend for pyRDDLGym: ``RDDLEnv(domain, instance, backend=B200RDDLSimulator,
-backend_kwargs={'n_envs': 4096, 'device': 'cuda:0'})``.
+backend_kwargs={'device': 'cuda:0'})`` (``RDDLEnv`` drives one environment, n_envs == 1; batches
+of environments go through ``B200RDDLSimulator(model, n_envs=N)`` directly or through
+``pyrddlgym_b200.vector_env.BatchedRDDLEnv``).
 
 The plug-in point is the reference's own (/root/reference/pyRDDLGym/core/env.py:47-48,
 107-110: ``backend(self.model, logger=..., keep_tensors=..., **backend_kwargs)``; "a backend is
@@ -35,7 +37,7 @@ def backend_class():
     from pyRDDLGym.core.simulator import RDDLSimulator
     from pyRDDLGym.core.compiler.initializer import RDDLValueInitializer
     from pyRDDLGym.core.debug.exception import (
-        RDDLActionPreconditionNotSatisfiedError, RDDLNotImplementedError,
+        RDDLActionPreconditionNotSatisfiedError, RDDLInvalidActionError, RDDLNotImplementedError,
         RDDLStateInvariantNotSatisfiedError, RDDLValueOutOfRangeError)
 
     class B200RDDLSimulator(RDDLSimulator):
@@ -147,6 +149,19 @@ def backend_class():
             self.state = self._state_dict(rddl.next_state.keys())
             obs = self._state_dict(rddl.observ_fluents) if self._pomdp else self.state
             return obs, float(self._host(reward)[0]), bool(self._host(done)[0])
+
+        def check_default_action_count(self, actions, enforce_for_non_bool=True):
+            """simulator.py:329-360. Batched mode: one device reduction over the action tensors
+            ([n_envs, ...]) instead of np.count_nonzero per fluent; any env above max-nondef-actions
+            raises the reference's RDDLInvalidActionError."""
+            if self.n_envs == 1:
+                return super().check_default_action_count(actions, enforce_for_non_bool)
+            try:
+                self.engine.check_default_action_count(actions, enforce_for_non_bool)
+            except ValueError as e:
+                if type(e).__name__ == 'InvalidActionCount':
+                    raise RDDLInvalidActionError(str(e))
+                raise
 
         def check_state_invariants(self, silent=False):
             ok = self.engine.check_state_invariants()

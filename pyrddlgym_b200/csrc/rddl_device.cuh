@@ -36,6 +36,7 @@ struct VmArgs {
   double* returns;
   double* rewards;
   int64_t tstride[RDDL_MAX_TENSORS];
+  VmPolicy pol;                // pol.n > 0: action fluents listed there are drawn in-kernel (device-side policy)
 };
 
 __device__ __forceinline__ double as_f(uint64_t v) { return __longlong_as_double((long long)v); }
@@ -107,6 +108,77 @@ __device__ __forceinline__ uint64_t red_combine(int op, uint64_t a, uint64_t b) 
     case RED_AND: return a & b;
     default: return a | b;
   }
+}
+
+// ---------------------------------------------------------------------------------------
+// Device-side random policy: the batched counterpart of RandomAgent.sample_action
+// (pyRDDLGym/core/policy.py:166-178) evaluated inside the kernels. Every draw is a pure function of
+// (seed, global env id, step, action fluent, grounding), restated in oracle/philox_np.py:policy_actions.
+// ---------------------------------------------------------------------------------------
+
+// Bernoulli(p) of one cell under the bit-sliced mapping of the plane kernels (rddl_plane.cuh: PBERN;
+// oracle/philox_np.py:bernoulli_bitsliced): the cell compares the top 8 bits of thr = floor(p * 2^64),
+// MSB first, with bit (cell % 32) of the Philox words of (cell / 32, level); ties take one 64-bit draw.
+__device__ __forceinline__ bool rddl_bern_bitsliced_cell(uint64_t seed, uint32_t env, uint32_t step, uint32_t node,
+                                                         uint64_t thr, bool always, uint64_t cell) {
+  if (always) return true;
+  const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  const uint32_t w = (uint32_t)(cell >> 5), bit = (uint32_t)cell & 31u;
+#pragma unroll 1
+  for (uint32_t b = 0; b < 2; ++b) {
+    const uint4 r4 = rddl_philox4x32_10(make_uint4(w, env, step, (node & 0xffffu) | ((0x8000u + b) << 16)), key);
+    const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t rb = (rw[q] >> bit) & 1u;
+      const uint32_t tb = (uint32_t)(thr >> (63 - (4 * b + q))) & 1u;
+      if (rb != tb) return tb != 0;
+    }
+  }
+  const uint4 r4 = rddl_philox4x32_10(make_uint4((uint32_t)cell, env, step, (node & 0xffffu) | (0xC000u << 16)), key);
+  return (((uint64_t)r4.x << 32) | r4.y) < (thr << 8);
+}
+
+// i-th candidate of the max-nondef selection: uniform in [0, j]
+__device__ __forceinline__ int64_t rddl_policy_pick(uint64_t seed, uint32_t env, uint32_t step, uint32_t i, int64_t j) {
+  const uint4 r4 = rddl_philox4x32_10(make_uint4(i, env, step, RDDL_POLICY_SELECT_NODE),
+                                      make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  return (int64_t)__umul64hi(((uint64_t)r4.x << 32) | r4.y, (uint64_t)(j + 1));
+}
+
+// The k groundings of [0, total) that keep their draw this step (Floyd's sampling without replacement
+// over the candidates pick[i] ~ U[0, total - k + i]): sel[i] = pick[i] unless already chosen, then
+// total - k + i. pick[] may alias sel[].
+__device__ __forceinline__ void rddl_policy_floyd(const int32_t* pick, int32_t* sel, int k, int64_t total) {
+  for (int i = 0; i < k; ++i) {
+    int32_t t = pick[i];
+    for (int q = 0; q < i; ++q)
+      if (sel[q] == t) { t = (int32_t)(total - k + i); break; }
+    sel[i] = t;
+  }
+}
+
+// Value (raw 64 bits) of grounding `elem` of policy entry e for (env, step); sel = the env's selected
+// groundings when the policy has a max-nondef rule (k > 0), else unused.
+__device__ __forceinline__ uint64_t rddl_policy_value(const VmPolicy& pol, const VmPolicyEntry& e, uint64_t seed,
+                                                      uint64_t env_global, uint64_t step, int64_t elem,
+                                                      const int32_t* sel) {
+  if (e.kind == POL_DEFAULT) return e.dflt;
+  if (pol.k > 0) {
+    bool chosen = false;
+    for (int i = 0; i < pol.k; ++i) chosen |= (int64_t)sel[i] == e.base + elem;
+    if (!chosen) return e.dflt;
+  }
+  const uint32_t node = RDDL_POLICY_NODE + (uint32_t)e.tensor;
+  if (e.kind == POL_BERNOULLI)
+    return rddl_bern_bitsliced_cell(seed, (uint32_t)env_global, (uint32_t)step, node, e.thr, e.always != 0, (uint64_t)elem);
+  const uint4 x = rddl_philox_draw(seed, env_global, step, node, (uint64_t)elem);
+  const double u = rddl_u53(x.x, x.y);
+  if (e.kind == POL_UNIFORM_REAL) return (uint64_t)__double_as_longlong(__dadd_rn(e.lo, __dmul_rn(__dsub_rn(e.hi, e.lo), u)));
+  // POL_UNIFORM_INT: lo + floor(u * (hi - lo + 1)), never above hi
+  const int64_t lo = (int64_t)e.lo, hi = (int64_t)e.hi;
+  int64_t v = lo + (int64_t)floor(__dmul_rn(u, (double)(hi - lo + 1)));
+  return (uint64_t)(v > hi ? hi : v);
 }
 
 // The constant / address-descriptor / reduction-slot pools a program executes from: device copies
@@ -183,6 +255,12 @@ __device__ __forceinline__ void vm_exec_one(const VmArgs& A, const VmPools& P, c
       }
       const int t = ad->tensor;
       if (op == OP_LOAD) {
+        if (A.pol.n > 0 && t >= 0 && A.pol.of_tensor[t]) {
+          // action fluent under a device-side policy: drawn here instead of read from HBM
+          r[dst] = rddl_policy_value(A.pol, A.pol.e[A.pol.of_tensor[t] - 1], A.seed, (uint64_t)(A.env_offset + env), step,
+                                     off, A.pol.sel + env * A.pol.k);
+          break;
+        }
         off += env * ad->env_stride;
         const void* base = A.tensors[t];
         const int dt = P.dtype[t];

@@ -194,7 +194,8 @@ static std::string plane_static_data(const PlaneProg& G, const RddlLaunch& L, co
        jit_fmt("#define PS_BLOCK %lld\n", block);
   s += "__device__ constexpr PlaneProg kG = {" + jit_fmt("%lld,", G.nops) + jit_fmt("%lld,", G.nshared) +
        jit_fmt("%lld,", G.w32_shift) + jit_fmt("%lld,", G.wpe_shift) + jit_fmt("%lld,", G.nfused) +
-       jit_fmt("%lld,", G.fused_nregs) + jit_fmt("%lld,", G.rollout_ok) + jit_fmt("%lld,\n{", G.pad);
+       jit_fmt("%lld,", G.fused_nregs) + jit_fmt("%lld,", G.rollout_ok) + jit_fmt("%lld,", G.pad) +
+       jit_fmt("%lld,", G.pol_k) + jit_fmt("%lld,\n{", G.pol_pad);
   jit_launch_init(s, G.fused[0]);
   s += ",\n";
   jit_launch_init(s, G.fused[1]);
@@ -418,6 +419,7 @@ static JitDriver& jit_driver() {
 // One specialised kernel of a program: (launch index, words per thread, tile geometry).
 struct JitKernel {
   int launch = -1, wpt = 0, G = 0, ipt = 0, minb = 0;
+  uint64_t sig = 0;     // 0: the program as lowered; else hash of its policy-rewritten PlaneProg
   CUmodule mod = nullptr;
   CUfunction fn = nullptr;
   bool failed = false;

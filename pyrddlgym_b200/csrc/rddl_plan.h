@@ -27,9 +27,11 @@ enum RddlOp : uint8_t {
   OP_PLD, OP_PLDC, OP_PST, OP_PCONST, OP_PLUT, OP_PSHARE, OP_PCOUNT, OP_PBERN, OP_PRED,
   OP_SUMLOOP,
   OP_SAMPLE,
+  OP_PPOLSEL,
   OP_COUNT_
 };
 
+// (OP_PPOLSEL: plane op the host inserts for device-side policies with a max-nondef rule; never in an op table)
 enum RddlRed { RED_SUM_I, RED_SUM_F, RED_PROD_I, RED_PROD_F, RED_MIN_I, RED_MIN_F, RED_MAX_I, RED_MAX_F,
                RED_AND, RED_OR };
 enum RddlDtype { DT_BOOL = 0, DT_INT = 1, DT_REAL = 2,
@@ -83,6 +85,30 @@ struct RddlLaunch {    // 176 bytes
 };
 
 struct RddlRedSlot { int32_t op, chunks; };
+
+// Device-side random policy (rddl_rollout_policy / rddl_policy_sample): how each action fluent is drawn
+// inside the kernels instead of being read from a caller buffer. Philox node ids of the draws:
+// RDDL_POLICY_NODE + tensor id for the values, RDDL_POLICY_SELECT_NODE for the max-nondef selection.
+#define RDDL_MAX_POLICY 8
+#define RDDL_POLICY_MAX_SELECT 32
+#define RDDL_POLICY_NODE 0xF000u
+#define RDDL_POLICY_SELECT_NODE 0xFF00u
+enum RddlPolicyKind { POL_NONE = 0, POL_BERNOULLI = 1, POL_UNIFORM_REAL = 2, POL_UNIFORM_INT = 3, POL_DEFAULT = 4 };
+struct VmPolicyEntry {   // 64 bytes
+  int32_t tensor, kind;
+  double lo, hi;         // uniform bounds (POL_BERNOULLI: lo = p)
+  uint64_t thr;          // POL_BERNOULLI: floor(p * 2^64), 2^64 - 1 when p >= 1
+  uint64_t dflt;         // raw 64-bit default (noop) value of the fluent
+  int64_t base, nelem;   // first flat grounding index of this fluent in the policy's grounding order, #groundings
+  int32_t always, pad;   // POL_BERNOULLI: p >= 1
+};
+struct VmPolicy {
+  int32_t n, k;          // entries; k > 0: only k randomly chosen groundings per (env, step) keep their draw
+  int64_t total;         // groundings over all entries
+  int32_t* sel;          // scratch int32[n_envs, k]: the selected groundings of the current step (scalar kernels)
+  uint8_t of_tensor[RDDL_MAX_TENSORS];   // tensor id -> entry index + 1 (0: not policy-driven)
+  VmPolicyEntry e[RDDL_MAX_POLICY];
+};
 struct RddlVariate { int32_t node, kind; int64_t nelem; };
 
 static_assert(sizeof(RddlInsn) == 16, "insn");

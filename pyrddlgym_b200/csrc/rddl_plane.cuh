@@ -38,6 +38,7 @@ struct PlaneOp {        // 32 bytes, pre-decoded from RddlInsn + its Fin descrip
 struct PlaneProg {
   int32_t nops, nshared, w32_shift, wpe_shift;   // shifts: log2 of words per row / per env, or -1
   int32_t nfused, fused_nregs, rollout_ok, pad;  // scalar launches run in the epilogue (kind 2)
+  int32_t pol_k, pol_pad;                        // device-side policy with a max-nondef rule: groundings kept per (env, step)
   RddlLaunch fused[2];
   int32_t red_off[RDDL_MAX_RED], red_m[RDDL_MAX_RED];   // PRED op of reduction j: table offset, #planes
   PlaneOp ops[PLANE_MAX_OPS];
@@ -387,6 +388,7 @@ struct PlaneTile {
   uint32_t* queue;      // [8][PLANE_QUEUE]
   int* qn;              // [8]
   uint32_t* fix;        // [256][WPT]
+  int32_t* sel;         // [32][pol_k] groundings that keep their policy draw this step (PPOLSEL)
   int64_t env0, tile_byte0;
   int64_t gw_limit;     // last valid global word index this tile may touch (ragged tiles clamp loads to it)
   int W32, wpe, envs_per_tile, tile_words, chunks, chunk, pitch, tile_rows, plane_stride;
@@ -668,6 +670,24 @@ __device__ __forceinline__ void plane_exec(PlaneTile<WPT, BLOCK>& T, const VmArg
         }
         break;
       }
+      case OP_PPOLSEL: {
+        // max-nondef rule of a device-side policy: only the groundings selected for this (env, step)
+        // keep the draw already in the register, the others fall back to the fluent's default
+        const VmPolicyEntry& e = A.pol.e[o.imm];
+        const uint32_t dm = e.dflt ? 0xffffffffu : 0u;
+        const int k = G.pol_k;
+#pragma unroll
+        for (int j = 0; j < WPT; ++j) {
+          const int32_t* s = T.sel + C.env[j] * k;
+          uint32_t mask = 0;
+          for (int i = 0; i < k; ++i) {
+            const int64_t gi = (int64_t)s[i] - e.base;
+            if (gi >= 0 && gi < e.nelem && (gi >> 5) == C.wi[j]) mask |= 1u << (gi & 31);
+          }
+          C.at(o.dst, j) = (C.at(o.dst, j) & mask) | (dm & ~mask);
+        }
+        break;
+      }
       case OP_PRED: {
 #if defined(PLANE_ABLATE) && (PLANE_ABLATE & 4)
         break;
@@ -744,6 +764,7 @@ __device__ __forceinline__ void plane_tile(const VmArgs& A, const PlaneProg& G, 
   T.queue = reinterpret_cast<uint32_t*>(cnt + 32 * RDDL_MAX_RED);
   T.qn = reinterpret_cast<int*>(T.queue + 8 * PLANE_QUEUE);
   T.fix = reinterpret_cast<uint32_t*>(T.qn + 8);
+  T.sel = reinterpret_cast<int32_t*>(T.fix + BLOCK * WPT);
   if (L.nred > 0)
     for (int i = tid; i < 32 * RDDL_MAX_RED; i += BLOCK) cnt[i] = 0;
   for (int i = tid; i < G.nshared * plane_stride; i += BLOCK) S[i] = 0u;           // zero padding, once
@@ -788,6 +809,7 @@ __device__ __forceinline__ void plane_tile(const VmArgs& A, const PlaneProg& G, 
   double ret_acc = 0.0, disc = 1.0;
   bool alive = true;
   const int NT = A.n_steps > 1 ? A.n_steps : 1;
+  const bool rollout = A.returns != nullptr;     // rddl_rollout (any n_steps >= 1): returns / per-step rewards are accumulated
 #pragma unroll 1
   for (int t = 0; t < NT; ++t) {
   const bool last_step = t == NT - 1;
@@ -797,6 +819,20 @@ __device__ __forceinline__ void plane_tile(const VmArgs& A, const PlaneProg& G, 
 #else
   if (full && !last_step) plane_run_ops<WPT, BLOCK, PLANE_PREFETCH_NEXT, 0>(T, A, G, L, DT, t, last_step);
 #endif
+  if (G.pol_k > 0) {
+    // device-side policy with a max-nondef rule: the pol_k groundings of each env of the tile that keep
+    // their draw this step -- candidates in parallel, then Floyd's resolution by one thread per env
+    // (the same functions as the scalar kernels' rddl_policy_select_kernel)
+    const int k = G.pol_k;
+    for (int i = tid; i < envs_per_tile * k; i += BLOCK) {
+      const int e = i / k, q = i - e * k;
+      T.sel[i] = (int32_t)rddl_policy_pick(A.seed, (uint32_t)(A.env_offset + env0 + e), (uint32_t)(A.step + t), (uint32_t)q,
+                                           A.pol.total - k + q);
+    }
+    __syncthreads();
+    if (tid < envs_per_tile) rddl_policy_floyd(T.sel + tid * k, T.sel + tid * k, k, A.pol.total);
+    __syncthreads();
+  }
   plane_run_ops<WPT, BLOCK, PLANE_RUN, 0>(T, A, G, L, DT, t, last_step);
 
   // Specialised single-tile launches with a fused scalar program: the thread that runs env e's
@@ -866,12 +902,12 @@ __device__ __forceinline__ void plane_tile(const VmArgs& A, const PlaneProg& G, 
         uint64_t r1[40];
         vm_exec_static<kG.fused[1].pc_begin, kG.fused[1].pc_end>(A, P, kG.fused[1], ge, A.step + t, idx0, rv, r1, cap, G.pad, red_local);
       }
-      if (NT > 1) {
+      if (rollout) {
         const double rwd = as_f(cap[0]);
         const bool done_now = cap[1] != 0;
 #else
       for (int f = 0; f < G.nfused; ++f) vm_exec_element<40>(A, G.fused[f], ge, A.step + t, idx0, rv);
-      if (NT > 1) {
+      if (rollout) {
         // BaseAgent.evaluate (pyRDDLGym/core/policy.py:100-117): total += reward * gamma^t until done
         const double rwd = __ldcg(reinterpret_cast<const double*>(A.tensors[G.pad]) + ge);
         const bool done_now = __ldcg(reinterpret_cast<const uint8_t*>(A.tensors[G.pad + 1]) + ge) != 0;
@@ -884,7 +920,7 @@ __device__ __forceinline__ void plane_tile(const VmArgs& A, const PlaneProg& G, 
     }
   }
   }   // step loop
-  if (NT > 1 && A.returns && tid < envs_per_tile && env0 + tid < A.n_envs) A.returns[env0 + tid] += ret_acc;
+  if (rollout && tid < envs_per_tile && env0 + tid < A.n_envs) A.returns[env0 + tid] += ret_acc;
 }
 
 #ifdef PLANE_STATIC

@@ -76,6 +76,15 @@ struct rddl_program {
   std::vector<PlaneProg> plane_progs;   // per launch index; pre-decoded programs of plane launches
   uint8_t* d_alive = nullptr;           // rollout (general path): env still running
   int64_t alive_capacity = 0;
+  // device-side policies (rddl_rollout_policy): plane programs rewritten per policy (the action planes
+  // are drawn in registers), scratch for the max-nondef selection, and which tensors some kernel reads
+  // through a raw pointer (SUMLOOP terms, contraction operands, stencil halos) -- those are
+  // materialised in HBM each step instead
+  struct PolicyProg { int launch; uint64_t polsig, sig; PlaneProg G; };
+  std::vector<PolicyProg*> policy_progs;
+  std::vector<uint8_t> direct_read;
+  int32_t* d_polsel = nullptr;
+  int64_t polsel_capacity = 0;
   // run-time specialised plane kernels (rddl_jit.h), built on first use per (launch, tile geometry)
   bool specialize = true;
   std::vector<RddlInsn> h_insns;          // host copies for the specialised epilogue (rddl_jit.h)
@@ -121,16 +130,18 @@ static int plane_static_min_blocks(int wpt, const RddlLaunch& adj, int64_t n_env
 
 // The specialised kernel of plane launch `li` for the tile geometry `adj` / wpt, or nullptr (then the
 // interpreter kernel runs): compiled with NVRTC on first use, cubins cached on disk.
-static JitKernel* jit_get(rddl_program* g, int li, int wpt, int blk, const RddlLaunch& adj, int64_t n_envs) {
+static JitKernel* jit_get(rddl_program* g, int li, int wpt, int blk, const RddlLaunch& adj, int64_t n_envs,
+                          const PlaneProg* prog = nullptr, uint64_t sig = 0) {
   if (!g->specialize) return nullptr;
   const int minb = plane_static_min_blocks(wpt, adj, n_envs);
   for (JitKernel& k : g->jit)
-    if (k.launch == li && k.wpt == wpt && k.G == adj.G && k.ipt == adj.ipt && k.minb == minb) return k.failed ? nullptr : &k;
+    if (k.launch == li && k.wpt == wpt && k.G == adj.G && k.ipt == adj.ipt && k.minb == minb && k.sig == sig)
+      return k.failed ? nullptr : &k;
   JitKernel k;
-  k.launch = li; k.wpt = wpt; k.G = adj.G; k.ipt = adj.ipt; k.minb = minb;
+  k.launch = li; k.wpt = wpt; k.G = adj.G; k.ipt = adj.ipt; k.minb = minb; k.sig = sig;
   uint8_t dt[RDDL_MAX_TENSORS] = {0};
   for (size_t i = 0; i < g->tensors.size(); ++i) dt[i] = (uint8_t)g->tensors[i].dtype;
-  const std::string data = plane_static_data(g->plane_progs[li], adj, dt, wpt, minb, blk, g->pools());
+  const std::string data = plane_static_data(prog ? *prog : g->plane_progs[li], adj, dt, wpt, minb, blk, g->pools());
   std::string cubin, err;
   bool hit = false;
   JitDriver& drv = jit_driver();
@@ -408,6 +419,25 @@ static int parse_program(const void* optable, size_t nbytes, int device, rddl_pr
       if (src < 0) ok = false;
       else o.a = src + 1;
     }
+    // The fused scalar epilogue runs through the scalar LOAD / STORE / SUMLOOP, which know neither the
+    // per-step strides of an action sequence nor the state carried on chip: a fused program that
+    // touches any fluent other than the outputs (__reward, __done, __chk) keeps the per-step path.
+    for (int f = 0; f < G->nfused && ok; ++f) {
+      for (int pc = G->fused[f].pc_begin; pc < G->fused[f].pc_end && ok; ++pc) {
+        const RddlInsn& in = g->h_insns[pc];
+        auto fluent = [&](uint32_t ai) {
+          if (ai >= g->h_addrs.size()) return true;
+          const int t = g->h_addrs[ai].tensor;
+          return t >= 0 && t < reward_tensor && g->tensors[t].kind == KIND_ENV;
+        };
+        if ((in.op == OP_LOAD || in.op == OP_STORE) && fluent(in.imm)) ok = false;
+        if (in.op == OP_SUMLOOP) {
+          if (fluent(in.imm)) ok = false;
+          if ((in.b & 2u) && pc + 1 < G->fused[f].pc_end && fluent(g->h_insns[pc + 1].imm)) ok = false;
+          ++pc;   // data word
+        }
+      }
+    }
     G->rollout_ok = ok;
   }
   for (auto& L : g->launches) {
@@ -422,6 +452,23 @@ static int parse_program(const void* optable, size_t nbytes, int device, rddl_pr
   int64_t acc = 0;
   for (auto& s : g->redslots) { g->red_off.push_back(acc); acc += s.chunks; }
   g->red_total = acc;
+  // tensors some kernel reads through a raw pointer instead of LOAD / PLD (see rddl_program::direct_read)
+  g->direct_read.assign(g->tensors.size(), 0);
+  for (size_t li = 0; li < g->launches.size(); ++li) {
+    const RddlLaunch& L = g->launches[li];
+    auto mark = [&](int64_t t) { if (t >= 0 && (size_t)t < g->direct_read.size()) g->direct_read[(size_t)t] = 1; };
+    if (L.kind == 3) { mark(L.red_slot[0]); mark(L.red_slot[1]); mark(L.red_slot[2]); continue; }
+    for (int pc = L.pc_begin; pc < L.pc_end; ++pc) {
+      const RddlInsn& in = g->h_insns[pc];
+      if (L.kind == 1) {
+        if (in.op == OP_PSHARE && in.imm != 0xffffffffu && L.chunks > 1) mark(in.imm);
+      } else if (in.op == OP_SUMLOOP) {
+        if (in.imm < g->h_addrs.size()) mark(g->h_addrs[in.imm].tensor);
+        if ((in.b & 2u) && pc + 1 < L.pc_end && g->h_insns[pc + 1].imm < g->h_addrs.size()) mark(g->h_addrs[g->h_insns[pc + 1].imm].tensor);
+        ++pc;
+      }
+    }
+  }
   for (int i = 0; i < 9; ++i) secs[i] = sec[i];
   memcpy(hdr_out, hdr, sizeof hdr);
   *out = g;
@@ -542,6 +589,8 @@ extern "C" void rddl_program_destroy(rddl_program_t* g) {
   cudaFree(g->d_pool); cudaFree(g->d_variates); cudaFree(g->d_redslots); cudaFree(g->d_red_off);
   cudaFree(g->d_red);
   cudaFree(g->d_alive);
+  cudaFree(g->d_polsel);
+  for (auto* pp : g->policy_progs) delete pp;
   for (JitKernel& k : g->jit)
     if (k.mod) jit_driver().ModuleUnload(k.mod);
   if (g->level_mod) jit_driver().ModuleUnload(g->level_mod);
@@ -576,9 +625,187 @@ struct RolloutArgs {
   const int64_t* stride_bytes;
 };
 
+// ---------------------------------------------------------------------------------------
+// device-side policies
+// ---------------------------------------------------------------------------------------
+
+// The groundings that keep their draw at `step`, one thread per env: sel[env, 0..k)
+__global__ void rddl_policy_select_kernel(const __grid_constant__ VmPolicy pol, int32_t* sel, int64_t n_envs,
+                                          int64_t env_offset, uint64_t seed, uint64_t step) {
+  const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= n_envs) return;
+  int32_t* s = sel + env * pol.k;
+  for (int i = 0; i < pol.k; ++i)
+    s[i] = (int32_t)rddl_policy_pick(seed, (uint32_t)(env_offset + env), (uint32_t)step, (uint32_t)i, pol.total - pol.k + i);
+  rddl_policy_floyd(s, s, pol.k, pol.total);
+}
+
+// RandomAgent.sample_action for every env (pyRDDLGym/core/policy.py:166-178): writes the step's
+// actions of one policy entry into its action tensor, one thread per (env, grounding).
+__global__ void rddl_policy_sample_kernel(const __grid_constant__ VmPolicy pol, int entry, void* out, int dtype,
+                                          int64_t n_envs, int64_t env_offset, uint64_t seed, uint64_t step) {
+  const VmPolicyEntry& e = pol.e[entry];
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_envs * e.nelem) return;
+  const int64_t env = i / e.nelem, elem = i - env * e.nelem;
+  const uint64_t v = rddl_policy_value(pol, e, seed, (uint64_t)(env_offset + env), step, elem, pol.sel + env * pol.k);
+  if (dtype == DT_BOOL) reinterpret_cast<uint8_t*>(out)[i] = v != 0;
+  else reinterpret_cast<uint64_t*>(out)[i] = v;
+}
+
+// check_default_action_count (pyRDDLGym/core/simulator.py:329-360) as a device reduction: one warp per
+// env counts the groundings of the listed action tensors that differ from their default value.
+struct ActionCountArgs {
+  int32_t n;
+  const void* ptr[16];
+  int64_t nelem[16];
+  uint64_t dflt[16];
+  uint8_t dtype[16];
+};
+__global__ void rddl_action_count_kernel(const __grid_constant__ ActionCountArgs a, int32_t* counts, int64_t n_envs) {
+  const int64_t env = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (env >= n_envs) return;
+  int c = 0;
+  for (int t = 0; t < a.n; ++t) {
+    const int64_t n = a.nelem[t];
+    if (a.dtype[t] == DT_BOOL) {
+      const uint8_t* p = reinterpret_cast<const uint8_t*>(a.ptr[t]) + env * n;
+      const bool d = a.dflt[t] != 0;
+      for (int64_t i = lane; i < n; i += 32) c += (p[i] != 0) != d;
+    } else if (a.dtype[t] == DT_REAL) {
+      const double* p = reinterpret_cast<const double*>(a.ptr[t]) + env * n;
+      const double d = __longlong_as_double((long long)a.dflt[t]);
+      for (int64_t i = lane; i < n; i += 32) c += p[i] != d;
+    } else {
+      const uint64_t* p = reinterpret_cast<const uint64_t*>(a.ptr[t]) + env * n;
+      for (int64_t i = lane; i < n; i += 32) c += p[i] != a.dflt[t];
+    }
+  }
+  c = __reduce_add_sync(0xffffffffu, c);
+  if (lane == 0) counts[env] = c;
+}
+
+static uint64_t fnv_bytes(uint64_t h, const void* p, size_t n) {
+  const unsigned char* c = (const unsigned char*)p;
+  for (size_t i = 0; i < n; ++i) { h ^= c[i]; h *= 0x100000001b3ull; }
+  return h;
+}
+
+// Validates the public descriptor and converts it to the kernels' form.
+static int make_policy(rddl_program* g, const rddl_policy_t* P, VmPolicy* out) {
+  memset(out, 0, sizeof *out);
+  if (!P || P->n_entries < 0 || P->n_entries > RDDL_MAX_POLICY) { g->err = "policy: bad entry count"; return RDDL_ERR_ARG; }
+  const int n_user = (int)g->tensors.size() - 3;
+  int64_t total = 0;
+  for (int i = 0; i < P->n_entries; ++i) {
+    const rddl_policy_entry_t& pe = P->entries[i];
+    VmPolicyEntry& e = out->e[i];
+    if (pe.tensor < 0 || pe.tensor >= n_user || g->tensors[pe.tensor].kind != KIND_ENV || out->of_tensor[pe.tensor]) {
+      g->err = "policy: entry does not name an action tensor (or names one twice)";
+      return RDDL_ERR_ARG;
+    }
+    const int dt = g->tensors[pe.tensor].dtype;
+    const bool kind_ok = (pe.kind == POL_BERNOULLI && dt == DT_BOOL && pe.lo >= 0.0 && pe.lo <= 1.0) ||
+                         (pe.kind == POL_UNIFORM_REAL && dt == DT_REAL && pe.lo <= pe.hi) ||
+                         (pe.kind == POL_UNIFORM_INT && dt == DT_INT && pe.lo <= pe.hi) || pe.kind == POL_DEFAULT;
+    if (!kind_ok || dt == DT_PACKED) { g->err = "policy: kind / range does not fit the fluent's type"; return RDDL_ERR_ARG; }
+    e.tensor = pe.tensor; e.kind = pe.kind; e.lo = pe.lo; e.hi = pe.hi;
+    e.dflt = dt == DT_REAL ? (uint64_t)0 : (dt == DT_BOOL ? (uint64_t)(pe.dflt != 0.0) : (uint64_t)(int64_t)pe.dflt);
+    if (dt == DT_REAL) memcpy(&e.dflt, &pe.dflt, 8);
+    if (pe.kind == POL_BERNOULLI) {
+      e.always = pe.lo >= 1.0;
+      e.thr = e.always ? ~0ull : (uint64_t)(pe.lo * 18446744073709551616.0);
+    }
+    e.base = total;
+    e.nelem = g->tensors[pe.tensor].nelem;
+    total += e.nelem;
+    out->of_tensor[pe.tensor] = (uint8_t)(i + 1);
+  }
+  out->n = P->n_entries;
+  out->total = total;
+  if (total >= (1ll << 31)) { g->err = "policy: more than 2^31 action groundings"; return RDDL_ERR_ARG; }
+  if (P->max_nondef >= 0 && P->max_nondef < total) {
+    if (P->max_nondef == 0) {
+      for (int i = 0; i < out->n; ++i) out->e[i].kind = POL_DEFAULT;
+    } else if (P->max_nondef > RDDL_POLICY_MAX_SELECT) {
+      g->err = "policy: max_nondef between 33 and the number of groundings is not supported on the device";
+      return RDDL_ERR_ARG;
+    } else {
+      out->k = P->max_nondef;
+    }
+  }
+  return RDDL_OK;
+}
+
+// The plane program of launch li with the loads of policy-driven action planes replaced by in-register
+// draws: PLD -> PBERN over a constant table (same bit-sliced sampler and Philox counters as a
+// Bernoulli CPF, node id RDDL_POLICY_NODE + tensor) [+ PPOLSEL for the max-nondef rule] or PCONST.
+static const rddl_program::PolicyProg* policy_prog(rddl_program* g, int li, const VmPolicy& pol) {
+  uint64_t polsig = 0xcbf29ce484222325ull;
+  polsig = fnv_bytes(polsig, &pol.n, sizeof pol.n);
+  polsig = fnv_bytes(polsig, &pol.k, sizeof pol.k);
+  for (int i = 0; i < pol.n; ++i) polsig = fnv_bytes(polsig, &pol.e[i], sizeof pol.e[i]);
+  for (auto* pp : g->policy_progs)
+    if (pp->launch == li && pp->polsig == polsig) return pp;
+  auto* pp = new rddl_program::PolicyProg();
+  pp->launch = li;
+  pp->polsig = polsig;
+  const PlaneProg& S = g->plane_progs[li];
+  PlaneProg& G = pp->G;
+  G = S;
+  G.nops = 0;
+  G.pol_k = pol.k;
+  int nw = 0;
+  for (int i = 0; i < PLANE_WORDS; ++i) if (S.words[i]) nw = i + 1;
+  nw = (nw + 3) & ~3;
+  bool ok = true;
+  for (int a = 0; a < S.nops && ok; ++a) {
+    PlaneOp o = S.ops[a];
+    const int pe = (o.op == OP_PLD && o.a == 0 && o.imm < RDDL_MAX_TENSORS) ? pol.of_tensor[o.imm] : 0;
+    if (!pe) {
+      if (G.nops >= PLANE_MAX_OPS) { ok = false; break; }
+      G.ops[G.nops++] = o;
+      continue;
+    }
+    const VmPolicyEntry& e = pol.e[pe - 1];
+    if (e.kind == POL_DEFAULT) {
+      o.op = OP_PCONST; o.imm = e.dflt ? 1u : 0u;
+      if (G.nops >= PLANE_MAX_OPS) { ok = false; break; }
+      G.ops[G.nops++] = o;
+      continue;
+    }
+    if (e.kind != POL_BERNOULLI || nw + 2 + PLANE_BERN_LEVELS + 4 > PLANE_WORDS || G.nops + 2 > PLANE_MAX_OPS) { ok = false; break; }
+    // tables of a Bernoulli over zero index planes: bad, always, the threshold's top bits, thr, p
+    o.op = OP_PBERN; o.m = 0; o.idx = 0; o.off = nw; o.a = 0;
+    o.b = (e.always ? 2 : 0) | (int32_t)(((RDDL_POLICY_NODE + (uint32_t)e.tensor) & 0xffffu) << 8);
+    G.words[nw++] = 0u;
+    G.words[nw++] = e.always ? 0xffffffffu : 0u;
+    for (int j = 0; j < PLANE_BERN_LEVELS; ++j) G.words[nw++] = ((e.thr >> (63 - j)) & 1ull) ? 0xffffffffu : 0u;
+    G.words[nw++] = (uint32_t)e.thr; G.words[nw++] = (uint32_t)(e.thr >> 32);
+    uint64_t pbits; memcpy(&pbits, &e.lo, 8);
+    G.words[nw++] = (uint32_t)pbits; G.words[nw++] = (uint32_t)(pbits >> 32);
+    G.ops[G.nops++] = o;
+    if (pol.k > 0) {
+      PlaneOp q; memset(&q, 0, sizeof q);
+      q.op = OP_PPOLSEL; q.dst = o.dst; q.imm = (uint32_t)(pe - 1);
+      G.ops[G.nops++] = q;
+    }
+  }
+  if (!ok) { delete pp; return nullptr; }
+  pp->sig = fnv_bytes(fnv_bytes(0xcbf29ce484222325ull, &G, sizeof G), "policy", 6) | 1ull;
+  g->policy_progs.push_back(pp);
+  return pp;
+}
+
+static void rddl_program_destroy_host(rddl_program* g) {   // programs parsed without a device (precompile)
+  for (auto* pp : g->policy_progs) delete pp;
+  delete g;
+}
+
 static int run_plan(rddl_program* g, int plan, void* const* tensors, const double* const* injected,
                     uint32_t* status, int64_t n_envs, int64_t env_offset, uint64_t seed, uint64_t step,
-                    cudaStream_t stream, const RolloutArgs* ro = nullptr) {
+                    cudaStream_t stream, const RolloutArgs* ro = nullptr, const VmPolicy* pol = nullptr) {
   std::string* errp = &g->err;
   if (!tensors || n_envs <= 0 || !status) { g->err = "bad arguments"; return RDDL_ERR_ARG; }
   CK(cudaSetDevice(g->device));
@@ -603,6 +830,10 @@ static int run_plan(rddl_program* g, int plan, void* const* tensors, const doubl
   }
   for (size_t i = 0; i < g->tensors.size(); ++i) { A.tensors[i] = tensors[i]; A.dtype[i] = (uint8_t)g->tensors[i].dtype; }
   if (injected) for (size_t i = 0; i < g->variates.size(); ++i) A.inj[i] = injected[i];
+  if (pol && pol->n > 0) {
+    A.pol = *pol;
+    A.pol.sel = g->d_polsel;     // (filled for this step by policy_prepare)
+  }
   for (const RddlLaunch& L : g->launches) {
     if (L.plan != plan || L.kind == 2) continue;   // kind 2 runs inside the preceding plane launch
     A.L = L;
@@ -610,10 +841,15 @@ static int run_plan(rddl_program* g, int plan, void* const* tensors, const doubl
     int jit_block = 256;
     int wpt = 1;
     JitKernel* jk = nullptr;
+    const rddl_program::PolicyProg* pp = nullptr;
     if (L.kind == 1) {
       const int li = (int)(&L - g->launches.data());
+      if (A.pol.n > 0) {
+        pp = policy_prog(g, li, A.pol);
+        if (!pp) { g->err = "policy: the plane program of this launch cannot take the policy (table space)"; return RDDL_ERR_ARG; }
+      }
       wpt = plane_geometry(L, n_envs, &A.L, &jit_block, g->specialize);
-      jk = jit_get(g, li, wpt, jit_block, A.L, n_envs);
+      jk = jit_get(g, li, wpt, jit_block, A.L, n_envs, pp ? &pp->G : nullptr, pp ? pp->sig : 0);
       if (!jk && g->specialize) wpt = plane_geometry(L, n_envs, &A.L, &jit_block, false);   // interpreter kernel
     }
     const int envs_per_cta = L.kind == 1 ? A.L.G : 256 / L.G;
@@ -642,12 +878,12 @@ static int run_plan(rddl_program* g, int plan, void* const* tensors, const doubl
                                                         (double*)tensors[L.red_slot[2]], n_envs, N, K,
                                                         (int64_t)L.red_op[0], (int64_t)L.red_op[1]);
     } else if (L.kind == 1) {
-      const PlaneProg& G = g->plane_progs[(size_t)(&L - g->launches.data())];
+      const PlaneProg& G = pp ? pp->G : g->plane_progs[(size_t)(&L - g->launches.data())];
       const int W32 = (int)((L.rank == 2 ? L.extent[1] : L.extent[0]) >> 5);
       const size_t smem = sizeof(uint32_t) * ((size_t)L.nregs * wpt * block +
                                               (size_t)G.nshared * ((A.L.ipt / W32 + A.L.G + 2) * (W32 + 2)) +
                                               32 * RDDL_MAX_RED +
-                                              8 * PLANE_QUEUE + 8 + block * wpt);
+                                              8 * PLANE_QUEUE + 8 + block * wpt + 32 * G.pol_k);
       const size_t smem_static = smem - sizeof(uint32_t) * ((size_t)L.nregs * wpt * block + (size_t)(block - jit_block) * wpt);
       if (jk) {
         void* params[] = {(void*)&A};
@@ -751,6 +987,173 @@ extern "C" int rddl_rollout(rddl_program_t* g, void* const* tensors, uint32_t* s
     }
   }
   *state_in_next = n_steps & 1;
+  return RDDL_OK;
+}
+
+// Per step of a policy-driven plan: the max-nondef selection of the step (scalar kernels read it from
+// d_polsel; the plane kernels recompute it on chip) and the action tensors that some kernel reads
+// through a raw pointer (`force`: all of them -- rddl_policy_sample).
+static int policy_prepare(rddl_program* g, VmPolicy* pol, void* const* tensors, int64_t n_envs, int64_t env_offset,
+                          uint64_t seed, uint64_t step, cudaStream_t stream, bool force) {
+  std::string* errp = &g->err;
+  if (pol->k > 0) {
+    if (g->polsel_capacity < n_envs * pol->k) {
+      CK(cudaStreamSynchronize(stream));
+      cudaFree(g->d_polsel);
+      g->d_polsel = nullptr;
+      CK(cudaMalloc((void**)&g->d_polsel, (size_t)(n_envs * RDDL_POLICY_MAX_SELECT) * sizeof(int32_t)));
+      g->polsel_capacity = n_envs * RDDL_POLICY_MAX_SELECT;
+    }
+    rddl_policy_select_kernel<<<(unsigned)((n_envs + 127) / 128), 128, 0, stream>>>(*pol, g->d_polsel, n_envs, env_offset, seed, step);
+    CK(cudaGetLastError());
+    ++g->launches_issued;
+  }
+  pol->sel = g->d_polsel;
+  for (int i = 0; i < pol->n; ++i) {
+    const VmPolicyEntry& e = pol->e[i];
+    if (!force && !g->direct_read[(size_t)e.tensor]) continue;
+    if (!tensors[e.tensor]) { g->err = "policy: action tensor pointer is NULL"; return RDDL_ERR_ARG; }
+    const int64_t n = n_envs * e.nelem;
+    rddl_policy_sample_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(*pol, i, tensors[e.tensor], g->tensors[e.tensor].dtype,
+                                                                                n_envs, env_offset, seed, step);
+    CK(cudaGetLastError());
+    ++g->launches_issued;
+  }
+  return RDDL_OK;
+}
+
+// Host only: the specialised plane kernels of the op table under `policy` for batches of n_envs, into
+// the disk cache (see rddl_plane_precompile). Returns the number of kernels, < 0 on error.
+extern "C" int rddl_policy_precompile(const void* optable, size_t nbytes, int64_t n_envs, const rddl_policy_t* policy) {
+  rddl_program* g = nullptr;
+  const uint8_t* sec[9];
+  int64_t hdr[16];
+  int rc = parse_program(optable, nbytes, 0, &g, sec, hdr);
+  if (rc) return rc;
+  VmPolicy pol;
+  if ((rc = make_policy(g, policy, &pol))) { g_create_error = g->err; rddl_program_destroy_host(g); return rc; }
+  uint8_t dt[RDDL_MAX_TENSORS] = {0};
+  for (size_t i = 0; i < g->tensors.size(); ++i) dt[i] = (uint8_t)g->tensors[i].dtype;
+  int n = 0;
+  for (size_t i = 0; i < g->launches.size(); ++i) {
+    if (g->launches[i].kind != 1 || g->launches[i].plan != RDDL_PLAN_STEP) continue;
+    const rddl_program::PolicyProg* pp = policy_prog(g, (int)i, pol);
+    if (!pp) { g_create_error = "policy: plane program cannot take the policy"; rddl_program_destroy_host(g); return RDDL_ERR_ARG; }
+    RddlLaunch adj;
+    int blk = 256;
+    const int wpt = plane_geometry(g->launches[i], n_envs, &adj, &blk);
+    std::string cubin, err;
+    if (!jit_compile_plane(plane_static_data(pp->G, adj, dt, wpt, plane_static_min_blocks(wpt, adj, n_envs), blk, g->pools()), &cubin,
+                           &err, nullptr)) {
+      g_create_error = err;
+      rddl_program_destroy_host(g);
+      return RDDL_ERR_FORMAT;
+    }
+    ++n;
+  }
+  rddl_program_destroy_host(g);
+  return n;
+}
+
+extern "C" int rddl_policy_sample(rddl_program_t* g, const rddl_policy_t* policy, void* const* tensors, int64_t n_envs,
+                                  int64_t env_offset, uint64_t seed, uint64_t step, void* cuda_stream) {
+  if (!g) return RDDL_ERR_ARG;
+  if (!tensors || n_envs <= 0) { g->err = "rddl_policy_sample: bad arguments"; return RDDL_ERR_ARG; }
+  std::string* errp = &g->err;
+  CK(cudaSetDevice(g->device));
+  VmPolicy pol;
+  int rc = make_policy(g, policy, &pol);
+  if (rc) return rc;
+  return policy_prepare(g, &pol, tensors, n_envs, env_offset, seed, step, (cudaStream_t)cuda_stream, true);
+}
+
+extern "C" int rddl_rollout_policy(rddl_program_t* g, const rddl_policy_t* policy, void* const* tensors, uint32_t* status,
+                                   int64_t n_envs, int64_t env_offset, uint64_t seed, uint64_t step0, int32_t n_steps,
+                                   double gamma, double* returns, double* rewards, int32_t* state_in_next,
+                                   void* cuda_stream) {
+  if (!g) return RDDL_ERR_ARG;
+  if (n_steps < 1 || !returns || !state_in_next || !tensors || n_envs <= 0) { g->err = "rddl_rollout_policy: bad arguments"; return RDDL_ERR_ARG; }
+  cudaStream_t stream = (cudaStream_t)cuda_stream;
+  std::string* errp = &g->err;
+  CK(cudaSetDevice(g->device));
+  VmPolicy pol;
+  int rc = make_policy(g, policy, &pol);
+  if (rc) return rc;
+  bool direct = false;
+  for (int i = 0; i < pol.n; ++i) direct |= g->direct_read[(size_t)pol.e[i].tensor] != 0;
+  // fused path: one single-tile plane launch runs every step with the state on chip and the action
+  // planes drawn in registers -- nothing but the final state and the returns touches HBM
+  int n_step_launches = 0;
+  const PlaneProg* G = nullptr;
+  for (size_t i = 0; i < g->launches.size(); ++i) {
+    if (g->launches[i].plan != RDDL_PLAN_STEP || g->launches[i].kind == 2) continue;
+    ++n_step_launches;
+    if (g->launches[i].kind == 1) G = &g->plane_progs[i];
+  }
+  if (n_step_launches == 1 && G && G->rollout_ok && !direct) {
+    RolloutArgs ro{n_steps, gamma, returns, rewards, nullptr};
+    *state_in_next = 1;
+    return run_plan(g, RDDL_PLAN_STEP, tensors, nullptr, status, n_envs, env_offset, seed, step0, stream, &ro, &pol);
+  }
+  if (g->alive_capacity < n_envs) {
+    CK(cudaStreamSynchronize(stream));
+    cudaFree(g->d_alive);
+    g->d_alive = nullptr;
+    CK(cudaMalloc((void**)&g->d_alive, (size_t)n_envs));
+    g->alive_capacity = n_envs;
+  }
+  const size_t nt = g->tensors.size();
+  std::vector<void*> cur(tensors, tensors + nt);
+  const int reward_tensor = (int)nt - 3;
+  double disc = 1.0;
+  for (int t = 0; t < n_steps; ++t) {
+    if ((rc = policy_prepare(g, &pol, cur.data(), n_envs, env_offset, seed, step0 + t, stream, false))) return rc;
+    if ((rc = run_plan(g, RDDL_PLAN_STEP, cur.data(), nullptr, status, n_envs, env_offset, seed, step0 + t, stream, nullptr, &pol)))
+      return rc;
+    rddl_accumulate_returns<<<(unsigned)((n_envs + 255) / 256), 256, 0, stream>>>(
+        returns, rewards ? rewards + (int64_t)t * n_envs : nullptr, (const double*)cur[reward_tensor],
+        (const uint8_t*)cur[reward_tensor + 1], g->d_alive, disc, n_envs, t == 0);
+    CK(cudaGetLastError());
+    ++g->launches_issued;
+    disc *= gamma;
+    for (size_t i = 0; i < nt; ++i) {
+      const int pair = g->tensors[i].pair;
+      if (pair >= 0) std::swap(cur[i], cur[pair]);
+    }
+  }
+  *state_in_next = n_steps & 1;
+  return RDDL_OK;
+}
+
+extern "C" int rddl_action_count(rddl_program_t* g, void* const* tensors, const int32_t* action_tensors,
+                                 const double* default_values, int32_t n_actions, int32_t* counts, int64_t n_envs,
+                                 void* cuda_stream) {
+  if (!g) return RDDL_ERR_ARG;
+  if (!tensors || !counts || n_envs <= 0 || n_actions < 0 || n_actions > 16 || (n_actions && (!action_tensors || !default_values))) {
+    g->err = "rddl_action_count: bad arguments (at most 16 action tensors)";
+    return RDDL_ERR_ARG;
+  }
+  std::string* errp = &g->err;
+  CK(cudaSetDevice(g->device));
+  ActionCountArgs a;
+  memset(&a, 0, sizeof a);
+  a.n = n_actions;
+  for (int i = 0; i < n_actions; ++i) {
+    const int t = action_tensors[i];
+    if (t < 0 || (size_t)t >= g->tensors.size() || !tensors[t] || g->tensors[t].dtype == DT_PACKED) {
+      g->err = "rddl_action_count: bad action tensor";
+      return RDDL_ERR_ARG;
+    }
+    a.ptr[i] = tensors[t];
+    a.nelem[i] = g->tensors[t].nelem;
+    a.dtype[i] = (uint8_t)g->tensors[t].dtype;
+    const double d = default_values[i];
+    if (a.dtype[i] == DT_REAL) memcpy(&a.dflt[i], &d, 8);
+    else a.dflt[i] = a.dtype[i] == DT_BOOL ? (uint64_t)(d != 0.0) : (uint64_t)(int64_t)d;
+  }
+  rddl_action_count_kernel<<<(unsigned)((n_envs * 32 + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(a, counts, n_envs);
+  CK(cudaGetLastError());
+  ++g->launches_issued;
   return RDDL_OK;
 }
 

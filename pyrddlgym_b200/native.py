@@ -12,6 +12,22 @@ LIB_PATH = os.environ.get('RDDL_B200_LIB') or os.path.join(_HERE, 'csrc', 'librd
 
 _lib = None
 
+POLICY_BERNOULLI, POLICY_UNIFORM_REAL, POLICY_UNIFORM_INT, POLICY_DEFAULT = 1, 2, 3, 4
+MAX_POLICY_ENTRIES = 8
+MAX_POLICY_SELECT = 32
+
+
+class PolicyEntry(ctypes.Structure):
+    """rddl_policy_entry_t (include/rddl_b200.h)."""
+    _fields_ = [('tensor', ctypes.c_int32), ('kind', ctypes.c_int32), ('lo', ctypes.c_double),
+                ('hi', ctypes.c_double), ('dflt', ctypes.c_double)]
+
+
+class Policy(ctypes.Structure):
+    """rddl_policy_t (include/rddl_b200.h)."""
+    _fields_ = [('n_entries', ctypes.c_int32), ('max_nondef', ctypes.c_int32),
+                ('entries', PolicyEntry * MAX_POLICY_ENTRIES)]
+
 
 class NativeError(RuntimeError):
     pass
@@ -42,6 +58,16 @@ def load():
     lib.rddl_rollout.argtypes = [vp, ctypes.POINTER(vp), vp, i64, i64, u64, u64, ctypes.c_int32,
                                  ctypes.POINTER(i64), ctypes.c_double, vp, vp, ctypes.POINTER(ctypes.c_int32), vp]
     lib.rddl_rollout.restype = ctypes.c_int
+    lib.rddl_rollout_policy.argtypes = [vp, ctypes.POINTER(Policy), ctypes.POINTER(vp), vp, i64, i64, u64, u64,
+                                        ctypes.c_int32, ctypes.c_double, vp, vp, ctypes.POINTER(ctypes.c_int32), vp]
+    lib.rddl_rollout_policy.restype = ctypes.c_int
+    lib.rddl_policy_sample.argtypes = [vp, ctypes.POINTER(Policy), ctypes.POINTER(vp), i64, i64, u64, u64, vp]
+    lib.rddl_policy_sample.restype = ctypes.c_int
+    lib.rddl_action_count.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_int32),
+                                      ctypes.POINTER(ctypes.c_double), ctypes.c_int32, vp, i64, vp]
+    lib.rddl_action_count.restype = ctypes.c_int
+    lib.rddl_policy_precompile.argtypes = [ctypes.c_char_p, ctypes.c_size_t, i64, ctypes.POINTER(Policy)]
+    lib.rddl_policy_precompile.restype = ctypes.c_int
     lib.rddl_profile.argtypes = [vp, ctypes.c_int]
     lib.rddl_profile.restype = ctypes.c_int
     lib.rddl_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64), ctypes.c_int]
@@ -63,7 +89,8 @@ def load():
 
 EXPORTS = ['rddl_program_create', 'rddl_program_destroy', 'rddl_last_error', 'rddl_program_info',
            'rddl_step', 'rddl_check', 'rddl_rollout', 'rddl_profile', 'rddl_profile_read',
-           'rddl_return_stats', 'rddl_program_option', 'rddl_jit_error', 'rddl_plane_precompile', 'rddl_plane_source']
+           'rddl_return_stats', 'rddl_program_option', 'rddl_jit_error', 'rddl_plane_precompile', 'rddl_plane_source',
+           'rddl_rollout_policy', 'rddl_policy_sample', 'rddl_action_count', 'rddl_policy_precompile']
 
 OPTION_SPECIALIZE = 0
 OPTION_SCALAR_HOT = 1       # scalar launches a program issues before its scalar kernels are specialised
@@ -86,6 +113,16 @@ def precompile(blob, n_envs):
     rc = lib.rddl_plane_precompile(blob, len(blob), int(n_envs))
     if rc < 0:
         raise NativeError('rddl_plane_precompile failed (%d): %s' % (rc, lib.rddl_last_error(None).decode()))
+    return rc
+
+
+def precompile_policy(blob, n_envs, policy):
+    """Like ``precompile`` for the plane kernels a device-side policy (``Policy``) specialises."""
+    lib = load()
+    blob = bytes(blob)
+    rc = lib.rddl_policy_precompile(blob, len(blob), int(n_envs), ctypes.byref(policy))
+    if rc < 0:
+        raise NativeError('rddl_policy_precompile failed (%d): %s' % (rc, lib.rddl_last_error(None).decode()))
     return rc
 
 
@@ -141,6 +178,25 @@ class NativeProgram:
                                           n_steps, strides, gamma, returns_ptr, rewards_ptr,
                                           ctypes.byref(swapped), stream), 'rddl_rollout')
         return bool(swapped.value)
+
+    def rollout_policy(self, policy, ptrs, status_ptr, n_envs, env_offset, seed, step0, n_steps, gamma,
+                       returns_ptr, rewards_ptr, stream):
+        swapped = ctypes.c_int32(0)
+        self._check(self.lib.rddl_rollout_policy(self.handle, ctypes.byref(policy), ptrs, status_ptr, n_envs,
+                                                 env_offset, seed, step0, n_steps, gamma, returns_ptr, rewards_ptr,
+                                                 ctypes.byref(swapped), stream), 'rddl_rollout_policy')
+        return bool(swapped.value)
+
+    def policy_sample(self, policy, ptrs, n_envs, env_offset, seed, step, stream):
+        self._check(self.lib.rddl_policy_sample(self.handle, ctypes.byref(policy), ptrs, n_envs, env_offset, seed,
+                                                step, stream), 'rddl_policy_sample')
+
+    def action_count(self, ptrs, tensor_ids, defaults, counts_ptr, n_envs, stream):
+        n = len(tensor_ids)
+        ids = (ctypes.c_int32 * max(1, n))(*tensor_ids)
+        dfl = (ctypes.c_double * max(1, n))(*defaults)
+        self._check(self.lib.rddl_action_count(self.handle, ptrs, ids, dfl, n, counts_ptr, n_envs, stream),
+                    'rddl_action_count')
 
     def profile(self, enable):
         self._check(self.lib.rddl_profile(self.handle, 1 if enable else 0), 'rddl_profile')

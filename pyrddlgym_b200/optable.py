@@ -46,6 +46,8 @@ _OPS = [
     'SUMLOOP',
     # rejection / search samplers on a private Philox stream (flags = distribution id)
     'SAMPLE',
+    # plane op the native library inserts for device-side policies with a max-nondef rule (never emitted here)
+    'PPOLSEL',
 ]
 OP = {name: i for i, name in enumerate(_OPS)}
 

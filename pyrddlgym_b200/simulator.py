@@ -28,6 +28,15 @@ class StatusError(RuntimeError):
         self.status = status
 
 
+class InvalidActionCount(ValueError):
+    """More non-default actions than max-nondef-actions allows (the reference raises
+    RDDLInvalidActionError, simulator.py:356-360; the drop-in subclass converts)."""
+
+    def __init__(self, msg, counts):
+        super().__init__(msg)
+        self.counts = counts
+
+
 class _States(collections.abc.Mapping):
     """Lazy name -> tensor view of the current state (bit-packed fluents unpack on access)."""
 
@@ -44,6 +53,10 @@ class _States(collections.abc.Mapping):
 
     def __len__(self):
         return len(self._sim.state_names)
+
+    def copy(self):
+        """Shallow dict copy, like ``RDDLSimulator.states`` (simulator.py:176-179): name -> tensor."""
+        return {name: self[name] for name in self}
 
 
 class BatchedSimulator:
@@ -101,7 +114,8 @@ class BatchedSimulator:
         self._ptrs = (ctypes.c_void_p * len(self.names))()
         self._inj = (ctypes.c_void_p * max(1, len(self.table.variates)))()
         self._external = {}
-        self.step_count = 0
+        self.step_count = 0          # Philox step index: advances with every transition, across resets
+        self.episode_step = 0        # transitions since the last reset
         self.reset()
 
     # ------------------------------------------------------------------ plumbing
@@ -113,7 +127,9 @@ class BatchedSimulator:
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def seed(self, seed):
+        """simulator.py:129-134. Also restarts the Philox step index (see ``reset``)."""
         self.seed_value = int(seed)
+        self.step_count = 0
 
     @property
     def launches_issued(self):
@@ -149,7 +165,10 @@ class BatchedSimulator:
                 self.t[name].copy_(v.expand_as(self.t[name]))
         self._owned_is_default = set(self.action_names)
         self.status.zero_()
-        self.step_count = 0
+        # step_count -- the Philox step index -- is NOT rewound: like the reference's generator, whose
+        # stream keeps advancing across episodes (simulator.py:129-134 seeds it once), every episode
+        # after a reset draws fresh noise. Only seed() restarts it.
+        self.episode_step = 0
         done = self.check_terminal_states()
         return self.states, done
 
@@ -246,6 +265,7 @@ class BatchedSimulator:
         for s, ns in self.program.next_state.items():
             self.t[s], self.t[ns] = self.t[ns], self.t[s]
         self.step_count += 1
+        self.episode_step += 1
         self._keep = keep
         return self.states, self.t['__reward'], self.t['__done']
 
@@ -286,6 +306,7 @@ class BatchedSimulator:
             for s, ns in self.program.next_state.items():
                 self.t[s], self.t[ns] = self.t[ns], self.t[s]
         self.step_count += int(n_steps)
+        self.episode_step += int(n_steps)
         # the action fluents now hold the last step's actions: a read-only view of the caller's
         # sequence (zero-copy, like set_actions; reset / set_actions go back to owned storage)
         for name in actions:
@@ -293,6 +314,115 @@ class BatchedSimulator:
             self.t[name] = last[-1] if last.dim() == self._owned_actions[name].dim() + 1 else last
         self._keep = keep
         return returns, rewards
+
+    # ------------------------------------------------------------------ device-side policies
+    def policy_descriptor(self, spec, max_nondef=None):
+        """Builds the C descriptor (``native.Policy``, rddl_policy_t) of a device-side random policy.
+
+        spec: action fluent name -> ('bernoulli', p) | ('uniform', lo, hi) | ('default',); fluents not
+        listed are read from their buffers like explicit actions. ``max_nondef``: None = the instance's
+        max-nondef-actions (``program.max_allowed_actions``); the kernels keep that many randomly chosen
+        groundings per (env, step) when it is smaller than the number of groundings
+        (RandomAgent, /root/reference/pyRDDLGym/core/policy.py:166-178)."""
+        pol = native.Policy()
+        if len(spec) > native.MAX_POLICY_ENTRIES:
+            raise ValueError('a device-side policy drives at most %d action fluents' % native.MAX_POLICY_ENTRIES)
+        for i, (name, how) in enumerate(spec.items()):
+            if name not in self.action_names:
+                raise KeyError(f'<{name}> is not an action-fluent')
+            dt = self.program.tensors[name].dtype
+            e = pol.entries[i]
+            e.tensor = self.tid[name]
+            e.dflt = float(np.asarray(self.program.init[name]).reshape(-1)[0])
+            if np.any(np.asarray(self.program.init[name]) != np.asarray(self.program.init[name]).reshape(-1)[0]):
+                raise ValueError(f'<{name}>: per-grounding default values are not supported by device-side policies')
+            kind = how[0]
+            if kind == 'default':
+                e.kind = native.POLICY_DEFAULT
+            elif kind == 'bernoulli':
+                if dt != 'b':
+                    raise ValueError(f'<{name}> is not a bool fluent')
+                e.kind, e.lo = native.POLICY_BERNOULLI, float(how[1])
+            elif kind == 'uniform':
+                if dt == 'b':
+                    raise ValueError(f'<{name}> is a bool fluent: use ("bernoulli", p)')
+                e.kind = native.POLICY_UNIFORM_INT if dt == 'i' else native.POLICY_UNIFORM_REAL
+                e.lo, e.hi = float(how[1]), float(how[2])
+            else:
+                raise ValueError(f'unknown policy kind {kind!r}')
+        pol.n_entries = len(spec)
+        k = self.program.max_allowed_actions if max_nondef is None else max_nondef
+        total = sum(int(self._owned_actions[n][0].numel()) for n in spec)
+        pol.max_nondef = -1 if (k is None or k >= total) else int(k)
+        return pol
+
+    def rollout_policy(self, policy, n_steps, gamma=None, returns=None, keep_rewards=False):
+        """``n_steps`` transitions under a device-side policy (``policy_descriptor``): the loop of
+        BaseAgent.evaluate with a RandomAgent (/root/reference/pyRDDLGym/core/policy.py:85-117) for all
+        envs, with the actions drawn inside the kernels -- no action tensor is produced, copied or read.
+        Returns (returns f64[N], rewards f64[n_steps, N] or None). Identical to materialising each
+        step's actions with ``sample_policy_actions`` and stepping with them."""
+        gamma = float(self.program.discount) if gamma is None else float(gamma)
+        for name, own in self._owned_actions.items():
+            self.t[name] = own          # (kernels that read an action through a raw pointer get it materialised here)
+        self._owned_is_default.clear()
+        if returns is None:
+            returns = torch.zeros(self.n_envs, dtype=torch.float64, device=self.device)
+        rewards = torch.empty((n_steps, self.n_envs), dtype=torch.float64, device=self.device) if keep_rewards else None
+        self._refresh_ptrs()
+        swapped = self.native.rollout_policy(
+            policy, self._ptrs, ctypes.c_void_p(self.status.data_ptr()), self.n_envs, self.env_offset, self.seed_value,
+            self.step_count, int(n_steps), gamma, ctypes.c_void_p(returns.data_ptr()),
+            ctypes.c_void_p(rewards.data_ptr()) if rewards is not None else None, self._stream())
+        if not self._jit_warned:
+            self._jit_check()
+        if swapped:
+            for s, ns in self.program.next_state.items():
+                self.t[s], self.t[ns] = self.t[ns], self.t[s]
+        self.step_count += int(n_steps)
+        self.episode_step += int(n_steps)
+        return returns, rewards
+
+    def sample_policy_actions(self, policy, step=None):
+        """Materialises the actions the device-side policy takes at Philox step ``step`` (default: the
+        next transition) into the simulator's action buffers -> {name: tensor [N, *shape]}
+        (RandomAgent.sample_action for every env, policy.py:166-178)."""
+        for name, own in self._owned_actions.items():
+            self.t[name] = own
+        self._owned_is_default.clear()
+        self._refresh_ptrs()
+        self.native.policy_sample(policy, self._ptrs, self.n_envs, self.env_offset, self.seed_value,
+                                  self.step_count if step is None else int(step), self._stream())
+        ids = {policy.entries[i].tensor for i in range(policy.n_entries)}
+        return {name: self.t[name] for name in self.action_names if self.tid[name] in ids}
+
+    def count_nondefault_actions(self, actions=None, enforce_for_non_bool=True):
+        """int32[N]: groundings whose value differs from the fluent's default, per env -- the counting
+        part of check_default_action_count (simulator.py:329-360) as one device reduction."""
+        if actions:
+            self.set_actions(actions)
+        names = [n for n in self.action_names if enforce_for_non_bool or self.program.tensors[n].dtype == 'b']
+        counts = torch.zeros(self.n_envs, dtype=torch.int32, device=self.device)
+        for k in range(0, len(names), 16):
+            part = names[k:k + 16]
+            c = counts if k == 0 else torch.zeros_like(counts)
+            self._refresh_ptrs()
+            self.native.action_count(self._ptrs, [self.tid[n] for n in part],
+                                     [float(np.asarray(self.program.init[n]).reshape(-1)[0]) for n in part],
+                                     ctypes.c_void_p(c.data_ptr()), self.n_envs, self._stream())
+            if k:
+                counts += c
+        return counts
+
+    def check_default_action_count(self, actions=None, enforce_for_non_bool=True):
+        """simulator.py:329-360 for all envs: raises ``InvalidActionCount`` if any env has more than
+        ``max_allowed_actions`` non-default action groundings (one device reduction + one scalar read)."""
+        limit = self.program.max_allowed_actions
+        counts = self.count_nondefault_actions(actions, enforce_for_non_bool)
+        worst = int(counts.max().item())
+        if worst > limit:
+            env = int(counts.argmax().item())
+            raise InvalidActionCount(f'Expected at most {limit} non-default actions, got {worst} (env {env}).', counts)
 
     def _run_check(self, plan):
         self._refresh_ptrs()

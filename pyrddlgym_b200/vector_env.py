@@ -5,7 +5,10 @@ calling convention of ``gymnasium.vector.VectorEnv`` (duck-typed: gymnasium is n
 N environments advance in lock-step on the device. ``step`` returns ``(obs, reward, terminated,
 truncated, info)`` with tensors of leading dimension N: ``terminated`` is the RDDL termination of
 the new state (env.py:262-264), ``truncated`` the horizon (env.py:265-266: an episode ends after
-``horizon`` steps). With ``auto_reset`` (default) the environments whose episode ended are reset in
+``horizon`` steps, and env.py:260: it is also truncated when a state invariant fails). ``info['status']``
+is the per-env error word of the step (invalid distribution parameters, clamped object indices: the
+reference raises RDDLValueOutOfRangeError; ``raise_on_status=True`` does the same here at the cost of
+one device synchronisation per step). With ``auto_reset`` (default) the environments whose episode ended are reset in
 place after the step -- only their rows of the state tensors are re-initialised, the others keep
 running -- and ``info['episode_return']`` / ``info['episode_length']`` carry the finished episodes'
 discounted return and length (NaN / 0 elsewhere). Observations are the state fluents (MDP) or the
@@ -17,7 +20,8 @@ from pyrddlgym_b200.simulator import BatchedSimulator
 
 
 class BatchedRDDLEnv:
-    def __init__(self, program, n_envs, device='cuda:0', seed=0, horizon=None, auto_reset=True, **sim_kwargs):
+    def __init__(self, program, n_envs, device='cuda:0', seed=0, horizon=None, auto_reset=True,
+                 raise_on_status=False, **sim_kwargs):
         self.sim = program if isinstance(program, BatchedSimulator) else BatchedSimulator(
             program, n_envs=n_envs, device=device, seed=seed, **sim_kwargs)
         self.program = self.sim.program
@@ -26,6 +30,7 @@ class BatchedRDDLEnv:
         self.horizon = int(self.program.horizon if horizon is None else horizon)
         self.discount = float(self.program.discount)
         self.auto_reset = bool(auto_reset)
+        self.raise_on_status = bool(raise_on_status)
         observ = self.program.names_of_kind('observ')
         self.observation_names = list(observ) if observ else list(self.sim.state_names)
         self.action_names = list(self.sim.action_names)
@@ -60,8 +65,12 @@ class BatchedRDDLEnv:
         self._disc *= self.discount
         self.episode_step += 1
         truncated = (self.episode_step >= self.horizon) & ~terminated
+        if self.sim.table.n_checks['invariant']:
+            truncated |= ~self.sim.check_state_invariants() & ~terminated       # env.py:260
+        if self.raise_on_status:
+            self.sim.raise_for_status()
         ended = terminated | truncated
-        info = {'episode_return': torch.where(ended, self.episode_return, torch.full_like(self.episode_return, float('nan'))),
+        info = {'status': self.sim.status.clone(), 'episode_return': torch.where(ended, self.episode_return, torch.full_like(self.episode_return, float('nan'))),
                 'episode_length': torch.where(ended, self.episode_step, torch.zeros_like(self.episode_step))}
         if self.auto_reset:
             self.sim.reset_envs(ended)

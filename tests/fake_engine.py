@@ -19,6 +19,7 @@ class EmulatorEngine:
 
     def seed(self, seed):
         self.sim.seed = int(seed)
+        self.sim.step_count = 0
 
     @property
     def states(self):

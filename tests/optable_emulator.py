@@ -460,6 +460,7 @@ class EmulatedSimulator:
         self.seed = seed
         self.env_offset = env_offset
         self.em = Emulator(optable)
+        self.step_count = 0      # Philox step index: not rewound by reset (BatchedSimulator.reset)
         self.reset()
 
     def reset(self):
@@ -473,7 +474,6 @@ class EmulatedSimulator:
             else:
                 self.bufs[tid] = np.zeros(self.N * nelem, dtype=npdt)
         self.status = np.zeros(self.N, dtype=np.uint32)
-        self.step_count = 0
         self.em.run(ot.PLAN_TERMINAL, self.bufs, self.N, self.status, None, self.seed, self.step_count, self.env_offset)
         return self.fluent('__done').astype(bool).reshape(-1)
 
