@@ -37,7 +37,8 @@ void rddl_program_destroy(rddl_program_t* prog);
 const char* rddl_last_error(const rddl_program_t* prog);
 
 /* what: 0 = #tensors, 1 = #variate slots, 2 = #launches of the step plan, 3 = total #instructions,
- * 4 = kernel launches issued since create, 5-7 = specialisation counters (below). */
+ * 4 = kernel launches issued since create, 5-7 = specialisation counters (below), 1000 + tensor id =
+ * 1 if a device-side policy has to materialise that action tensor in the caller's buffer each step. */
 int64_t rddl_program_info(const rddl_program_t* prog, int what);
 
 /* Replaces RDDLSimulator.step (pyRDDLGym/core/simulator.py:442-502) for n_envs environments:
@@ -135,6 +136,10 @@ int rddl_return_stats(const double* returns, int64_t n, double* out5, void* cuda
  *                                    environment has RDDL_B200_JIT=0): specialise
  *   rddl_program_option(prog, 1, n)  scalar kernels are specialised after n scalar launches
  *                                    (default 24, $RDDL_B200_JIT_HOT; 0 = on first use)
+ *   rddl_program_option(prog, 2, v)  sum-product contractions (sum_{?a} W(?a,?b) * x(?a), simulator.py:584-637,766-779):
+ *                                    v = 0 (default) exact FP64 tensor-core kernel (DMMA); v = 1 the Blackwell
+ *                                    tcgen05 kernel on three-term bfloat16 splits of both operands with float32
+ *                                    accumulation in tensor memory (TMA operand loads) -- within 1e-5 relative
  *   rddl_program_info(prog, 5 | 6 | 7)  specialised kernels in use | launches that fell back to the
  *                                    interpreter (rddl_jit_error has the compiler log) | cubins
  *                                    taken from the disk cache (<library dir>/jit_cache or

@@ -8,7 +8,7 @@ Generates, by running the UNMODIFIED reference front end and simulator:
     instances (base variates injected per AST node, see oracle/ast_builders.py) -- the
     golden vectors that pin oracle/oracle_sim.py and the CUDA path.
 
-    python -m oracle.gen_fixtures
+    python -m oracle.gen_fixtures [case ...]      (default: every case)
 """
 import os
 import sys
@@ -31,6 +31,8 @@ CASES = {
     'reservoir30': (lambda: workloads.reservoir(30), 3, 6, dict(real=(-1.0, 10.0))),
     'reservoir30_exp': (lambda: workloads.reservoir(30, rain='exponential'), 3, 6, dict(real=(0.0, 10.0))),
     'pair16': (lambda: workloads.pair_contraction(16), 3, 6, dict(real=(-12.0, 12.0))),
+    # BASELINE config [2] at full size: the shape that takes the env-tiled CSR gather kernels
+    'reservoir1000': (lambda: workloads.reservoir(1000), 2, 3, dict(real=(-1.0, 10.0))),
 }
 
 # programs without golden trajectories (natively sampled distributions: moment / KS tests only)
@@ -83,7 +85,8 @@ def gen_case(name):
 def main():
     os.makedirs(os.path.join(ROOT, 'tests', 'golden'), exist_ok=True)
     os.makedirs(os.path.join(ROOT, 'pyrddlgym_b200', 'programs'), exist_ok=True)
-    for name in CASES:
+    only = [a for a in sys.argv[1:] if a in CASES]
+    for name in (only or CASES):
         p, out = gen_case(name)
         path = workloads.program_path(p.name)
         types, objects = p.types, p.objects
@@ -94,7 +97,7 @@ def main():
         np.savez_compressed(os.path.join(ROOT, 'tests', 'golden', name + '.npz'), **out)
         print(name, '->', os.path.relpath(path, ROOT), os.path.getsize(path), 'B;',
               'golden', os.path.getsize(os.path.join(ROOT, 'tests', 'golden', name + '.npz')), 'B')
-    for name, factory in PROGRAM_ONLY.items():
+    for name, factory in ({} if only else PROGRAM_ONLY).items():
         p = reference_program(factory())
         path = workloads.program_path(p.name)
         p.types, p.objects = {}, {}

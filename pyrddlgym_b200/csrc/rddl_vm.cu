@@ -21,6 +21,7 @@
 
 #include "../../include/rddl_b200.h"
 #include "rddl_contract.cuh"
+#include "rddl_contract_tc.cuh"
 #include "rddl_device.cuh"
 
 #include "rddl_plane.cuh"
@@ -85,6 +86,13 @@ struct rddl_program {
   std::vector<uint8_t> direct_read;
   int32_t* d_polsel = nullptr;
   int64_t polsel_capacity = 0;
+  // tcgen05 path of the contraction (rddl_contract_tc.cuh; option 2): bf16 splits of the shared W
+  // matrices (made once per W tensor) and of the per-step x operand
+  int contract_tc = 0;
+  struct TcWeights { const void* W; int N, K; int64_t sk, sn; __nv_bfloat16* Wb; int Np, Kp; CUtensorMap map; };
+  std::vector<TcWeights> tc_w;
+  __nv_bfloat16* d_xb = nullptr;
+  int64_t xb_capacity = 0;
   // run-time specialised plane kernels (rddl_jit.h), built on first use per (launch, tile geometry)
   bool specialize = true;
   std::vector<RddlInsn> h_insns;          // host copies for the specialised epilogue (rddl_jit.h)
@@ -590,6 +598,8 @@ extern "C" void rddl_program_destroy(rddl_program_t* g) {
   cudaFree(g->d_red);
   cudaFree(g->d_alive);
   cudaFree(g->d_polsel);
+  cudaFree(g->d_xb);
+  for (auto& w : g->tc_w) cudaFree(w.Wb);
   for (auto* pp : g->policy_progs) delete pp;
   for (JitKernel& k : g->jit)
     if (k.mod) jit_driver().ModuleUnload(k.mod);
@@ -613,7 +623,11 @@ extern "C" int64_t rddl_program_info(const rddl_program_t* g, int what) {
     case 6: return g->jit_failed;       // plane launches that fell back to the interpreter kernel (rddl_jit_error)
     case 7: return g->jit_cache_hits;
     case 8: { JitApi& a = jit_api(); return a.ok ? a.major * 100 + a.minor : 0; }   // NVRTC version in use
-    default: return -1;
+    default:
+      // 1000 + tensor id: 1 if some kernel reads the tensor through a raw pointer (a device-side policy
+      // then materialises it in the caller's buffer every step instead of drawing it in registers only)
+      if (what >= 1000 && (size_t)(what - 1000) < g->direct_read.size()) return g->direct_read[(size_t)(what - 1000)];
+      return -1;
   }
 }
 
@@ -798,6 +812,81 @@ static const rddl_program::PolicyProg* policy_prog(rddl_program* g, int li, cons
   return pp;
 }
 
+// ---------------------------------------------------------------------------------------
+// tcgen05 contraction (rddl_contract_tc.cuh): tensor maps + launches
+// ---------------------------------------------------------------------------------------
+typedef CUresult (*TcEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static TcEncodeFn tc_encode_fn() {
+  static TcEncodeFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    cudaDriverEntryPointQueryResult q;
+    void* p = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (TcEncodeFn)p;
+    cudaGetLastError();
+  }
+  return fn;
+}
+
+// Tensor map over the split layout [term][K/8][rows][8] (bf16): dims (fastest first) 8, rows, K/8, 3.
+static bool tc_make_map(CUtensorMap* map, void* base, int rows_p, int Kp, int box_rows) {
+  TcEncodeFn enc = tc_encode_fn();
+  if (!enc) return false;
+  const cuuint64_t dims[4] = {8, (cuuint64_t)rows_p, (cuuint64_t)(Kp / 8), 3};
+  const cuuint64_t strides[3] = {16, (cuuint64_t)rows_p * 16, (cuuint64_t)rows_p * (cuuint64_t)Kp * 2};
+  const cuuint32_t box[4] = {8, (cuuint32_t)box_rows, TC_BK / 8, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static int run_contract_tc(rddl_program* g, const double* W, const double* x, double* out, int64_t n_envs, int N, int K,
+                           int64_t sk, int64_t sn, cudaStream_t stream) {
+  std::string* errp = &g->err;
+  const int Kp = (K + TC_BK - 1) / TC_BK * TC_BK;
+  rddl_program::TcWeights* tw = nullptr;
+  for (auto& w : g->tc_w)
+    if (w.W == W && w.N == N && w.K == K && w.sk == sk && w.sn == sn) tw = &w;
+  if (!tw) {
+    rddl_program::TcWeights w;
+    memset(&w, 0, sizeof w);
+    w.W = W; w.N = N; w.K = K; w.sk = sk; w.sn = sn;
+    w.Np = (N + TC_BN - 1) / TC_BN * TC_BN; w.Kp = Kp;
+    CK(cudaMalloc((void**)&w.Wb, (size_t)3 * w.Np * w.Kp * sizeof(__nv_bfloat16)));
+    const int64_t n = (int64_t)w.Np * (w.Kp / 8);
+    rddl_tc_split<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(W, sn, sk, N, K, w.Np, w.Kp, w.Wb);   // B(n, k) = W(k, n)
+    CK(cudaGetLastError());
+    if (!tc_make_map(&w.map, w.Wb, w.Np, w.Kp, TC_BN)) { cudaFree(w.Wb); g->err = "cuTensorMapEncodeTiled failed (W)"; return RDDL_ERR_CUDA; }
+    g->tc_w.push_back(w);
+    tw = &g->tc_w.back();
+    CK(cudaFuncSetAttribute((const void*)rddl_contract_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+  }
+  const int64_t Mp = (n_envs + TC_BM - 1) / TC_BM * TC_BM;
+  if (g->xb_capacity < 3 * Mp * Kp) {
+    CK(cudaStreamSynchronize(stream));
+    cudaFree(g->d_xb);
+    g->d_xb = nullptr;
+    CK(cudaMalloc((void**)&g->d_xb, (size_t)(3 * Mp * Kp) * sizeof(__nv_bfloat16)));
+    g->xb_capacity = 3 * Mp * Kp;
+  }
+  CUtensorMap map_x;
+  if (!tc_make_map(&map_x, g->d_xb, (int)Mp, Kp, TC_BM)) { g->err = "cuTensorMapEncodeTiled failed (x)"; return RDDL_ERR_CUDA; }
+  const int64_t n = Mp * (Kp / 8);
+  rddl_tc_split<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(x, K, 1, n_envs, K, Mp, Kp, g->d_xb);
+  CK(cudaGetLastError());
+  dim3 grid((unsigned)(tw->Np / TC_BN), (unsigned)(Mp / TC_BM));
+  rddl_contract_tc<<<grid, 128, TC_SMEM_BYTES, stream>>>(map_x, tw->map, out, n_envs, N, Kp / TC_BK);
+  CK(cudaGetLastError());
+  g->launches_issued += 1;     // (the caller counts the contraction launch itself)
+  return RDDL_OK;
+}
+
 static void rddl_program_destroy_host(rddl_program* g) {   // programs parsed without a device (precompile)
   for (auto* pp : g->policy_progs) delete pp;
   delete g;
@@ -863,7 +952,12 @@ static int run_plan(rddl_program* g, int plan, void* const* tensors, const doubl
       CK(cudaEventCreate(&tm.e1));
       CK(cudaEventRecord(tm.e0, stream));
     }
-    if (L.kind == 3) {
+    if (L.kind == 3 && g->contract_tc) {
+      int rc = run_contract_tc(g, (const double*)tensors[L.red_slot[0]], (const double*)tensors[L.red_slot[1]],
+                               (double*)tensors[L.red_slot[2]], n_envs, (int)L.extent[0], (int)L.extent[1],
+                               (int64_t)L.red_op[0], (int64_t)L.red_op[1], stream);
+      if (rc) return rc;
+    } else if (L.kind == 3) {
       const int N = (int)L.extent[0], K = (int)L.extent[1];
       // 64 x 64 CTA tiles; 64 x 32 when that grid would not give every SM two CTAs (RDDL_CONTRACT_BN overrides)
       int bn = ((int64_t)((N + 63) / 64) * ((n_envs + CT_BM - 1) / CT_BM) < 2 * 148) ? 32 : 64;
@@ -1209,6 +1303,7 @@ extern "C" int rddl_program_option(rddl_program_t* g, int what, int64_t value) {
   if (!g) return RDDL_ERR_ARG;
   if (what == 0) { g->specialize = value != 0; return RDDL_OK; }
   if (what == 1) { g->level_hot = value; return RDDL_OK; }
+  if (what == 2) { g->contract_tc = value != 0; return RDDL_OK; }
   g->err = "rddl_program_option: unknown option";
   return RDDL_ERR_ARG;
 }

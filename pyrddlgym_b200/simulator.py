@@ -364,8 +364,11 @@ class BatchedSimulator:
         step's actions with ``sample_policy_actions`` and stepping with them."""
         gamma = float(self.program.discount) if gamma is None else float(gamma)
         for name, own in self._owned_actions.items():
-            self.t[name] = own          # (kernels that read an action through a raw pointer get it materialised here)
-        self._owned_is_default.clear()
+            self.t[name] = own
+            # kernels that read an action through a raw pointer get it materialised in the owned buffer;
+            # otherwise the policy's draws live in registers only and the buffer keeps its defaults
+            if self.native.info(1000 + self.tid[name]) == 1:
+                self._owned_is_default.discard(name)
         if returns is None:
             returns = torch.zeros(self.n_envs, dtype=torch.float64, device=self.device)
         rewards = torch.empty((n_steps, self.n_envs), dtype=torch.float64, device=self.device) if keep_rewards else None

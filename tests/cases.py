@@ -17,6 +17,7 @@ SPECS = {
     'reservoir30': lambda: workloads.reservoir(30),
     'reservoir30_exp': lambda: workloads.reservoir(30, rain='exponential'),
     'pair16': lambda: workloads.pair_contraction(16),
+    'reservoir1000': lambda: workloads.reservoir(1000),
 }
 
 # float tolerance of the north star: 1e-5 relative (bool / int are compared exactly)

@@ -386,9 +386,11 @@ def test_batched_evaluate_random_and_noop_policies():
     # reward 1 per step while the pole is up; a random policy drops it after a few dozen steps
     assert set(st) == {'mean', 'median', 'min', 'max', 'std'}
     assert 5.0 < st['mean'] < 80.0 and st['min'] >= 1.0 and st['max'] <= p.horizon
-    # more episodes than envs: successive rollouts of the batch under seeds of their own
+    # more episodes than envs: successive rollouts of the batch; the Philox step index keeps advancing
+    # across the resets, so no rollout repeats another's noise (seed= reseeds the simulator, like
+    # env.reset(seed=seed) in the reference's evaluate)
     st3 = evaluate(sim, RandomPolicy(bounds={'force': (-10.0, 10.0)}), seed=1, episodes=1300)
-    assert sim.seed_value == 4 and abs(st3['mean'] - st['mean']) < 0.25 * st['mean'] and st3['min'] >= 1.0
+    assert sim.seed_value == 1 and abs(st3['mean'] - st['mean']) < 0.25 * st['mean'] and st3['min'] >= 1.0
     assert st3['mean'] != st['mean']            # (not three copies of the first rollout)
     st0 = evaluate(sim, NoOpPolicy())
     assert st0['std'] == 0.0 and st0['mean'] == p.horizon      # zero force from rest: never falls

@@ -80,6 +80,7 @@ def _with_scalar_action(p):
     p.init['u'] = np.zeros((), dtype=np.float64)
     load = hir.Node('load', tensor='u', index=[], dtype='f', scope=[])
     p.reward = hir.Node('bin', op='sub', args=[p.reward, load], dtype='f', scope=[])
+    p.max_allowed_actions += 1
     return p
 
 
