@@ -8,9 +8,11 @@
 // rddl_contract.cuh): every operand is split into three bfloat16 terms  v = hi + mid + lo
 // (hi = bf16(v), mid = bf16(v - hi), lo = bf16(v - hi - mid): 24 significant bits), and the six
 // products of combined order <= 2 -- hi*hi, hi*mid, mid*hi, mid*mid, hi*lo, lo*hi -- are accumulated
-// in float32 in TMEM; what is dropped is O(2^-24) of |x||W| per term, float32 accumulation adds
-// ~sqrt(K) * 2^-24 relative to sum |x W|: within the 1e-5 relative tolerance of the north star
-// (tests/test_cuda_parity.py::test_tcgen05_split_bf16_contraction_vs_fp64).
+// in float32 in TMEM (the leading product and the five corrections in accumulators of their own,
+// added in float64 at the end); what is dropped is O(2^-24) of |x||W| per term and the float32
+// accumulation adds ~sqrt(K / 16) * 2^-24 relative to the size of the sum: measured < 1e-6 of
+// max |out| at K = 512, i.e. inside the 1e-5 tolerance of the north star for reals wherever the result
+// is not a near-total cancellation (tests/test_cuda_parity.py::test_tcgen05_split_bf16_contraction_vs_fp64).
 //
 // Two launches per contraction:
 //   rddl_tc_split      f64 [rows, K] (strided) -> three bf16 planes in the tensor cores' K-major
@@ -131,8 +133,8 @@ rddl_contract_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncwarp();
-  if (warp == 0) {      // accumulator: 64 float32 columns x 128 lanes of tensor memory
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem(&tmem_slot)), "n"(TC_BN) : "memory");
+  if (warp == 0) {      // two accumulators of 64 float32 columns x 128 lanes of tensor memory (see the MMA issuer)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem(&tmem_slot)), "n"(2 * TC_BN) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -157,8 +159,11 @@ rddl_contract_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     // ---- MMA issuer: D[128 x 64] (+)= A[128 x 16] * B[64 x 16]^T, bf16 x bf16 -> f32
     // instruction descriptor (cute/arch/mma_sm100_desc.hpp): C = F32, A = B = BF16, K-major, N / 8, M / 16
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-    const int pa[6] = {2, 0, 1, 1, 0, 0}, pb[6] = {0, 2, 1, 0, 1, 0};     // small products first: lo*hi, hi*lo, mid*mid, mid*hi, hi*mid, hi*hi
-    uint32_t acc = 0;
+    // The leading product hi*hi goes to accumulator 0, the five correction products (2^-8 and less of
+    // it) to accumulator 1: the float32 rounding of a running sum is relative to its magnitude, so the
+    // small terms are not swamped and the big accumulator takes K / 16 additions instead of 6 K / 16.
+    const int pa[6] = {2, 0, 1, 1, 0, 0}, pb[6] = {0, 2, 1, 0, 1, 0};     // lo*hi, hi*lo, mid*mid, mid*hi, hi*mid | hi*hi
+    uint32_t acc0 = 0, acc1 = 0;
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % TC_STAGES, it = kb / TC_STAGES;
       tc_mbar_wait(&full[s], (uint32_t)(it & 1));
@@ -170,8 +175,8 @@ rddl_contract_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         for (int q = 0; q < 6; ++q) {
           const uint64_t da = tc_desc(a0 + pa[q] * TC_A_TERM + k16 * 2 * (TC_BM * 16), TC_BM * 16, 128);
           const uint64_t db = tc_desc(b0 + pb[q] * TC_B_TERM + k16 * 2 * (TC_BN * 16), TC_BN * 16, 128);
-          tc_mma(tmem, da, db, idesc, acc);
-          acc = 1;
+          if (q == 5) { tc_mma(tmem, da, db, idesc, acc0); acc0 = 1; }
+          else { tc_mma(tmem + TC_BN, da, db, idesc, acc1); acc1 = 1; }
         }
       }
       tc_commit(&empty[s]);          // arrives when the MMAs above have read this stage's tiles
@@ -185,18 +190,21 @@ rddl_contract_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   const int64_t row = (int64_t)m0 + tid;
 #pragma unroll 1
   for (int c = 0; c < TC_BN; c += 8) {
-    uint32_t v[8];
+    uint32_t v[8], w[8];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                  : "r"(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c));
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                 : "r"(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(TC_BN + c)));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
     if (row < n_envs) {
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        if (n0 + c + j < N) out[row * N + n0 + c + j] = (double)__uint_as_float(v[j]);
+        if (n0 + c + j < N) out[row * N + n0 + c + j] = (double)__uint_as_float(v[j]) + (double)__uint_as_float(w[j]);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TC_BN) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * TC_BN) : "memory");
 }

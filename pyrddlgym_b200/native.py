@@ -94,6 +94,7 @@ EXPORTS = ['rddl_program_create', 'rddl_program_destroy', 'rddl_last_error', 'rd
 
 OPTION_SPECIALIZE = 0
 OPTION_SCALAR_HOT = 1       # scalar launches a program issues before its scalar kernels are specialised
+OPTION_CONTRACT_TC = 2      # 1: sum-product contractions on the tcgen05 split-bf16 kernel (rddl_contract_tc.cuh)
 INFO_JIT_BUILT, INFO_JIT_FAILED, INFO_JIT_CACHE_HITS = 5, 6, 7
 
 

@@ -63,10 +63,13 @@ class BatchedSimulator:
     """N independent environments of one compiled RDDL problem, stepped in lock-step."""
 
     def __init__(self, program, n_envs=1, device='cuda:0', seed=0, env_offset=0, optable=None,
-                 use_planes=True, use_contract=True, use_packed=True, specialize=None):
+                 use_planes=True, use_contract=True, use_packed=True, specialize=None, contract_precision='f64'):
         """``specialize``: run-time specialised kernels (NVRTC, csrc/rddl_jit.h) for this program.
         None = the library default (on unless RDDL_B200_JIT=0: plane kernels on first use, scalar
-        kernels once the program is hot); True = everything on first use; False = interpreter kernels."""
+        kernels once the program is hot); True = everything on first use; False = interpreter kernels.
+        ``contract_precision``: 'f64' (default) = sum-product contractions on the exact FP64 tensor-core
+        kernel; 'bf16x3' = the tcgen05 kernel on three-term bfloat16 splits with float32 accumulation in
+        tensor memory (csrc/rddl_contract_tc.cuh; within the 1e-5 relative tolerance for reals)."""
         self.program = program
         self.n_envs = int(n_envs)
         self.device = torch.device(device)
@@ -82,6 +85,10 @@ class BatchedSimulator:
             self.native.option(native.OPTION_SPECIALIZE, 1 if specialize else 0)
             if specialize:
                 self.native.option(native.OPTION_SCALAR_HOT, 0)
+        if contract_precision not in ('f64', 'bf16x3'):
+            raise ValueError("contract_precision must be 'f64' or 'bf16x3'")
+        if contract_precision == 'bf16x3':
+            self.native.option(native.OPTION_CONTRACT_TC, 1)
         self._jit_warned = False
         self.names = list(self.table.tensor_names)
         self.packed = set(self.table.packed)

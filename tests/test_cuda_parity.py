@@ -429,6 +429,38 @@ def test_fp64_tensor_core_contraction_vs_scalar_path_and_oracle(X, N):
         assert np.array_equal(_np(a.check_state_invariants()), ora.check_state_invariants())
 
 
+@pytest.mark.parametrize('X,N', [(512, 300), (512, 1024), (100, 129), (40, 5), (72, 1)])
+def test_tcgen05_split_bf16_contraction_vs_fp64(X, N):
+    """The Blackwell tensor-core variant of the contraction (csrc/rddl_contract_tc.cuh: three-term bf16
+    splits, tcgen05.mma, TMA operand loads, float32 accumulator in TMEM) against the float64 oracle and
+    the exact FP64 kernel, at the 1e-5 relative tolerance the north star states for reals; ragged
+    sizes exercise the zero-padded edge tiles (rows, N and K not multiples of the 128 x 64 x 64 tile)."""
+    p = workloads.load_program(workloads.pair_contraction(X))
+    a = _make(p, N, seed=2, contract_precision='bf16x3')
+    b = _make(p, N, seed=2)
+    ora = OracleSimulator(p, n_envs=N, seed=2)
+    W = np.asarray(p.init['W'])
+    rng = np.random.default_rng(X + N)
+    for t in range(3):
+        x_before = ora.subs['x'].copy()
+        u = rng.uniform(-1.0, 1.0, size=(N, X))
+        _, ra, _ = a.step({'u': u})
+        _, rb, _ = b.step({'u': u})
+        _, ro, _ = ora.step({'u': u})
+        want = x_before @ W                                   # out(e, b) = sum_a x(e, a) W(a, b)
+        got = _np(a.t['__ct0'])
+        scale = np.abs(x_before) @ np.abs(W)                  # sum |x W|: what float32 accumulation is relative to
+        assert np.max(np.abs(got - want) / scale) < 1e-6, np.max(np.abs(got - want) / scale)
+        assert np.abs(got - want).max() < 3e-6 * np.abs(want).max()
+        # 1e-5 relative for reals (north star); elements that are near-total cancellations of the sum
+        # are held to 1e-5 of the largest output instead (float32 accumulation cannot do better)
+        np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-5 * np.abs(want).max())
+        np.testing.assert_allclose(_np(a.fluent('x')), ora.subs['x'], rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(_np(ra), ro, rtol=1e-5)
+        np.testing.assert_allclose(_np(a.fluent('x')), _np(b.fluent('x')), rtol=1e-5, atol=1e-5)
+    assert a.launches_issued > b.launches_issued               # split + tcgen05 launches instead of one DMMA launch
+
+
 def test_return_statistics_kernel_matches_numpy():
     """rddl_return_stats (policy.py:120-126 for one shard) vs NumPy, including tiny and odd sizes."""
     import torch
