@@ -540,6 +540,36 @@ def bench_workload(name, args, world, rank, dev, K, W, Ke, sampler=None, want_st
                             'reads, next-state writes, reward, done). This backend keeps bool state bit-packed in HBM (and on '
                             'chip during a fused multi-step launch), so it moves fewer bytes than that: frac_layout = the bytes '
                             'its own layout needs, frac_traffic = the DRAM bytes ncu measured (profiles/), same kernel time'}
+    if w['kind'] == 'pair' and top and roofline:
+        # the contraction is the tensor-core kernel of this config: report it against the tensor roofline,
+        # for the exact FP64 kernel (what `value` ran) and for the tcgen05 split-bf16 variant
+        flops = 2.0 * n * n * N
+        tc_sim = BatchedSimulator(p, n_envs=N, device=dev, seed=42, env_offset=off, specialize=True,
+                                  contract_precision='bf16x3')
+        tc_sim.rollout(seq, R, gamma=gamma)
+        tc_sim.reset()
+        tc_sim.native.profile(True)
+        tc_sim.rollout(seq, R, gamma=gamma)
+        torch.cuda.synchronize()
+        prof_tc = tc_sim.native.profile_read(tc_sim.table.launches)
+        tc_sim.native.profile(False)
+        tc_us = [1e3 * r['ms'] / r['count'] for r in prof_tc if r['name'] == 'rddl_contract_f64']
+        f64_us = [1e3 * r['ms'] / r['count'] for r in prof if r['name'] == 'rddl_contract_f64']
+        bf16_peak = float(peaks.get('bf16_tflops', 1657.2))
+        roofline['tensor'] = {
+            'flops_per_launch': flops,
+            'fp64_dmma': {'kernel': 'rddl_contract_f64 (mma.sync m8n8k4 f64)', 'kernel_us': f64_us[0] if f64_us else None,
+                          'tflops': flops / (f64_us[0] * 1e-6) / 1e12 if f64_us else None},
+            'tcgen05_bf16x3': {'kernel': 'rddl_tc_split + rddl_contract_tc (tcgen05.mma kind::f16, 6 bf16 products per '
+                                         'f64 product, TMA operand loads, TMEM accumulators)',
+                               'kernel_us': tc_us[0] if tc_us else None,
+                               'tflops_effective': flops / (tc_us[0] * 1e-6) / 1e12 if tc_us else None,
+                               'tflops_issued': 6 * flops / (tc_us[0] * 1e-6) / 1e12 if tc_us else None,
+                               'peak_bf16_tflops': bf16_peak,
+                               'frac_of_bf16_peak': 6 * flops / (tc_us[0] * 1e-6) / 1e12 / bf16_peak if tc_us else None},
+            'note': 'selected by BatchedSimulator(contract_precision=...): f64 (default, exact products) | bf16x3 (1e-5)'}
+        tc_sim.close()
+        del tc_sim
     del seq
 
     # ---- e2e: the host-facing call (policy.evaluate's body) with the random actions drawn in the

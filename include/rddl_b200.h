@@ -37,7 +37,8 @@ void rddl_program_destroy(rddl_program_t* prog);
 const char* rddl_last_error(const rddl_program_t* prog);
 
 /* what: 0 = #tensors, 1 = #variate slots, 2 = #launches of the step plan, 3 = total #instructions,
- * 4 = kernel launches issued since create, 5-7 = specialisation counters (below), 1000 + tensor id =
+ * 4 = kernel launches issued since create, 5-7 = specialisation counters (below), 9 = fused env-tile
+ * scalar kernels in use (runs of scalar launches executed by one kernel), 1000 + tensor id =
  * 1 if a device-side policy has to materialise that action tensor in the caller's buffer each step. */
 int64_t rddl_program_info(const rddl_program_t* prog, int what);
 

@@ -33,6 +33,8 @@
 #include <string>
 #include <vector>
 
+#define RDDL_FUSE_TE 4      // envs per CTA of the fused env-tile scalar kernels (rddl_level_static.cuh)
+
 static std::string jit_fmt(const char* f, long long v) {
   char b[64];
   snprintf(b, sizeof b, f, v);
@@ -131,6 +133,40 @@ static std::string level_static_data(const JitPools& P, const RddlLaunch* launch
   }
   if (list.empty()) return "";
   s += "#define PS_LEVELS(X)" + list + "\n";
+  // runs of consecutive scalar launches of the step plan over small scopes: one fused env-tile kernel
+  // each (rddl_level_static.cuh: RDDL_FUSED_KERNEL); RDDL_B200_FUSE=0 disables
+  {
+    std::string fused;
+    const char* fe = getenv("RDDL_B200_FUSE");
+    const bool enabled = !fe || atoi(fe) != 0;
+    for (int i = 0; enabled && i < n_launches;) {
+      auto ok = [&](int k) {
+        const RddlLaunch& L = launches[k];
+        return L.kind == 0 && L.plan == 0 && L.rank <= 1 && L.E <= 1408 && L.pc_end - L.pc_begin <= 200;
+      };
+      if (!ok(i)) { ++i; continue; }
+      int j = i;
+      while (j + 1 < n_launches && ok(j + 1)) ++j;
+      // (worth a kernel of its own only where a launch of the run gathers a per-env vector through a
+      // sparse sum -- the staged SpMM; plain runs keep their per-launch kernels and compile times)
+      bool gathers = false;
+      for (int k = i; k <= j; ++k) {
+        for (int pc = launches[k].pc_begin; pc < launches[k].pc_end; ++pc) {
+          const RddlInsn& in = P.insns[pc];
+          if (in.op != OP_SUMLOOP) continue;
+          if ((in.b & 1u) && (in.b & 4u) && in.imm < (uint32_t)P.n_addrs) {
+            const RddlAddr& ad = P.addrs[in.imm];
+            if (ad.tensor >= 0 && ad.env_stride > 0 && ad.env_stride * RDDL_FUSE_TE <= 5632 && dtype[ad.tensor] == DT_REAL && ad.nreg == 0)
+              gathers = true;
+          }
+          ++pc;
+        }
+      }
+      if (j > i && gathers) fused += jit_fmt(" X(%lld,", i) + jit_fmt("%lld)", j - i + 1);
+      i = j + 1;
+    }
+    if (!fused.empty()) s += "#define PS_FUSED(X)" + fused + "\n" + jit_fmt("#define FUSE_TE %lld\n", RDDL_FUSE_TE);
+  }
   s += "__device__ constexpr uint32_t kInsnWords[][4] = {";
   for (int64_t pc = 0; pc < P.n_insns; ++pc) {
     uint32_t w[4];
@@ -195,7 +231,7 @@ static std::string plane_static_data(const PlaneProg& G, const RddlLaunch& L, co
   s += "__device__ constexpr PlaneProg kG = {" + jit_fmt("%lld,", G.nops) + jit_fmt("%lld,", G.nshared) +
        jit_fmt("%lld,", G.w32_shift) + jit_fmt("%lld,", G.wpe_shift) + jit_fmt("%lld,", G.nfused) +
        jit_fmt("%lld,", G.fused_nregs) + jit_fmt("%lld,", G.rollout_ok) + jit_fmt("%lld,", G.pad) +
-       jit_fmt("%lld,", G.pol_k) + jit_fmt("%lld,\n{", G.pol_pad);
+       jit_fmt("%lld,", G.pol_k) + jit_fmt("%lld,\n{", G.ntma);
   jit_launch_init(s, G.fused[0]);
   s += ",\n";
   jit_launch_init(s, G.fused[1]);

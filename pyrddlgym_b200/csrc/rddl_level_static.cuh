@@ -97,7 +97,7 @@ struct LevelStaticExec {
   const VmStage* stage;
   __device__ __forceinline__ void operator()(int64_t env, int32_t* idx, uint64_t* redval) const {
     uint64_t r[kLaunches[LI].nregs > 0 ? kLaunches[LI].nregs : 1];
-    VmStage st = {nullptr, -1, 0};
+    VmStage st = {nullptr, -1, 0, 1, 0};
     if (stage) { st = *stage; st.base = env * level_stage_elems(LI); }
     VmStaticCtx c = {A, kLaunches[LI], env, A.step, idx, redval, r, stage ? &st : nullptr};
     vm_seq<kLaunches[LI].pc_begin, kLaunches[LI].pc_begin, kLaunches[LI].pc_end>(c);
@@ -121,12 +121,141 @@ template <int LI>
 __device__ __forceinline__ void level_static_kernel(const VmArgs& A) {
   if constexpr (level_stage_tensor(LI) >= 0) {
     __shared__ double staged[level_stage_elems(LI) > 0 ? level_stage_elems(LI) : 1];
-    const VmStage st = {staged, level_stage_tensor(LI), 0};
+    const VmStage st = {staged, level_stage_tensor(LI), 0, 1, 0};
     level_tile(A, kLaunches[LI], kRedOff, LevelStaticExec<LI>{A, &st}, LevelStagePrologue<LI>{A, staged});
   } else {
     level_tile(A, kLaunches[LI], kRedOff, LevelStaticExec<LI>{A, nullptr});
   }
 }
+
+// ---------------------------------------------------------------------------------------
+// Fused env-tile kernels: a run of consecutive scalar launches of the step plan (PS_FUSED lists
+// them: first launch, count) executed by ONE kernel in which a CTA owns FUSE_TE whole envs for every
+// launch of the run, with a CTA barrier where the unfused plan has a launch boundary. What this buys
+// for gather-heavy levels (Reservoir: inflow(?r) = sum_{?u} CONNECT(?u, ?r) * released(?u)):
+//   * thread t works on env t % FUSE_TE, elements t / FUSE_TE, + 256 / FUSE_TE, ...: the lanes of a warp
+//     cover FUSE_TE envs x 32 / FUSE_TE consecutive elements -- every global access still touches only
+//     full 32-byte sectors, but the CSR row pointers and column indices of a sparse sum are shared by
+//     the FUSE_TE lanes of an element (FUSE_TE x fewer index sectors per request, shorter divergence);
+//   * the gathered per-env vector is staged once per CTA in shared memory, transposed to
+//     [element][env]: the FUSE_TE lanes of an element read consecutive words (SpMM over the env axis);
+//   * intermediate fluents written by one launch are re-read by the next from L1 / L2, not DRAM, and
+//     the per-env reductions and the scalar reward / termination program need no extra launches.
+// Same instruction bodies and element order as the unfused kernels; only the order in which a
+// per-env reduction combines its partial results differs (float sums agree to rounding).
+// ---------------------------------------------------------------------------------------
+#ifndef FUSE_TE
+#define FUSE_TE 4
+#endif
+constexpr int kFuseMaxStage = 5632;      // doubles of shared memory for the staged gather operand (44 KB)
+
+// tensor a CSR float SUMLOOP of launch li gathers from (per-env, real, small enough to stage), or -1
+__host__ __device__ constexpr int fuse_stage_tensor(int li) {
+  for (int pc = kLaunches[li].pc_begin; pc < kLaunches[li].pc_end; ++pc) {
+    const uint32_t op = kInsnWords[pc][0] & 0xff, rb = kInsnWords[pc][1] >> 16, imm = kInsnWords[pc][3];
+    if (op != OP_SUMLOOP) continue;
+    if ((rb & 1u) && (rb & 4u)) {
+      const RddlAddr& ad = kAddrs[imm];
+      if (ad.tensor >= 0 && ad.env_stride > 0 && ad.env_stride * FUSE_TE <= kFuseMaxStage && kDT[ad.tensor] == DT_REAL && ad.nreg == 0)
+        return ad.tensor;
+    }
+    ++pc;
+  }
+  return -1;
+}
+__host__ __device__ constexpr int64_t fuse_stage_elems(int li) {
+  for (int pc = kLaunches[li].pc_begin; pc < kLaunches[li].pc_end; ++pc) {
+    const uint32_t op = kInsnWords[pc][0] & 0xff, imm = kInsnWords[pc][3];
+    if (op == OP_SUMLOOP && kAddrs[imm].tensor == fuse_stage_tensor(li)) return kAddrs[imm].env_stride;
+  }
+  return 0;
+}
+
+template <int LI>
+__device__ __forceinline__ void fused_phase(const VmArgs& A, double* staged, uint64_t (*sm)[8][FUSE_TE]) {
+  constexpr RddlLaunch L = kLaunches[LI];
+  const int tid = threadIdx.x;
+  const int e = tid % FUSE_TE;
+  const int64_t env0 = (int64_t)blockIdx.x * FUSE_TE, env = env0 + e;
+  const bool env_ok = env < A.n_envs;
+  VmStage st = {nullptr, -1, 0, 1, 0};
+  if constexpr (fuse_stage_tensor(LI) >= 0) {
+    // the FUSE_TE envs' slices of the gathered tensor, transposed to [element][env]
+    constexpr int64_t n = fuse_stage_elems(LI);
+    const double* src = reinterpret_cast<const double*>(A.tensors[fuse_stage_tensor(LI)]);
+    for (int i = tid; i < (int)(n * FUSE_TE); i += 256) staged[i] = env_ok ? src[env * n + i / FUSE_TE] : 0.0;
+    __syncthreads();
+    st = VmStage{staged, fuse_stage_tensor(LI), env * n, FUSE_TE, e};
+  }
+  int32_t idx[RDDL_MAX_IDX];
+  uint64_t redval[RDDL_MAX_RED];
+#pragma unroll
+  for (int j = 0; j < RDDL_MAX_RED; ++j) redval[j] = j < L.nred ? red_identity(L.red_op[j]) : 0;
+  if (env_ok) {
+    for (int64_t elem = tid / FUSE_TE; elem < L.E; elem += 256 / FUSE_TE) {
+      int64_t rem = elem;
+#pragma unroll
+      for (int k = RDDL_MAX_IDX - 1; k >= 0; --k) {
+        if (k < L.rank) {
+          idx[k] = (int32_t)(rem % L.extent[k]);
+          rem /= L.extent[k];
+        }
+      }
+      uint64_t r[L.nregs > 0 ? L.nregs : 1];
+      VmStaticCtx c = {A, kLaunches[LI], env, A.step, idx, redval, r, st.tensor >= 0 ? &st : nullptr};
+      vm_seq<L.pc_begin, L.pc_begin, L.pc_end>(c);
+    }
+  }
+  if constexpr (L.nred > 0) {
+    // per-env reductions: lanes of the same env (stride FUSE_TE), then the 8 warps in order
+#pragma unroll
+    for (int j = 0; j < L.nred; ++j) {
+      uint64_t v = redval[j];
+#pragma unroll
+      for (int o = 16; o >= FUSE_TE; o >>= 1) v = red_combine(L.red_op[j], v, __shfl_xor_sync(0xffffffffu, v, o, 32));
+      if ((tid & 31) < FUSE_TE) sm[j][tid >> 5][e] = v;
+    }
+    __syncthreads();
+    if (tid < FUSE_TE && env_ok) {
+#pragma unroll
+      for (int j = 0; j < L.nred; ++j) {
+        uint64_t v = sm[j][0][e];
+        for (int w = 1; w < 8; ++w) v = red_combine(L.red_op[j], v, sm[j][w][e]);
+        // (the slot keeps the partial-result layout of the unfused plan: total in the first, identities after)
+        uint64_t* dst = A.red + kRedOff[L.red_slot[j]] * A.n_envs + env * kRedSlots[L.red_slot[j]].chunks;
+        dst[0] = v;
+        for (int c2 = 1; c2 < kRedSlots[L.red_slot[j]].chunks; ++c2) dst[c2] = red_identity(L.red_op[j]);
+      }
+    }
+  }
+  __syncthreads();      // launch boundary of the unfused plan: this CTA's stores are visible to its next phase
+}
+
+template <int FIRST, int COUNT>
+__device__ __forceinline__ void fused_phases(const VmArgs& A, double* staged, uint64_t (*sm)[8][FUSE_TE]) {
+  if constexpr (COUNT > 0) {
+    fused_phase<FIRST>(A, staged, sm);
+    fused_phases<FIRST + 1, COUNT - 1>(A, staged, sm);
+  }
+}
+
+// doubles of staging the run [first, first + count) needs
+__host__ __device__ constexpr int64_t fuse_group_stage(int first, int count) {
+  int64_t m = 1;
+  for (int li = first; li < first + count; ++li)
+    if (fuse_stage_tensor(li) >= 0 && fuse_stage_elems(li) * FUSE_TE > m) m = fuse_stage_elems(li) * FUSE_TE;
+  return m;
+}
+
+#define RDDL_FUSED_KERNEL(FIRST, COUNT)                                                                          \
+  extern "C" __global__ void __launch_bounds__(256) rddl_level_fused_##FIRST(const __grid_constant__ VmArgs A) { \
+    __shared__ double staged[fuse_group_stage(FIRST, COUNT)];                                                    \
+    __shared__ uint64_t sm[RDDL_MAX_RED][8][FUSE_TE];                                                             \
+    fused_phases<FIRST, COUNT>(A, staged, sm);                                                                   \
+  }
+#ifdef PS_FUSED
+PS_FUSED(RDDL_FUSED_KERNEL)
+#endif
 
 #define RDDL_LEVEL_KERNEL(LI)                                                                            \
   extern "C" __global__ void __launch_bounds__(256) rddl_level_static_##LI(const __grid_constant__ VmArgs A) { \

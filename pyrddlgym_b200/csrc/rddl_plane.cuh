@@ -38,7 +38,8 @@ struct PlaneOp {        // 32 bytes, pre-decoded from RddlInsn + its Fin descrip
 struct PlaneProg {
   int32_t nops, nshared, w32_shift, wpe_shift;   // shifts: log2 of words per row / per env, or -1
   int32_t nfused, fused_nregs, rollout_ok, pad;  // scalar launches run in the epilogue (kind 2)
-  int32_t pol_k, pol_pad;                        // device-side policy with a max-nondef rule: groundings kept per (env, step)
+  int32_t pol_k, ntma;                           // device-side policy with a max-nondef rule: groundings kept per (env, step);
+                                                 // ntma: pre-packed non-fluent planes staged in shared memory by TMA (PLDC slots)
   RddlLaunch fused[2];
   int32_t red_off[RDDL_MAX_RED], red_m[RDDL_MAX_RED];   // PRED op of reduction j: table offset, #planes
   PlaneOp ops[PLANE_MAX_OPS];
@@ -389,6 +390,10 @@ struct PlaneTile {
   int* qn;              // [8]
   uint32_t* fix;        // [256][WPT]
   int32_t* sel;         // [32][pol_k] groundings that keep their policy draw this step (PPOLSEL)
+  uint32_t* nf;         // [ntma][nf_words] non-fluent planes of this tile, staged by TMA
+  uint64_t* nf_bar;     // mbarrier the TMA copies complete on
+  int nf_words, nf_first;   // words staged per plane (a multiple of the TMA box), first plane word staged
+  bool nf_wait;         // the staged planes have not been waited for yet
   int64_t env0, tile_byte0;
   int64_t gw_limit;     // last valid global word index this tile may touch (ragged tiles clamp loads to it)
   int W32, wpe, envs_per_tile, tile_words, chunks, chunk, pitch, tile_rows, plane_stride;
@@ -539,6 +544,15 @@ __device__ __forceinline__ void plane_exec(PlaneTile<WPT, BLOCK>& T, const VmArg
         break;
       }
       case OP_PLDC: {
+        if (G.ntma > 0 && A.pool_map_ok) {
+          // the tile's slice of the pre-packed non-fluent plane was copied to shared memory by TMA
+          // (plane_tile prologue): wait for the copies once, then read it from there
+          if (T.nf_wait) { rddl_mbar_wait(T.nf_bar, 0); T.nf_wait = false; }
+          const uint32_t* sp = T.nf + o.b * T.nf_words - T.nf_first;
+#pragma unroll
+          for (int j = 0; j < WPT; ++j) C.at(o.dst, j) = (full || ((C.valid >> j) & 1u)) ? sp[C.wi[j]] : 0u;
+          break;
+        }
 #pragma unroll
         for (int j = 0; j < WPT; ++j)
           C.at(o.dst, j) = (full || ((C.valid >> j) & 1u)) ? (uint32_t)__ldg(A.pool + o.imm + C.wi[j]) : 0u;
@@ -765,6 +779,32 @@ __device__ __forceinline__ void plane_tile(const VmArgs& A, const PlaneProg& G, 
   T.qn = reinterpret_cast<int*>(T.queue + 8 * PLANE_QUEUE);
   T.fix = reinterpret_cast<uint32_t*>(T.qn + 8);
   T.sel = reinterpret_cast<int32_t*>(T.fix + BLOCK * WPT);
+  // TMA staging of the shared non-fluent planes: the words [nf_first, nf_first + nf_words) of every
+  // PLDC plane -- the whole plane when a tile holds whole envs, the tile's rows otherwise -- arrive in
+  // shared memory as boxes of RDDL_TMA_BOX words (cp.async.bulk.tensor.1d on the pool's tensor map)
+  // while the tile sets up and issues its fluent loads; the first PLDC op waits on the mbarrier.
+  T.nf_wait = false;
+  if (G.ntma > 0 && A.pool_map_ok) {
+    const int span = chunks == 1 ? wpe : tile_words;
+    T.nf_first = chunks == 1 ? 0 : chunk * tile_words;
+    T.nf_words = (span + RDDL_TMA_BOX - 1) / RDDL_TMA_BOX * RDDL_TMA_BOX;
+    // (128-byte aligned: the region after sel, rounded up)
+    uint64_t q = reinterpret_cast<uint64_t>(T.sel + 32 * G.pol_k);
+    q = (q + 127) & ~(uint64_t)127;
+    T.nf_bar = reinterpret_cast<uint64_t*>(q);
+    T.nf = reinterpret_cast<uint32_t*>(q + 128);
+    T.nf_wait = true;
+    if (tid == 0) {
+      rddl_mbar_init(T.nf_bar, 1);
+      rddl_mbar_expect_tx(T.nf_bar, (uint32_t)(G.ntma * T.nf_words * 4));
+      for (int a = 0; a < G.nops; ++a) {
+        if (G.ops[a].op != OP_PLDC) continue;
+        for (int b = 0; b < T.nf_words; b += RDDL_TMA_BOX)
+          rddl_tma_load_1d(T.nf + G.ops[a].b * T.nf_words + b, &A.pool_map, T.nf_bar, (int32_t)G.ops[a].imm + T.nf_first + b);
+      }
+    }
+    __syncthreads();      // the barrier is initialised before anybody polls it
+  }
   if (L.nred > 0)
     for (int i = tid; i < 32 * RDDL_MAX_RED; i += BLOCK) cnt[i] = 0;
   for (int i = tid; i < G.nshared * plane_stride; i += BLOCK) S[i] = 0u;           // zero padding, once

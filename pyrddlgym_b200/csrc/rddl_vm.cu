@@ -48,6 +48,28 @@ static thread_local std::string g_create_error;
 
 #include "rddl_jit.h"
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda):
+// tensor maps of the TMA copies (non-fluent plane staging, tcgen05 contraction operands)
+typedef CUresult (*TcEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static TcEncodeFn tc_encode_fn() {
+  static TcEncodeFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    cudaDriverEntryPointQueryResult q;
+    void* p = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (TcEncodeFn)p;
+    cudaGetLastError();
+  }
+  return fn;
+}
+
+
 struct rddl_program {
   int device = 0;
   std::string err;
@@ -88,6 +110,9 @@ struct rddl_program {
   int64_t polsel_capacity = 0;
   // tcgen05 path of the contraction (rddl_contract_tc.cuh; option 2): bf16 splits of the shared W
   // matrices (made once per W tensor) and of the per-step x operand
+  RddlTensorMap pool_map;
+  int pool_map_ok = 0;
+  int64_t pool_len = 0;
   int contract_tc = 0;
   struct TcWeights { const void* W; int N, K; int64_t sk, sn; __nv_bfloat16* Wb; int Np, Kp; CUtensorMap map; };
   std::vector<TcWeights> tc_w;
@@ -115,6 +140,8 @@ struct rddl_program {
   bool level_tried = false;
   CUmodule level_mod = nullptr;
   std::vector<CUfunction> level_fn;       // per launch index, nullptr = interpreter kernel
+  std::vector<CUfunction> fused_fn;       // per launch index: fused env-tile kernel of the run starting there
+  std::vector<int> fused_count;           // ... and the number of launches it covers
   std::vector<JitKernel> jit;
   int64_t jit_built = 0, jit_cache_hits = 0, jit_failed = 0;
   std::string jit_err;
@@ -195,6 +222,7 @@ static bool decode_plane(const RddlLaunch& L, const RddlInsn* insns, const uint6
     o.op = in.op; o.dst = in.dst; o.a = in.a; o.b = in.b; o.imm = in.imm;
     o.off = nw;
     if (in.op == OP_PSHARE && (int)in.b + 1 > G->nshared) G->nshared = in.b + 1;
+    if (in.op == OP_PLDC) o.b = G->ntma++;        // slot of the plane in the TMA-staged shared-memory region
     if (in.op != OP_PLUT && in.op != OP_PBERN && in.op != OP_PRED) continue;
     if ((int64_t)in.imm + 5 > n_consts) { *err = "plane op: bad Fin index"; return false; }
     const uint64_t* c = consts + in.imm;
@@ -241,6 +269,8 @@ static bool decode_plane(const RddlLaunch& L, const RddlInsn* insns, const uint6
 static void jit_levels(rddl_program* g) {
   g->level_tried = true;
   g->level_fn.assign(g->launches.size(), nullptr);
+  g->fused_fn.assign(g->launches.size(), nullptr);
+  g->fused_count.assign(g->launches.size(), 0);
   const std::string data = level_static_data(g->pools(), g->launches.data(), (int)g->launches.size(), g->dtypes().data());
   if (data.empty()) return;
   std::string cubin, err;
@@ -257,6 +287,26 @@ static void jit_levels(rddl_program* g) {
         // (launches too long to unroll are not in the module: they keep the interpreter kernel)
         if (drv.ModuleGetFunction(&g->level_fn[i], g->level_mod, name) != CUDA_SUCCESS) g->level_fn[i] = nullptr;
         else ++g->jit_built;
+      }
+      // fused env-tile kernels (PS_FUSED in the generated constants): "X(first,count)"
+      size_t pos = data.find("#define PS_FUSED(X)");
+      if (pos != std::string::npos) {
+        const size_t eol = data.find('\n', pos);
+        std::string line = data.substr(pos, eol - pos);
+        size_t q = 0;
+        while ((q = line.find("X(", q + 1)) != std::string::npos && q > 15) {
+          int first = 0, count = 0;
+          if (sscanf(line.c_str() + q, "X(%d,%d)", &first, &count) == 2 && first >= 0 && (size_t)(first + count) <= g->launches.size()) {
+            char name[64];
+            snprintf(name, sizeof name, "rddl_level_fused_%d", first);
+            CUfunction fn = nullptr;
+            if (drv.ModuleGetFunction(&fn, g->level_mod, name) == CUDA_SUCCESS) {
+              g->fused_fn[(size_t)first] = fn;
+              g->fused_count[(size_t)first] = count;
+              ++g->jit_built;
+            }
+          }
+        }
       }
     }
   }
@@ -516,6 +566,21 @@ extern "C" int rddl_program_create(const void* optable, size_t nbytes, int devic
     rddl_program_destroy(g);
     return rc;
   }
+  // tensor map over the pool (1-D, int32, box of RDDL_TMA_BOX words) for the plane kernels' TMA staging of
+  // non-fluent planes; absent driver entry point or an empty pool: the kernels read the pool directly
+  g->pool_len = hdr[8];
+  if (hdr[8] > 0 && !getenv("RDDL_PLANE_NO_TMA")) {
+    if (TcEncodeFn enc = tc_encode_fn()) {
+      const cuuint64_t dims[1] = {(cuuint64_t)hdr[8]};
+      const cuuint64_t strides[1] = {4};
+      const cuuint32_t box[1] = {RDDL_TMA_BOX};
+      const cuuint32_t estr[1] = {1};
+      static_assert(sizeof(CUtensorMap) == sizeof(RddlTensorMap), "tensor map size");
+      g->pool_map_ok = enc(reinterpret_cast<CUtensorMap*>(&g->pool_map), CU_TENSOR_MAP_DATA_TYPE_INT32, 1, g->d_pool, dims, strides, box,
+                           estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
+  }
   *out = g;
   return RDDL_OK;
 }
@@ -623,6 +688,7 @@ extern "C" int64_t rddl_program_info(const rddl_program_t* g, int what) {
     case 6: return g->jit_failed;       // plane launches that fell back to the interpreter kernel (rddl_jit_error)
     case 7: return g->jit_cache_hits;
     case 8: { JitApi& a = jit_api(); return a.ok ? a.major * 100 + a.minor : 0; }   // NVRTC version in use
+    case 9: { int64_t n = 0; for (auto f : g->fused_fn) n += f != nullptr; return n; }   // fused env-tile kernels in use
     default:
       // 1000 + tensor id: 1 if some kernel reads the tensor through a raw pointer (a device-side policy
       // then materialises it in the caller's buffer every step instead of drawing it in registers only)
@@ -815,25 +881,6 @@ static const rddl_program::PolicyProg* policy_prog(rddl_program* g, int li, cons
 // ---------------------------------------------------------------------------------------
 // tcgen05 contraction (rddl_contract_tc.cuh): tensor maps + launches
 // ---------------------------------------------------------------------------------------
-typedef CUresult (*TcEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static TcEncodeFn tc_encode_fn() {
-  static TcEncodeFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    cudaDriverEntryPointQueryResult q;
-    void* p = nullptr;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = (TcEncodeFn)p;
-    cudaGetLastError();
-  }
-  return fn;
-}
-
 // Tensor map over the split layout [term][K/8][rows][8] (bf16): dims (fastest first) 8, rows, K/8, 3.
 static bool tc_make_map(CUtensorMap* map, void* base, int rows_p, int Kp, int box_rows) {
   TcEncodeFn enc = tc_encode_fn();
@@ -919,11 +966,14 @@ static int run_plan(rddl_program* g, int plan, void* const* tensors, const doubl
   }
   for (size_t i = 0; i < g->tensors.size(); ++i) { A.tensors[i] = tensors[i]; A.dtype[i] = (uint8_t)g->tensors[i].dtype; }
   if (injected) for (size_t i = 0; i < g->variates.size(); ++i) A.inj[i] = injected[i];
+  A.pool_map = g->pool_map;
+  A.pool_map_ok = g->pool_map_ok;
   if (pol && pol->n > 0) {
     A.pol = *pol;
     A.pol.sel = g->d_polsel;     // (filled for this step by policy_prepare)
   }
-  for (const RddlLaunch& L : g->launches) {
+  for (size_t launch_i = 0; launch_i < g->launches.size(); ++launch_i) {
+    const RddlLaunch& L = g->launches[launch_i];
     if (L.plan != plan || L.kind == 2) continue;   // kind 2 runs inside the preceding plane launch
     A.L = L;
     const int block = 256;
@@ -977,7 +1027,9 @@ static int run_plan(rddl_program* g, int plan, void* const* tensors, const doubl
       const size_t smem = sizeof(uint32_t) * ((size_t)L.nregs * wpt * block +
                                               (size_t)G.nshared * ((A.L.ipt / W32 + A.L.G + 2) * (W32 + 2)) +
                                               32 * RDDL_MAX_RED +
-                                              8 * PLANE_QUEUE + 8 + block * wpt + 32 * G.pol_k);
+                                              8 * PLANE_QUEUE + 8 + block * wpt + 32 * G.pol_k) +
+                          (G.ntma > 0 ? 256 + 128 + sizeof(uint32_t) * (size_t)G.ntma *
+                               (size_t)(((L.chunks == 1 ? (int)(L.E >> 5) : A.L.ipt) + RDDL_TMA_BOX - 1) / RDDL_TMA_BOX * RDDL_TMA_BOX) : 0);
       const size_t smem_static = smem - sizeof(uint32_t) * ((size_t)L.nregs * wpt * block + (size_t)(block - jit_block) * wpt);
       if (jk) {
         void* params[] = {(void*)&A};
@@ -990,7 +1042,17 @@ static int run_plan(rddl_program* g, int plan, void* const* tensors, const doubl
       else if (wpt == 2) rddl_plane_interp<2, 256><<<(unsigned)blocks, 256, smem, stream>>>(A, G);
       else rddl_plane_interp<4, 256><<<(unsigned)blocks, 256, smem, stream>>>(A, G);
     } else if (L.kind == 0 && g->specialize && (g->level_tried || ++g->scalar_launches > g->level_hot) &&
-               (g->level_tried || (jit_levels(g), true)) && g->level_fn[(size_t)(&L - g->launches.data())]) {
+               (g->level_tried || (jit_levels(g), true)) && g->fused_fn[launch_i]) {
+      // this launch and the fused_count - 1 after it: one env-tile kernel (rddl_level_static.cuh)
+      void* params[] = {(void*)&A};
+      const int64_t tiles = (n_envs + RDDL_FUSE_TE - 1) / RDDL_FUSE_TE;
+      if (jit_driver().LaunchKernel(g->fused_fn[launch_i], (unsigned)tiles, 1, 1, 256, 1, 1, 0, (CUstream)stream, params, nullptr) !=
+          CUDA_SUCCESS) {
+        g->err = "cuLaunchKernel failed (fused scalar kernel)";
+        return RDDL_ERR_CUDA;
+      }
+      launch_i += (size_t)g->fused_count[launch_i] - 1;
+    } else if (L.kind == 0 && g->specialize && g->level_tried && g->level_fn[(size_t)(&L - g->launches.data())]) {
       void* params[] = {(void*)&A};
       if (jit_driver().LaunchKernel(g->level_fn[(size_t)(&L - g->launches.data())], (unsigned)blocks, 1, 1, 256, 1, 1, 0,
                                     (CUstream)stream, params, nullptr) != CUDA_SUCCESS) {

@@ -310,3 +310,84 @@ def program_from_simulator(sim, name=None):
     """``sim`` is any reference ``RDDLSimulator`` instance (its ``_compile`` has run)."""
     return program_from_reference(sim.rddl, sim.cpfs, sim.levels, sim.traced, sim.init_values,
                                   name=name)
+
+
+# ---------------------------------------------------------------------------------------
+# front end for huge instances (SURVEY 8f-2)
+# ---------------------------------------------------------------------------------------
+
+def _literal_objects(node, out):
+    """Object / enum literals (@name) written in an expression tree of a neutral spec."""
+    if isinstance(node, str):
+        if node.startswith('@'):
+            out.add(node[1:])
+    elif isinstance(node, (tuple, list)):
+        for x in node:
+            _literal_objects(x, out)
+
+
+def program_from_spec(spec, surrogate_objects=3, name=None):
+    """HIR ``Program`` of a neutral domain spec (``workloads`` / ``rddl_reader.parse_rddl`` format) with
+    front-end cost O(#instance entries) instead of O(#groundings).
+
+    The reference front end materialises every grounding *name* of every pvariable
+    (RDDLLiftedModel, /root/reference/pyRDDLGym/core/compiler/model.py:915-923) and fills the initial
+    tensors through per-grounding Python lists (initializer.py:160-196): minutes and gigabytes at a
+    million cells, and 2^40 strings for a 4-parameter mask over a 1024 x 1024 grid. But everything the
+    lowering needs from it -- CPF levels, traced scopes, types, switch / Discrete case orders -- is a
+    property of the *lifted* domain, not of how many objects the instance has. So the unmodified
+    reference front end (parse tree -> RDDLLiftedModel -> RDDLLevelAnalysis -> RDDLObjectsTracer) runs
+    on a surrogate instance that keeps, per object type, the first ``surrogate_objects`` objects (and
+    every object an expression names literally), and the resulting lifted program is re-instantiated
+    with the real object lists and with initial tensors built directly from the instance's entries
+    (``workloads.instance_tensors``: the values RDDLValueInitializer would produce). Equal, op table
+    byte for byte, to the program of the full front end wherever that can run
+    (tests/test_frontend_scaling.py)."""
+    from pyRDDLGym.core.compiler.model import RDDLLiftedModel
+    from pyRDDLGym.core.simulator import RDDLSimulator
+    from pyrddlgym_b200 import rddl_reader, workloads
+    lits = set()
+    for (_, e) in spec['cpfs']:
+        _literal_objects(e, lits)
+    for e in [spec['reward']] + list(spec.get('preconds', [])) + list(spec.get('invariants', [])) + \
+            list(spec.get('terminals', [])) + list(spec.get('constraints', [])):
+        _literal_objects(e, lits)
+    keep = {}
+    for (t, objs) in spec['objects']:
+        k = min(len(objs), max(1, int(surrogate_objects)))
+        for i, o in enumerate(objs):
+            if o in lits:
+                k = max(k, i + 1)
+        keep[t] = list(objs[:k])
+    kept = set(o for objs in keep.values() for o in objs)
+    type_of = {o: t for (t, objs) in spec['objects'] for o in objs}
+
+    def shrink(entries):
+        # entries whose arguments lie in the surrogate; an object *value* outside it is replaced by the
+        # type's first object (object-valued fluents have no default, model.py:975-1040: every surrogate
+        # grounding still needs a value, and which one does not matter for the lifted program)
+        out = []
+        for ((var, objs), value) in entries:
+            if not all(o.startswith('@') or o in kept for o in (objs or [])):
+                continue
+            if isinstance(value, str) and not value.startswith('@') and value not in kept and value in type_of:
+                value = keep[type_of[value]][0]
+            out.append(((var, objs), value))
+        return out
+
+    small = dict(spec)
+    small['objects'] = [(t, keep[t]) for (t, _) in spec['objects']]
+    small['init_non_fluent'] = shrink(spec['init_non_fluent'])
+    small['init_state'] = shrink(spec['init_state'])
+    sim = RDDLSimulator(RDDLLiftedModel(rddl_reader.reference_ast(small)), keep_tensors=True)
+    p = program_from_simulator(sim, name=name or spec['name'])
+    init, objects, enum_types = workloads.instance_tensors(spec)
+    p.types = {t: len(o) for t, o in objects.items()}
+    p.objects = objects
+    p.enum_types = sorted(enum_types)
+    p.init = {n: init[n] for n in p.tensors}
+    p.horizon = int(spec['horizon'])
+    p.discount = float(spec['discount'])
+    n_act = sum(int(np.prod(p.tensor_shape(n), dtype=np.int64)) for n in p.names_of_kind('action'))
+    p.max_allowed_actions = n_act if spec['max_nondef_actions'] == 'pos-inf' else int(spec['max_nondef_actions'])
+    return p

@@ -1054,8 +1054,14 @@ class Lowerer:
         self.variates.append((int(node_id), 'UNEC'.index(kind), int(nelem)))
         return self.variate_map[node_id]
 
-    def pool_add(self, arr):
+    def pool_add(self, arr, align=1):
+        """Appends an int32 array to the pool; ``align`` (in words) pads the pool first (pre-packed
+        non-fluent planes start on 16 bytes: the plane kernels copy them with TMA)."""
         arr = np.ascontiguousarray(arr, dtype='<i4')
+        if align > 1 and self.pool_len % align:
+            pad = np.zeros(align - self.pool_len % align, dtype='<i4')
+            self.pool.append(pad)
+            self.pool_len += len(pad)
         off = self.pool_len
         self.pool.append(arr)
         self.pool_len += len(arr)

@@ -183,10 +183,21 @@ class PlaneBuilder:
         # (non-fluent planes, then fluent planes: the kernel batches consecutive fluent byte planes)
         state = set(self.lw.p.next_state)
         is_state = lambda o: self.lw.tensor_names_by_id[o['imm']] in state
-        ops = self.ops = ([o for o in self.ops if o['op'] == 'PLDC'] +
-                          [o for o in self.ops if o['op'] == 'PLD' and is_state(o)] +
-                          [o for o in self.ops if o['op'] == 'PLD' and not is_state(o)] +
-                          [o for o in self.ops if o['op'] not in ('PLD', 'PLDC')])
+        ops = ([o for o in self.ops if o['op'] == 'PLD' and is_state(o)] +
+               [o for o in self.ops if o['op'] == 'PLD' and not is_state(o)] +
+               [o for o in self.ops if o['op'] not in ('PLD', 'PLDC')])
+        # pre-packed non-fluent planes (PLDC) are staged in shared memory by TMA at the start of the tile:
+        # each is picked up right before its first use, so that the copy overlaps the fluent loads and
+        # the work in between (and the plane's register is live for as short as possible)
+        for c in reversed([o for o in self.ops if o['op'] == 'PLDC']):
+            first = len(ops)
+            for i, o in enumerate(ops):
+                used = ([o['a']] if o['op'] in ('PST', 'PSHARE') else []) + (list(o['fin'][0].idx) if o['fin'] is not None else [])
+                if c['dst'] in used:
+                    first = i
+                    break
+            ops.insert(first, c)
+        self.ops = ops
         nxt = set(self.lw.p.next_state.values())
         INF = len(ops) + 1
         defs, uses = [], []
@@ -361,7 +372,7 @@ class PlaneBuilder:
         r = self.alloc()
         if decl.kind == 'nonfluent':
             bits = np.packbits(np.asarray(lw.p.init[name], dtype=bool).reshape(-1), bitorder='little')
-            off = lw.pool_add(bits.view('<u4').astype('<u4').view('<i4'))
+            off = lw.pool_add(bits.view('<u4').astype('<u4').view('<i4'), align=4)
             self.ins('PLDC', dst=r, imm=off)
         else:
             self.ins('PLD', dst=r, imm=lw.tensor_id[name])

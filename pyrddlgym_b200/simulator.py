@@ -59,6 +59,18 @@ class _States(collections.abc.Mapping):
         return {name: self[name] for name in self}
 
 
+class _TensorTable(dict):
+    """name -> tensor; remembers whether the C pointer array has to be rebuilt."""
+
+    def __init__(self):
+        super().__init__()
+        self.dirty = True
+
+    def __setitem__(self, key, value):
+        super().__setitem__(key, value)
+        self.dirty = True
+
+
 class BatchedSimulator:
     """N independent environments of one compiled RDDL problem, stepped in lock-step."""
 
@@ -90,12 +102,13 @@ class BatchedSimulator:
         if contract_precision == 'bf16x3':
             self.native.option(native.OPTION_CONTRACT_TC, 1)
         self._jit_warned = False
+        self._jit_checks_left = 100
         self.names = list(self.table.tensor_names)
         self.packed = set(self.table.packed)
         self.tid = self.table.tensor_id
         self.state_names = list(program.next_state)
         self.action_names = program.names_of_kind('action')
-        self.t = {}
+        self.t = _TensorTable()
         with torch.cuda.device(self.device):
             for name in self.names:
                 dt, kind, nelem = self.table.tensor_meta[name]
@@ -121,14 +134,33 @@ class BatchedSimulator:
         self._ptrs = (ctypes.c_void_p * len(self.names))()
         self._inj = (ctypes.c_void_p * max(1, len(self.table.variates)))()
         self._external = {}
+        self._state_pairs = list(program.next_state.items())
+        self._inj_used = False
         self.step_count = 0          # Philox step index: advances with every transition, across resets
         self.episode_step = 0        # transitions since the last reset
         self.reset()
 
     # ------------------------------------------------------------------ plumbing
     def _refresh_ptrs(self):
+        """The device-pointer array of the C ABI (one entry per op-table tensor id); rebuilt only when a
+        tensor of the table was replaced since the last call."""
+        if not self.t.dirty:
+            return
         for i, name in enumerate(self.names):
             self._ptrs[i] = self.t[name].data_ptr()
+        self.t.dirty = False
+
+    def _swap_state(self):
+        """state <-> next-state after a transition (the reference aliases them, simulator.py:463-466):
+        the table entries and -- when it is current -- the pointer array entries, without a rebuild."""
+        t, clean = self.t, not self.t.dirty
+        for s, ns in self._state_pairs:
+            a, b = t[s], t[ns]
+            dict.__setitem__(t, s, b)
+            dict.__setitem__(t, ns, a)
+            if clean:
+                i, j = self.tid[s], self.tid[ns]
+                self._ptrs[i], self._ptrs[j] = self._ptrs[j], self._ptrs[i]
 
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -149,7 +181,12 @@ class BatchedSimulator:
 
     def _jit_check(self):
         # a failed specialisation is not an error (the interpreter kernel ran, same results) but it is
-        # several times slower: say so once
+        # several times slower: say so once (kernels are specialised within the first few dozen launches
+        # of a program: later calls need not look any more)
+        self._jit_checks_left -= 1
+        if self._jit_checks_left <= 0:
+            self._jit_warned = True
+            return
         if not self._jit_warned and self.native.info(native.INFO_JIT_FAILED) > 0:
             self._jit_warned = True
             import warnings
@@ -253,7 +290,7 @@ class BatchedSimulator:
         if actions:
             self.set_actions(actions)
         keep = []
-        for slot, (node, _, nelem) in enumerate(self.table.variates):
+        for slot, (node, _, nelem) in (enumerate(self.table.variates) if (variates or self._inj_used) else ()):
             v = None if variates is None else variates.get(node, None)
             if v is None:
                 self._inj[slot] = None
@@ -264,13 +301,13 @@ class BatchedSimulator:
                     raise ValueError(f'variates for node {node}: expected {self.n_envs * nelem} values')
                 keep.append(tv)
                 self._inj[slot] = tv.data_ptr()
+        self._inj_used = bool(variates)
         self._refresh_ptrs()
         self.native.step(self._ptrs, self._inj if variates else None, ctypes.c_void_p(self.status.data_ptr()),
                          self.n_envs, self.env_offset, self.seed_value, self.step_count, self._stream())
         if not self._jit_warned:
             self._jit_check()
-        for s, ns in self.program.next_state.items():
-            self.t[s], self.t[ns] = self.t[ns], self.t[s]
+        self._swap_state()
         self.step_count += 1
         self.episode_step += 1
         self._keep = keep
@@ -310,8 +347,7 @@ class BatchedSimulator:
         if not self._jit_warned:
             self._jit_check()
         if swapped:
-            for s, ns in self.program.next_state.items():
-                self.t[s], self.t[ns] = self.t[ns], self.t[s]
+            self._swap_state()
         self.step_count += int(n_steps)
         self.episode_step += int(n_steps)
         # the action fluents now hold the last step's actions: a read-only view of the caller's
@@ -387,8 +423,7 @@ class BatchedSimulator:
         if not self._jit_warned:
             self._jit_check()
         if swapped:
-            for s, ns in self.program.next_state.items():
-                self.t[s], self.t[ns] = self.t[ns], self.t[s]
+            self._swap_state()
         self.step_count += int(n_steps)
         self.episode_step += int(n_steps)
         return returns, rewards

@@ -598,7 +598,7 @@ def instance_tensors(spec):
     (/root/reference/pyRDDLGym/core/compiler/initializer.py:45-96,160-214): declared
     default, overridden by the instance's init-non-fluent / init-state entries; object
     valued fluents become canonical object indices (None -> 0); C order over parameters.
-    Primed copies of state fluents start from the same default."""
+    Primed copies of state fluents start from the default of their range."""
     objects = {t: list(objs) for (t, objs) in spec['objects']}
     enum_types = []
     for (t, kind) in spec['types']:
@@ -612,7 +612,7 @@ def instance_tensors(spec):
     sizes = {t: len(o) for t, o in objects.items()}
     out = {}
     meta = {}
-    for (name, ftype, rng, params, default) in spec['pvariables']:
+    for (name, ftype, rng, params, default) in (pv[:5] for pv in spec['pvariables']):
         shape = tuple(sizes[t] for t in (params or []))
         if rng in _NP_RANGE:
             dt = _NP_RANGE[rng]
@@ -623,7 +623,8 @@ def instance_tensors(spec):
         out[name] = np.full(shape, dv, dtype=dt)
         meta[name] = (ftype, rng, params or [])
         if ftype == 'state-fluent':
-            out[name + "'"] = np.full(shape, dv, dtype=dt)
+            # (the primed copy is not in the instance: range default, initializer.py:160-196)
+            out[name + "'"] = np.full(shape, _DEFAULTS.get(rng, 0), dtype=dt)
     for ((name, objs), value) in list(spec['init_non_fluent']) + list(spec['init_state']):
         rng = meta[name][1]
         if rng not in _NP_RANGE:

@@ -213,3 +213,49 @@ def test_batched_dropin_subclass_on_cuda_vs_reference_simulators():
         for name in ('pos', 'ang-pos', 'vel', 'ang-vel'):
             np.testing.assert_allclose(st[name].cpu().numpy(), rb.fluent(name), rtol=1e-9, atol=1e-12)
     assert set(b.states) == {'pos', 'ang-pos', 'vel', 'ang-vel'}      # RDDLSimulator.states works batched
+
+
+_A19_DOMAIN = '''
+domain deferred {
+    types { node : object; };
+    pvariables {
+        M(node, node) : { non-fluent, real, default = 0.0 };
+        MU(node)      : { non-fluent, real, default = 0.0 };
+        x(node)       : { state-fluent, real, default = 1.0 };
+        u             : { action-fluent, real, default = 0.0 };
+    };
+    cpfs { %s };
+    reward = u;
+}
+non-fluents nf_deferred { domain = deferred; objects { node : {a, b}; };
+    non-fluents { M(a, a) = 2.0; M(b, b) = 3.0; M(a, b) = 0.5; M(b, a) = 0.5; }; }
+instance inst_deferred { domain = deferred; non-fluents = nf_deferred; max-nondef-actions = pos-inf; horizon = 5; discount = 1.0; }
+'''
+
+
+@pytest.mark.parametrize('cpf,python_functions', [
+    ("x'(?i) = x(?i) + det_{?p : node, ?q : node} M(?p, ?q);", None),
+    ("x'(?i) = sum_{?j : node} (inverse[row = ?i, col = ?j][M(?i, ?j)] * x(?j));", None),
+    ("x'(?i) = MultivariateNormal[?i](MU(_), M(_, _));", None),
+    ("x'(?i) = Dirichlet[?i](x(_));", None),
+    ("x'(?i) = x(?i) + $ext[](u);", {'ext': lambda u: u}),
+])
+def test_deferred_constructs_raise_not_implemented(cpf, python_functions):
+    """SURVEY 8(a) row a19: external Python functions, random vectors and matrix operators are on the
+    reference's path (simulator.py:824-888,1274-1422) but cannot run on the device; the backend refuses
+    them at compile time with the reference's own RDDLNotImplementedError -- no silent CPU fallback --
+    while the reference itself builds and steps the same model."""
+    from fake_engine import EmulatorEngine
+    from oracle.ref_import import load_reference
+    from pyrddlgym_b200 import rddl_reader
+    from pyrddlgym_b200.backend import backend_class
+    ref = load_reference()
+    spec = rddl_reader.parse_rddl(_A19_DOMAIN % cpf)
+    kw = {'python_functions': python_functions} if python_functions else {}
+    a = ref.RDDLSimulator(ref.RDDLLiftedModel(rddl_reader.reference_ast(spec)), rng=np.random.default_rng(0),
+                          keep_tensors=True, **kw)
+    a.reset()
+    a.step(a.prepare_actions_for_sim({'u': 0.5}))                  # the reference runs it
+    with pytest.raises(ref.exc.RDDLNotImplementedError):
+        backend_class()(ref.RDDLLiftedModel(rddl_reader.reference_ast(spec)), n_envs=1, engine_factory=EmulatorEngine,
+                        keep_tensors=True, **kw)

@@ -461,6 +461,52 @@ def test_tcgen05_split_bf16_contraction_vs_fp64(X, N):
     assert a.launches_issued > b.launches_issued               # split + tcgen05 launches instead of one DMMA launch
 
 
+@pytest.mark.parametrize('N', [5, 7, 64])
+def test_reservoir1000_fused_env_tile_kernel(N):
+    """BASELINE config [2] at full size (R = 1000: VERDICT r1 weak #1, the shape the benchmark runs): the
+    fused env-tile kernel (one launch per step, gather operand staged in shared memory, csrc/
+    rddl_level_static.cuh) against the NumPy oracle in lock-step under injected variates, against the
+    interpreter kernels bit for bit on every fluent, and on the reference-generated golden trajectory.
+    N = 5, 7: partial env tiles."""
+    import torch
+    spec = workloads.reservoir(1000)
+    p = workloads.load_program(spec)
+    a = _make(p, N, seed=11, specialize=True)
+    b = _make(p, N, seed=11, specialize=False)
+    ora = OracleSimulator(p, n_envs=N, seed=11)
+    rng = np.random.default_rng(N)
+    for t in range(4):
+        acts = harness.random_actions(p, N, rng)
+        acts['release'] = rng.uniform(-1.0, 10.0, size=(N, 1000))
+        var = harness.random_variates(p, N, rng) if t < 3 else None       # last step: native Philox
+        cases.compare('pre', _np(a.check_action_preconditions(acts)), ora.check_action_preconditions(acts))
+        _, ra, da = a.step(acts, var)
+        _, rb, db = b.step(acts, var)
+        _, ro, do = ora.step(acts, var)
+        cases.compare(f'reward/{t}', _np(ra), ro)
+        assert torch.allclose(ra, rb, rtol=1e-13, atol=0) and torch.equal(da, db)
+        for nm in ('rain', 'released', 'inflow', 'rlevel'):
+            cases.compare(f'{nm}/{t}', _np(a.fluent(nm)), ora.subs[nm])
+            assert torch.equal(a.fluent(nm).view(torch.int64), b.fluent(nm).view(torch.int64)), (nm, t)
+        cases.compare('inv', _np(a.check_state_invariants()), ora.check_state_invariants())
+    assert a.native.info(9) >= 1, a.native.jit_error()          # the fused kernel ran
+    la, lb = a.launches_issued, b.launches_issued
+    a.step(acts)
+    b.step(acts)
+    assert b.native.info(9) == 0 and a.launches_issued - la == 1 and b.launches_issued - lb == 3
+    if N == 5:
+        sim = cases.replay('reservoir1000', lambda p_, n_: _make(p_, n_, specialize=True), to_np=_np)
+        assert sim.native.info(9) >= 1
+        # a 20-step rollout equals 20 steps (same fused kernel, returns accumulated by the host loop)
+        c, d = _make(p, N, seed=3, specialize=True), _make(p, N, seed=3, specialize=True)
+        seq = torch.from_numpy(rng.uniform(0.0, 10.0, size=(6, N, 1000))).cuda()
+        ret, rew = c.rollout({'release': seq}, 6, keep_rewards=True)
+        for t in range(6):
+            _, r, _ = d.step({'release': seq[t]})
+            assert torch.equal(rew[t], r)
+        assert torch.equal(c.fluent('rlevel'), d.fluent('rlevel'))
+
+
 def test_return_statistics_kernel_matches_numpy():
     """rddl_return_stats (policy.py:120-126 for one shard) vs NumPy, including tiny and odd sizes."""
     import torch
@@ -496,7 +542,12 @@ def test_specialised_scalar_kernels_equal_interpreter_kernels(name, spec, N):
         acts = harness.random_actions(p, N, rng, p_bool=0.3)
         _, ra, da = a.step(acts)
         _, rb, db = b.step(acts)
-        assert torch.equal(ra.view(torch.int64), rb.view(torch.int64)), t
+        if name.startswith('reservoir'):
+            # the fused env-tile kernel combines the partial results of a per-env float reduction in its
+            # own order (csrc/rddl_level_static.cuh): equal to rounding, every fluent still bit-identical
+            assert torch.allclose(ra, rb, rtol=1e-13, atol=0), t
+        else:
+            assert torch.equal(ra.view(torch.int64), rb.view(torch.int64)), t
         assert torch.equal(da, db)
         for nm in p.tensors:
             if p.tensors[nm].kind != 'nonfluent':
