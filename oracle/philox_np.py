@@ -95,22 +95,22 @@ def bernoulli_thresholds(p):
 BERN_LEVELS = 8
 
 
-def bernoulli_bitsliced(seed, env_ids, step, node_id, p):
-    """Bit-sliced Bernoulli sampler of the plane interpreter (csrc/rddl_plane.cuh: PBERN).
+def bitsliced_less_than(seed, env_ids, step, node_id, T):
+    """[U < T] per cell for the bit-sliced uniform U of the plane kernels (csrc/rddl_plane.cuh).
 
-    p: float64 [len(env_ids), n_cells] with n_cells % 32 == 0 (C-order cells of the scope).
-    T = floor(p * 2^64). Cell c of env e first compares T's top BERN_LEVELS bits, MSB first,
-    against random bits: bit j of the cell is bit (c % 32) of word (j % 4) of
+    T: uint64 [len(env_ids), n_cells] with n_cells % 32 == 0 (C-order cells of the scope). Cell c of
+    env e first compares T's top BERN_LEVELS bits, MSB first, against random bits: bit j of the cell
+    is bit (c % 32) of word (j % 4) of
     Philox4x32-10(key = seed, counter = (c // 32, e, step, (node & 0xffff) | ((0x8000 + j // 4) << 16))).
     The first level where the random bit differs decides (random bit 0 -> True). A cell still
     tied after BERN_LEVELS levels draws u64 = (x << 32) | y from
     Philox4x32-10(counter = (c, e, step, (node & 0xffff) | (0xC000 << 16))) and is True iff
-    u64 < (T << BERN_LEVELS) mod 2^64. Cells with p >= 1 are always True."""
-    p = np.asarray(p, dtype=np.float64)
-    N, n_cells = p.shape
+    u64 < (T << BERN_LEVELS) mod 2^64. Comparisons of one cell against several thresholds under the
+    same node share these bits (one uniform per cell)."""
+    T = np.asarray(T, dtype=np.uint64)
+    N, n_cells = T.shape
     assert n_cells % 32 == 0
     G = n_cells // 32
-    T, always = bernoulli_thresholds(p)
     env = (np.asarray(env_ids, dtype=np.uint64)[:, None] & MASK).astype(np.uint32)
     g = np.arange(G, dtype=np.uint32)[None, :]
     lane = np.arange(32, dtype=np.uint32)
@@ -133,8 +133,15 @@ def bernoulli_bitsliced(seed, env_ids, step, node_id, p):
     x, y, _, _ = philox4x32_10(cell, env, st, c3, k0, k1)
     u64 = (x.astype(np.uint64) << np.uint64(32)) | y.astype(np.uint64)
     tail = u64 < (T << np.uint64(BERN_LEVELS))
-    out = np.where(und.reshape(N, n_cells), tail, res.reshape(N, n_cells))
-    return out | always
+    return np.where(und.reshape(N, n_cells), tail, res.reshape(N, n_cells))
+
+
+def bernoulli_bitsliced(seed, env_ids, step, node_id, p):
+    """Bit-sliced Bernoulli sampler of the plane interpreter (csrc/rddl_plane.cuh: PBERN):
+    [U < floor(p * 2^64)] with the bit-sliced uniform of ``bitsliced_less_than``; cells with p >= 1
+    are always True. p: float64 [len(env_ids), n_cells], n_cells % 32 == 0."""
+    T, always = bernoulli_thresholds(np.asarray(p, dtype=np.float64))
+    return bitsliced_less_than(seed, env_ids, step, node_id, T) | always
 
 
 # ---------------------------------------------------------------------------------------
@@ -187,9 +194,23 @@ def policy_actions(entries, max_nondef, seed, env_ids, step):
         else:
             k = int(max_nondef)
     sel = policy_select(seed, env_ids, step, k, total) if k else None
+    # Two consecutive Bernoulli entries of the same size are drawn from ONE uniform per cell (half the
+    # random bits): a = [U < T(p)], b = [T(p) - T(pq) <= U < T(p) - T(pq) + T(q)], T(x) = floor(x 2^64) --
+    # P(a) = p, P(b) = q, P(a and b) = pq: independent, like the agent's per-key draws. U lives under
+    # the first entry's node. (Not when the two intervals would come within 2^-32 of covering [0, 1).)
+    pair = {}
+    i = 0
+    while i + 1 < len(entries):
+        a, b = entries[i], entries[i + 1]
+        if (kinds[i] == POL_BERNOULLI and kinds[i + 1] == POL_BERNOULLI and sizes[i] == sizes[i + 1]
+                and a['lo'] < 1.0 and b['lo'] < 1.0 and (1.0 - a['lo']) * (1.0 - b['lo']) >= 2.0 ** -32):
+            pair[i + 1] = i
+            i += 2
+        else:
+            i += 1
     out = {}
     base = 0
-    for e, kind, n in zip(entries, kinds, sizes):
+    for idx, (e, kind, n) in enumerate(zip(entries, kinds, sizes)):
         npdt = {'b': np.bool_, 'i': np.int64, 'f': np.float64}[e['dtype']]
         dflt = np.asarray(e['dflt']).astype(npdt)
         node = POLICY_NODE + int(e['tensor'])
@@ -197,8 +218,17 @@ def policy_actions(entries, max_nondef, seed, env_ids, step):
             v = np.full((N, n), dflt, dtype=npdt)
         elif kind == POL_BERNOULLI:
             pad = (-n) % 32      # the bit-sliced mapping is defined per 32-cell word; a ragged last word is cut
-            p = np.full((N, n + pad), float(e['lo']), dtype=np.float64)
-            v = bernoulli_bitsliced(seed, env_ids, step, node, p)[:, :n]
+            thr = lambda x: int(bernoulli_thresholds(np.array([x]))[0][0])
+            if idx in pair:
+                first = entries[pair[idx]]
+                node = POLICY_NODE + int(first['tensor'])
+                lo = thr(float(first['lo'])) - thr(float(first['lo']) * float(e['lo']))
+                hi = lo + thr(float(e['lo']))
+                below = bitsliced_less_than(seed, env_ids, step, node, np.full((N, n + pad), lo, dtype=np.uint64))
+                v = (bitsliced_less_than(seed, env_ids, step, node, np.full((N, n + pad), hi, dtype=np.uint64)) & ~below)[:, :n]
+            else:
+                p = np.full((N, n + pad), float(e['lo']), dtype=np.float64)
+                v = bernoulli_bitsliced(seed, env_ids, step, node, p)[:, :n]
         else:
             u = base_variates('U', seed, env_ids, step, node, (n,))
             if kind == POL_UNIFORM_REAL:

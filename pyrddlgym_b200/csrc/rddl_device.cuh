@@ -57,7 +57,10 @@ __device__ __forceinline__ void rddl_mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void rddl_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rddl_smem_addr(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void rddl_mbar_wait(uint64_t* bar, uint32_t parity) {
+// Returns 0 once the phase has completed. No "memory" clobber (it would pin every load of the kernel
+// on one side of the wait): the caller orders its reads of the copied data after the wait by making
+// their address depend on the returned value.
+__device__ __forceinline__ uint32_t rddl_mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t a = rddl_smem_addr(bar);
   for (uint32_t spins = 0;; ++spins) {      // (bounded: a copy that never lands traps instead of hanging the GPU)
     uint32_t ok;
@@ -66,8 +69,8 @@ __device__ __forceinline__ void rddl_mbar_wait(uint64_t* bar, uint32_t parity) {
         ".reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t"
-        "}" : "=r"(ok) : "r"(a), "r"(parity) : "memory");
-    if (ok) return;
+        "}" : "=r"(ok) : "r"(a), "r"(parity));
+    if (ok) return ok - 1u;
     if (spins > (1u << 24)) __trap();
   }
 }
@@ -160,6 +163,7 @@ __device__ __forceinline__ uint64_t red_combine(int op, uint64_t a, uint64_t b) 
 __device__ __forceinline__ bool rddl_bern_bitsliced_cell(uint64_t seed, uint32_t env, uint32_t step, uint32_t node,
                                                          uint64_t thr, bool always, uint64_t cell) {
   if (always) return true;
+  if (thr == 0) return false;
   const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
   const uint32_t w = (uint32_t)(cell >> 5), bit = (uint32_t)cell & 31u;
 #pragma unroll 1
@@ -207,9 +211,10 @@ __device__ __forceinline__ uint64_t rddl_policy_value(const VmPolicy& pol, const
     for (int i = 0; i < pol.k; ++i) chosen |= (int64_t)sel[i] == e.base + elem;
     if (!chosen) return e.dflt;
   }
-  const uint32_t node = RDDL_POLICY_NODE + (uint32_t)e.tensor;
-  if (e.kind == POL_BERNOULLI)
-    return rddl_bern_bitsliced_cell(seed, (uint32_t)env_global, (uint32_t)step, node, e.thr, e.always != 0, (uint64_t)elem);
+  const uint32_t node = e.node;
+  if (e.kind == POL_BERNOULLI)     // [thr_lo <= U < thr] on the cell's bit-sliced uniform (both compares see the same bits)
+    return rddl_bern_bitsliced_cell(seed, (uint32_t)env_global, (uint32_t)step, node, e.thr, e.always != 0, (uint64_t)elem) &&
+           !rddl_bern_bitsliced_cell(seed, (uint32_t)env_global, (uint32_t)step, node, e.thr_lo, false, (uint64_t)elem);
   const uint4 x = rddl_philox_draw(seed, env_global, step, node, (uint64_t)elem);
   const double u = rddl_u53(x.x, x.y);
   if (e.kind == POL_UNIFORM_REAL) return (uint64_t)__double_as_longlong(__dadd_rn(e.lo, __dmul_rn(__dsub_rn(e.hi, e.lo), u)));

@@ -231,7 +231,13 @@ static std::string plane_static_data(const PlaneProg& G, const RddlLaunch& L, co
   s += "__device__ constexpr PlaneProg kG = {" + jit_fmt("%lld,", G.nops) + jit_fmt("%lld,", G.nshared) +
        jit_fmt("%lld,", G.w32_shift) + jit_fmt("%lld,", G.wpe_shift) + jit_fmt("%lld,", G.nfused) +
        jit_fmt("%lld,", G.fused_nregs) + jit_fmt("%lld,", G.rollout_ok) + jit_fmt("%lld,", G.pad) +
-       jit_fmt("%lld,", G.pol_k) + jit_fmt("%lld,\n{", G.ntma);
+       jit_fmt("%lld,", G.pol_k) + jit_fmt("%lld,", G.ntma) + jit_fmt("%lld,", G.npol) + jit_fmt("%lld,\n{", G.pad2);
+  for (int i = 0; i < RDDL_MAX_POLICY; ++i) s += "{" + jit_fmt("0x%llxull,", (long long)G.pol_thr[i][0]) + jit_fmt("0x%llxull},", (long long)G.pol_thr[i][1]);
+  s += "},{";
+  for (int i = 0; i < RDDL_MAX_POLICY; ++i) s += jit_fmt("%lluu,", G.pol_node[i]);
+  s += "},{";
+  for (int i = 0; i < RDDL_MAX_POLICY; ++i) s += jit_fmt("%lld,", G.pol_always[i]);
+  s += "},\n{";
   jit_launch_init(s, G.fused[0]);
   s += ",\n";
   jit_launch_init(s, G.fused[1]);

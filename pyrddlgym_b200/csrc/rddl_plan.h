@@ -28,10 +28,12 @@ enum RddlOp : uint8_t {
   OP_SUMLOOP,
   OP_SAMPLE,
   OP_PPOLSEL,
+  OP_PPOL,
   OP_COUNT_
 };
 
-// (OP_PPOLSEL: plane op the host inserts for device-side policies with a max-nondef rule; never in an op table)
+// (OP_PPOL / OP_PPOLSEL: plane ops the host inserts for device-side policies -- the Bernoulli draw of one or
+// two action planes, the max-nondef selection; never in an op table)
 enum RddlRed { RED_SUM_I, RED_SUM_F, RED_PROD_I, RED_PROD_F, RED_MIN_I, RED_MIN_F, RED_MAX_I, RED_MAX_F,
                RED_AND, RED_OR };
 enum RddlDtype { DT_BOOL = 0, DT_INT = 1, DT_REAL = 2,
@@ -94,13 +96,15 @@ struct RddlRedSlot { int32_t op, chunks; };
 #define RDDL_POLICY_NODE 0xF000u
 #define RDDL_POLICY_SELECT_NODE 0xFF00u
 enum RddlPolicyKind { POL_NONE = 0, POL_BERNOULLI = 1, POL_UNIFORM_REAL = 2, POL_UNIFORM_INT = 3, POL_DEFAULT = 4 };
-struct VmPolicyEntry {   // 64 bytes
+struct VmPolicyEntry {   // 80 bytes
   int32_t tensor, kind;
   double lo, hi;         // uniform bounds (POL_BERNOULLI: lo = p)
-  uint64_t thr;          // POL_BERNOULLI: floor(p * 2^64), 2^64 - 1 when p >= 1
-  uint64_t dflt;         // raw 64-bit default (noop) value of the fluent
+  uint64_t thr;          // POL_BERNOULLI: the draw is [thr_lo <= U < thr], U the cell's bit-sliced uniform under `node`;
+  uint64_t dflt;         //   unpaired: thr_lo = 0, thr = floor(p * 2^64).   dflt: raw 64-bit default (noop) value
   int64_t base, nelem;   // first flat grounding index of this fluent in the policy's grounding order, #groundings
-  int32_t always, pad;   // POL_BERNOULLI: p >= 1
+  int32_t always, pair;  // POL_BERNOULLI: p >= 1; pair: 0 = own uniform, 1 / 2 = first / second of two Bernoulli
+  uint64_t thr_lo;       //   fluents drawn from one uniform per cell (second: thr_lo = T(p1) - T(p1 p2), thr = thr_lo + T(p2))
+  uint32_t node, pad;    // Philox node id of the draw (the first fluent's for a pair)
 };
 struct VmPolicy {
   int32_t n, k;          // entries; k > 0: only k randomly chosen groundings per (env, step) keep their draw

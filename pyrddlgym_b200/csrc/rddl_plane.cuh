@@ -40,6 +40,12 @@ struct PlaneProg {
   int32_t nfused, fused_nregs, rollout_ok, pad;  // scalar launches run in the epilogue (kind 2)
   int32_t pol_k, ntma;                           // device-side policy with a max-nondef rule: groundings kept per (env, step);
                                                  // ntma: pre-packed non-fluent planes staged in shared memory by TMA (PLDC slots)
+  int32_t npol, pad2;                            // PPOL ops (device-side policy draws) in the program
+  // thresholds / Philox node of the policy's Bernoulli entries (copied from the policy descriptor when the
+  // program is rewritten for it: compile-time constants of the specialised build, like every other table)
+  uint64_t pol_thr[RDDL_MAX_POLICY][2];          // [entry]: thr, thr_lo -- the draw is [thr_lo <= U < thr]
+  uint32_t pol_node[RDDL_MAX_POLICY];
+  int32_t pol_always[RDDL_MAX_POLICY];           // p >= 1
   RddlLaunch fused[2];
   int32_t red_off[RDDL_MAX_RED], red_m[RDDL_MAX_RED];   // PRED op of reduction j: table offset, #planes
   PlaneOp ops[PLANE_MAX_OPS];
@@ -170,7 +176,7 @@ struct PlaneCtx {
   __device__ __forceinline__ uint32_t& at(int r, int j) {
     // the register file starts at offset 0 of the dynamic shared memory; naming the extern array
     // here keeps the accesses in the shared address space (LDS/STS instead of generic LD/ST)
-    extern __shared__ uint32_t plane_smem_base[];
+    extern __shared__ __align__(128) uint32_t plane_smem_base[];
     return plane_smem_base[(r * WPT + j) * BLOCK + threadIdx.x];
   }
 #endif
@@ -317,6 +323,125 @@ __device__ PLANE_OUTLINE void plane_bernoulli(PlaneCtx<WPT, BLOCK>& C, const VmA
   }
 }
 
+// Device-side policy draw of one or two bool action planes (OP_PPOL; rddl_device.cuh: rddl_policy_value is
+// the per-cell form, oracle/philox_np.py: policy_actions the restatement): plane of entry e is
+// [e.thr_lo <= U < e.thr] for the cell's bit-sliced uniform U under node e.node -- eight levels of
+// Philox words compared MSB first against every threshold at once, ties finished with one 64-bit draw
+// per cell by the warp together (same scheme as plane_bernoulli). Two entries of a pair share U.
+//   o.dst / o.imm: register and policy entry of the first plane; o.a / o.b: of the second (o.a < 0: none)
+//   cmp: [4][BLOCK * WPT] words of shared memory (results per comparator, patched by the tail)
+template <int WPT, int BLOCK>
+__device__ PLANE_OUTLINE void plane_policy(PlaneCtx<WPT, BLOCK>& C, const VmArgs& A, const PlaneProg& G, const PlaneOp& o,
+                                          uint32_t* queue, int* qn, uint32_t* cmp, int64_t env0, uint32_t step) {
+  const bool two = o.a >= 0;
+  const int i0 = (int)o.imm, i1 = two ? o.b : (int)o.imm;
+  const bool always0 = G.pol_always[i0] != 0, always1 = G.pol_always[i1] != 0;
+  // comparators [U < Tk]: 0 = first.thr, 1 = first.thr_lo, 2 = second.thr, 3 = second.thr_lo (0 = unused: never
+  // true; in the specialised build the thresholds are constants: unused comparators and all masks fold away)
+  const uint64_t Tk[4] = {always0 ? 0ull : G.pol_thr[i0][0], G.pol_thr[i0][1], (two && !always1) ? G.pol_thr[i1][0] : 0ull,
+                          two ? G.pol_thr[i1][1] : 0ull};
+  const uint2 key = make_uint2((uint32_t)A.seed, (uint32_t)(A.seed >> 32));
+  const uint32_t node = G.pol_node[i0] & 0xffffu;
+  const uint32_t e0g = (uint32_t)(A.env_offset + env0);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (lane == 0) qn[warp] = 0;
+  __syncwarp();
+  PLANE_UNROLL_DYN
+  for (int j0 = 0; j0 < WPT; j0 += 2) {
+    constexpr int NW = WPT >= 2 ? 2 : 1;
+    uint32_t res[NW][4], und[NW][4];
+#pragma unroll
+    for (int jj = 0; jj < NW; ++jj) {
+      const bool ok = (C.valid >> (j0 + jj)) & 1u;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { res[jj][k] = 0u; und[jj][k] = (ok && Tk[k] != 0ull) ? 0xffffffffu : 0u; }
+    }
+#pragma unroll
+    for (int b = 0; b < PLANE_BERN_LEVELS / 4; ++b) {
+      uint32_t rw[NW][4];
+#pragma unroll
+      for (int jj = 0; jj < NW; ++jj) {
+        const uint4 r4 = rddl_philox4x32_10(
+            make_uint4((uint32_t)C.wi[j0 + jj], e0g + (uint32_t)C.env[j0 + jj], step, node | ((0x8000u + b) << 16)), key);
+        rw[jj][0] = r4.x; rw[jj][1] = r4.y; rw[jj][2] = r4.z; rw[jj][3] = r4.w;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t tb = ((Tk[k] >> (63 - (4 * b + q))) & 1ull) ? 0xffffffffu : 0u;     // (warp-uniform)
+#pragma unroll
+          for (int jj = 0; jj < NW; ++jj) {
+            res[jj][k] |= und[jj][k] & ~rw[jj][q] & tb;
+            und[jj][k] &= ~(rw[jj][q] ^ tb);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int jj = 0; jj < NW; ++jj) {
+      const int j = j0 + jj;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (Tk[k] != 0ull) cmp[k * (BLOCK * WPT) + tid * WPT + j] = res[jj][k];
+      uint32_t u = und[jj][0] | und[jj][1] | und[jj][2] | und[jj][3];
+      while (u) {      // cells still tied on some threshold (4 x 2^-8 of them): queued per warp
+        const int b = __ffs(u) - 1;
+        u &= u - 1;
+        const uint32_t km = ((und[jj][0] >> b) & 1u) | (((und[jj][1] >> b) & 1u) << 1) | (((und[jj][2] >> b) & 1u) << 2) |
+                            (((und[jj][3] >> b) & 1u) << 3);
+        const int slot = atomicAdd(&qn[warp], 1);
+        if (slot < PLANE_QUEUE) {
+          queue[warp * PLANE_QUEUE + slot] = (uint32_t)lane | ((uint32_t)j << 5) | ((uint32_t)b << 8) | (km << 13);
+        } else {     // queue full (practically never): finish inline
+          const uint4 r4 = rddl_philox4x32_10(
+              make_uint4(((uint32_t)C.wi[j] << 5) | b, e0g + (uint32_t)C.env[j], step, node | (0xC000u << 16)), key);
+          const uint64_t u64 = ((uint64_t)r4.x << 32) | r4.y;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (((km >> k) & 1u) && u64 < (Tk[k] << PLANE_BERN_LEVELS)) cmp[k * (BLOCK * WPT) + tid * WPT + j] |= 1u << b;
+        }
+      }
+    }
+  }
+  __syncwarp();
+  const int n = min(qn[warp], PLANE_QUEUE);
+  for (int i = lane; i < n; i += 32) {
+    const uint32_t en = queue[warp * PLANE_QUEUE + i];
+    const int ol = en & 31, oj = (en >> 5) & 7, b = (en >> 8) & 31;
+    const uint32_t km = en >> 13;
+    const int ow = oj * BLOCK + warp * 32 + ol;       // the owner's word coordinates, from the tile geometry
+    int env_l, wi_l;
+    if (PLANE_LAUNCH(A).chunks == 1) {
+      const int wpe = (int)(PLANE_LAUNCH(A).E >> 5);
+      env_l = ow / wpe;
+      wi_l = ow - env_l * wpe;
+    } else {
+      env_l = 0;
+      wi_l = (blockIdx.x % PLANE_LAUNCH(A).chunks) * PLANE_LAUNCH(A).ipt + ow;
+    }
+    const uint4 r4 = rddl_philox4x32_10(make_uint4(((uint32_t)wi_l << 5) | b, e0g + (uint32_t)env_l, step, node | (0xC000u << 16)), key);
+    const uint64_t u64 = ((uint64_t)r4.x << 32) | r4.y;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (((km >> k) & 1u) && u64 < (Tk[k] << PLANE_BERN_LEVELS))
+        atomicOr(&cmp[k * (BLOCK * WPT) + (warp * 32 + ol) * WPT + oj], 1u << b);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < WPT; ++j) {
+    const bool ok = (C.valid >> j) & 1u;
+    const uint32_t c0 = Tk[0] != 0ull ? cmp[tid * WPT + j] : 0u, c1 = Tk[1] != 0ull ? cmp[BLOCK * WPT + tid * WPT + j] : 0u;
+    C.at(o.dst, j) = always0 ? (ok ? 0xffffffffu : 0u) : (c0 & ~c1);
+    if (two) {
+      const uint32_t c2 = Tk[2] != 0ull ? cmp[2 * BLOCK * WPT + tid * WPT + j] : 0u;
+      const uint32_t c3 = Tk[3] != 0ull ? cmp[3 * BLOCK * WPT + tid * WPT + j] : 0u;
+      C.at(o.a, j) = always1 ? (ok ? 0xffffffffu : 0u) : (c2 & ~c3);
+    }
+  }
+  __syncwarp();
+}
+
 template <int M, int WPT, int BLOCK>
 __device__ __forceinline__ void plane_lut(PlaneCtx<WPT, BLOCK>& C, const PlaneProg& G, const PlaneOp& o) {
   constexpr int CH = WPT < 4 ? WPT : 4;
@@ -390,10 +515,8 @@ struct PlaneTile {
   int* qn;              // [8]
   uint32_t* fix;        // [256][WPT]
   int32_t* sel;         // [32][pol_k] groundings that keep their policy draw this step (PPOLSEL)
-  uint32_t* nf;         // [ntma][nf_words] non-fluent planes of this tile, staged by TMA
-  uint64_t* nf_bar;     // mbarrier the TMA copies complete on
-  int nf_words, nf_first;   // words staged per plane (a multiple of the TMA box), first plane word staged
-  bool nf_wait;         // the staged planes have not been waited for yet
+  uint32_t* cmp;        // [4][BLOCK * WPT] comparator results of the policy draws (PPOL), when the program has any
+  int tma_off;          // word offset (from S) of the TMA region: mbarrier (128 B) | [ntma][nf_words] staged non-fluent planes
   int64_t env0, tile_byte0;
   int64_t gw_limit;     // last valid global word index this tile may touch (ragged tiles clamp loads to it)
   int W32, wpe, envs_per_tile, tile_words, chunks, chunk, pitch, tile_rows, plane_stride;
@@ -546,9 +669,13 @@ __device__ __forceinline__ void plane_exec(PlaneTile<WPT, BLOCK>& T, const VmArg
       case OP_PLDC: {
         if (G.ntma > 0 && A.pool_map_ok) {
           // the tile's slice of the pre-packed non-fluent plane was copied to shared memory by TMA
-          // (plane_tile prologue): wait for the copies once, then read it from there
-          if (T.nf_wait) { rddl_mbar_wait(T.nf_bar, 0); T.nf_wait = false; }
-          const uint32_t* sp = T.nf + o.b * T.nf_words - T.nf_first;
+          // (plane_tile prologue): make sure the copies have landed (a completed mbarrier phase answers
+          // at once), then read it from there
+          uint32_t* tma = T.S + T.tma_off;
+          uint32_t landed = 0;
+          if (t == 0) landed = rddl_mbar_wait(reinterpret_cast<uint64_t*>(tma), 0);       // 0 (later steps: already there)
+          const int nf_words = ((chunks == 1 ? wpe : tile_words) + RDDL_TMA_BOX - 1) / RDDL_TMA_BOX * RDDL_TMA_BOX;
+          const uint32_t* sp = tma + 32 + o.b * nf_words - (chunks == 1 ? 0 : chunk * tile_words) + landed;
 #pragma unroll
           for (int j = 0; j < WPT; ++j) C.at(o.dst, j) = (full || ((C.valid >> j) & 1u)) ? sp[C.wi[j]] : 0u;
           break;
@@ -684,6 +811,10 @@ __device__ __forceinline__ void plane_exec(PlaneTile<WPT, BLOCK>& T, const VmArg
         }
         break;
       }
+      case OP_PPOL: {
+        plane_policy<WPT, BLOCK>(C, A, G, o, queue, qn, T.cmp, env0, (uint32_t)(A.step + t));
+        break;
+      }
       case OP_PPOLSEL: {
         // max-nondef rule of a device-side policy: only the groundings selected for this (env, step)
         // keep the draw already in the register, the others fall back to the fluent's default
@@ -765,7 +896,7 @@ __device__ __forceinline__ void plane_tile(const VmArgs& A, const PlaneProg& G, 
 
   // dynamic shared memory: (interpreter only: plane registers [nregs][WPT][256]) |
   // [nshared] padded stencil planes | cnt | queue | qn | fix
-  extern __shared__ uint32_t smem[];
+  extern __shared__ __align__(128) uint32_t smem[];
   const int plane_stride = (tile_rows + envs_per_tile + 2) * pitch;
   PlaneTile<WPT, BLOCK> T;
 #ifdef PLANE_STATIC
@@ -783,24 +914,21 @@ __device__ __forceinline__ void plane_tile(const VmArgs& A, const PlaneProg& G, 
   // PLDC plane -- the whole plane when a tile holds whole envs, the tile's rows otherwise -- arrive in
   // shared memory as boxes of RDDL_TMA_BOX words (cp.async.bulk.tensor.1d on the pool's tensor map)
   // while the tile sets up and issues its fluent loads; the first PLDC op waits on the mbarrier.
-  T.nf_wait = false;
+  // (region offset: everything before it, rounded up to 128 bytes; the dynamic shared memory is 128-byte aligned)
+  T.cmp = reinterpret_cast<uint32_t*>(T.sel + 32 * G.pol_k);
+  T.tma_off = (int)(((T.cmp + (G.npol > 0 ? 4 * BLOCK * WPT : 0) - S) + 31) & ~31);
   if (G.ntma > 0 && A.pool_map_ok) {
-    const int span = chunks == 1 ? wpe : tile_words;
-    T.nf_first = chunks == 1 ? 0 : chunk * tile_words;
-    T.nf_words = (span + RDDL_TMA_BOX - 1) / RDDL_TMA_BOX * RDDL_TMA_BOX;
-    // (128-byte aligned: the region after sel, rounded up)
-    uint64_t q = reinterpret_cast<uint64_t>(T.sel + 32 * G.pol_k);
-    q = (q + 127) & ~(uint64_t)127;
-    T.nf_bar = reinterpret_cast<uint64_t*>(q);
-    T.nf = reinterpret_cast<uint32_t*>(q + 128);
-    T.nf_wait = true;
+    uint32_t* tma = S + T.tma_off;
+    const int nf_words = ((chunks == 1 ? wpe : tile_words) + RDDL_TMA_BOX - 1) / RDDL_TMA_BOX * RDDL_TMA_BOX;
+    const int nf_first = chunks == 1 ? 0 : chunk * tile_words;
     if (tid == 0) {
-      rddl_mbar_init(T.nf_bar, 1);
-      rddl_mbar_expect_tx(T.nf_bar, (uint32_t)(G.ntma * T.nf_words * 4));
+      uint64_t* bar = reinterpret_cast<uint64_t*>(tma);
+      rddl_mbar_init(bar, 1);
+      rddl_mbar_expect_tx(bar, (uint32_t)(G.ntma * nf_words * 4));
       for (int a = 0; a < G.nops; ++a) {
         if (G.ops[a].op != OP_PLDC) continue;
-        for (int b = 0; b < T.nf_words; b += RDDL_TMA_BOX)
-          rddl_tma_load_1d(T.nf + G.ops[a].b * T.nf_words + b, &A.pool_map, T.nf_bar, (int32_t)G.ops[a].imm + T.nf_first + b);
+        for (int b = 0; b < nf_words; b += RDDL_TMA_BOX)
+          rddl_tma_load_1d(tma + 32 + G.ops[a].b * nf_words + b, &A.pool_map, bar, (int32_t)G.ops[a].imm + nf_first + b);
       }
     }
     __syncthreads();      // the barrier is initialised before anybody polls it

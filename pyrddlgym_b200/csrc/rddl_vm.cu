@@ -497,6 +497,16 @@ static int parse_program(const void* optable, size_t nbytes, int device, rddl_pr
       }
     }
     G->rollout_ok = ok;
+    // TMA staging of the pre-packed non-fluent planes (rddl_plane.cuh: cp.async.bulk.tensor.1d into shared
+    // memory + mbarrier): implemented and parity-tested, but measured SLOWER than reading the (L1 / L2
+    // resident, 4 KB per tile) planes directly on both Wildfire configurations -- 1024 x 1024 x 4096 envs:
+    // 2429 -> 2752 us per step, 32 x 32 x 4096 envs fused rollout: 344 -> 373 us --
+    // so it is off unless the program is created under RDDL_PLANE_TMA=1.
+    {
+      bool tma = false;
+      if (const char* e = getenv("RDDL_PLANE_TMA")) tma = atoi(e) != 0;
+      if (!tma) G->ntma = 0;
+    }
   }
   for (auto& L : g->launches) {
     const bool bad_scalar = L.kind != 1 && L.kind != 3 && (L.nregs > RDDL_MAX_REGS || L.G > 256 || (L.G & (L.G - 1)));
@@ -569,7 +579,7 @@ extern "C" int rddl_program_create(const void* optable, size_t nbytes, int devic
   // tensor map over the pool (1-D, int32, box of RDDL_TMA_BOX words) for the plane kernels' TMA staging of
   // non-fluent planes; absent driver entry point or an empty pool: the kernels read the pool directly
   g->pool_len = hdr[8];
-  if (hdr[8] > 0 && !getenv("RDDL_PLANE_NO_TMA")) {
+  if (hdr[8] > 0) {
     if (TcEncodeFn enc = tc_encode_fn()) {
       const cuuint64_t dims[1] = {(cuuint64_t)hdr[8]};
       const cuuint64_t strides[1] = {4};
@@ -793,6 +803,7 @@ static int make_policy(rddl_program* g, const rddl_policy_t* P, VmPolicy* out) {
     e.tensor = pe.tensor; e.kind = pe.kind; e.lo = pe.lo; e.hi = pe.hi;
     e.dflt = dt == DT_REAL ? (uint64_t)0 : (dt == DT_BOOL ? (uint64_t)(pe.dflt != 0.0) : (uint64_t)(int64_t)pe.dflt);
     if (dt == DT_REAL) memcpy(&e.dflt, &pe.dflt, 8);
+    e.node = RDDL_POLICY_NODE + (uint32_t)pe.tensor;
     if (pe.kind == POL_BERNOULLI) {
       e.always = pe.lo >= 1.0;
       e.thr = e.always ? ~0ull : (uint64_t)(pe.lo * 18446744073709551616.0);
@@ -804,6 +815,24 @@ static int make_policy(rddl_program* g, const rddl_policy_t* P, VmPolicy* out) {
   }
   out->n = P->n_entries;
   out->total = total;
+  // Two consecutive Bernoulli entries of the same size share ONE uniform per cell (half the Philox work):
+  // a = [U < T(p)], b = [T(p) - T(pq) <= U < T(p) - T(pq) + T(q)] -- P(a) = p, P(b) = q, P(a and b) = pq.
+  // (oracle/philox_np.py: policy_actions states the same rule.)
+  auto T = [](double x) { return x >= 1.0 ? ~0ull : (uint64_t)(x * 18446744073709551616.0); };
+  for (int i = 0; i + 1 < out->n;) {
+    VmPolicyEntry &a = out->e[i], &b = out->e[i + 1];
+    if (a.kind == POL_BERNOULLI && b.kind == POL_BERNOULLI && a.nelem == b.nelem && a.lo < 1.0 && b.lo < 1.0 &&
+        (1.0 - a.lo) * (1.0 - b.lo) >= 2.3283064365386963e-10 /* 2^-32 */) {
+      a.pair = 1;
+      b.pair = 2;
+      b.node = a.node;
+      b.thr_lo = T(a.lo) - T(a.lo * b.lo);
+      b.thr = b.thr_lo + T(b.lo);
+      i += 2;
+    } else {
+      ++i;
+    }
+  }
   if (total >= (1ll << 31)) { g->err = "policy: more than 2^31 action groundings"; return RDDL_ERR_ARG; }
   if (P->max_nondef >= 0 && P->max_nondef < total) {
     if (P->max_nondef == 0) {
@@ -836,12 +865,16 @@ static const rddl_program::PolicyProg* policy_prog(rddl_program* g, int li, cons
   G = S;
   G.nops = 0;
   G.pol_k = pol.k;
-  int nw = 0;
-  for (int i = 0; i < PLANE_WORDS; ++i) if (S.words[i]) nw = i + 1;
-  nw = (nw + 3) & ~3;
+  for (int i = 0; i < pol.n && i < RDDL_MAX_POLICY; ++i) {
+    G.pol_thr[i][0] = pol.e[i].thr; G.pol_thr[i][1] = pol.e[i].thr_lo;
+    G.pol_node[i] = pol.e[i].node; G.pol_always[i] = pol.e[i].always;
+  }
   bool ok = true;
+  int partner_done = -1;       // op index of a paired plane's load that the first plane's PPOL already covered
+  G.npol = 0;
   for (int a = 0; a < S.nops && ok; ++a) {
     PlaneOp o = S.ops[a];
+    if (a == partner_done) continue;
     const int pe = (o.op == OP_PLD && o.a == 0 && o.imm < RDDL_MAX_TENSORS) ? pol.of_tensor[o.imm] : 0;
     if (!pe) {
       if (G.nops >= PLANE_MAX_OPS) { ok = false; break; }
@@ -855,17 +888,30 @@ static const rddl_program::PolicyProg* policy_prog(rddl_program* g, int li, cons
       G.ops[G.nops++] = o;
       continue;
     }
-    if (e.kind != POL_BERNOULLI || nw + 2 + PLANE_BERN_LEVELS + 4 > PLANE_WORDS || G.nops + 2 > PLANE_MAX_OPS) { ok = false; break; }
-    // tables of a Bernoulli over zero index planes: bad, always, the threshold's top bits, thr, p
-    o.op = OP_PBERN; o.m = 0; o.idx = 0; o.off = nw; o.a = 0;
-    o.b = (e.always ? 2 : 0) | (int32_t)(((RDDL_POLICY_NODE + (uint32_t)e.tensor) & 0xffffu) << 8);
-    G.words[nw++] = 0u;
-    G.words[nw++] = e.always ? 0xffffffffu : 0u;
-    for (int j = 0; j < PLANE_BERN_LEVELS; ++j) G.words[nw++] = ((e.thr >> (63 - j)) & 1ull) ? 0xffffffffu : 0u;
-    G.words[nw++] = (uint32_t)e.thr; G.words[nw++] = (uint32_t)(e.thr >> 32);
-    uint64_t pbits; memcpy(&pbits, &e.lo, 8);
-    G.words[nw++] = (uint32_t)pbits; G.words[nw++] = (uint32_t)(pbits >> 32);
+    if (e.kind != POL_BERNOULLI || G.nops + 3 > PLANE_MAX_OPS) { ok = false; break; }
+    // the Bernoulli draw of this plane -- and, for the first of a pair whose partner's load follows
+    // with nothing but loads in between, of both planes from the one shared uniform (OP_PPOL)
+    o.op = OP_PPOL; o.m = 0; o.idx = 0; o.off = 0; o.imm = (uint32_t)(pe - 1); o.a = -1; o.b = -1;
+    if (e.pair == 1) {
+      for (int c = a + 1; c < S.nops; ++c) {
+        const PlaneOp& oc = S.ops[c];
+        if (oc.op == OP_PLD && oc.a == 0 && oc.imm < RDDL_MAX_TENSORS && pol.of_tensor[oc.imm] == pe + 1) {
+          // (the partner's register is written here, before its own load: nothing in between may write it)
+          bool clash = false;
+          for (int d = a + 1; d < c; ++d) clash |= S.ops[d].dst == oc.dst;
+          if (!clash && oc.dst != o.dst) { o.a = oc.dst; o.b = pe; partner_done = c; }
+          break;
+        }
+        if (oc.op != OP_PLD && oc.op != OP_PLDC) break;
+      }
+    }
+    ++G.npol;
     G.ops[G.nops++] = o;
+    if (o.a >= 0 && pol.k > 0) {       // (the partner's selection mask: emitted here, its own load is skipped below)
+      PlaneOp q; memset(&q, 0, sizeof q);
+      q.op = OP_PPOLSEL; q.dst = o.a; q.imm = (uint32_t)pe;
+      G.ops[G.nops++] = q;
+    }
     if (pol.k > 0) {
       PlaneOp q; memset(&q, 0, sizeof q);
       q.op = OP_PPOLSEL; q.dst = o.dst; q.imm = (uint32_t)(pe - 1);
@@ -1027,7 +1073,7 @@ static int run_plan(rddl_program* g, int plan, void* const* tensors, const doubl
       const size_t smem = sizeof(uint32_t) * ((size_t)L.nregs * wpt * block +
                                               (size_t)G.nshared * ((A.L.ipt / W32 + A.L.G + 2) * (W32 + 2)) +
                                               32 * RDDL_MAX_RED +
-                                              8 * PLANE_QUEUE + 8 + block * wpt + 32 * G.pol_k) +
+                                              8 * PLANE_QUEUE + 8 + block * wpt + 32 * G.pol_k + (G.npol > 0 ? 4 * block * wpt : 0)) +
                           (G.ntma > 0 ? 256 + 128 + sizeof(uint32_t) * (size_t)G.ntma *
                                (size_t)(((L.chunks == 1 ? (int)(L.E >> 5) : A.L.ipt) + RDDL_TMA_BOX - 1) / RDDL_TMA_BOX * RDDL_TMA_BOX) : 0);
       const size_t smem_static = smem - sizeof(uint32_t) * ((size_t)L.nregs * wpt * block + (size_t)(block - jit_block) * wpt);

@@ -47,7 +47,7 @@ _OPS = [
     # rejection / search samplers on a private Philox stream (flags = distribution id)
     'SAMPLE',
     # plane op the native library inserts for device-side policies with a max-nondef rule (never emitted here)
-    'PPOLSEL',
+    'PPOLSEL', 'PPOL',
 ]
 OP = {name: i for i, name in enumerate(_OPS)}
 

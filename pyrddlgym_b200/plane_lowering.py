@@ -190,6 +190,9 @@ class PlaneBuilder:
         # each is picked up right before its first use, so that the copy overlaps the fluent loads and
         # the work in between (and the plane's register is live for as short as possible)
         for c in reversed([o for o in self.ops if o['op'] == 'PLDC']):
+            if _os.environ.get('RDDL_PLDC_EARLY') == '1':       # experiment knob: non-fluent planes first
+                ops.insert(0, c)
+                continue
             first = len(ops)
             for i, o in enumerate(ops):
                 used = ([o['a']] if o['op'] in ('PST', 'PSHARE') else []) + (list(o['fin'][0].idx) if o['fin'] is not None else [])

@@ -13,15 +13,24 @@ place after the step -- only their rows of the state tensors are re-initialised,
 running -- and ``info['episode_return']`` / ``info['episode_length']`` carry the finished episodes'
 discounted return and length (NaN / 0 elsewhere). Observations are the state fluents (MDP) or the
 observ-fluents (POMDP, env.py:270-273).
+
+``action_bounds`` / ``observation_bounds``: name -> (lower, upper) device tensors of the fluent's shape,
+the box bounds RDDLEnv derives for its gym spaces from the preconditions and invariants
+(RDDLConstraints, constraints.py:107-229; env.py:152-193) -- computed once on the host
+(pyrddlgym_b200/constraints.py) and kept on the device; ``clip_actions=True`` clamps real / int actions
+into them before every step (what a Box space does for an RL library), ``random_policy()`` is the
+device-side RandomAgent over exactly these bounds.
 """
+import numpy as np
 import torch
 
+from pyrddlgym_b200.constraints import BoxBounds
 from pyrddlgym_b200.simulator import BatchedSimulator
 
 
 class BatchedRDDLEnv:
     def __init__(self, program, n_envs, device='cuda:0', seed=0, horizon=None, auto_reset=True,
-                 raise_on_status=False, **sim_kwargs):
+                 raise_on_status=False, clip_actions=False, max_bound=float('inf'), **sim_kwargs):
         self.sim = program if isinstance(program, BatchedSimulator) else BatchedSimulator(
             program, n_envs=n_envs, device=device, seed=seed, **sim_kwargs)
         self.program = self.sim.program
@@ -31,9 +40,14 @@ class BatchedRDDLEnv:
         self.discount = float(self.program.discount)
         self.auto_reset = bool(auto_reset)
         self.raise_on_status = bool(raise_on_status)
+        self.clip_actions = bool(clip_actions)
+        self.box = BoxBounds(self.program, max_bound=max_bound)
+        dev_bounds = self.box.to_device(self.device)
         observ = self.program.names_of_kind('observ')
         self.observation_names = list(observ) if observ else list(self.sim.state_names)
         self.action_names = list(self.sim.action_names)
+        self.action_bounds = {n: dev_bounds[n] for n in self.action_names}
+        self.observation_bounds = {n: dev_bounds[n] for n in self.observation_names if n in dev_bounds}
         N, dev = self.num_envs, self.device
         self.episode_step = torch.zeros(N, dtype=torch.int64, device=dev)
         self.episode_return = torch.zeros(N, dtype=torch.float64, device=dev)
@@ -58,6 +72,12 @@ class BatchedRDDLEnv:
         like RDDLEnv.step's partial action dicts)."""
         full = {name: self.sim._init[name].expand_as(self.sim._owned_actions[name]) for name in self.action_names}
         full.update(actions or {})
+        if self.clip_actions:
+            for name, v in list(full.items()):
+                if self.program.tensors[name].dtype != 'b':
+                    lo, hi = self.action_bounds[name]
+                    v = v if isinstance(v, torch.Tensor) else torch.as_tensor(v)
+                    full[name] = torch.clamp(v.to(self.device), min=lo.to(v.dtype), max=hi.to(v.dtype))
         _, reward, terminated = self.sim.step(full)
         reward = reward.clone()
         terminated = terminated.to(torch.bool).clone()
@@ -79,6 +99,21 @@ class BatchedRDDLEnv:
             self._disc = torch.where(ended, torch.ones_like(self._disc), self._disc)
             self.episode_step *= (~ended).to(torch.int64)
         return self._obs(), reward, terminated, truncated, info
+
+    def random_policy(self, p_bool=0.5, max_allowed_actions=None):
+        """RandomAgent over the box bounds (policy.py:129-178 samples the gym action space RDDLEnv builds
+        from them): a device-side ``RandomPolicy``. Needs finite bounds that are the same for every
+        grounding of a fluent (the device policy takes one range per fluent)."""
+        from pyrddlgym_b200.policy import RandomPolicy
+        bounds = {}
+        for name in self.action_names:
+            if self.program.tensors[name].dtype == 'b':
+                continue
+            lo, hi = self.box.bounds[name]
+            if not (np.isfinite(lo).all() and np.isfinite(hi).all()) or np.ptp(lo) != 0 or np.ptp(hi) != 0:
+                raise ValueError(f'<{name}>: bounds are not finite and uniform over its groundings')
+            bounds[name] = (float(np.asarray(lo).reshape(-1)[0]), float(np.asarray(hi).reshape(-1)[0]))
+        return RandomPolicy(bounds=bounds, p_bool=p_bool, max_allowed_actions=max_allowed_actions)
 
     def close(self):
         self.sim.close()
