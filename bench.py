@@ -555,6 +555,30 @@ def bench_workload(name, args, world, rank, dev, K, W, Ke, sampler=None, want_st
         tc_sim.native.profile(False)
         tc_us = [1e3 * r['ms'] / r['count'] for r in prof_tc if r['name'] == 'rddl_contract_f64']
         f64_us = [1e3 * r['ms'] / r['count'] for r in prof if r['name'] == 'rddl_contract_f64']
+
+        def graph_step_us(s):
+            # whole transitions (contraction + the scalar launches behind it) replayed from a CUDA graph: the
+            # per-launch events above include the host's launch latency between the two kernels of the
+            # tcgen05 path, a graph does not
+            try:
+                s.reset()
+                torch.cuda.synchronize()
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    s.rollout(seq, R, gamma=gamma)
+                for _ in range(3):
+                    gr.replay()
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record()
+                for _ in range(5):
+                    gr.replay()
+                g1.record()
+                torch.cuda.synchronize()
+                return 1e3 * g0.elapsed_time(g1) / (5 * R)
+            except Exception:
+                torch.cuda.synchronize()
+                return None
+        step_us = {'f64': graph_step_us(sim), 'bf16x3': graph_step_us(tc_sim)}
         bf16_peak = float(peaks.get('bf16_tflops', 1657.2))
         roofline['tensor'] = {
             'flops_per_launch': flops,
@@ -567,7 +591,10 @@ def bench_workload(name, args, world, rank, dev, K, W, Ke, sampler=None, want_st
                                'tflops_issued': 6 * flops / (tc_us[0] * 1e-6) / 1e12 if tc_us else None,
                                'peak_bf16_tflops': bf16_peak,
                                'frac_of_bf16_peak': 6 * flops / (tc_us[0] * 1e-6) / 1e12 / bf16_peak if tc_us else None},
-            'note': 'selected by BatchedSimulator(contract_precision=...): f64 (default, exact products) | bf16x3 (1e-5)'}
+            'transition_us_graph_replay': step_us,
+            'note': 'selected by BatchedSimulator(contract_precision=...): f64 (default, exact products) | bf16x3 (1e-5). '
+                    'kernel_us: CUDA events around the launch(es) of the contraction, issued eagerly; '
+                    'transition_us_graph_replay: the whole transition (contraction + scalar launches) replayed from a CUDA graph'}
         tc_sim.close()
         del tc_sim
     del seq

@@ -380,6 +380,12 @@ static bool jit_compile(const std::string& data, const char* data_name, const ch
   snprintf(name, sizeof name, "/%s_%016llx.cubin", prefix, (unsigned long long)h);
   const std::string path = cache_dir + name;
   if (cache_hit) *cache_hit = false;
+  if (const char* dump = getenv("RDDL_B200_JIT_DUMP")) {
+    // offline inspection (nvcc -cubin / cuobjdump -sass of the specialised source): <dir>/<prefix>_<hash>.inc
+    snprintf(name, sizeof name, "/%s_%016llx.inc", prefix, (unsigned long long)h);
+    if (FILE* f = fopen((std::string(dump) + name).c_str(), "wb")) { fwrite(data.data(), 1, data.size(), f); fclose(f); }
+    snprintf(name, sizeof name, "/%s_%016llx.cubin", prefix, (unsigned long long)h);
+  }
   if (jit_read_file(path, cubin) && cubin->size() > 64) {
     if (cache_hit) *cache_hit = true;
     return true;

@@ -114,10 +114,12 @@ struct rddl_program {
   int pool_map_ok = 0;
   int64_t pool_len = 0;
   int contract_tc = 0;
-  struct TcWeights { const void* W; int N, K; int64_t sk, sn; __nv_bfloat16* Wb; int Np, Kp; CUtensorMap map; };
+  struct TcWeights { const void* W; int N, K; int64_t sk, sn; __nv_bfloat16* Wb; int Np, Kp, bn; CUtensorMap map; };
   std::vector<TcWeights> tc_w;
   __nv_bfloat16* d_xb = nullptr;
   int64_t xb_capacity = 0;
+  CUtensorMap xb_map;                     // tensor map of d_xb for the padded shape (xb_map_rows, xb_map_k)
+  int64_t xb_map_rows = 0, xb_map_k = 0;
   // run-time specialised plane kernels (rddl_jit.h), built on first use per (launch, tile geometry)
   bool specialize = true;
   std::vector<RddlInsn> h_insns;          // host copies for the specialised epilogue (rddl_jit.h)
@@ -927,54 +929,75 @@ static const rddl_program::PolicyProg* policy_prog(rddl_program* g, int li, cons
 // ---------------------------------------------------------------------------------------
 // tcgen05 contraction (rddl_contract_tc.cuh): tensor maps + launches
 // ---------------------------------------------------------------------------------------
-// Tensor map over the split layout [term][K/8][rows][8] (bf16): dims (fastest first) 8, rows, K/8, 3.
+// Tensor map over the split layout [term][rows][K] (bf16): dims (fastest first) K, rows, 3; boxes of
+// 64 k x box_rows rows x 1 term land in shared memory in the 128-byte-swizzled K-major layout.
 static bool tc_make_map(CUtensorMap* map, void* base, int rows_p, int Kp, int box_rows) {
   TcEncodeFn enc = tc_encode_fn();
   if (!enc) return false;
-  const cuuint64_t dims[4] = {8, (cuuint64_t)rows_p, (cuuint64_t)(Kp / 8), 3};
-  const cuuint64_t strides[3] = {16, (cuuint64_t)rows_p * 16, (cuuint64_t)rows_p * (cuuint64_t)Kp * 2};
-  const cuuint32_t box[4] = {8, (cuuint32_t)box_rows, TC_BK / 8, 1};
-  const cuuint32_t estr[4] = {1, 1, 1, 1};
-  return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  const cuuint64_t dims[3] = {(cuuint64_t)Kp, (cuuint64_t)rows_p, 3};
+  const cuuint64_t strides[2] = {(cuuint64_t)Kp * 2, (cuuint64_t)rows_p * (cuuint64_t)Kp * 2};
+  const cuuint32_t box[3] = {TC_BK, (cuuint32_t)box_rows, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 static int run_contract_tc(rddl_program* g, const double* W, const double* x, double* out, int64_t n_envs, int N, int K,
                            int64_t sk, int64_t sn, cudaStream_t stream) {
   std::string* errp = &g->err;
   const int Kp = (K + TC_BK - 1) / TC_BK * TC_BK;
+  const int64_t Mp = (n_envs + TC_BM - 1) / TC_BM * TC_BM;
+  // N tile: 64 columns, or 32 when the 64-column grid would leave SMs without a CTA (RDDL_CONTRACT_TC_BN overrides)
+  int bn = ((int64_t)((N + 63) / 64) * (Mp / TC_BM) < 148) ? 32 : 64;
+  if (const char* e = getenv("RDDL_CONTRACT_TC_BN")) bn = atoi(e) == 32 ? 32 : 64;
   rddl_program::TcWeights* tw = nullptr;
   for (auto& w : g->tc_w)
-    if (w.W == W && w.N == N && w.K == K && w.sk == sk && w.sn == sn) tw = &w;
+    if (w.W == W && w.N == N && w.K == K && w.sk == sk && w.sn == sn && w.bn == bn) tw = &w;
   if (!tw) {
     rddl_program::TcWeights w;
     memset(&w, 0, sizeof w);
-    w.W = W; w.N = N; w.K = K; w.sk = sk; w.sn = sn;
-    w.Np = (N + TC_BN - 1) / TC_BN * TC_BN; w.Kp = Kp;
+    w.W = W; w.N = N; w.K = K; w.sk = sk; w.sn = sn; w.bn = bn;
+    w.Np = (N + TC_BN_MAX - 1) / TC_BN_MAX * TC_BN_MAX; w.Kp = Kp;
     CK(cudaMalloc((void**)&w.Wb, (size_t)3 * w.Np * w.Kp * sizeof(__nv_bfloat16)));
     const int64_t n = (int64_t)w.Np * (w.Kp / 8);
     rddl_tc_split<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(W, sn, sk, N, K, w.Np, w.Kp, w.Wb);   // B(n, k) = W(k, n)
     CK(cudaGetLastError());
-    if (!tc_make_map(&w.map, w.Wb, w.Np, w.Kp, TC_BN)) { cudaFree(w.Wb); g->err = "cuTensorMapEncodeTiled failed (W)"; return RDDL_ERR_CUDA; }
+    if (!tc_make_map(&w.map, w.Wb, w.Np, w.Kp, bn)) { cudaFree(w.Wb); g->err = "cuTensorMapEncodeTiled failed (W)"; return RDDL_ERR_CUDA; }
     g->tc_w.push_back(w);
     tw = &g->tc_w.back();
-    CK(cudaFuncSetAttribute((const void*)rddl_contract_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    CK(cudaFuncSetAttribute((const void*)rddl_contract_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES(32)));
+    CK(cudaFuncSetAttribute((const void*)rddl_contract_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES(64)));
   }
-  const int64_t Mp = (n_envs + TC_BM - 1) / TC_BM * TC_BM;
   if (g->xb_capacity < 3 * Mp * Kp) {
     CK(cudaStreamSynchronize(stream));
     cudaFree(g->d_xb);
     g->d_xb = nullptr;
     CK(cudaMalloc((void**)&g->d_xb, (size_t)(3 * Mp * Kp) * sizeof(__nv_bfloat16)));
     g->xb_capacity = 3 * Mp * Kp;
+    g->xb_map_rows = 0;
   }
-  CUtensorMap map_x;
-  if (!tc_make_map(&map_x, g->d_xb, (int)Mp, Kp, TC_BM)) { g->err = "cuTensorMapEncodeTiled failed (x)"; return RDDL_ERR_CUDA; }
+  if (g->xb_map_rows != Mp || g->xb_map_k != Kp) {      // the x tensor map only depends on the buffer and its padded shape
+    if (!tc_make_map(&g->xb_map, g->d_xb, (int)Mp, Kp, TC_BM)) { g->err = "cuTensorMapEncodeTiled failed (x)"; return RDDL_ERR_CUDA; }
+    g->xb_map_rows = Mp; g->xb_map_k = Kp;
+  }
   const int64_t n = Mp * (Kp / 8);
   rddl_tc_split<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(x, K, 1, n_envs, K, Mp, Kp, g->d_xb);
   CK(cudaGetLastError());
-  dim3 grid((unsigned)(tw->Np / TC_BN), (unsigned)(Mp / TC_BM));
-  rddl_contract_tc<<<grid, 128, TC_SMEM_BYTES, stream>>>(map_x, tw->map, out, n_envs, N, Kp / TC_BK);
+  // launched as a programmatic dependent of the split: its prologue overlaps the split's execution
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3((unsigned)((N + bn - 1) / bn), (unsigned)(Mp / TC_BM));
+  cfg.blockDim = dim3(128);
+  cfg.dynamicSmemBytes = bn == 32 ? TC_SMEM_BYTES(32) : TC_SMEM_BYTES(64);
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  const int nkb = Kp / TC_BK;
+  if (bn == 32) CK(cudaLaunchKernelEx(&cfg, rddl_contract_tc<32>, g->xb_map, tw->map, out, n_envs, N, nkb));
+  else CK(cudaLaunchKernelEx(&cfg, rddl_contract_tc<64>, g->xb_map, tw->map, out, n_envs, N, nkb));
   CK(cudaGetLastError());
   g->launches_issued += 1;     // (the caller counts the contraction launch itself)
   return RDDL_OK;
