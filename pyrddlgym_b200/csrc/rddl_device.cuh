@@ -233,6 +233,7 @@ struct VmPools {
   const int64_t* red_off;
   const RddlCsr* csrs;
   const uint8_t* dtype;      // per tensor id
+  const uint8_t* may_policy; // per tensor id: may a device-side policy drive it (null: not known here -- ask the descriptor)
 };
 
 // A per-env tensor slice staged in shared memory by the CTA (specialised scalar kernels whose CTA
@@ -299,7 +300,7 @@ __device__ __forceinline__ void vm_exec_one(const VmArgs& A, const VmPools& P, c
       }
       const int t = ad->tensor;
       if (op == OP_LOAD) {
-        if (A.pol.n > 0 && t >= 0 && A.pol.of_tensor[t]) {
+        if (A.pol.n > 0 && t >= 0 && (!P.may_policy || P.may_policy[t]) && A.pol.of_tensor[t]) {
           // action fluent under a device-side policy: drawn here instead of read from HBM
           r[dst] = rddl_policy_value(A.pol, A.pol.e[A.pol.of_tensor[t] - 1], A.seed, (uint64_t)(A.env_offset + env), step,
                                      off, A.pol.sel + env * A.pol.k);
@@ -329,7 +330,9 @@ __device__ __forceinline__ void vm_exec_one(const VmArgs& A, const VmPools& P, c
           uint4 x = rddl_philox_draw(A.seed, (uint64_t)(A.env_offset + env), step, node, (uint64_t)off);
           const double u = rddl_u53(x.x, x.y);
           if (op == OP_RANDU) v = u;
-          else if (op == OP_RANDN) v = sqrt(-2.0 * log(1.0 - u)) * cos(2.0 * 3.141592653589793 * rddl_u53(x.z, x.w));
+          // cospi(2 u): the cosine of Box-Muller without the argument reduction of cos(2 pi u) (no Payne-Hanek
+          // path, no stack slot for its quadrant); equal to it within a few ulp of 1
+          else if (op == OP_RANDN) v = sqrt(-2.0 * log(1.0 - u)) * cospi(2.0 * rddl_u53(x.z, x.w));
           else if (op == OP_RANDE) v = -log1p(-u);
           else v = tan(3.141592653589793 * (u - 0.5));
         }
@@ -505,6 +508,7 @@ __device__ __forceinline__ void vm_exec_one(const VmArgs& A, const VmPools& P, c
       }
       int32_t j0 = 0, j1 = (int32_t)arg;
       const int32_t* cols = nullptr;
+      int64_t cs_col_off = 0;
       if (is_csr) {
         const RddlCsr* cs = P.csrs + arg;
         int64_t row = cs->row_c0;
@@ -512,6 +516,7 @@ __device__ __forceinline__ void vm_exec_one(const VmArgs& A, const VmPools& P, c
         j0 = __ldg(A.pool + cs->rowptr_off + row);
         j1 = __ldg(A.pool + cs->rowptr_off + row + 1);
         cols = A.pool + cs->col_off[0];
+        cs_col_off = cs->col_off[0];
       }
       if (stage && is_csr && !two && flt && (P.addrs + imm)->tensor == stage->tensor && dts[0] == DT_REAL) {
         // sparse float sum of a per-env vector staged in shared memory (fused env-tile kernels): 32-bit
@@ -523,13 +528,23 @@ __device__ __forceinline__ void vm_exec_one(const VmArgs& A, const VmPools& P, c
         // terms with the next batch's indices prefetched 233 us -- more registers, fewer resident warps)
         double acc = 0.0;
         int32_t j = j0;
+        // the column indices of the row are read four at a time (one 128-bit load: the pool is 256-byte aligned,
+        // so cols + j is 16-byte aligned when (col_off + j) % 4 == 0) after up to three single reads: the lanes
+        // of a warp work on 8 different rows, i.e. every index load is 8 sectors through the L1 data pipe --
+        // ncu showed that pipe 59 % busy with 21 single-index loads per element (Reservoir R = 1000)
+        const int32_t jh = min(j1, j + (int32_t)((4u - (uint32_t)((cs_col_off + j) & 3)) & 3u));
+        for (; j < jh; ++j) {
+          double v;
+          asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(s0 + (uint32_t)(sk * __ldg(cols + j))));
+          acc = __dadd_rn(acc, v);
+        }
         for (; j + 4 <= j1; j += 4) {
-          const int32_t c0 = __ldg(cols + j), c1 = __ldg(cols + j + 1), c2 = __ldg(cols + j + 2), c3 = __ldg(cols + j + 3);
+          const int4 c = __ldg(reinterpret_cast<const int4*>(cols + j));
           double v0, v1, v2, v3;
-          asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v0) : "r"(s0 + (uint32_t)(sk * c0)));
-          asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v1) : "r"(s0 + (uint32_t)(sk * c1)));
-          asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v2) : "r"(s0 + (uint32_t)(sk * c2)));
-          asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v3) : "r"(s0 + (uint32_t)(sk * c3)));
+          asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v0) : "r"(s0 + (uint32_t)(sk * c.x)));
+          asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v1) : "r"(s0 + (uint32_t)(sk * c.y)));
+          asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v2) : "r"(s0 + (uint32_t)(sk * c.z)));
+          asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v3) : "r"(s0 + (uint32_t)(sk * c.w)));
           acc = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(acc, v0), v1), v2), v3);
         }
         for (; j < j1; ++j) {

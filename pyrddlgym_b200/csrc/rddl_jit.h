@@ -61,6 +61,7 @@ struct JitPools {
   const RddlRedSlot* redslots; int64_t n_redslots;
   const int64_t* red_off;
   const RddlCsr* csrs; int64_t n_csrs;
+  const uint8_t* may_policy;      // [RDDL_MAX_TENSORS]: tensors a device-side policy may drive (action fluents)
 };
 
 // The scalar programs fused into a plane launch's epilogue (reward / termination from the
@@ -165,7 +166,12 @@ static std::string level_static_data(const JitPools& P, const RddlLaunch* launch
       if (j > i && gathers) fused += jit_fmt(" X(%lld,", i) + jit_fmt("%lld)", j - i + 1);
       i = j + 1;
     }
-    if (!fused.empty()) s += "#define PS_FUSED(X)" + fused + "\n" + jit_fmt("#define FUSE_TE %lld\n", RDDL_FUSE_TE);
+    if (!fused.empty()) {
+      s += "#define PS_FUSED(X)" + fused + "\n" + jit_fmt("#define FUSE_TE %lld\n", RDDL_FUSE_TE);
+      // resident CTAs per SM the fused kernels are compiled for (4 = 64 registers; experiments: RDDL_FUSE_MINB)
+      const char* mb = getenv("RDDL_FUSE_MINB");
+      s += jit_fmt("#define FUSE_MINB %lld\n", mb && atoi(mb) > 0 ? atoi(mb) : 4);
+    }
   }
   s += "__device__ constexpr uint32_t kInsnWords[][4] = {";
   for (int64_t pc = 0; pc < P.n_insns; ++pc) {
@@ -213,6 +219,8 @@ static std::string level_static_data(const JitPools& P, const RddlLaunch* launch
   for (int i = 0; i < n_launches; ++i) { jit_launch_init(s, launches[i]); s += ",\n"; }
   s += "};\n__device__ constexpr uint8_t kDT[RDDL_MAX_TENSORS] = {";
   for (int i = 0; i < RDDL_MAX_TENSORS; ++i) s += jit_fmt("%lld,", dtype[i]);
+  s += "};\n__device__ constexpr uint8_t kMayPolicy[RDDL_MAX_TENSORS] = {";
+  for (int i = 0; i < RDDL_MAX_TENSORS; ++i) s += jit_fmt("%lld,", P.may_policy ? P.may_policy[i] : 1);
   s += "};\n";
   return s;
 }

@@ -18,7 +18,61 @@ struct VmStaticCtx {
   uint64_t* redval;
   uint64_t* r;
   const VmStage* stage;
+  uint64_t* pre;        // values of the launch's preloaded LOADs (vm_preload), or null
 };
+
+// Preloaded LOADs. A launch's program reads its fluents one LOAD at a time, each immediately before its
+// first use (and, in the generic instruction body, behind the branch that separates policy-drawn action
+// fluents from stored ones), so an element pays one full memory latency per fluent, back to back -- ncu on
+// Reservoir R = 1000: 9 long-scoreboard stalls per issued instruction, one per LOAD. The LOADs whose address
+// depends on nothing but the element's scope coordinates -- outside every loop, no index registers, tensor
+// not stored earlier in the same launch -- are therefore all issued up front (vm_preload: one batch of
+// independent loads, one latency), and the program picks the values up from registers where it would have
+// loaded them. Same loads, same values; only their place in the instruction stream changes.
+constexpr int kMaxPreload = 12;
+constexpr int kNumInsn = (int)(sizeof(kInsnWords) / sizeof(kInsnWords[0]));
+constexpr int kNumLaunch = (int)(sizeof(kLaunches) / sizeof(kLaunches[0]));
+__host__ __device__ constexpr int level_insn_len(int pc) { return (kInsnWords[pc][0] & 0xff) == OP_SUMLOOP ? 2 : 1; }
+struct LevelPreTable { signed char slot[kNumInsn]; };      // per instruction: preload slot of an eligible LOAD, or -1
+__host__ __device__ constexpr LevelPreTable level_make_pre() {
+  LevelPreTable t{};
+  for (int i = 0; i < kNumInsn; ++i) t.slot[i] = -1;
+  for (int li = 0; li < kNumLaunch; ++li) {
+    bool stored[RDDL_MAX_TENSORS] = {};
+    int depth = 0, n = 0;
+    for (int q = kLaunches[li].pc_begin; q < kLaunches[li].pc_end && q < kNumInsn; q += level_insn_len(q)) {
+      const uint32_t o = kInsnWords[q][0] & 0xff;
+      if (o == OP_LOOP || o == OP_CSRLOOP) ++depth;
+      if (o == OP_ENDLOOP || o == OP_CSREND) --depth;
+      if (o != OP_LOAD && o != OP_STORE) continue;
+      const RddlAddr& ad = kAddrs[kInsnWords[q][3]];
+      if (ad.tensor < 0 || ad.tensor >= RDDL_MAX_TENSORS) continue;
+      if (o == OP_STORE) { stored[ad.tensor] = true; continue; }
+      if (depth == 0 && ad.nreg == 0 && !stored[ad.tensor] && n < kMaxPreload) t.slot[q] = (signed char)n++;
+    }
+  }
+  return t;
+}
+__device__ constexpr LevelPreTable kPre = level_make_pre();
+__host__ __device__ constexpr bool level_preload_ok(int base, int pc) { return kPre.slot[pc] >= 0; }
+__host__ __device__ constexpr int level_preload_slot(int base, int pc) { return kPre.slot[pc]; }
+
+template <int BASE, int PC, int END>
+__device__ __forceinline__ void vm_preload(VmStaticCtx& c) {
+  if constexpr (PC < END) {
+    if constexpr (level_preload_ok(BASE, PC)) {
+      constexpr uint4 raw = {kInsnWords[PC][0], kInsnWords[PC][1], kInsnWords[PC][2], kInsnWords[PC][3]};
+      const VmPools P = {kConsts, kAddrs, kRedSlots, kRedOff, kCsrs, kDT, kMayPolicy};
+      int pc = 0;
+      // (the LOAD's own instruction body, into its destination register -- dead at this point of the program --
+      // and from there into the preload slot)
+      vm_exec_one<RDDL_MAX_REGS, (int)OP_LOAD>(c.A, P, c.L, c.env, c.step, c.idx, c.redval, c.r, nullptr, nullptr, nullptr, pc,
+                                               raw, nullptr, 0);
+      c.pre[level_preload_slot(BASE, PC)] = c.r[raw.x >> 16];
+    }
+    vm_preload<BASE, PC + level_insn_len(PC), END>(c);
+  }
+}
 
 // Shared-memory staging of a gathered vector: when a launch's CTA works on one env (G = 256) and its
 // program sums real values of a per-env tensor through a CSR list (SUMLOOP), the CTA first copies that
@@ -54,7 +108,7 @@ __device__ __forceinline__ void vm_seq(VmStaticCtx& c) {
   if constexpr (PC < END) {
     constexpr uint4 raw = {kInsnWords[PC][0], kInsnWords[PC][1], kInsnWords[PC][2], kInsnWords[PC][3]};
     constexpr uint32_t op = raw.x & 0xff, ra = raw.y & 0xffff, rb = raw.y >> 16, imm = raw.w;
-    const VmPools P = {kConsts, kAddrs, kRedSlots, kRedOff, kCsrs, kDT};
+    const VmPools P = {kConsts, kAddrs, kRedSlots, kRedOff, kCsrs, kDT, kMayPolicy};
     if constexpr (op == OP_LOOP) {
       // dense loop over axis slot ra, extent imm; rb = pc after the matching ENDLOOP
       constexpr int AFTER = BASE + (int)rb;
@@ -76,6 +130,15 @@ __device__ __forceinline__ void vm_seq(VmStaticCtx& c) {
         vm_seq<BASE, PC + 1, AFTER - 1>(c);
       }
       vm_seq<BASE, AFTER, END>(c);
+    } else if constexpr (op == OP_LOAD && level_preload_ok(BASE, PC)) {
+      if (c.pre) {
+        c.r[raw.x >> 16] = c.pre[level_preload_slot(BASE, PC)];
+      } else {
+        int pc = 0;
+        vm_exec_one<RDDL_MAX_REGS, (int)op>(c.A, P, c.L, c.env, c.step, c.idx, c.redval, c.r, nullptr, nullptr, nullptr, pc, raw,
+                                   nullptr, 0);
+      }
+      vm_seq<BASE, PC + 1, END>(c);
     } else if constexpr (op == OP_SUMLOOP) {
       constexpr uint4 raw2 = {kInsnWords[PC + 1][0], kInsnWords[PC + 1][1], kInsnWords[PC + 1][2], kInsnWords[PC + 1][3]};
       int pc = 0;
@@ -99,7 +162,9 @@ struct LevelStaticExec {
     uint64_t r[kLaunches[LI].nregs > 0 ? kLaunches[LI].nregs : 1];
     VmStage st = {nullptr, -1, 0, 1, 0};
     if (stage) { st = *stage; st.base = env * level_stage_elems(LI); }
-    VmStaticCtx c = {A, kLaunches[LI], env, A.step, idx, redval, r, stage ? &st : nullptr};
+    uint64_t pre[kMaxPreload];
+    VmStaticCtx c = {A, kLaunches[LI], env, A.step, idx, redval, r, stage ? &st : nullptr, pre};
+    vm_preload<kLaunches[LI].pc_begin, kLaunches[LI].pc_begin, kLaunches[LI].pc_end>(c);
     vm_seq<kLaunches[LI].pc_begin, kLaunches[LI].pc_begin, kLaunches[LI].pc_end>(c);
   }
 };
@@ -146,6 +211,9 @@ __device__ __forceinline__ void level_static_kernel(const VmArgs& A) {
 // ---------------------------------------------------------------------------------------
 #ifndef FUSE_TE
 #define FUSE_TE 4
+#endif
+#ifndef FUSE_MINB
+#define FUSE_MINB 4
 #endif
 constexpr int kFuseMaxStage = 5632;      // doubles of shared memory for the staged gather operand (44 KB)
 
@@ -202,7 +270,9 @@ __device__ __forceinline__ void fused_phase(const VmArgs& A, double* staged, uin
         }
       }
       uint64_t r[L.nregs > 0 ? L.nregs : 1];
-      VmStaticCtx c = {A, kLaunches[LI], env, A.step, idx, redval, r, st.tensor >= 0 ? &st : nullptr};
+      uint64_t pre[kMaxPreload];
+      VmStaticCtx c = {A, kLaunches[LI], env, A.step, idx, redval, r, st.tensor >= 0 ? &st : nullptr, pre};
+      vm_preload<L.pc_begin, L.pc_begin, L.pc_end>(c);
       vm_seq<L.pc_begin, L.pc_begin, L.pc_end>(c);
     }
   }
@@ -248,7 +318,7 @@ __host__ __device__ constexpr int64_t fuse_group_stage(int first, int count) {
 }
 
 #define RDDL_FUSED_KERNEL(FIRST, COUNT)                                                                          \
-  extern "C" __global__ void __launch_bounds__(256) rddl_level_fused_##FIRST(const __grid_constant__ VmArgs A) { \
+  extern "C" __global__ void __launch_bounds__(256, FUSE_MINB) rddl_level_fused_##FIRST(const __grid_constant__ VmArgs A) { \
     __shared__ double staged[fuse_group_stage(FIRST, COUNT)];                                                    \
     __shared__ uint64_t sm[RDDL_MAX_RED][8][FUSE_TE];                                                             \
     fused_phases<FIRST, COUNT>(A, staged, sm);                                                                   \

@@ -131,10 +131,14 @@ struct rddl_program {
     for (size_t i = 0; i < tensors.size(); ++i) d[i] = (uint8_t)tensors[i].dtype;
     return d;
   }
+  // tensors a device-side policy may drive (= action fluents as far as the op table shows: per-env, not
+  // one half of a state pair, never written by the program); the specialised kernels compile the policy
+  // draw into the LOADs of these tensors only
+  std::vector<uint8_t> may_policy;
   JitPools pools() const {
     return JitPools{h_insns.data(), (int64_t)h_insns.size(), h_consts.data(), (int64_t)h_consts.size(),
                     h_addrs.data(), (int64_t)h_addrs.size(), redslots.data(), (int64_t)redslots.size(), red_off.data(),
-                    h_csrs.data(), (int64_t)h_csrs.size()};
+                    h_csrs.data(), (int64_t)h_csrs.size(), may_policy.data()};
   }
   // specialised scalar kernels (rddl_level_static.cuh): one module per program, built once the
   // program has issued `level_hot` scalar launches (tiered: short-lived programs never pay for it)
@@ -539,6 +543,29 @@ static int parse_program(const void* optable, size_t nbytes, int device, rddl_pr
       }
     }
   }
+  g->may_policy.assign(RDDL_MAX_TENSORS, 0);
+  for (int t = 0; t < reward_tensor && t < RDDL_MAX_TENSORS; ++t)
+    g->may_policy[(size_t)t] = g->tensors[(size_t)t].kind == KIND_ENV && g->tensors[(size_t)t].pair < 0;
+  for (auto& tt : g->tensors)        // (primed partners of state fluents)
+    if (tt.pair >= 0 && tt.pair < RDDL_MAX_TENSORS) g->may_policy[(size_t)tt.pair] = 0;
+  for (size_t li = 0; li < g->launches.size(); ++li) {
+    const RddlLaunch& L = g->launches[li];
+    if (L.kind == 3) { if (L.red_slot[2] >= 0 && L.red_slot[2] < RDDL_MAX_TENSORS) g->may_policy[(size_t)L.red_slot[2]] = 0; continue; }
+    if (L.kind == 1) {
+      const PlaneProg& G = g->plane_progs[li];
+      for (int a = 0; a < G.nops; ++a)
+        if (G.ops[a].op == OP_PST && G.ops[a].imm < RDDL_MAX_TENSORS) g->may_policy[G.ops[a].imm] = 0;
+      continue;
+    }
+    for (int pc = L.pc_begin; pc < L.pc_end; ++pc) {
+      const RddlInsn& in = g->h_insns[pc];
+      if (in.op == OP_SUMLOOP) { ++pc; continue; }
+      if (in.op == OP_STORE && in.imm < g->h_addrs.size()) {
+        const int t = g->h_addrs[in.imm].tensor;
+        if (t >= 0 && t < RDDL_MAX_TENSORS) g->may_policy[(size_t)t] = 0;
+      }
+    }
+  }
   for (int i = 0; i < 9; ++i) secs[i] = sec[i];
   memcpy(hdr_out, hdr, sizeof hdr);
   *out = g;
@@ -793,7 +820,8 @@ static int make_policy(rddl_program* g, const rddl_policy_t* P, VmPolicy* out) {
   for (int i = 0; i < P->n_entries; ++i) {
     const rddl_policy_entry_t& pe = P->entries[i];
     VmPolicyEntry& e = out->e[i];
-    if (pe.tensor < 0 || pe.tensor >= n_user || g->tensors[pe.tensor].kind != KIND_ENV || out->of_tensor[pe.tensor]) {
+    if (pe.tensor < 0 || pe.tensor >= n_user || pe.tensor >= RDDL_MAX_TENSORS || !g->may_policy[(size_t)pe.tensor] ||
+        out->of_tensor[pe.tensor]) {
       g->err = "policy: entry does not name an action tensor (or names one twice)";
       return RDDL_ERR_ARG;
     }

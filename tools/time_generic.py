@@ -8,7 +8,7 @@ name, size, N, K = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv
 spec = {'reservoir': lambda: workloads.reservoir(size), 'reservoir_exp': lambda: workloads.reservoir(size, rain='exponential'),
         'pair': lambda: workloads.pair_contraction(size), 'cartpole': lambda: workloads.cartpole()}[name]()
 p = workloads.load_program(spec)
-sim = BatchedSimulator(p, n_envs=N, seed=1)
+sim = BatchedSimulator(p, n_envs=N, seed=1, specialize=True)
 print([(l['kernel'], l['scope'], l['n_insns'], l['nregs']) for l in sim.table.launches if l['plan'] == 0])
 g = torch.Generator(device='cuda').manual_seed(0)
 acts = {}
