@@ -50,21 +50,28 @@ def _u53(a, b):
 
 def base_variates(kind, seed, env_ids, step, node_id, scope_shape):
     """Base variates of ``kind`` ('U','N','E','C') for every (env, scope element).
-    Returns float64 array of shape [len(env_ids), *scope_shape]."""
+    Returns float64 array of shape [len(env_ids), *scope_shape].
+
+    Normals come in Box-Muller pairs: elements 2q and 2q + 1 share the Philox block of counter q and take the
+    cosine and the sine branch (csrc/rddl_device.cuh: rddl_randn) -- the fused scalar kernels compute both
+    from one logarithm and one square root."""
     n_elem = int(np.prod(scope_shape, dtype=np.int64)) if len(scope_shape) else 1
     elem = np.arange(n_elem, dtype=np.uint64)
+    ctr = elem >> np.uint64(1) if kind == 'N' else elem
     env = np.asarray(env_ids, dtype=np.uint64)[:, None]
-    c0 = (elem & MASK).astype(np.uint32)[None, :]
+    c0 = (ctr & MASK).astype(np.uint32)[None, :]
     c1 = (env & MASK).astype(np.uint32)
     c2 = np.uint32(step & 0xFFFFFFFF)
-    c3 = (np.uint64(node_id & 0xFFFF) | ((elem >> np.uint64(32)) << np.uint64(16))).astype(np.uint32)[None, :]
+    c3 = (np.uint64(node_id & 0xFFFF) | ((ctr >> np.uint64(32)) << np.uint64(16))).astype(np.uint32)[None, :]
     r0, r1, r2, r3 = philox4x32_10(c0, c1, c2, c3, seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
     u = _u53(r0, r1)
     if kind == 'U':
         out = u
     elif kind == 'N':
         u2 = _u53(r2, r3)
-        out = np.sqrt(-2.0 * np.log(1.0 - u)) * np.cos(2.0 * np.pi * u2)
+        rad = np.sqrt(-2.0 * np.log(1.0 - u))
+        odd = (elem & np.uint64(1)).astype(bool)[None, :]
+        out = rad * np.where(odd, np.sin(2.0 * np.pi * u2), np.cos(2.0 * np.pi * u2))
     elif kind == 'E':
         out = -np.log1p(-u)
     elif kind == 'C':

@@ -129,12 +129,11 @@ __device__ __forceinline__ uint64_t red_identity(int op) {
   }
 }
 
-__device__ __forceinline__ double np_fmin(double a, double b) {
-  return (isnan(a) || isnan(b)) ? NAN : fmin(a, b);
-}
-__device__ __forceinline__ double np_fmax(double a, double b) {
-  return (isnan(a) || isnan(b)) ? NAN : fmax(a, b);
-}
+// np.minimum / np.maximum: a NaN in either operand propagates. (a < b || a != a) ? a : b is the expression of
+// NumPy's own loops: a NaN `a` is taken by the second test, a NaN `b` because the comparison is false. Two DSETP
+// + four FSEL, against 13 instructions for the fmin() + isnan() form (no f64 min / max instruction on sm_100).
+__device__ __forceinline__ double np_fmin(double a, double b) { return (a < b || a != a) ? a : b; }
+__device__ __forceinline__ double np_fmax(double a, double b) { return (a > b || a != a) ? a : b; }
 
 __device__ __forceinline__ uint64_t red_combine(int op, uint64_t a, uint64_t b) {
   switch (op) {
@@ -224,6 +223,21 @@ __device__ __forceinline__ uint64_t rddl_policy_value(const VmPolicy& pol, const
   return (uint64_t)(v > hi ? hi : v);
 }
 
+// Standard normals of elements 2q and 2q + 1 of a variate: the two branches of one Box-Muller transform of the
+// Philox block of counter q -- z0 = R cos(2 pi u2), z1 = R sin(2 pi u2), R = sqrt(-2 ln(1 - u1)). A kernel whose
+// thread owns both elements (fused env-tile kernels, rddl_level_static.cuh) pays for one block, one logarithm and
+// one square root per pair; thread-per-element kernels compute the pair and keep their branch (same bits).
+// sincospi(2 u): no argument reduction of 2 pi u (no Payne-Hanek path, no stack slot for its quadrant).
+__device__ __forceinline__ void rddl_randn_pair(uint64_t seed, uint64_t env, uint64_t step, uint32_t node, uint64_t q,
+                                                double* z0, double* z1) {
+  const uint4 x = rddl_philox_draw(seed, env, step, node, q);
+  const double rad = sqrt(-2.0 * log(1.0 - rddl_u53(x.x, x.y)));
+  double sn, cs;
+  sincospi(2.0 * rddl_u53(x.z, x.w), &sn, &cs);
+  *z0 = rad * cs;
+  *z1 = rad * sn;
+}
+
 // The constant / address-descriptor / reduction-slot pools a program executes from: device copies
 // of the op table (interpreter) or the constants of a specialised build.
 struct VmPools {
@@ -243,6 +257,7 @@ struct VmStage {
   int tensor;
   int64_t base;
   int mul, add;     // staged index of element offset o (relative to base) = o * mul + add  (env-tiled staging: mul = envs per tile)
+  int pad;          // 1: the staged slice is followed by one zero per env (element index = slice length): padded CSR rows
 };
 
 // One instruction (raw = its four 32-bit words) of the program of launch L for one (env, element):
@@ -327,14 +342,18 @@ __device__ __forceinline__ void vm_exec_one(const VmArgs& A, const VmPools& P, c
           v = inj[env * ad->env_stride + off];
         } else {
           const uint32_t node = (uint32_t)A.variates[slot].node;
-          uint4 x = rddl_philox_draw(A.seed, (uint64_t)(A.env_offset + env), step, node, (uint64_t)off);
-          const double u = rddl_u53(x.x, x.y);
-          if (op == OP_RANDU) v = u;
-          // cospi(2 u): the cosine of Box-Muller without the argument reduction of cos(2 pi u) (no Payne-Hanek
-          // path, no stack slot for its quadrant); equal to it within a few ulp of 1
-          else if (op == OP_RANDN) v = sqrt(-2.0 * log(1.0 - u)) * cospi(2.0 * rddl_u53(x.z, x.w));
-          else if (op == OP_RANDE) v = -log1p(-u);
-          else v = tan(3.141592653589793 * (u - 0.5));
+          if (op == OP_RANDN) {
+            // Box-Muller pair of elements 2q, 2q + 1 (one Philox block): this element's branch
+            double z0, z1;
+            rddl_randn_pair(A.seed, (uint64_t)(A.env_offset + env), step, node, (uint64_t)off >> 1, &z0, &z1);
+            v = (off & 1) ? z1 : z0;
+          } else {
+            uint4 x = rddl_philox_draw(A.seed, (uint64_t)(A.env_offset + env), step, node, (uint64_t)off);
+            const double u = rddl_u53(x.x, x.y);
+            if (op == OP_RANDU) v = u;
+            else if (op == OP_RANDE) v = -log1p(-u);
+            else v = tan(3.141592653589793 * (u - 0.5));
+          }
         }
         SETF(v);
       }
@@ -522,6 +541,33 @@ __device__ __forceinline__ void vm_exec_one(const VmArgs& A, const VmPools& P, c
         // sparse float sum of a per-env vector staged in shared memory (fused env-tile kernels): 32-bit
         // shared addresses, one LDG (column index, shared by the lanes of the element) + one LDS per
         // term, accumulation in index order like the general loop below
+        const RddlCsr* cs4 = P.csrs + arg;
+        const RddlAddr* ad4 = P.addrs + imm;
+        if (stage->pad && cs4->rowptr4_off != 0 && ad4->naxis == 1 && ad4->coef[0] == 1 && ad4->c0 == 0 && ad4->nreg == 0 &&
+            ad4->env_stride == cs4->sentinel4) {
+          // the whole per-env vector is staged and followed by a zero: the padded copy of the list (rows of 4 k
+          // entries on 16-byte boundaries, filler = the index of that zero) needs no single-index loops before
+          // and after the 128-bit index loads -- they were a third of this loop's instructions on Reservoir
+          // R = 1000 (rows of 21 +- 4 entries). Adding the trailing zeros leaves the sum unchanged (acc is never -0).
+          int64_t row4 = cs4->row_c0;
+          for (int i = 0; i < cs4->row_naxis; ++i) row4 += cs4->row_coef[i] * (int64_t)idx[cs4->row_axis[i]];
+          const int2 q = make_int2(__ldg(A.pool + cs4->rowptr4_off + row4), __ldg(A.pool + cs4->rowptr4_off + row4 + 1));
+          const int4* c4 = reinterpret_cast<const int4*>(A.pool + cs4->col4_off);
+          const uint32_t s4 = (uint32_t)__cvta_generic_to_shared(stage->ptr) + 8u * (uint32_t)stage->add;
+          const uint32_t k4 = 8u * (uint32_t)stage->mul;
+          double acc4 = 0.0;
+          for (int32_t g4 = q.x >> 2; g4 < (q.y >> 2); ++g4) {
+            const int4 c = __ldg(c4 + g4);
+            double v0, v1, v2, v3;
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v0) : "r"(s4 + k4 * (uint32_t)c.x));
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v1) : "r"(s4 + k4 * (uint32_t)c.y));
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v2) : "r"(s4 + k4 * (uint32_t)c.z));
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v3) : "r"(s4 + k4 * (uint32_t)c.w));
+            acc4 = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(acc4, v0), v1), v2), v3);
+          }
+          r[dst] = from_f(acc4);
+          break;
+        }
         const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(stage->ptr) + 8u * (uint32_t)(stage->add + (int32_t)base[0]);
         const int32_t sk = 8 * (int32_t)stride[0];
         // (measured on B200, Reservoir R = 1000 x 4096 envs: four terms per batch 200 us per step; eight

@@ -213,7 +213,8 @@ static std::string level_static_data(const JitPools& P, const RddlLaunch* launch
     for (int k = 0; k < 8; ++k) s += jit_fmt("%lld,", c.row_axis[k]);
     s += "},{";
     for (int k = 0; k < 8; ++k) s += jit_fmt("%lldll,", (long long)c.row_coef[k]);
-    s += "}},\n";
+    s += "}," + jit_fmt("%lldll,", (long long)c.rowptr4_off) + jit_fmt("%lldll,", (long long)c.col4_off) +
+         jit_fmt("%lldll", (long long)c.sentinel4) + "},\n";
   }
   s += "{}};\n__device__ constexpr RddlLaunch kLaunches[] = {";
   for (int i = 0; i < n_launches; ++i) { jit_launch_init(s, launches[i]); s += ",\n"; }

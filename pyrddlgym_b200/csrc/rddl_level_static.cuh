@@ -19,6 +19,8 @@ struct VmStaticCtx {
   uint64_t* r;
   const VmStage* stage;
   uint64_t* pre;        // values of the launch's preloaded LOADs (vm_preload), or null
+  double* zpair;        // pair mode (fused env-tile kernels): second normals of the element pair's RANDNs, or null
+  int half;             // pair mode: 0 = even element of the pair (draws both normals), 1 = odd element (takes the second)
 };
 
 // Preloaded LOADs. A launch's program reads its fluents one LOAD at a time, each immediately before its
@@ -56,6 +58,51 @@ __host__ __device__ constexpr LevelPreTable level_make_pre() {
 __device__ constexpr LevelPreTable kPre = level_make_pre();
 __host__ __device__ constexpr bool level_preload_ok(int base, int pc) { return kPre.slot[pc] >= 0; }
 __host__ __device__ constexpr int level_preload_slot(int base, int pc) { return kPre.slot[pc]; }
+
+// Box-Muller pairs. A RANDN outside every loop whose variate offset is the launch's flat element index draws, for
+// elements 2q and 2q + 1, the two branches of ONE Box-Muller transform (rddl_randn_pair). A fused env-tile kernel
+// gives both elements of a pair to the same thread, which computes the transform at the even element and keeps
+// the sine branch in a register for the odd one: half of the Philox blocks, logarithms and square roots.
+constexpr int kMaxZPair = 4;
+__host__ __device__ constexpr int level_launch_of(int pc) {
+  for (int li = 0; li < kNumLaunch; ++li)
+    if (pc >= kLaunches[li].pc_begin && pc < kLaunches[li].pc_end) return li;
+  return 0;
+}
+__host__ __device__ constexpr bool level_addr_is_flat_index(const RddlAddr& ad, const RddlLaunch& L) {
+  if (ad.nreg != 0 || ad.c0 != 0 || ad.naxis != L.rank) return false;
+  for (int k = 0; k < L.rank; ++k) {
+    int64_t want = 1;
+    for (int j = k + 1; j < L.rank; ++j) want *= L.extent[j];
+    bool found = false;
+    for (int i = 0; i < ad.naxis; ++i) found = found || (ad.axis[i] == k && ad.coef[i] == want);
+    if (!found) return false;
+  }
+  return true;
+}
+struct LevelPairTable { signed char slot[kNumInsn]; };   // per instruction: pair slot of an eligible RANDN, or -1
+__host__ __device__ constexpr LevelPairTable level_make_pairs() {
+  LevelPairTable t{};
+  for (int i = 0; i < kNumInsn; ++i) t.slot[i] = -1;
+  for (int li = 0; li < kNumLaunch; ++li) {
+    if (kLaunches[li].kind != 0) continue;
+    int depth = 0, n = 0;
+    for (int q = kLaunches[li].pc_begin; q < kLaunches[li].pc_end && q < kNumInsn; q += level_insn_len(q)) {
+      const uint32_t o = kInsnWords[q][0] & 0xff;
+      if (o == OP_LOOP || o == OP_CSRLOOP) ++depth;
+      if (o == OP_ENDLOOP || o == OP_CSREND) --depth;
+      if (o == OP_RANDN && depth == 0 && n < kMaxZPair && level_addr_is_flat_index(kAddrs[kInsnWords[q][3]], kLaunches[li]))
+        t.slot[q] = (signed char)n++;
+    }
+  }
+  return t;
+}
+__device__ constexpr LevelPairTable kPairs = level_make_pairs();
+__host__ __device__ constexpr bool level_launch_has_pair(int li) {
+  for (int q = kLaunches[li].pc_begin; q < kLaunches[li].pc_end && q < kNumInsn; ++q)
+    if (kPairs.slot[q] >= 0) return true;
+  return false;
+}
 
 template <int BASE, int PC, int END>
 __device__ __forceinline__ void vm_preload(VmStaticCtx& c) {
@@ -139,6 +186,28 @@ __device__ __forceinline__ void vm_seq(VmStaticCtx& c) {
                                    nullptr, 0);
       }
       vm_seq<BASE, PC + 1, END>(c);
+    } else if constexpr (op == OP_RANDN && kPairs.slot[PC] >= 0) {
+      if (c.zpair && !c.A.inj[ra]) {
+        if (c.half == 0) {
+          constexpr RddlAddr ad = kAddrs[imm];
+          int64_t off = 0;                     // (= the flat element index, even here)
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (i < ad.naxis) off += ad.coef[i] * (int64_t)c.idx[ad.axis[i]];
+          double z0, z1;
+          rddl_randn_pair(c.A.seed, (uint64_t)(c.A.env_offset + c.env), c.step, (uint32_t)c.A.variates[ra].node,
+                          (uint64_t)off >> 1, &z0, &z1);
+          c.r[raw.x >> 16] = from_f(z0);
+          c.zpair[kPairs.slot[PC]] = z1;
+        } else {
+          c.r[raw.x >> 16] = from_f(c.zpair[kPairs.slot[PC]]);
+        }
+      } else {
+        int pc = 0;
+        vm_exec_one<RDDL_MAX_REGS, (int)op>(c.A, P, c.L, c.env, c.step, c.idx, c.redval, c.r, nullptr, nullptr, nullptr, pc, raw,
+                                   nullptr, 0);
+      }
+      vm_seq<BASE, PC + 1, END>(c);
     } else if constexpr (op == OP_SUMLOOP) {
       constexpr uint4 raw2 = {kInsnWords[PC + 1][0], kInsnWords[PC + 1][1], kInsnWords[PC + 1][2], kInsnWords[PC + 1][3]};
       int pc = 0;
@@ -160,10 +229,10 @@ struct LevelStaticExec {
   const VmStage* stage;
   __device__ __forceinline__ void operator()(int64_t env, int32_t* idx, uint64_t* redval) const {
     uint64_t r[kLaunches[LI].nregs > 0 ? kLaunches[LI].nregs : 1];
-    VmStage st = {nullptr, -1, 0, 1, 0};
+    VmStage st = {nullptr, -1, 0, 1, 0, 0};
     if (stage) { st = *stage; st.base = env * level_stage_elems(LI); }
     uint64_t pre[kMaxPreload];
-    VmStaticCtx c = {A, kLaunches[LI], env, A.step, idx, redval, r, stage ? &st : nullptr, pre};
+    VmStaticCtx c = {A, kLaunches[LI], env, A.step, idx, redval, r, stage ? &st : nullptr, pre, nullptr, 0};
     vm_preload<kLaunches[LI].pc_begin, kLaunches[LI].pc_begin, kLaunches[LI].pc_end>(c);
     vm_seq<kLaunches[LI].pc_begin, kLaunches[LI].pc_begin, kLaunches[LI].pc_end>(c);
   }
@@ -178,6 +247,7 @@ struct LevelStagePrologue {
     constexpr int64_t n = level_stage_elems(LI);
     const double* src = reinterpret_cast<const double*>(A.tensors[level_stage_tensor(LI)]) + env * n;
     for (int i = threadIdx.x; i < (int)n; i += 256) smem[i] = env_ok ? src[i] : 0.0;
+    if (threadIdx.x == 0) smem[n] = 0.0;      // the zero the padded CSR rows point at
     __syncthreads();
   }
 };
@@ -185,8 +255,8 @@ struct LevelStagePrologue {
 template <int LI>
 __device__ __forceinline__ void level_static_kernel(const VmArgs& A) {
   if constexpr (level_stage_tensor(LI) >= 0) {
-    __shared__ double staged[level_stage_elems(LI) > 0 ? level_stage_elems(LI) : 1];
-    const VmStage st = {staged, level_stage_tensor(LI), 0, 1, 0};
+    __shared__ double staged[(level_stage_elems(LI) > 0 ? level_stage_elems(LI) : 1) + 1];
+    const VmStage st = {staged, level_stage_tensor(LI), 0, 1, 0, 1};
     level_tile(A, kLaunches[LI], kRedOff, LevelStaticExec<LI>{A, &st}, LevelStagePrologue<LI>{A, staged});
   } else {
     level_tile(A, kLaunches[LI], kRedOff, LevelStaticExec<LI>{A, nullptr});
@@ -224,7 +294,7 @@ __host__ __device__ constexpr int fuse_stage_tensor(int li) {
     if (op != OP_SUMLOOP) continue;
     if ((rb & 1u) && (rb & 4u)) {
       const RddlAddr& ad = kAddrs[imm];
-      if (ad.tensor >= 0 && ad.env_stride > 0 && ad.env_stride * FUSE_TE <= kFuseMaxStage && kDT[ad.tensor] == DT_REAL && ad.nreg == 0)
+      if (ad.tensor >= 0 && ad.env_stride > 0 && (ad.env_stride + 1) * FUSE_TE <= kFuseMaxStage && kDT[ad.tensor] == DT_REAL && ad.nreg == 0)
         return ad.tensor;
     }
     ++pc;
@@ -246,34 +316,48 @@ __device__ __forceinline__ void fused_phase(const VmArgs& A, double* staged, uin
   const int e = tid % FUSE_TE;
   const int64_t env0 = (int64_t)blockIdx.x * FUSE_TE, env = env0 + e;
   const bool env_ok = env < A.n_envs;
-  VmStage st = {nullptr, -1, 0, 1, 0};
+  VmStage st = {nullptr, -1, 0, 1, 0, 0};
   if constexpr (fuse_stage_tensor(LI) >= 0) {
     // the FUSE_TE envs' slices of the gathered tensor, transposed to [element][env]
     constexpr int64_t n = fuse_stage_elems(LI);
     const double* src = reinterpret_cast<const double*>(A.tensors[fuse_stage_tensor(LI)]);
-    for (int i = tid; i < (int)(n * FUSE_TE); i += 256) staged[i] = env_ok ? src[env * n + i / FUSE_TE] : 0.0;
+    // (thread t always copies env t % FUSE_TE: 256 is a multiple of FUSE_TE; 32-bit indices, four loads in flight)
+    const double* srce = src + (env_ok ? env * n : 0);
+#pragma unroll 4
+    for (int i = tid; i < (int)(n * FUSE_TE); i += 256) staged[i] = env_ok ? srce[(uint32_t)i / FUSE_TE] : 0.0;
+    if (tid < FUSE_TE) staged[n * FUSE_TE + tid] = 0.0;      // the zeros the padded CSR rows point at
     __syncthreads();
-    st = VmStage{staged, fuse_stage_tensor(LI), env * n, FUSE_TE, e};
+    st = VmStage{staged, fuse_stage_tensor(LI), env * n, FUSE_TE, e, 1};
   }
   int32_t idx[RDDL_MAX_IDX];
   uint64_t redval[RDDL_MAX_RED];
 #pragma unroll
   for (int j = 0; j < RDDL_MAX_RED; ++j) redval[j] = j < L.nred ? red_identity(L.red_op[j]) : 0;
+  // elements per thread step: pairs (2p, 2p + 1) when the launch draws Box-Muller pairs, else single elements
+  constexpr int EPS = level_launch_has_pair(LI) ? 2 : 1;
   if (env_ok) {
-    for (int64_t elem = tid / FUSE_TE; elem < L.E; elem += 256 / FUSE_TE) {
-      int64_t rem = elem;
+    for (int64_t e0 = (int64_t)(tid / FUSE_TE) * EPS; e0 < L.E; e0 += (256 / FUSE_TE) * EPS) {
+      double zpair[kMaxZPair];
 #pragma unroll
-      for (int k = RDDL_MAX_IDX - 1; k >= 0; --k) {
-        if (k < L.rank) {
-          idx[k] = (int32_t)(rem % L.extent[k]);
-          rem /= L.extent[k];
+      for (int half = 0; half < EPS; ++half) {
+        const int64_t elem = e0 + half;
+        if (elem < L.E) {
+          int64_t rem = elem;
+#pragma unroll
+          for (int k = RDDL_MAX_IDX - 1; k >= 0; --k) {
+            if (k < L.rank) {
+              idx[k] = (int32_t)(rem % L.extent[k]);
+              rem /= L.extent[k];
+            }
+          }
+          uint64_t r[L.nregs > 0 ? L.nregs : 1];
+          uint64_t pre[kMaxPreload];
+          VmStaticCtx c = {A, kLaunches[LI], env, A.step, idx, redval, r, st.tensor >= 0 ? &st : nullptr, pre,
+                           EPS == 2 ? zpair : nullptr, half};
+          vm_preload<L.pc_begin, L.pc_begin, L.pc_end>(c);
+          vm_seq<L.pc_begin, L.pc_begin, L.pc_end>(c);
         }
       }
-      uint64_t r[L.nregs > 0 ? L.nregs : 1];
-      uint64_t pre[kMaxPreload];
-      VmStaticCtx c = {A, kLaunches[LI], env, A.step, idx, redval, r, st.tensor >= 0 ? &st : nullptr, pre};
-      vm_preload<L.pc_begin, L.pc_begin, L.pc_end>(c);
-      vm_seq<L.pc_begin, L.pc_begin, L.pc_end>(c);
     }
   }
   if constexpr (L.nred > 0) {
@@ -313,7 +397,7 @@ __device__ __forceinline__ void fused_phases(const VmArgs& A, double* staged, ui
 __host__ __device__ constexpr int64_t fuse_group_stage(int first, int count) {
   int64_t m = 1;
   for (int li = first; li < first + count; ++li)
-    if (fuse_stage_tensor(li) >= 0 && fuse_stage_elems(li) * FUSE_TE > m) m = fuse_stage_elems(li) * FUSE_TE;
+    if (fuse_stage_tensor(li) >= 0 && (fuse_stage_elems(li) + 1) * FUSE_TE > m) m = (fuse_stage_elems(li) + 1) * FUSE_TE;
   return m;
 }
 

@@ -4,7 +4,7 @@
 #include "rddl_stdint.h"
 
 #define RDDL_MAGIC 0x31304C444452ll
-#define RDDL_VERSION 9
+#define RDDL_VERSION 10
 #define RDDL_MAX_IDX 8
 #define RDDL_MAX_RED 8
 #define RDDL_MAX_REGS 96
@@ -59,7 +59,7 @@ struct RddlAddr {      // 184 bytes: element offset = env*env_stride + c0 + sum 
   int64_t rextent[4];
 };
 
-struct RddlCsr {       // 152 bytes
+struct RddlCsr {       // 176 bytes
   int64_t rowptr_off;
   int32_t ncols, pad;
   int64_t col_off[4];
@@ -68,6 +68,9 @@ struct RddlCsr {       // 152 bytes
   int32_t row_naxis, pad2;
   uint8_t row_axis[8];
   int64_t row_coef[8];
+  // single-column lists: a copy whose rows start on 16 bytes and hold a multiple of four entries, padded with
+  // sentinel4 (= the extent of the reduced axis: one past the last element); rowptr4_off == 0: absent
+  int64_t rowptr4_off, col4_off, sentinel4;
 };
 
 struct RddlTensor { int16_t dtype, pair; int32_t kind; int64_t nelem; };   // pair: next-state tensor id of a state fluent, else -1
@@ -117,5 +120,5 @@ struct RddlVariate { int32_t node, kind; int64_t nelem; };
 
 static_assert(sizeof(RddlInsn) == 16, "insn");
 static_assert(sizeof(RddlAddr) == 184, "addr");
-static_assert(sizeof(RddlCsr) == 152, "csr");
+static_assert(sizeof(RddlCsr) == 176, "csr");
 static_assert(sizeof(RddlLaunch) == 176, "launch");

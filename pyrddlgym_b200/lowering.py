@@ -1175,6 +1175,24 @@ class Lowerer:
         for i, (a, c) in enumerate(zip(axes, cols)):
             row['col_off'][i] = self.pool_add(c)
             row['slot'][i] = a
+        if len(axes) == 1 and len(rowptr) > 1:
+            # padded copy for the staged sparse sums (rddl_device.cuh, SUMLOOP): rows start on 16-byte
+            # boundaries and hold a multiple of four entries, the filler being the extent of the reduced
+            # axis -- one past the last element, where the staged vector keeps a zero
+            rp = np.asarray(rowptr, dtype=np.int64)
+            n = np.diff(rp)
+            n4 = (n + 3) // 4 * 4
+            rp4 = np.concatenate([[0], np.cumsum(n4)])
+            if rp4[-1] < 2 ** 31:
+                c4 = np.full(int(rp4[-1]), int(ext[axes[0]]), dtype='<i4')
+                src = np.asarray(cols[0], dtype='<i4')
+                pos = np.repeat(rp4[:-1] - rp[:-1], n) + np.arange(len(src))
+                c4[pos] = src
+                row['rowptr4_off'] = self.pool_add(rp4.astype('<i4'), align=4)
+                row['col4_off'] = self.pool_add(c4, align=4)
+                row['sentinel4'] = int(ext[axes[0]])
+                if row['rowptr4_off'] == 0:       # (0 means absent: an empty pool gets a filler first)
+                    raise LoweringError('internal: padded list at pool offset 0')
         s = 1
         coefs = []
         for a in reversed(row_axes):

@@ -13,7 +13,7 @@ slots the kernels need. It is a flat little-endian blob:
 import numpy as np
 
 MAGIC = 0x31304C444452  # "RDDL01"
-VERSION = 9
+VERSION = 10
 MAX_IDX = 8          # index variables per thread: scope axes + nested loop axes
 MAX_RED = 8          # reduction outputs per launch
 MAX_REGS = 96        # virtual 64-bit registers per thread
@@ -71,7 +71,11 @@ ADDR = np.dtype([('tensor', '<i4'), ('naxis', '<i4'), ('env_stride', '<i8'), ('c
                  ('reg', '<i4', (4,)), ('rstride', '<i8', (4,)), ('rextent', '<i8', (4,))])
 CSR = np.dtype([('rowptr_off', '<i8'), ('ncols', '<i4'), ('pad', '<i4'), ('col_off', '<i8', (4,)),
                 ('slot', '<i4', (4,)), ('row_c0', '<i8'), ('row_naxis', '<i4'), ('pad2', '<i4'),
-                ('row_axis', 'u1', (8,)), ('row_coef', '<i8', (8,))])
+                ('row_axis', 'u1', (8,)), ('row_coef', '<i8', (8,)),
+                # single-column lists: a second copy with every row padded to a multiple of four entries
+                # (16-byte aligned; padding entries = sentinel4, the extent of the reduced axis) for the
+                # 128-bit index loads of the staged sparse sums; rowptr4_off = 0: absent
+                ('rowptr4_off', '<i8'), ('col4_off', '<i8'), ('sentinel4', '<i8')])
 TENSOR = np.dtype([('dtype', '<i2'), ('pair', '<i2'), ('kind', '<i4'), ('nelem', '<i8')])  # pair: id of the primed partner of a state fluent, else -1
 LAUNCH = np.dtype([('plan', '<i4'), ('rank', '<i4'), ('extent', '<i8', (8,)), ('E', '<i8'),
                    ('pc_begin', '<i4'), ('pc_end', '<i4'), ('nred', '<i4'), ('G', '<i4'),
@@ -80,7 +84,7 @@ LAUNCH = np.dtype([('plan', '<i4'), ('rank', '<i4'), ('extent', '<i8', (8,)), ('
 REDSLOT = np.dtype([('op', '<i4'), ('chunks', '<i4')])
 VARIATE = np.dtype([('node', '<i4'), ('kind', '<i4'), ('nelem', '<i8')])
 
-assert INSN.itemsize == 16 and ADDR.itemsize == 184 and CSR.itemsize == 152
+assert INSN.itemsize == 16 and ADDR.itemsize == 184 and CSR.itemsize == 176
 assert TENSOR.itemsize == 16 and LAUNCH.itemsize == 176 and REDSLOT.itemsize == 8
 
 

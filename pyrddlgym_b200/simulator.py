@@ -135,7 +135,17 @@ class BatchedSimulator:
         self._inj = (ctypes.c_void_p * max(1, len(self.table.variates)))()
         self._external = {}
         self._state_pairs = list(program.next_state.items())
+        # (state, next-state, their op-table ids): what a transition swaps, resolved once
+        self._swap_plan = [(s_, ns_, self.tid[s_], self.tid[ns_]) for s_, ns_ in self._state_pairs]
         self._inj_used = False
+        # per-transition call: everything that does not change between steps is resolved here (the C entry
+        # point, the status pointer, the raw-stream getter), so that step() is a handful of attribute reads
+        self._step_fn = self.native.lib.rddl_step
+        self._handle = self.native.handle
+        self._status_ptr = ctypes.c_void_p(self.status.data_ptr())
+        self._dev_index = index
+        self._raw_stream = getattr(torch._C, '_cuda_getCurrentRawStream', None)
+        self._states_view = _States(self)
         self.step_count = 0          # Philox step index: advances with every transition, across resets
         self.episode_step = 0        # transitions since the last reset
         self.reset()
@@ -153,17 +163,19 @@ class BatchedSimulator:
     def _swap_state(self):
         """state <-> next-state after a transition (the reference aliases them, simulator.py:463-466):
         the table entries and -- when it is current -- the pointer array entries, without a rebuild."""
-        t, clean = self.t, not self.t.dirty
-        for s, ns in self._state_pairs:
+        t, ptrs, put = self.t, self._ptrs, dict.__setitem__
+        clean = not t.dirty
+        for s, ns, i, j in self._swap_plan:
             a, b = t[s], t[ns]
-            dict.__setitem__(t, s, b)
-            dict.__setitem__(t, ns, a)
+            put(t, s, b)
+            put(t, ns, a)
             if clean:
-                i, j = self.tid[s], self.tid[ns]
-                self._ptrs[i], self._ptrs[j] = self._ptrs[j], self._ptrs[i]
+                ptrs[i], ptrs[j] = ptrs[j], ptrs[i]
 
     def _stream(self):
-        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        if self._raw_stream is not None:
+            return self._raw_stream(self._dev_index)
+        return torch.cuda.current_stream(self.device).cuda_stream
 
     def seed(self, seed):
         """simulator.py:129-134. Also restarts the Philox step index (see ``reset``)."""
@@ -256,7 +268,7 @@ class BatchedSimulator:
         """name -> tensor [N, *shape] of the current state. Byte / int64 / float64 fluents are
         views of the live buffers (valid until the next step, like the reference's aliasing dict,
         simulator.py:176-179); bit-packed bool fluents are unpacked into a fresh tensor."""
-        return _States(self)
+        return self._states_view
 
     def fluent(self, name):
         if name in self.packed:
@@ -272,9 +284,12 @@ class BatchedSimulator:
                 raise KeyError(f'<{name}> is not an action-fluent')
             dst = self._owned_actions[name]
             if isinstance(v, torch.Tensor):
-                if (v.device == dst.device and v.dtype == dst.dtype and v.shape == dst.shape
-                        and v.is_contiguous()):
-                    self.t[name] = v              # zero-copy: read the caller's buffer directly
+                if (v.dtype is dst.dtype and v.shape == dst.shape and v.is_contiguous()
+                        and v.device == dst.device):
+                    # zero-copy: read the caller's buffer directly (table entry + its C pointer, in place)
+                    dict.__setitem__(self.t, name, v)
+                    if not self.t.dirty:
+                        self._ptrs[self.tid[name]] = v.data_ptr()
                     continue
                 dst.copy_(v.to(dst.dtype).expand_as(dst) if v.shape != dst.shape else v, non_blocking=True)
             else:
@@ -302,16 +317,20 @@ class BatchedSimulator:
                 keep.append(tv)
                 self._inj[slot] = tv.data_ptr()
         self._inj_used = bool(variates)
-        self._refresh_ptrs()
-        self.native.step(self._ptrs, self._inj if variates else None, ctypes.c_void_p(self.status.data_ptr()),
-                         self.n_envs, self.env_offset, self.seed_value, self.step_count, self._stream())
+        if self.t.dirty:
+            self._refresh_ptrs()
+        rc = self._step_fn(self._handle, self._ptrs, self._inj if variates else None, self._status_ptr,
+                           self.n_envs, self.env_offset, self.seed_value, self.step_count, self._stream())
+        if rc != 0:
+            self.native._check(rc, 'rddl_step')
         if not self._jit_warned:
             self._jit_check()
         self._swap_state()
         self.step_count += 1
         self.episode_step += 1
         self._keep = keep
-        return self.states, self.t['__reward'], self.t['__done']
+        t = self.t
+        return self._states_view, t['__reward'], t['__done']
 
     def rollout(self, actions, n_steps, gamma=None, returns=None, keep_rewards=False):
         """``n_steps`` transitions with pre-drawn action sequences -- the loop of
