@@ -52,12 +52,12 @@ def base_variates(kind, seed, env_ids, step, node_id, scope_shape):
     """Base variates of ``kind`` ('U','N','E','C') for every (env, scope element).
     Returns float64 array of shape [len(env_ids), *scope_shape].
 
-    Normals come in Box-Muller pairs: elements 2q and 2q + 1 share the Philox block of counter q and take the
-    cosine and the sine branch (csrc/rddl_device.cuh: rddl_randn) -- the fused scalar kernels compute both
-    from one logarithm and one square root."""
+    Normals come in Box-Muller pairs: elements e and e + 8 (bit 3 of e clear) share the Philox block of counter
+    q = e with bit 3 removed and take the cosine and the sine branch (csrc/rddl_device.cuh: rddl_randn_pair,
+    rddl_randn_counter) -- the fused scalar kernels compute both from one logarithm and one square root."""
     n_elem = int(np.prod(scope_shape, dtype=np.int64)) if len(scope_shape) else 1
     elem = np.arange(n_elem, dtype=np.uint64)
-    ctr = elem >> np.uint64(1) if kind == 'N' else elem
+    ctr = (((elem >> np.uint64(4)) << np.uint64(3)) | (elem & np.uint64(7))) if kind == 'N' else elem
     env = np.asarray(env_ids, dtype=np.uint64)[:, None]
     c0 = (ctr & MASK).astype(np.uint32)[None, :]
     c1 = (env & MASK).astype(np.uint32)
@@ -70,7 +70,7 @@ def base_variates(kind, seed, env_ids, step, node_id, scope_shape):
     elif kind == 'N':
         u2 = _u53(r2, r3)
         rad = np.sqrt(-2.0 * np.log(1.0 - u))
-        odd = (elem & np.uint64(1)).astype(bool)[None, :]
+        odd = ((elem >> np.uint64(3)) & np.uint64(1)).astype(bool)[None, :]
         out = rad * np.where(odd, np.sin(2.0 * np.pi * u2), np.cos(2.0 * np.pi * u2))
     elif kind == 'E':
         out = -np.log1p(-u)

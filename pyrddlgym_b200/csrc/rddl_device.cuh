@@ -223,11 +223,15 @@ __device__ __forceinline__ uint64_t rddl_policy_value(const VmPolicy& pol, const
   return (uint64_t)(v > hi ? hi : v);
 }
 
-// Standard normals of elements 2q and 2q + 1 of a variate: the two branches of one Box-Muller transform of the
-// Philox block of counter q -- z0 = R cos(2 pi u2), z1 = R sin(2 pi u2), R = sqrt(-2 ln(1 - u1)). A kernel whose
-// thread owns both elements (fused env-tile kernels, rddl_level_static.cuh) pays for one block, one logarithm and
-// one square root per pair; thread-per-element kernels compute the pair and keep their branch (same bits).
+// Standard normals come in Box-Muller pairs: elements e and e + 8 of a variate (e with bit 3 clear) are the two
+// branches of one transform of the Philox block of counter q(e) = e with bit 3 removed -- z0 = R cos(2 pi u2) for
+// e, z1 = R sin(2 pi u2) for e + 8, R = sqrt(-2 ln(1 - u1)). A kernel whose thread owns both elements (fused
+// env-tile kernels, rddl_level_static.cuh) pays for one block, one logarithm and one square root per pair;
+// thread-per-element kernels compute the pair and keep their branch (same bits). Partners are 8 apart, not
+// adjacent, so that the lanes of such a kernel still walk consecutive elements (full sectors) in each half.
 // sincospi(2 u): no argument reduction of 2 pi u (no Payne-Hanek path, no stack slot for its quadrant).
+__device__ __forceinline__ uint64_t rddl_randn_counter(uint64_t e) { return ((e >> 4) << 3) | (e & 7u); }
+__device__ __forceinline__ bool rddl_randn_branch(uint64_t e) { return ((e >> 3) & 1u) != 0; }
 __device__ __forceinline__ void rddl_randn_pair(uint64_t seed, uint64_t env, uint64_t step, uint32_t node, uint64_t q,
                                                 double* z0, double* z1) {
   const uint4 x = rddl_philox_draw(seed, env, step, node, q);
@@ -345,8 +349,8 @@ __device__ __forceinline__ void vm_exec_one(const VmArgs& A, const VmPools& P, c
           if (op == OP_RANDN) {
             // Box-Muller pair of elements 2q, 2q + 1 (one Philox block): this element's branch
             double z0, z1;
-            rddl_randn_pair(A.seed, (uint64_t)(A.env_offset + env), step, node, (uint64_t)off >> 1, &z0, &z1);
-            v = (off & 1) ? z1 : z0;
+            rddl_randn_pair(A.seed, (uint64_t)(A.env_offset + env), step, node, rddl_randn_counter((uint64_t)off), &z0, &z1);
+            v = rddl_randn_branch((uint64_t)off) ? z1 : z0;
           } else {
             uint4 x = rddl_philox_draw(A.seed, (uint64_t)(A.env_offset + env), step, node, (uint64_t)off);
             const double u = rddl_u53(x.x, x.y);
@@ -527,15 +531,23 @@ __device__ __forceinline__ void vm_exec_one(const VmArgs& A, const VmPools& P, c
       }
       int32_t j0 = 0, j1 = (int32_t)arg;
       const int32_t* cols = nullptr;
-      int64_t cs_col_off = 0;
+      int64_t sentinel = -2;                   // (filler index of a padded list; never a real index)
       if (is_csr) {
         const RddlCsr* cs = P.csrs + arg;
         int64_t row = cs->row_c0;
         for (int i = 0; i < cs->row_naxis; ++i) row += cs->row_coef[i] * (int64_t)idx[cs->row_axis[i]];
-        j0 = __ldg(A.pool + cs->rowptr_off + row);
-        j1 = __ldg(A.pool + cs->rowptr_off + row + 1);
-        cols = A.pool + cs->col_off[0];
-        cs_col_off = cs->col_off[0];
+        if (cs->rowptr4_off != 0) {
+          // single-column lists are summed from their padded copy (rows of 4 k entries in the bank-scheduled order
+          // of lowering._bank_schedule, filler = sentinel4): ONE order of the terms for every kernel and path
+          j0 = __ldg(A.pool + cs->rowptr4_off + row);
+          j1 = __ldg(A.pool + cs->rowptr4_off + row + 1);
+          cols = A.pool + cs->col4_off;
+          sentinel = cs->sentinel4;
+        } else {
+          j0 = __ldg(A.pool + cs->rowptr_off + row);
+          j1 = __ldg(A.pool + cs->rowptr_off + row + 1);
+          cols = A.pool + cs->col_off[0];
+        }
       }
       if (stage && is_csr && !two && flt && (P.addrs + imm)->tensor == stage->tensor && dts[0] == DT_REAL) {
         // sparse float sum of a per-env vector staged in shared memory (fused env-tile kernels): 32-bit
@@ -556,55 +568,65 @@ __device__ __forceinline__ void vm_exec_one(const VmArgs& A, const VmPools& P, c
           const uint32_t s4 = (uint32_t)__cvta_generic_to_shared(stage->ptr) + 8u * (uint32_t)stage->add;
           const uint32_t k4 = 8u * (uint32_t)stage->mul;
           double acc4 = 0.0;
-          for (int32_t g4 = q.x >> 2; g4 < (q.y >> 2); ++g4) {
-            const int4 c = __ldg(c4 + g4);
-            double v0, v1, v2, v3;
-            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v0) : "r"(s4 + k4 * (uint32_t)c.x));
-            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v1) : "r"(s4 + k4 * (uint32_t)c.y));
-            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v2) : "r"(s4 + k4 * (uint32_t)c.z));
-            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v3) : "r"(s4 + k4 * (uint32_t)c.w));
-            acc4 = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(acc4, v0), v1), v2), v3);
+          int32_t g4 = q.x >> 2;
+          const int32_t g4l = (q.y >> 2) - 1;          // last group of the row
+#define RDDL_SUM4(c)                                                                         \
+  {                                                                                           \
+    double v0, v1, v2, v3;                                                                    \
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v0) : "r"(s4 + k4 * (uint32_t)(c).x));              \
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v1) : "r"(s4 + k4 * (uint32_t)(c).y));              \
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v2) : "r"(s4 + k4 * (uint32_t)(c).z));              \
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v3) : "r"(s4 + k4 * (uint32_t)(c).w));              \
+    acc4 = __dadd_rn(acc4, __dadd_rn(__dadd_rn(v0, v1), __dadd_rn(v2, v3)));                  \
+  }
+          // one group of four per half trip, the next group's indices in flight while this one is summed; two index
+          // register sets used alternately (no copies), the look-ahead index clamped to the row's last group instead
+          // of predicated (no default values to move). Measured on B200 and not kept (Reservoir R = 1000 x 4096 envs,
+          // all within 124 +- 4 us): L1 prefetch of the thread's next row and next element, the warp's index
+          // groups copied once into shared memory with coalesced loads -- the kernel is bound by the L1 data pipe
+          // (ncu: l1tex__data_pipe_lsu_wavefronts 75 % of peak), and each of these only moves wavefronts around.
+          if (g4 <= g4l) {
+            int4 ca = __ldg(c4 + g4), cb;
+#pragma unroll 1
+            for (;;) {
+              cb = __ldg(c4 + min(g4 + 1, g4l));
+              RDDL_SUM4(ca)
+              if (++g4 > g4l) break;
+              ca = __ldg(c4 + min(g4 + 1, g4l));
+              RDDL_SUM4(cb)
+              if (++g4 > g4l) break;
+            }
           }
+#undef RDDL_SUM4
           r[dst] = from_f(acc4);
           break;
         }
         const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(stage->ptr) + 8u * (uint32_t)(stage->add + (int32_t)base[0]);
         const int32_t sk = 8 * (int32_t)stride[0];
-        // (measured on B200, Reservoir R = 1000 x 4096 envs: four terms per batch 200 us per step; eight
-        // terms with the next batch's indices prefetched 233 us -- more registers, fewer resident warps)
+        // (lists without a padded copy, or a staged slice that is not the whole vector: single index loads, the
+        // same groups of four from the start of the row as every other float SUMLOOP)
         double acc = 0.0;
-        int32_t j = j0;
-        // the column indices of the row are read four at a time (one 128-bit load: the pool is 256-byte aligned,
-        // so cols + j is 16-byte aligned when (col_off + j) % 4 == 0) after up to three single reads: the lanes
-        // of a warp work on 8 different rows, i.e. every index load is 8 sectors through the L1 data pipe --
-        // ncu showed that pipe 59 % busy with 21 single-index loads per element (Reservoir R = 1000)
-        const int32_t jh = min(j1, j + (int32_t)((4u - (uint32_t)((cs_col_off + j) & 3)) & 3u));
-        for (; j < jh; ++j) {
-          double v;
-          asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(s0 + (uint32_t)(sk * __ldg(cols + j))));
-          acc = __dadd_rn(acc, v);
-        }
-        for (; j + 4 <= j1; j += 4) {
-          const int4 c = __ldg(reinterpret_cast<const int4*>(cols + j));
-          double v0, v1, v2, v3;
-          asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v0) : "r"(s0 + (uint32_t)(sk * c.x)));
-          asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v1) : "r"(s0 + (uint32_t)(sk * c.y)));
-          asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v2) : "r"(s0 + (uint32_t)(sk * c.z)));
-          asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v3) : "r"(s0 + (uint32_t)(sk * c.w)));
-          acc = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(acc, v0), v1), v2), v3);
-        }
-        for (; j < j1; ++j) {
-          double v;
-          asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(s0 + (uint32_t)(sk * __ldg(cols + j))));
-          acc = __dadd_rn(acc, v);
+        for (int32_t j = j0; j < j1; j += 4) {
+          double v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            v[u] = 0.0;
+            const int32_t cu = j + u < j1 ? __ldg(cols + j + u) : (int32_t)sentinel;
+            if (cu != (int32_t)sentinel) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v[u]) : "r"(s0 + (uint32_t)(sk * cu)));
+          }
+          acc = __dadd_rn(acc, __dadd_rn(__dadd_rn(v[0], v[1]), __dadd_rn(v[2], v[3])));
         }
         r[dst] = from_f(acc);
         break;
       }
       double facc = 0.0;
       int64_t iacc = 0;
-      // four terms at a time: their (dependent) index and value loads are issued together, the
-      // accumulation stays in index order (same rounding as the reference's left-to-right sum)
+      // four terms at a time: their (dependent) index and value loads are issued together. Float sums add each
+      // group of four consecutive terms (from the start of the row; missing terms = +0) as (t0 + t1) + (t2 + t3) and
+      // then to the running sum: ONE dependent addition per group on the loop-carried chain instead of four -- the
+      // staged sums of the fused kernels were bound by that chain's latency (FP64 adds, ILP 1, 8 warps per
+      // scheduler). Every float SUMLOOP path uses this order, so all kernels agree bit for bit; against the
+      // reference (NumPy's own pairwise order) sums agree to rounding, as before.
       for (int32_t j = j0; j < j1; j += 4) {
         int64_t k[4];
         double fv[4][2];
@@ -612,6 +634,9 @@ __device__ __forceinline__ void vm_exec_one(const VmArgs& A, const VmPools& P, c
 #pragma unroll
         for (int u = 0; u < 4; ++u)
           k[u] = j + u < j1 ? (is_csr ? (int64_t)__ldg(cols + j + u) : (int64_t)(j + u)) : -1;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (k[u] == sentinel) k[u] = -1;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           fv[u][0] = fv[u][1] = 1.0;
@@ -629,11 +654,17 @@ __device__ __forceinline__ void vm_exec_one(const VmArgs& A, const VmPools& P, c
             }
           }
         }
+        if (flt) {
+          double t[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (k[u] < 0) continue;
-          if (flt) facc = __dadd_rn(facc, two ? __dmul_rn(fv[u][0], fv[u][1]) : fv[u][0]);
-          else iacc += two ? iv[u][0] * iv[u][1] : iv[u][0];
+          for (int u = 0; u < 4; ++u) t[u] = k[u] < 0 ? 0.0 : (two ? __dmul_rn(fv[u][0], fv[u][1]) : fv[u][0]);
+          facc = __dadd_rn(facc, __dadd_rn(__dadd_rn(t[0], t[1]), __dadd_rn(t[2], t[3])));
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (k[u] < 0) continue;
+            iacc += two ? iv[u][0] * iv[u][1] : iv[u][0];
+          }
         }
       }
       r[dst] = flt ? from_f(facc) : (uint64_t)iacc;

@@ -60,9 +60,9 @@ __host__ __device__ constexpr bool level_preload_ok(int base, int pc) { return k
 __host__ __device__ constexpr int level_preload_slot(int base, int pc) { return kPre.slot[pc]; }
 
 // Box-Muller pairs. A RANDN outside every loop whose variate offset is the launch's flat element index draws, for
-// elements 2q and 2q + 1, the two branches of ONE Box-Muller transform (rddl_randn_pair). A fused env-tile kernel
-// gives both elements of a pair to the same thread, which computes the transform at the even element and keeps
-// the sine branch in a register for the odd one: half of the Philox blocks, logarithms and square roots.
+// elements e and e + 8 (bit 3 of e clear), the two branches of ONE Box-Muller transform (rddl_randn_pair). A fused env-tile kernel
+// gives both elements of a pair to the same thread, which computes the transform at the first element and keeps
+// the sine branch in a register for its partner: half of the Philox blocks, logarithms and square roots.
 constexpr int kMaxZPair = 4;
 __host__ __device__ constexpr int level_launch_of(int pc) {
   for (int li = 0; li < kNumLaunch; ++li)
@@ -190,13 +190,13 @@ __device__ __forceinline__ void vm_seq(VmStaticCtx& c) {
       if (c.zpair && !c.A.inj[ra]) {
         if (c.half == 0) {
           constexpr RddlAddr ad = kAddrs[imm];
-          int64_t off = 0;                     // (= the flat element index, even here)
+          int64_t off = 0;                     // (= the flat element index, bit 3 clear here)
 #pragma unroll
           for (int i = 0; i < 8; ++i)
             if (i < ad.naxis) off += ad.coef[i] * (int64_t)c.idx[ad.axis[i]];
           double z0, z1;
           rddl_randn_pair(c.A.seed, (uint64_t)(c.A.env_offset + c.env), c.step, (uint32_t)c.A.variates[ra].node,
-                          (uint64_t)off >> 1, &z0, &z1);
+                          rddl_randn_counter((uint64_t)off), &z0, &z1);
           c.r[raw.x >> 16] = from_f(z0);
           c.zpair[kPairs.slot[PC]] = z1;
         } else {
@@ -282,6 +282,7 @@ __device__ __forceinline__ void level_static_kernel(const VmArgs& A) {
 #ifndef FUSE_TE
 #define FUSE_TE 4
 #endif
+static_assert((256 / FUSE_TE) % 8 == 0, "pair steps walk blocks of 16 elements with 8 threads per env");
 #ifndef FUSE_MINB
 #define FUSE_MINB 4
 #endif
@@ -335,13 +336,20 @@ __device__ __forceinline__ void fused_phase(const VmArgs& A, double* staged, uin
   for (int j = 0; j < RDDL_MAX_RED; ++j) redval[j] = j < L.nred ? red_identity(L.red_op[j]) : 0;
   // elements per thread step: pairs (2p, 2p + 1) when the launch draws Box-Muller pairs, else single elements
   constexpr int EPS = level_launch_has_pair(LI) ? 2 : 1;
-  if (env_ok) {
-    for (int64_t e0 = (int64_t)(tid / FUSE_TE) * EPS; e0 < L.E; e0 += (256 / FUSE_TE) * EPS) {
+  // (the trip count is the same for every thread of the CTA)
+  constexpr int64_t kSteps = (L.E + (256 / FUSE_TE) * EPS - 1) / ((256 / FUSE_TE) * EPS);
+  {
+    for (int64_t step_i = 0; step_i < kSteps; ++step_i) {
+      // single elements: thread j = tid / FUSE_TE of the 256 / FUSE_TE takes element j of the step's block; pairs:
+      // of each 16 consecutive elements, eight threads take elements 0..7 and then their partners 8..15
+      const int j = tid / FUSE_TE;
+      const int64_t e0 = EPS == 1 ? j + step_i * (256 / FUSE_TE) : step_i * (2 * (256 / FUSE_TE)) + (j >> 3) * 16 + (j & 7);
       double zpair[kMaxZPair];
 #pragma unroll
       for (int half = 0; half < EPS; ++half) {
-        const int64_t elem = e0 + half;
-        if (elem < L.E) {
+        const int64_t elem = e0 + half * 8;
+        const bool active = env_ok && elem < L.E;
+        if (active) {
           int64_t rem = elem;
 #pragma unroll
           for (int k = RDDL_MAX_IDX - 1; k >= 0; --k) {

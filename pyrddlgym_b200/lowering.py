@@ -36,6 +36,54 @@ _HOIST_MIN = 16
 _CSR_DENSE_LIMIT = 1 << 27
 
 
+def _bank_schedule(rowptr, cols):
+    """Order of the entries inside each row of a padded CSR list (the order in which every float SUMLOOP adds
+    them). The fused env-tile kernels gather the terms from a vector staged in shared memory as
+    [element][4 envs]: the bank group an entry hits is ``col % 4``, and the four rows a half warp sums in
+    lock-step (rows 4 b .. 4 b + 3) conflict at a position whenever two of their entries share a group. The
+    four rows of a block are therefore ordered together: at every position the assignment of distinct groups
+    to rows that serves the most rows (and, among those, leaves the fullest groups for later) is taken; a
+    row that cannot be served takes an entry of its fullest group (ncu, Reservoir R = 1000: 3.45
+    shared-memory wavefronts per 8-byte gather in index order, 1.77 without conflicts)."""
+    import itertools
+    perms = list(itertools.permutations(range(4)))
+    out = np.array(cols, dtype='<i4', copy=True)
+    nrows = len(rowptr) - 1
+    for b0 in range(0, nrows, 4):
+        rows = list(range(b0, min(b0 + 4, nrows)))
+        groups = []
+        for r in rows:
+            row = out[int(rowptr[r]):int(rowptr[r + 1])]
+            gs = [list(row[row % 4 == g]) for g in range(4)]
+            for g in gs:
+                g.reverse()                      # pop() takes entries in index order
+            groups.append(gs)
+        orders = [[] for _ in rows]
+        left = [int(rowptr[r + 1] - rowptr[r]) for r in rows]
+        while any(left):
+            best, best_score = None, None
+            for pm in perms:
+                served = fill = 0
+                for i in range(len(rows)):
+                    if left[i] and groups[i][pm[i]]:
+                        served += 1
+                        fill += len(groups[i][pm[i]])
+                score = (served, fill)
+                if best_score is None or score > best_score:
+                    best, best_score = pm, score
+            for i in range(len(rows)):
+                if not left[i]:
+                    continue
+                g = groups[i][best[i]]
+                if not g:
+                    g = max(groups[i], key=len)
+                orders[i].append(g.pop())
+                left[i] -= 1
+        for i, r in enumerate(rows):
+            out[int(rowptr[r]):int(rowptr[r + 1])] = orders[i]
+    return out
+
+
 def _promote(a, b):
     return _ORDER[max(_ORDER.index(a), _ORDER.index(b))]
 
@@ -1187,7 +1235,7 @@ class Lowerer:
                 c4 = np.full(int(rp4[-1]), int(ext[axes[0]]), dtype='<i4')
                 src = np.asarray(cols[0], dtype='<i4')
                 pos = np.repeat(rp4[:-1] - rp[:-1], n) + np.arange(len(src))
-                c4[pos] = src
+                c4[pos] = _bank_schedule(rp, src) if len(n) <= (1 << 16) else src
                 row['rowptr4_off'] = self.pool_add(rp4.astype('<i4'), align=4)
                 row['col4_off'] = self.pool_add(c4, align=4)
                 row['sentinel4'] = int(ext[axes[0]])
