@@ -96,8 +96,8 @@ def algorithmic_bytes_per_env_step(name):
 MEASURED_TRAFFIC_BYTES_PER_ENV_STEP = {
     # rddl_plane_static, fused 20-step rollout of 4096 envs (r01_ncu_full_plane_static_rollout20_32x32_4096env.csv)
     'wildfire32': (168.882688e6 + 4.095232e6) / (20 * 4096),
-    # rddl_plane_static, one step of 128 envs (r01_ncu_full_plane_static_1024x1024_128env.csv)
-    'wildfire1024': (302.261760e6 + 9.407744e6) / 128,
+    # rddl_plane_static, one step of 4096 envs (r02_ncu_full_plane_static_1024x1024_4096env.csv)
+    'wildfire1024': (9.681582e9 + 1.051713e9) / 4096,
 }
 
 
@@ -529,7 +529,10 @@ def bench_workload(name, args, world, rank, dev, K, W, Ke, sampler=None, want_st
                     'traffic': traffic,
                     'peak_source': peak_src,
                     'kernel': ({'rddl_plane_interp': 'rddl_plane_static (NVRTC-specialised build of rddl_plane_interp)',
-                                'rddl_level_interp': 'rddl_level_static_%d (NVRTC-specialised build of rddl_level_interp)' % top['launch']
+                                'rddl_level_interp': (
+                                    'rddl_level_fused_%d (NVRTC-specialised: the scalar launches of the step as one env-tile kernel)'
+                                    if sim.native.info(9) > 0 else
+                                    'rddl_level_static_%d (NVRTC-specialised build of rddl_level_interp)') % top['launch']
                                 }.get(top['name'], top['name']) if sim.specialised_kernels else top['name']),
                     'kernel_us': per_launch_ms * 1e3, 'env_steps_per_launch': steps_per_launch,
                     'kernel_share_of_rollout': top['ms'] / max(1e-9, sum(r['ms'] for r in prof)),

@@ -242,6 +242,11 @@ __device__ __forceinline__ void rddl_randn_pair(uint64_t seed, uint64_t env, uin
   *z1 = rad * sn;
 }
 
+// Entry j of a column-index list: int32, or uint16 (padded lists whose indices fit)
+__device__ __forceinline__ int32_t rddl_csr_col(const int32_t* cols, int32_t j, bool u16) {
+  return u16 ? (int32_t)__ldg(reinterpret_cast<const uint16_t*>(cols) + j) : __ldg(cols + j);
+}
+
 // The constant / address-descriptor / reduction-slot pools a program executes from: device copies
 // of the op table (interpreter) or the constants of a specialised build.
 struct VmPools {
@@ -532,6 +537,7 @@ __device__ __forceinline__ void vm_exec_one(const VmArgs& A, const VmPools& P, c
       int32_t j0 = 0, j1 = (int32_t)arg;
       const int32_t* cols = nullptr;
       int64_t sentinel = -2;                   // (filler index of a padded list; never a real index)
+      bool u16 = false;                        // the padded list holds uint16 entries
       if (is_csr) {
         const RddlCsr* cs = P.csrs + arg;
         int64_t row = cs->row_c0;
@@ -543,6 +549,7 @@ __device__ __forceinline__ void vm_exec_one(const VmArgs& A, const VmPools& P, c
           j1 = __ldg(A.pool + cs->rowptr4_off + row + 1);
           cols = A.pool + cs->col4_off;
           sentinel = cs->sentinel4;
+          u16 = cs->col4_u16 != 0;
         } else {
           j0 = __ldg(A.pool + cs->rowptr_off + row);
           j1 = __ldg(A.pool + cs->rowptr_off + row + 1);
@@ -568,18 +575,27 @@ __device__ __forceinline__ void vm_exec_one(const VmArgs& A, const VmPools& P, c
           const uint32_t s4 = (uint32_t)__cvta_generic_to_shared(stage->ptr) + 8u * (uint32_t)stage->add;
           const uint32_t k4 = 8u * (uint32_t)stage->mul;
           double acc4 = 0.0;
-          int32_t g4 = q.x >> 2;
-          const int32_t g4l = (q.y >> 2) - 1;          // last group of the row
-#define RDDL_SUM4(c)                                                                         \
+          // 16-byte groups: four int32 or eight uint16 entries
+          const int sh = cs4->col4_u16 ? 3 : 2;
+          int32_t g4 = q.x >> sh;
+          const int32_t g4l = (q.y >> sh) - 1;         // last group of the row
+#define RDDL_SUM4(X, Y, Z, W)                                                                \
   {                                                                                           \
     double v0, v1, v2, v3;                                                                    \
-    asm("ld.shared.f64 %0, [%1];" : "=d"(v0) : "r"(s4 + k4 * (uint32_t)(c).x));              \
-    asm("ld.shared.f64 %0, [%1];" : "=d"(v1) : "r"(s4 + k4 * (uint32_t)(c).y));              \
-    asm("ld.shared.f64 %0, [%1];" : "=d"(v2) : "r"(s4 + k4 * (uint32_t)(c).z));              \
-    asm("ld.shared.f64 %0, [%1];" : "=d"(v3) : "r"(s4 + k4 * (uint32_t)(c).w));              \
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v0) : "r"(s4 + k4 * (uint32_t)(X)));                \
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v1) : "r"(s4 + k4 * (uint32_t)(Y)));                \
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v2) : "r"(s4 + k4 * (uint32_t)(Z)));                \
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v3) : "r"(s4 + k4 * (uint32_t)(W)));                \
     acc4 = __dadd_rn(acc4, __dadd_rn(__dadd_rn(v0, v1), __dadd_rn(v2, v3)));                  \
   }
-          // one group of four per half trip, the next group's indices in flight while this one is summed; two index
+#define RDDL_SUMG(c)                                                                         \
+  if (cs4->col4_u16) {                                                                        \
+    RDDL_SUM4((c).x & 0xffffu, (uint32_t)(c).x >> 16, (c).y & 0xffffu, (uint32_t)(c).y >> 16) \
+    RDDL_SUM4((c).z & 0xffffu, (uint32_t)(c).z >> 16, (c).w & 0xffffu, (uint32_t)(c).w >> 16) \
+  } else {                                                                                    \
+    RDDL_SUM4((c).x, (c).y, (c).z, (c).w)                                                     \
+  }
+          // one 16-byte group per half trip, the next group's indices in flight while this one is summed; two index
           // register sets used alternately (no copies), the look-ahead index clamped to the row's last group instead
           // of predicated (no default values to move). Measured on B200 and not kept (Reservoir R = 1000 x 4096 envs,
           // all within 124 +- 4 us): L1 prefetch of the thread's next row and next element, the warp's index
@@ -590,13 +606,14 @@ __device__ __forceinline__ void vm_exec_one(const VmArgs& A, const VmPools& P, c
 #pragma unroll 1
             for (;;) {
               cb = __ldg(c4 + min(g4 + 1, g4l));
-              RDDL_SUM4(ca)
+              RDDL_SUMG(ca)
               if (++g4 > g4l) break;
               ca = __ldg(c4 + min(g4 + 1, g4l));
-              RDDL_SUM4(cb)
+              RDDL_SUMG(cb)
               if (++g4 > g4l) break;
             }
           }
+#undef RDDL_SUMG
 #undef RDDL_SUM4
           r[dst] = from_f(acc4);
           break;
@@ -611,7 +628,7 @@ __device__ __forceinline__ void vm_exec_one(const VmArgs& A, const VmPools& P, c
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             v[u] = 0.0;
-            const int32_t cu = j + u < j1 ? __ldg(cols + j + u) : (int32_t)sentinel;
+            const int32_t cu = j + u < j1 ? rddl_csr_col(cols, j + u, u16) : (int32_t)sentinel;
             if (cu != (int32_t)sentinel) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v[u]) : "r"(s0 + (uint32_t)(sk * cu)));
           }
           acc = __dadd_rn(acc, __dadd_rn(__dadd_rn(v[0], v[1]), __dadd_rn(v[2], v[3])));
@@ -633,7 +650,7 @@ __device__ __forceinline__ void vm_exec_one(const VmArgs& A, const VmPools& P, c
         int64_t iv[4][2];
 #pragma unroll
         for (int u = 0; u < 4; ++u)
-          k[u] = j + u < j1 ? (is_csr ? (int64_t)__ldg(cols + j + u) : (int64_t)(j + u)) : -1;
+          k[u] = j + u < j1 ? (is_csr ? (int64_t)rddl_csr_col(cols, j + u, u16) : (int64_t)(j + u)) : -1;
 #pragma unroll
         for (int u = 0; u < 4; ++u)
           if (k[u] == sentinel) k[u] = -1;

@@ -205,7 +205,7 @@ static std::string level_static_data(const JitPools& P, const RddlLaunch* launch
   s += "0};\n__device__ constexpr RddlCsr kCsrs[] = {";
   for (int64_t i = 0; i < P.n_csrs; ++i) {
     const RddlCsr& c = P.csrs[i];
-    s += "{" + jit_fmt("%lldll,", (long long)c.rowptr_off) + jit_fmt("%lld,", c.ncols) + jit_fmt("%lld,{", c.pad);
+    s += "{" + jit_fmt("%lldll,", (long long)c.rowptr_off) + jit_fmt("%lld,", c.ncols) + jit_fmt("%lld,{", c.col4_u16);
     for (int k = 0; k < 4; ++k) s += jit_fmt("%lldll,", (long long)c.col_off[k]);
     s += "},{";
     for (int k = 0; k < 4; ++k) s += jit_fmt("%lld,", c.slot[k]);

@@ -4,7 +4,7 @@
 #include "rddl_stdint.h"
 
 #define RDDL_MAGIC 0x31304C444452ll
-#define RDDL_VERSION 10
+#define RDDL_VERSION 11
 #define RDDL_MAX_IDX 8
 #define RDDL_MAX_RED 8
 #define RDDL_MAX_REGS 96
@@ -61,15 +61,16 @@ struct RddlAddr {      // 184 bytes: element offset = env*env_stride + c0 + sum 
 
 struct RddlCsr {       // 176 bytes
   int64_t rowptr_off;
-  int32_t ncols, pad;
+  int32_t ncols, col4_u16;
   int64_t col_off[4];
   int32_t slot[4];
   int64_t row_c0;
   int32_t row_naxis, pad2;
   uint8_t row_axis[8];
   int64_t row_coef[8];
-  // single-column lists: a copy whose rows start on 16 bytes and hold a multiple of four entries, padded with
-  // sentinel4 (= the extent of the reduced axis: one past the last element); rowptr4_off == 0: absent
+  // single-column lists: a copy whose rows start on 16 bytes and hold a multiple of four int32 entries -- or, when
+  // col4_u16 is set, of eight uint16 entries -- padded with sentinel4 (= the extent of the reduced axis: one past
+  // the last element), in the order lowering._bank_schedule chose; rowptr4 counts entries; rowptr4_off == 0: absent
   int64_t rowptr4_off, col4_off, sentinel4;
 };
 

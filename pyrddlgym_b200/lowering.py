@@ -1224,21 +1224,25 @@ class Lowerer:
             row['col_off'][i] = self.pool_add(c)
             row['slot'][i] = a
         if len(axes) == 1 and len(rowptr) > 1:
-            # padded copy for the staged sparse sums (rddl_device.cuh, SUMLOOP): rows start on 16-byte
-            # boundaries and hold a multiple of four entries, the filler being the extent of the reduced
-            # axis -- one past the last element, where the staged vector keeps a zero
+            # padded copy for the sparse sums (rddl_device.cuh, SUMLOOP): rows start on 16-byte boundaries and
+            # hold a multiple of four int32 (or eight uint16) entries, the filler being the extent of the
+            # reduced axis -- one past the last element, where the staged vector keeps a zero
             rp = np.asarray(rowptr, dtype=np.int64)
             n = np.diff(rp)
-            n4 = (n + 3) // 4 * 4
+            sent = int(ext[axes[0]])
+            u16 = sent <= 0xffff                  # eight 16-bit indices per 128-bit load instead of four
+            per = 8 if u16 else 4
+            n4 = (n + per - 1) // per * per
             rp4 = np.concatenate([[0], np.cumsum(n4)])
             if rp4[-1] < 2 ** 31:
-                c4 = np.full(int(rp4[-1]), int(ext[axes[0]]), dtype='<i4')
+                c4 = np.full(int(rp4[-1]), sent, dtype='<u2' if u16 else '<i4')
                 src = np.asarray(cols[0], dtype='<i4')
                 pos = np.repeat(rp4[:-1] - rp[:-1], n) + np.arange(len(src))
                 c4[pos] = _bank_schedule(rp, src) if len(n) <= (1 << 16) else src
                 row['rowptr4_off'] = self.pool_add(rp4.astype('<i4'), align=4)
-                row['col4_off'] = self.pool_add(c4, align=4)
-                row['sentinel4'] = int(ext[axes[0]])
+                row['col4_off'] = self.pool_add(c4.view('<i4'), align=4)
+                row['sentinel4'] = sent
+                row['col4_u16'] = 1 if u16 else 0
                 if row['rowptr4_off'] == 0:       # (0 means absent: an empty pool gets a filler first)
                     raise LoweringError('internal: padded list at pool offset 0')
         s = 1

@@ -13,7 +13,7 @@ slots the kernels need. It is a flat little-endian blob:
 import numpy as np
 
 MAGIC = 0x31304C444452  # "RDDL01"
-VERSION = 10
+VERSION = 11
 MAX_IDX = 8          # index variables per thread: scope axes + nested loop axes
 MAX_RED = 8          # reduction outputs per launch
 MAX_REGS = 96        # virtual 64-bit registers per thread
@@ -69,12 +69,13 @@ INSN = np.dtype([('op', 'u1'), ('flags', 'u1'), ('dst', '<u2'), ('a', '<u2'), ('
 ADDR = np.dtype([('tensor', '<i4'), ('naxis', '<i4'), ('env_stride', '<i8'), ('c0', '<i8'),
                  ('axis', 'u1', (8,)), ('coef', '<i8', (8,)), ('nreg', '<i4'), ('pad', '<i4'),
                  ('reg', '<i4', (4,)), ('rstride', '<i8', (4,)), ('rextent', '<i8', (4,))])
-CSR = np.dtype([('rowptr_off', '<i8'), ('ncols', '<i4'), ('pad', '<i4'), ('col_off', '<i8', (4,)),
+CSR = np.dtype([('rowptr_off', '<i8'), ('ncols', '<i4'), ('col4_u16', '<i4'), ('col_off', '<i8', (4,)),
                 ('slot', '<i4', (4,)), ('row_c0', '<i8'), ('row_naxis', '<i4'), ('pad2', '<i4'),
                 ('row_axis', 'u1', (8,)), ('row_coef', '<i8', (8,)),
-                # single-column lists: a second copy with every row padded to a multiple of four entries
-                # (16-byte aligned; padding entries = sentinel4, the extent of the reduced axis) for the
-                # 128-bit index loads of the staged sparse sums; rowptr4_off = 0: absent
+                # single-column lists: a second copy with every row padded to 16 bytes -- a multiple of four
+                # int32 entries, or (col4_u16 = 1, when the indices fit) of eight uint16 entries; padding
+                # entries = sentinel4, the extent of the reduced axis -- in the bank-scheduled order every
+                # float SUMLOOP adds them in; rowptr4_off = 0: absent. rowptr4 counts entries.
                 ('rowptr4_off', '<i8'), ('col4_off', '<i8'), ('sentinel4', '<i8')])
 TENSOR = np.dtype([('dtype', '<i2'), ('pair', '<i2'), ('kind', '<i4'), ('nelem', '<i8')])  # pair: id of the primed partner of a state fluent, else -1
 LAUNCH = np.dtype([('plan', '<i4'), ('rank', '<i4'), ('extent', '<i8', (8,)), ('E', '<i8'),
