@@ -30,6 +30,7 @@ struct VmArgs {
   uint32_t* status;
   int64_t n_envs, env_offset;
   uint64_t seed, step;
+  RddlPhiloxKeys rk;           // Philox round keys of `seed` (rddl_philox_round_keys; filled by the host)
   RddlLaunch L;
   void* tensors[RDDL_MAX_TENSORS];
   uint8_t dtype[RDDL_MAX_TENSORS];
@@ -232,9 +233,9 @@ __device__ __forceinline__ uint64_t rddl_policy_value(const VmPolicy& pol, const
 // sincospi(2 u): no argument reduction of 2 pi u (no Payne-Hanek path, no stack slot for its quadrant).
 __device__ __forceinline__ uint64_t rddl_randn_counter(uint64_t e) { return ((e >> 4) << 3) | (e & 7u); }
 __device__ __forceinline__ bool rddl_randn_branch(uint64_t e) { return ((e >> 3) & 1u) != 0; }
-__device__ __forceinline__ void rddl_randn_pair(uint64_t seed, uint64_t env, uint64_t step, uint32_t node, uint64_t q,
+__device__ __forceinline__ void rddl_randn_pair(const RddlPhiloxKeys& rk, uint64_t env, uint64_t step, uint32_t node, uint64_t q,
                                                 double* z0, double* z1) {
-  const uint4 x = rddl_philox_draw(seed, env, step, node, q);
+  const uint4 x = rddl_philox_draw(rk, env, step, node, q);
   const double rad = sqrt(-2.0 * log(1.0 - rddl_u53(x.x, x.y)));
   double sn, cs;
   sincospi(2.0 * rddl_u53(x.z, x.w), &sn, &cs);
@@ -354,10 +355,10 @@ __device__ __forceinline__ void vm_exec_one(const VmArgs& A, const VmPools& P, c
           if (op == OP_RANDN) {
             // Box-Muller pair of elements 2q, 2q + 1 (one Philox block): this element's branch
             double z0, z1;
-            rddl_randn_pair(A.seed, (uint64_t)(A.env_offset + env), step, node, rddl_randn_counter((uint64_t)off), &z0, &z1);
+            rddl_randn_pair(A.rk, (uint64_t)(A.env_offset + env), step, node, rddl_randn_counter((uint64_t)off), &z0, &z1);
             v = rddl_randn_branch((uint64_t)off) ? z1 : z0;
           } else {
-            uint4 x = rddl_philox_draw(A.seed, (uint64_t)(A.env_offset + env), step, node, (uint64_t)off);
+            uint4 x = rddl_philox_draw(A.rk, (uint64_t)(A.env_offset + env), step, node, (uint64_t)off);
             const double u = rddl_u53(x.x, x.y);
             if (op == OP_RANDU) v = u;
             else if (op == OP_RANDE) v = -log1p(-u);

@@ -195,7 +195,7 @@ __device__ __forceinline__ void vm_seq(VmStaticCtx& c) {
           for (int i = 0; i < 8; ++i)
             if (i < ad.naxis) off += ad.coef[i] * (int64_t)c.idx[ad.axis[i]];
           double z0, z1;
-          rddl_randn_pair(c.A.seed, (uint64_t)(c.A.env_offset + c.env), c.step, (uint32_t)c.A.variates[ra].node,
+          rddl_randn_pair(c.A.rk, (uint64_t)(c.A.env_offset + c.env), c.step, (uint32_t)c.A.variates[ra].node,
                           rddl_randn_counter((uint64_t)off), &z0, &z1);
           c.r[raw.x >> 16] = from_f(z0);
           c.zpair[kPairs.slot[PC]] = z1;

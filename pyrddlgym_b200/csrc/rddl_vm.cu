@@ -1056,6 +1056,7 @@ static int run_plan(rddl_program* g, int plan, void* const* tensors, const doubl
   A.pool = g->d_pool; A.variates = g->d_variates; A.redslots = g->d_redslots; A.red_off = g->d_red_off;
   A.red = g->d_red; A.status = status; A.n_envs = n_envs; A.env_offset = env_offset;
   A.seed = seed; A.step = step;
+  rddl_philox_round_keys(seed, &A.rk);
   A.n_steps = 1;
   if (ro) {
     A.n_steps = ro->n_steps; A.gamma = ro->gamma; A.returns = ro->returns; A.rewards = ro->rewards;
