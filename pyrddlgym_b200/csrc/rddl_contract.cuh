@@ -14,6 +14,12 @@
 // axis of each operand; tiles past the matrix edge are zero-filled. The K loop is software
 // pipelined: the global loads of step k + 1 are issued into registers before the DMMAs of step k
 // and stored into the other shared buffer after them (smaller CTA tiles for more CTAs measured slower).
+//
+// Split K (gridDim.z = S > 1): at 512 x 512 x 1024 envs the 64 x 64 tiling gives 128 CTAs of four warps --
+// one CTA per SM, 6 % warp occupancy, the DMMA pipe half idle behind its own latency. S CTAs per output
+// tile each take a K range (multiples of 16), write their partial tile to a scratch buffer, and the CTA
+// that arrives last at the tile's counter adds the S partials in range order and stores the result: the
+// sum has a fixed order whatever the arrival order (deterministic), and the counter resets itself.
 #pragma once
 #include <stdint.h>
 
@@ -32,14 +38,14 @@ __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, do
 // step k run (register double buffering; the shared tiles are double buffered too, one barrier per step).
 template <int CT_BN>
 __device__ __forceinline__ void contract_fetch(const double* __restrict__ X, const double* __restrict__ W, int64_t M, int N,
-                                               int K, int64_t w_stride_k, int64_t w_stride_n, int64_t m0, int n0, int k0,
-                                               int tid, double* xa, double* wb) {
+                                               int K, int kend, int64_t w_stride_k, int64_t w_stride_n, int64_t m0, int n0,
+                                               int k0, int tid, double* xa, double* wb) {
 #pragma unroll
   for (int q = 0; q < CT_BM * CT_BK / 128; ++q) {
     const int i = tid + 128 * q, r = i / CT_BK, c = i - r * CT_BK;
     const int64_t m = m0 + r;
     const int k = k0 + c;
-    xa[q] = (m < M && k < K) ? X[m * K + k] : 0.0;
+    xa[q] = (m < M && k < kend) ? X[m * K + k] : 0.0;      // (kend: end of this CTA's K range)
   }
 #pragma unroll
   for (int q = 0; q < CT_BK * CT_BN / 128; ++q) {
@@ -48,7 +54,7 @@ __device__ __forceinline__ void contract_fetch(const double* __restrict__ X, con
     if (w_stride_n == 1) { r = i / CT_BN; c = i - r * CT_BN; }
     else { c = i / CT_BK; r = i - c * CT_BK; }
     const int k = k0 + r, n = n0 + c;
-    wb[q] = (k < K && n < N) ? W[(int64_t)k * w_stride_k + (int64_t)n * w_stride_n] : 0.0;
+    wb[q] = (k < kend && n < N) ? W[(int64_t)k * w_stride_k + (int64_t)n * w_stride_n] : 0.0;
   }
 }
 
@@ -73,7 +79,9 @@ __device__ __forceinline__ void contract_stage(double (*As)[CT_BK + CT_PAD], dou
 template <int CT_BN>
 __global__ void __launch_bounds__(128) rddl_contract_f64(const double* __restrict__ X, const double* __restrict__ W,
                                                          double* __restrict__ Out, int64_t M, int N, int K,
-                                                         int64_t w_stride_k, int64_t w_stride_n) {
+                                                         int64_t w_stride_k, int64_t w_stride_n,
+                                                         double* __restrict__ partial = nullptr,
+                                                         unsigned int* __restrict__ arrived = nullptr, int k_per_split = 0) {
   __shared__ double As[2][CT_BM][CT_BK + CT_PAD];   // x tile: [env][k], double buffered
   __shared__ double Bs[2][CT_BN][CT_BK + CT_PAD];   // W tile, n-major: [n][k]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -87,14 +95,18 @@ __global__ void __launch_bounds__(128) rddl_contract_f64(const double* __restric
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
+  // this CTA's K range (everything without split K)
+  const int S = (int)gridDim.z;
+  const int kb = S > 1 ? (int)blockIdx.z * k_per_split : 0;
+  const int ke = S > 1 ? min(K, kb + k_per_split) : K;
   double xa[CT_BM * CT_BK / 128], wb[CT_BK * CT_BN / 128];
-  contract_fetch<CT_BN>(X, W, M, N, K, w_stride_k, w_stride_n, m0, n0, 0, tid, xa, wb);
+  contract_fetch<CT_BN>(X, W, M, N, K, ke, w_stride_k, w_stride_n, m0, n0, kb, tid, xa, wb);
   contract_stage<CT_BN>(As[0], Bs[0], w_stride_n, tid, xa, wb);
   __syncthreads();
   int cur = 0;
-  for (int k0 = 0; k0 < K; k0 += CT_BK) {
-    const bool more = k0 + CT_BK < K;
-    if (more) contract_fetch<CT_BN>(X, W, M, N, K, w_stride_k, w_stride_n, m0, n0, k0 + CT_BK, tid, xa, wb);   // in flight during the DMMAs
+  for (int k0 = kb; k0 < ke; k0 += CT_BK) {
+    const bool more = k0 + CT_BK < ke;
+    if (more) contract_fetch<CT_BN>(X, W, M, N, K, ke, w_stride_k, w_stride_n, m0, n0, k0 + CT_BK, tid, xa, wb);   // in flight during the DMMAs
 #pragma unroll
     for (int kk = 0; kk < CT_BK; kk += 4) {
       double a[4], b[TN];
@@ -111,6 +123,40 @@ __global__ void __launch_bounds__(128) rddl_contract_f64(const double* __restric
     if (more) contract_stage<CT_BN>(As[cur ^ 1], Bs[cur ^ 1], w_stride_n, tid, xa, wb);
     __syncthreads();
     cur ^= 1;
+  }
+  if (S > 1) {
+    // partial tiles: [tile][split][fragment slot][thread] -- a thread's slots are coalesced across the CTA
+    __shared__ int last;
+    const int64_t tile = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
+    double* mine = partial + (tile * S + blockIdx.z) * (CT_BM * CT_BN);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) {
+        mine[((i * TN + j) * 2 + 0) * 128 + tid] = acc[i][j][0];
+        mine[((i * TN + j) * 2 + 1) * 128 + tid] = acc[i][j][1];
+      }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned int t = atomicAdd(arrived + tile, 1u);
+      last = t == (unsigned int)(S - 1);
+      if (last) arrived[tile] = 0u;       // (every split has arrived: ready for the next launch)
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    const double* all = partial + tile * S * (CT_BM * CT_BN);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          double v = 0.0;
+          for (int sp = 0; sp < S; ++sp) v += __ldcg(all + (int64_t)sp * (CT_BM * CT_BN) + ((i * TN + j) * 2 + h) * 128 + tid);
+          acc[i][j][h] = v;
+        }
   }
   // C fragment: row = lane/4, cols = (lane%4)*2 + {0, 1}
 #pragma unroll
