@@ -1140,16 +1140,30 @@ static int run_plan(rddl_program* g, int plan, void* const* tensors, const doubl
         }
         grid.z = (unsigned)S;
       }
-      if (bn == 64)
-        rddl_contract_f64<64><<<grid, 128, 0, stream>>>((const double*)tensors[L.red_slot[1]], (const double*)tensors[L.red_slot[0]],
-                                                        (double*)tensors[L.red_slot[2]], n_envs, N, K,
-                                                        (int64_t)L.red_op[0], (int64_t)L.red_op[1], g->d_ct_partial,
-                                                        g->d_ct_arrived, kps);
+      const double* Xp = (const double*)tensors[L.red_slot[1]];
+      const double* Wp = (const double*)tensors[L.red_slot[0]];
+      double* Op = (double*)tensors[L.red_slot[2]];
+      const int64_t wsk = (int64_t)L.red_op[0], wsn = (int64_t)L.red_op[1];
+      // cp.async pipeline where 16-byte copies are possible (RDDL_CONTRACT_ASYNC=0: the register-staged loop)
+      bool async = wsn == 1 && (K & 1) == 0 && (N & 1) == 0 && (wsk & 1) == 0 && ((uintptr_t)Xp & 15) == 0 && ((uintptr_t)Wp & 15) == 0;
+      if (const char* e = getenv("RDDL_CONTRACT_ASYNC")) async = async && atoi(e) != 0;
+      if (async) {
+        static bool attr_set = false;
+        if (!attr_set) {
+          CK(cudaFuncSetAttribute(rddl_contract_f64<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_ASYNC_SMEM(64)));
+          CK(cudaFuncSetAttribute(rddl_contract_f64<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_ASYNC_SMEM(32)));
+          attr_set = true;
+        }
+        if (bn == 64)
+          rddl_contract_f64<64, true><<<grid, 128, CT_ASYNC_SMEM(64), stream>>>(Xp, Wp, Op, n_envs, N, K, wsk, wsn, g->d_ct_partial,
+                                                                                g->d_ct_arrived, kps);
+        else
+          rddl_contract_f64<32, true><<<grid, 128, CT_ASYNC_SMEM(32), stream>>>(Xp, Wp, Op, n_envs, N, K, wsk, wsn, g->d_ct_partial,
+                                                                                g->d_ct_arrived, kps);
+      } else if (bn == 64)
+        rddl_contract_f64<64><<<grid, 128, 0, stream>>>(Xp, Wp, Op, n_envs, N, K, wsk, wsn, g->d_ct_partial, g->d_ct_arrived, kps);
       else
-        rddl_contract_f64<32><<<grid, 128, 0, stream>>>((const double*)tensors[L.red_slot[1]], (const double*)tensors[L.red_slot[0]],
-                                                        (double*)tensors[L.red_slot[2]], n_envs, N, K,
-                                                        (int64_t)L.red_op[0], (int64_t)L.red_op[1], g->d_ct_partial,
-                                                        g->d_ct_arrived, kps);
+        rddl_contract_f64<32><<<grid, 128, 0, stream>>>(Xp, Wp, Op, n_envs, N, K, wsk, wsn, g->d_ct_partial, g->d_ct_arrived, kps);
     } else if (L.kind == 1) {
       const PlaneProg& G = pp ? pp->G : g->plane_progs[(size_t)(&L - g->launches.data())];
       const int W32 = (int)((L.rank == 2 ? L.extent[1] : L.extent[0]) >> 5);
