@@ -485,6 +485,52 @@ def bench_workload(name, args, world, rank, dev, K, W, Ke, sampler=None, want_st
     launches = K * launches_per_episode + K       # kernels of this library per episode + rddl_return_stats
     del graph
 
+    # ---- the same rollouts with the bool action planes handed over BIT-PACKED (packed_actions=True: int32 words,
+    # 32 cells each -- 1/8 of the action bytes of the reference boundary's layout), graph-replayed like `value`
+    packed_value = None
+    if w['kind'] == 'wildfire' and not args.no_packed:
+        psim = BatchedSimulator(p, n_envs=N, device=dev, seed=42, env_offset=off, specialize=True, packed_actions=True)
+        pseq = {k: torch.stack([BatchedSimulator.pack_bool(v[t]) for t in range(R)]) for k, v in seq.items()}
+        preturns = torch.zeros(N, dtype=torch.float64, device=dev)
+
+        def episode_packed():
+            psim.reset()
+            preturns.zero_()
+            psim.rollout(pseq, R, gamma=gamma, returns=preturns)
+            local_stats.copy_(parallel.local_return_stats(preturns))
+
+        for _ in range(3):
+            episode_packed()
+        torch.cuda.synchronize()
+        pgraph = None
+        if not args.no_graph:
+            try:
+                pgraph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(pgraph):
+                    episode_packed()
+                pgraph.replay()
+            except Exception as e:
+                sys.stderr.write('bench: CUDA graph capture failed for the packed-action rollout (%s)\n' % e)
+                pgraph = None
+        Kp = max(1, min(K, 10))
+        barrier()
+        e0.record()
+        for _ in range(Kp):
+            if pgraph is not None:
+                pgraph.replay()
+            else:
+                episode_packed()
+        e1.record()
+        barrier()
+        tp = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+        packed_value = G * R * Kp / (float(tp.item()) * 1e-3)
+        del pgraph, pseq
+        psim.close()
+        del psim
+        torch.cuda.empty_cache()
+
     # ---- one episode through the per-transition call (rddl_step per env-step), for comparison
     step_api_value = None
     if want_step_api:
@@ -675,6 +721,8 @@ def bench_workload(name, args, world, rank, dev, K, W, Ke, sampler=None, want_st
     }
     if step_api_value is not None:
         out['step_api_value'] = step_api_value
+    if packed_value is not None:
+        out['packed_actions_value'] = packed_value
     sim.close()
     del sim
     torch.cuda.empty_cache()
@@ -708,7 +756,7 @@ def run_gpu(args):
                 s = bench_workload(sname, args, world, rank, dev, max(3, min(K, 10)), 3, max(1, min(Ke, 5)),
                                    want_step_api=True)
                 secondary.append({k: s[k] for k in ('workload', 'value', 'unit', 'ms_per_step', 'steps', 'roofline', 'e2e',
-                                                    'launches', 'step_api_value') if k in s})
+                                                    'launches', 'step_api_value', 'packed_actions_value') if k in s})
             except Exception as e:      # a secondary entry must never take the headline down
                 secondary.append({'workload': workload_label(sname), 'error': repr(e)[:300]})
     if rank == 0:
@@ -729,6 +777,11 @@ def run_gpu(args):
                               f'all-gathered (NCCL) once per rollout on a side stream overlapping the next rollout')
         if 'step_api_value' in main:
             cfg['step_api_value'] = main['step_api_value']
+        if 'packed_actions_value' in main:
+            cfg['packed_actions_value'] = main['packed_actions_value']
+            cfg['packed_actions_note'] = ('value with the bool action planes handed over bit-packed (BatchedSimulator(packed_actions=True): '
+                                          'int32 words of 32 cells, 1/8 of the action bytes); same action sequence, bit-identical transitions '
+                                          '(tests/test_cuda_parity.py::test_bit_packed_action_input_equals_byte_actions)')
         if secondary:
             cfg['secondary'] = secondary
         line = {
@@ -761,6 +814,7 @@ def main():
     ap.add_argument('--sync-collective', action='store_true', help='run the statistics all-gather on the main stream')
     ap.add_argument('--no-graph', action='store_true', help='issue every episode eagerly instead of replaying a CUDA graph')
     ap.add_argument('--no-secondary', action='store_true', help='skip the secondary BASELINE configs')
+    ap.add_argument('--no-packed', action='store_true', help='skip the bit-packed-action variant of the Wildfire rollouts')
     ap.add_argument('--rollout', type=int, default=0, help='env-steps per rollout (default: per workload)')
     ap.add_argument('--e2e-steps', type=int, default=10, help='rollouts timed for the end-to-end figure (<= --steps)')
     args = ap.parse_args()

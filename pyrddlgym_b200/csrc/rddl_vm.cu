@@ -797,6 +797,10 @@ __global__ void rddl_action_count_kernel(const __grid_constant__ ActionCountArgs
       const uint8_t* p = reinterpret_cast<const uint8_t*>(a.ptr[t]) + env * n;
       const bool d = a.dflt[t] != 0;
       for (int64_t i = lane; i < n; i += 32) c += (p[i] != 0) != d;
+    } else if (a.dtype[t] == DT_PACKED) {     // bit-packed bool fluent (n is a multiple of 32): popcount of the differing bits
+      const uint32_t* p = reinterpret_cast<const uint32_t*>(a.ptr[t]) + env * (n >> 5);
+      const uint32_t d = a.dflt[t] != 0 ? 0xffffffffu : 0u;
+      for (int64_t i = lane; i < (n >> 5); i += 32) c += __popc(p[i] ^ d);
     } else if (a.dtype[t] == DT_REAL) {
       const double* p = reinterpret_cast<const double*>(a.ptr[t]) + env * n;
       const double d = __longlong_as_double((long long)a.dflt[t]);
@@ -1439,7 +1443,7 @@ extern "C" int rddl_action_count(rddl_program_t* g, void* const* tensors, const 
   a.n = n_actions;
   for (int i = 0; i < n_actions; ++i) {
     const int t = action_tensors[i];
-    if (t < 0 || (size_t)t >= g->tensors.size() || !tensors[t] || g->tensors[t].dtype == DT_PACKED) {
+    if (t < 0 || (size_t)t >= g->tensors.size() || !tensors[t]) {
       g->err = "rddl_action_count: bad action tensor";
       return RDDL_ERR_ARG;
     }
@@ -1448,7 +1452,7 @@ extern "C" int rddl_action_count(rddl_program_t* g, void* const* tensors, const 
     a.dtype[i] = (uint8_t)g->tensors[t].dtype;
     const double d = default_values[i];
     if (a.dtype[i] == DT_REAL) memcpy(&a.dflt[i], &d, 8);
-    else a.dflt[i] = a.dtype[i] == DT_BOOL ? (uint64_t)(d != 0.0) : (uint64_t)(int64_t)d;
+    else a.dflt[i] = (a.dtype[i] == DT_BOOL || a.dtype[i] == DT_PACKED) ? (uint64_t)(d != 0.0) : (uint64_t)(int64_t)d;
   }
   rddl_action_count_kernel<<<(unsigned)((n_envs * 32 + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(a, counts, n_envs);
   CK(cudaGetLastError());

@@ -1029,9 +1029,10 @@ SPECIALS = ['__reward', '__done', '__chk']
 
 class Lowerer:
 
-    def __init__(self, program, use_planes=True, use_contract=True, use_packed=True):
+    def __init__(self, program, use_planes=True, use_contract=True, use_packed=True, packed_actions=False):
         self.p = program
         self.use_packed = use_packed
+        self.packed_actions = packed_actions
         self.use_planes = use_planes
         self.use_contract = use_contract
         self.contract_items = {}
@@ -1627,6 +1628,19 @@ class Lowerer:
                 row[0] = 3
                 self.tensor_rows[t] = tuple(row)
                 self.out.packed.append(name)
+        if self.packed_actions:
+            # opt-in: bool action fluents the plane kernels read are taken bit-packed from the caller
+            # (uint32 [n_envs, cells / 32]: 1/8 of the bytes of the reference boundary's bool arrays);
+            # scalar programs that read them as well extract the bit (OP_LOAD of a packed tensor)
+            for name in p.names_of_kind('action'):
+                t = self.tensor_id[name]
+                nelem = self.out.tensor_meta[name][2]
+                if p.tensors[name].dtype != 'b' or nelem % 32 or t in scalar_w or t in other or t not in plane_rw:
+                    continue
+                row = list(self.tensor_rows[t])
+                row[0] = 3
+                self.tensor_rows[t] = tuple(row)
+                self.out.packed.append(name)
 
     def _or_all(self, exprs):
         out = exprs[0]
@@ -1674,7 +1688,8 @@ class Lowerer:
                 self.schedule(plan, items)
 
 
-def lower(program, use_planes=True, use_contract=True, use_packed=True):
+def lower(program, use_planes=True, use_contract=True, use_packed=True, packed_actions=False):
     """Lowers an HIR ``Program`` to an ``OpTable``. ``use_planes=False`` keeps every launch on
     the general scalar interpreter (used by tests to cross-check the two paths)."""
-    return Lowerer(program, use_planes=use_planes, use_contract=use_contract, use_packed=use_packed).lower()
+    return Lowerer(program, use_planes=use_planes, use_contract=use_contract, use_packed=use_packed,
+                   packed_actions=packed_actions).lower()

@@ -75,13 +75,18 @@ class BatchedSimulator:
     """N independent environments of one compiled RDDL problem, stepped in lock-step."""
 
     def __init__(self, program, n_envs=1, device='cuda:0', seed=0, env_offset=0, optable=None,
-                 use_planes=True, use_contract=True, use_packed=True, specialize=None, contract_precision='f64'):
+                 use_planes=True, use_contract=True, use_packed=True, specialize=None, contract_precision='f64',
+                 packed_actions=False):
         """``specialize``: run-time specialised kernels (NVRTC, csrc/rddl_jit.h) for this program.
         None = the library default (on unless RDDL_B200_JIT=0: plane kernels on first use, scalar
         kernels once the program is hot); True = everything on first use; False = interpreter kernels.
         ``contract_precision``: 'f64' (default) = sum-product contractions on the exact FP64 tensor-core
         kernel; 'bf16x3' = the tcgen05 kernel on three-term bfloat16 splits with float32 accumulation in
-        tensor memory (csrc/rddl_contract_tc.cuh; within the 1e-5 relative tolerance for reals)."""
+        tensor memory (csrc/rddl_contract_tc.cuh; within the 1e-5 relative tolerance for reals).
+        ``packed_actions``: bool action fluents the bit-plane kernels read are taken BIT-PACKED (int32
+        [n_envs, cells / 32], cell i -> bit i % 32 of word i / 32; ``pack_bool`` converts): 1/8 of the bytes of
+        the reference boundary's bool arrays. ``set_actions`` / ``step`` / ``rollout`` then accept either the packed
+        words (used in place) or bool arrays (packed on the way in); ``fluent`` still returns bools."""
         self.program = program
         self.n_envs = int(n_envs)
         self.device = torch.device(device)
@@ -90,7 +95,8 @@ class BatchedSimulator:
         self.seed_value = int(seed)
         self.env_offset = int(env_offset)
         self.table = optable if optable is not None else lowering.lower(
-            program, use_planes=use_planes, use_contract=use_contract, use_packed=use_packed)
+            program, use_planes=use_planes, use_contract=use_contract, use_packed=use_packed,
+            packed_actions=packed_actions)
         index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self.native = native.NativeProgram(self.table.blob, index)
         if specialize is not None:
@@ -255,8 +261,20 @@ class BatchedSimulator:
     def _pack(x):
         """bool [n, cells] -> int32 [n, cells / 32], cell i -> bit (i % 32) of word i / 32."""
         n = x.shape[0]
-        w = x.reshape(n, -1, 32).to(torch.int64) << torch.arange(32, device=x.device, dtype=torch.int64)
-        return w.sum(-1).to(torch.int32)
+        x = x.reshape(n, -1, 32)
+        # (row blocks: the int64 intermediate is 8 bytes per cell)
+        rows = max(1, (1 << 27) // max(1, x.shape[1] * 32))
+        sh = torch.arange(32, device=x.device, dtype=torch.int64)
+        out = torch.empty((n, x.shape[1]), dtype=torch.int32, device=x.device)
+        for r0 in range(0, n, rows):
+            out[r0:r0 + rows] = (x[r0:r0 + rows].to(torch.int64) << sh).sum(-1).to(torch.int32)
+        return out
+
+    @staticmethod
+    def pack_bool(x):
+        """bool [..., *shape] with prod(shape) % 32 == 0 over the LAST axes flattened per leading row ->
+        int32 [leading, cells / 32]: the layout of bit-packed fluents (leading = x.shape[0])."""
+        return BatchedSimulator._pack(x.reshape(x.shape[0], -1))
 
     @staticmethod
     def _unpack(w, shape):
@@ -283,6 +301,11 @@ class BatchedSimulator:
             if name not in self.tid or name not in self.action_names:
                 raise KeyError(f'<{name}> is not an action-fluent')
             dst = self._owned_actions[name]
+            if name in self.packed and not (isinstance(v, torch.Tensor) and v.dtype is torch.int32):
+                # bool values for a bit-packed action fluent: packed on the way in
+                b = v if isinstance(v, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(v))
+                shape = (self.n_envs,) + tuple(self.program.tensor_shape(name))
+                v = self.pack_bool(b.to(self.device).to(torch.bool).expand(shape))
             if isinstance(v, torch.Tensor):
                 if (v.dtype is dst.dtype and v.shape == dst.shape and v.is_contiguous()
                         and v.device == dst.device):
@@ -348,6 +371,11 @@ class BatchedSimulator:
                 raise KeyError(f'<{name}> is not an action-fluent')
             dst = self._owned_actions[name]
             v = v if isinstance(v, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(v))
+            if name in self.packed and v.dtype is not torch.int32:
+                # bool sequence [n_steps, N, *shape] (or [N, *shape]) for a bit-packed fluent
+                b = v.to(self.device).to(torch.bool)
+                lead = b.shape[:b.dim() - len(self.program.tensor_shape(name))]
+                v = self.pack_bool(b.reshape((-1,) + tuple(self.program.tensor_shape(name)))).reshape(tuple(lead) + (-1,))
             v = v.to(self.device, dtype=dst.dtype).contiguous()
             if tuple(v.shape) == (n_steps,) + tuple(dst.shape):
                 strides[self.tid[name]] = dst.numel() * dst.element_size()
@@ -392,6 +420,9 @@ class BatchedSimulator:
         for i, (name, how) in enumerate(spec.items()):
             if name not in self.action_names:
                 raise KeyError(f'<{name}> is not an action-fluent')
+            if name in self.packed:
+                raise ValueError(f'<{name}> is taken bit-packed (packed_actions=True): device-side policies draw into '
+                                 'the byte layout; build the simulator without packed_actions for them')
             dt = self.program.tensors[name].dtype
             e = pol.entries[i]
             e.tensor = self.tid[name]

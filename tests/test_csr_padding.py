@@ -73,3 +73,18 @@ def test_normal_variates_pair_elements_eight_apart():
     big = philox_np.base_variates('N', 1, np.arange(64), 0, 9, (4096,))
     assert abs(big.mean()) < 0.01 and abs(big.std() - 1.0) < 0.01
     assert abs(np.corrcoef(big[:, :8].ravel(), big[:, 8:16].ravel())[0, 1]) < 0.1
+
+
+def test_packed_actions_is_opt_in_and_covers_the_plane_read_action_fluents():
+    """lowering.lower(packed_actions=True): bool action fluents the plane launch reads get the packed dtype code."""
+    p = workloads.load_program(workloads.wildfire(32))
+    plain = lowering.lower(p)
+    packed = lowering.lower(p, packed_actions=True)
+    assert not ({'put-out', 'cut-out'} & set(plain.packed))
+    assert {'put-out', 'cut-out'} <= set(packed.packed)
+    tens = optable_emulator._sections(packed.blob)[0]
+    for name in ('put-out', 'cut-out'):
+        assert int(tens[packed.tensor_id[name]]['dtype']) == 3
+    # a real-valued action fluent is never packed
+    r = lowering.lower(workloads.load_program(workloads.reservoir(8)), packed_actions=True)
+    assert 'release' not in set(r.packed)
