@@ -97,7 +97,10 @@ MEASURED_TRAFFIC_BYTES_PER_ENV_STEP = {
     # rddl_plane_static, fused 20-step rollout of 4096 envs (r01_ncu_full_plane_static_rollout20_32x32_4096env.csv)
     'wildfire32': (168.882688e6 + 4.095232e6) / (20 * 4096),
     # rddl_plane_static, one step of 4096 envs (r02_ncu_full_plane_static_1024x1024_4096env.csv)
-    'wildfire1024': (9.681582e9 + 1.051713e9) / 4096,
+    'wildfire1024': (9.690350e9 + 1.051693e9) / 4096,
+    # rddl_level_fused_0, one step of 4096 envs (r02_ncu_full_level_fused_reservoir1000_4096env.csv): more than the
+    # algorithmic bytes because the three interm fluents (rain, released, inflow) are written out as well
+    'reservoir1000': (72.833792e6 + 80.861952e6) / 4096,
 }
 
 

@@ -9,7 +9,7 @@ from pyrddlgym_b200 import lowering, native, workloads
 
 OUT = os.path.join(ROOT, 'profiles')
 SO = os.path.join(ROOT, 'pyrddlgym_b200', 'csrc', 'librddl_b200.so')
-KEY = re.compile(r'UTC|UTMA|LDTM|STTM|SYNCS|ACQBULK|LDG\.E\.(EF\.)?128|STG\.E\.(EF\.)?128|LOP3|POPC|DMMA|DADD|DFMA|DMUL|MUFU|LDS|REDUX|SHFL|IMAD\.WIDE')
+KEY = re.compile(r'UTC|UTMA|LDTM|STTM|SYNCS|ACQBULK|LDGSTS|DEPBAR|LDG\.E\.(EF\.)?128|STG\.E\.(EF\.)?128|LOP3|POPC|DMMA|DADD|DFMA|DMUL|MUFU|LDS|REDUX|SHFL|IMAD\.WIDE')
 
 
 def histogram(sass):
@@ -47,6 +47,12 @@ for bn in (32, 64):
     fun = f'_Z16rddl_contract_tcILi{bn}EEv14CUtensorMap_stS0_Pdlii'
     write(f'r02_sass_contract_tc_bn{bn}.txt', f'rddl_contract_tc<{bn}> (csrc/rddl_contract_tc.cuh), sm_100a, from librddl_b200.so',
           sass_of(SO, fun), 'UTCHMMA = tcgen05.mma kind::f16, UTMALDG = cp.async.bulk.tensor, LDTM = tcgen05.ld, UTCBAR = tcgen05.commit')
+
+# 1b. FP64 DMMA contraction, cp.async pipeline (ahead of time)
+for bn in (32, 64):
+    fun = f'_Z17rddl_contract_f64ILi{bn}ELb1EEvPKdS1_PdliillS2_Pji'
+    write(f'r02_sass_contract_f64_async_bn{bn}.txt', f'rddl_contract_f64<{bn}, true> (csrc/rddl_contract.cuh), sm_100a, from librddl_b200.so',
+          sass_of(SO, fun), 'DMMA = mma.sync.m8n8k4.f64, LDGSTS = cp.async (16-byte copies global -> shared), LDGDEPBAR / DEPBAR = commit / wait group')
 
 # 2. specialised kernels: compile into a scratch cache and disassemble the cubins
 with tempfile.TemporaryDirectory() as tmp:
