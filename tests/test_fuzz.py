@@ -139,3 +139,15 @@ def test_fuzz_grid_cuda_plane_vs_scalar_vs_oracle(seed):
             assert torch.equal(c.fluent(f's{k}'), d.fluent(f's{k}'))
         assert torch.equal(rc, rd) and torch.equal(dc, dd)
     assert c.specialised_kernels >= 1 and d.specialised_kernels == 0, c.native.jit_error()
+    # bit-packed action input (packed_actions=True) on the same program: identical transitions, whichever build
+    if seed % 2 == 0:
+        e = BatchedSimulator(p, n_envs=N, seed=3, packed_actions=True, specialize=(None if seed % 4 == 0 else False))
+        f = BatchedSimulator(p, n_envs=N, seed=3)
+        for t in range(3):
+            acts = harness.random_actions(p, N, rng, p_bool=0.2)
+            _, re_, de = e.step(acts)
+            _, rf, df = f.step(acts)
+            for k in range(3):
+                assert torch.equal(e.fluent(f's{k}'), f.fluent(f's{k}'))
+            assert torch.equal(re_, rf) and torch.equal(de, df)
+            assert torch.equal(e.count_nondefault_actions(), f.count_nondefault_actions())
