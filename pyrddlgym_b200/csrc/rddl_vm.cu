@@ -1152,11 +1152,11 @@ static int run_plan(rddl_program* g, int plan, void* const* tensors, const doubl
       bool async = wsn == 1 && (K & 1) == 0 && (N & 1) == 0 && (wsk & 1) == 0 && ((uintptr_t)Xp & 15) == 0 && ((uintptr_t)Wp & 15) == 0;
       if (const char* e = getenv("RDDL_CONTRACT_ASYNC")) async = async && atoi(e) != 0;
       if (async) {
-        static bool attr_set = false;
-        if (!attr_set) {
+        static uint64_t attr_set = 0;          // per device (function attributes belong to the device's context)
+        if (!((attr_set >> (g->device & 63)) & 1ull)) {
           CK(cudaFuncSetAttribute(rddl_contract_f64<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_ASYNC_SMEM(64)));
           CK(cudaFuncSetAttribute(rddl_contract_f64<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_ASYNC_SMEM(32)));
-          attr_set = true;
+          attr_set |= 1ull << (g->device & 63);
         }
         if (bn == 64)
           rddl_contract_f64<64, true><<<grid, 128, CT_ASYNC_SMEM(64), stream>>>(Xp, Wp, Op, n_envs, N, K, wsk, wsn, g->d_ct_partial,

@@ -70,7 +70,8 @@ class BatchedRDDLEnv:
     def step(self, actions):
         """actions: name -> tensor / array [N, *shape] (missing action-fluents keep their defaults,
         like RDDLEnv.step's partial action dicts)."""
-        full = {name: self.sim._init[name].expand_as(self.sim._owned_actions[name]) for name in self.action_names}
+        full = {name: self.sim._init[name].expand((self.num_envs,) + tuple(self.sim._init[name].shape))
+                for name in self.action_names}
         full.update(actions or {})
         if self.clip_actions:
             for name, v in list(full.items()):
