@@ -1239,7 +1239,7 @@ class Lowerer:
                 c4 = np.full(int(rp4[-1]), sent, dtype='<u2' if u16 else '<i4')
                 src = np.asarray(cols[0], dtype='<i4')
                 pos = np.repeat(rp4[:-1] - rp[:-1], n) + np.arange(len(src))
-                c4[pos] = _bank_schedule(rp, src) if len(n) <= (1 << 16) else src
+                c4[pos] = _bank_schedule(rp, src) if len(n) <= 2048 else src      # (the fused env-tile kernels take scopes up to 1408)
                 row['rowptr4_off'] = self.pool_add(rp4.astype('<i4'), align=4)
                 row['col4_off'] = self.pool_add(c4.view('<i4'), align=4)
                 row['sentinel4'] = sent
