@@ -9,6 +9,12 @@
 #include "rddl_device.cuh"
 #include "level_static_data.inc"
 
+// envs a CTA of a fused env-tile kernel owns (the fused kernels further down; "level_static_data.inc" sets it)
+#ifndef FUSE_TE
+#define FUSE_TE 4
+#endif
+static_assert((256 / FUSE_TE) % 8 == 0, "pair steps walk blocks of 16 elements with 8 threads per env");
+
 struct VmStaticCtx {
   const VmArgs& A;
   const RddlLaunch& L;
@@ -21,6 +27,9 @@ struct VmStaticCtx {
   uint64_t* pre;        // values of the launch's preloaded LOADs (vm_preload), or null
   double* zpair;        // pair mode (fused env-tile kernels): second normals of the element pair's RANDNs, or null
   int half;             // pair mode: 0 = even element of the pair (draws both normals), 1 = odd element (takes the second)
+  double* fwd;          // fused kernels: staged copy the NEXT phase gathers from, filled by this phase's STOREs of fwd_tensor
+  int fwd_tensor;       //   (fuse_forward_tensor), or null / -1; element i of env slot fwd_e lives at fwd[i * FUSE_TE + fwd_e]
+  int fwd_e;
 };
 
 // Preloaded LOADs. A launch's program reads its fluents one LOAD at a time, each immediately before its
@@ -218,6 +227,11 @@ __device__ __forceinline__ void vm_seq(VmStaticCtx& c) {
       int pc = 0;
       vm_exec_one<RDDL_MAX_REGS, (int)op>(c.A, P, c.L, c.env, c.step, c.idx, c.redval, c.r, nullptr, nullptr, nullptr, pc, raw,
                                  nullptr, 0);
+      if constexpr (op == OP_STORE) {
+        // store forwarding: the vector the next phase of a fused kernel gathers from goes straight into its
+        // staged copy (same value as the global store above; that phase then skips re-reading it)
+        if (c.fwd && kAddrs[imm].tensor == c.fwd_tensor) c.fwd[c.idx[0] * FUSE_TE + c.fwd_e] = as_f(c.r[ra]);
+      }
       vm_seq<BASE, PC + 1, END>(c);
     }
   }
@@ -232,7 +246,7 @@ struct LevelStaticExec {
     VmStage st = {nullptr, -1, 0, 1, 0, 0};
     if (stage) { st = *stage; st.base = env * level_stage_elems(LI); }
     uint64_t pre[kMaxPreload];
-    VmStaticCtx c = {A, kLaunches[LI], env, A.step, idx, redval, r, stage ? &st : nullptr, pre, nullptr, 0};
+    VmStaticCtx c = {A, kLaunches[LI], env, A.step, idx, redval, r, stage ? &st : nullptr, pre, nullptr, 0, nullptr, -1, 0};
     vm_preload<kLaunches[LI].pc_begin, kLaunches[LI].pc_begin, kLaunches[LI].pc_end>(c);
     vm_seq<kLaunches[LI].pc_begin, kLaunches[LI].pc_begin, kLaunches[LI].pc_end>(c);
   }
@@ -279,10 +293,6 @@ __device__ __forceinline__ void level_static_kernel(const VmArgs& A) {
 // Same instruction bodies and element order as the unfused kernels; only the order in which a
 // per-env reduction combines its partial results differs (float sums agree to rounding).
 // ---------------------------------------------------------------------------------------
-#ifndef FUSE_TE
-#define FUSE_TE 4
-#endif
-static_assert((256 / FUSE_TE) % 8 == 0, "pair steps walk blocks of 16 elements with 8 threads per env");
 #ifndef FUSE_MINB
 #define FUSE_MINB 4
 #endif
@@ -310,9 +320,33 @@ __host__ __device__ constexpr int64_t fuse_stage_elems(int li) {
   return 0;
 }
 
-template <int LI>
+// Store forwarding between the phases of a fused kernel: the tensor launch li + 1 stages, when launch li (which must
+// not use the staging buffer itself) writes every element of it with exactly one STORE outside loops at the element's
+// own index -- that STORE then also fills the staged copy, and launch li + 1 skips its copy loop. -1: none.
+__host__ __device__ constexpr int fuse_forward_tensor(int li, int last) {
+  if (li + 1 > last || li + 1 >= kNumLaunch) return -1;
+  const int t = fuse_stage_tensor(li + 1);
+  if (t < 0 || fuse_stage_tensor(li) >= 0) return -1;
+  if (kLaunches[li].rank != 1 || kLaunches[li].E != fuse_stage_elems(li + 1)) return -1;
+  int n = 0, depth = 0;
+  for (int q = kLaunches[li].pc_begin; q < kLaunches[li].pc_end && q < kNumInsn; q += level_insn_len(q)) {
+    const uint32_t o = kInsnWords[q][0] & 0xff;
+    if (o == OP_LOOP || o == OP_CSRLOOP) ++depth;
+    if (o == OP_ENDLOOP || o == OP_CSREND) --depth;
+    if (o == OP_STORE && kAddrs[kInsnWords[q][3]].tensor == t) {
+      if (depth != 0 || !level_addr_is_flat_index(kAddrs[kInsnWords[q][3]], kLaunches[li])) return -1;
+      ++n;
+    }
+  }
+  return n == 1 ? t : -1;
+}
+
+template <int LI, int FIRST, int LAST>
 __device__ __forceinline__ void fused_phase(const VmArgs& A, double* staged, uint64_t (*sm)[8][FUSE_TE]) {
   constexpr RddlLaunch L = kLaunches[LI];
+  constexpr int FWD = fuse_forward_tensor(LI, LAST);                                  // filled for the next phase
+  constexpr bool FILLED = LI > FIRST && fuse_forward_tensor(LI - 1, LAST) >= 0 &&     // filled by the previous one
+                          fuse_forward_tensor(LI - 1, LAST) == fuse_stage_tensor(LI);
   const int tid = threadIdx.x;
   const int e = tid % FUSE_TE;
   const int64_t env0 = (int64_t)blockIdx.x * FUSE_TE, env = env0 + e;
@@ -324,8 +358,10 @@ __device__ __forceinline__ void fused_phase(const VmArgs& A, double* staged, uin
     const double* src = reinterpret_cast<const double*>(A.tensors[fuse_stage_tensor(LI)]);
     // (thread t always copies env t % FUSE_TE: 256 is a multiple of FUSE_TE; 32-bit indices, four loads in flight)
     const double* srce = src + (env_ok ? env * n : 0);
+    if constexpr (!FILLED) {
 #pragma unroll 4
-    for (int i = tid; i < (int)(n * FUSE_TE); i += 256) staged[i] = env_ok ? srce[(uint32_t)i / FUSE_TE] : 0.0;
+      for (int i = tid; i < (int)(n * FUSE_TE); i += 256) staged[i] = env_ok ? srce[(uint32_t)i / FUSE_TE] : 0.0;
+    }
     if (tid < FUSE_TE) staged[n * FUSE_TE + tid] = 0.0;      // the zeros the padded CSR rows point at
     __syncthreads();
     st = VmStage{staged, fuse_stage_tensor(LI), env * n, FUSE_TE, e, 1};
@@ -361,7 +397,7 @@ __device__ __forceinline__ void fused_phase(const VmArgs& A, double* staged, uin
           uint64_t r[L.nregs > 0 ? L.nregs : 1];
           uint64_t pre[kMaxPreload];
           VmStaticCtx c = {A, kLaunches[LI], env, A.step, idx, redval, r, st.tensor >= 0 ? &st : nullptr, pre,
-                           EPS == 2 ? zpair : nullptr, half};
+                           EPS == 2 ? zpair : nullptr, half, FWD >= 0 ? staged : nullptr, FWD, e};
           vm_preload<L.pc_begin, L.pc_begin, L.pc_end>(c);
           vm_seq<L.pc_begin, L.pc_begin, L.pc_end>(c);
         }
@@ -393,11 +429,11 @@ __device__ __forceinline__ void fused_phase(const VmArgs& A, double* staged, uin
   __syncthreads();      // launch boundary of the unfused plan: this CTA's stores are visible to its next phase
 }
 
-template <int FIRST, int COUNT>
+template <int LI, int FIRST, int LAST>
 __device__ __forceinline__ void fused_phases(const VmArgs& A, double* staged, uint64_t (*sm)[8][FUSE_TE]) {
-  if constexpr (COUNT > 0) {
-    fused_phase<FIRST>(A, staged, sm);
-    fused_phases<FIRST + 1, COUNT - 1>(A, staged, sm);
+  if constexpr (LI <= LAST) {
+    fused_phase<LI, FIRST, LAST>(A, staged, sm);
+    fused_phases<LI + 1, FIRST, LAST>(A, staged, sm);
   }
 }
 
@@ -413,7 +449,7 @@ __host__ __device__ constexpr int64_t fuse_group_stage(int first, int count) {
   extern "C" __global__ void __launch_bounds__(256, FUSE_MINB) rddl_level_fused_##FIRST(const __grid_constant__ VmArgs A) { \
     __shared__ double staged[fuse_group_stage(FIRST, COUNT)];                                                    \
     __shared__ uint64_t sm[RDDL_MAX_RED][8][FUSE_TE];                                                             \
-    fused_phases<FIRST, COUNT>(A, staged, sm);                                                                   \
+    fused_phases<FIRST, FIRST, FIRST + COUNT - 1>(A, staged, sm);                                                \
   }
 #ifdef PS_FUSED
 PS_FUSED(RDDL_FUSED_KERNEL)
