@@ -405,11 +405,12 @@ def test_batched_evaluate_random_and_noop_policies():
     assert stw['max'] <= 0.0 and stw['mean'] < 0.0
 
 
-@pytest.mark.parametrize('X,N', [(512, 70), (100, 129), (40, 5)])
+@pytest.mark.parametrize('X,N', [(512, 70), (100, 129), (40, 5), (33, 7), (257, 40)])
 def test_fp64_tensor_core_contraction_vs_scalar_path_and_oracle(X, N):
     """sum_{?a} W(?a,?b) * x(?a) on the FP64 tensor pipe (csrc/rddl_contract.cuh) against the
-    scalar SUMLOOP path (sequential float64 sum) and the NumPy oracle; ragged sizes exercise the
-    zero-filled edge tiles. Only the summation order differs: 1e-9 relative is ample."""
+    scalar SUMLOOP path (float64 sum) and the NumPy oracle; ragged sizes exercise the zero-filled edge
+    tiles, small batches the split-K fix-up, even sizes the cp.async operand ring and odd ones (33, 257:
+    no 16-byte copies) the register-staged loop. Only the summation order differs: 1e-9 relative is ample."""
     import torch
     p = workloads.load_program(workloads.pair_contraction(X))
     a = _make(p, N, seed=2)
