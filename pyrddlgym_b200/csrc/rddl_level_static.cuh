@@ -119,12 +119,19 @@ __device__ __forceinline__ void vm_preload(VmStaticCtx& c) {
     if constexpr (level_preload_ok(BASE, PC)) {
       constexpr uint4 raw = {kInsnWords[PC][0], kInsnWords[PC][1], kInsnWords[PC][2], kInsnWords[PC][3]};
       const VmPools P = {kConsts, kAddrs, kRedSlots, kRedOff, kCsrs, kDT, kMayPolicy};
-      int pc = 0;
-      // (the LOAD's own instruction body, into its destination register -- dead at this point of the program --
-      // and from there into the preload slot)
-      vm_exec_one<RDDL_MAX_REGS, (int)OP_LOAD>(c.A, P, c.L, c.env, c.step, c.idx, c.redval, c.r, nullptr, nullptr, nullptr, pc,
-                                               raw, nullptr, 0);
-      c.pre[level_preload_slot(BASE, PC)] = c.r[raw.x >> 16];
+      constexpr RddlAddr ad = kAddrs[raw.w];
+      if (c.stage && c.stage->pad && ad.tensor == c.stage->tensor && ad.naxis == 1 && ad.coef[0] == 1 && ad.c0 == 0 &&
+          ad.nreg == 0) {
+        // the element's own entry of the vector the CTA has staged whole: from shared memory, not from L1 / L2
+        c.pre[level_preload_slot(BASE, PC)] = from_f(c.stage->ptr[c.idx[ad.axis[0]] * c.stage->mul + c.stage->add]);
+      } else {
+        int pc = 0;
+        // (the LOAD's own instruction body, into its destination register -- dead at this point of the program --
+        // and from there into the preload slot)
+        vm_exec_one<RDDL_MAX_REGS, (int)OP_LOAD>(c.A, P, c.L, c.env, c.step, c.idx, c.redval, c.r, nullptr, nullptr, nullptr, pc,
+                                                 raw, nullptr, 0);
+        c.pre[level_preload_slot(BASE, PC)] = c.r[raw.x >> 16];
+      }
     }
     vm_preload<BASE, PC + level_insn_len(PC), END>(c);
   }
