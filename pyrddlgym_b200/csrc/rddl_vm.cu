@@ -1103,7 +1103,9 @@ static int run_plan(rddl_program* g, int plan, void* const* tensors, const doubl
     const int64_t blocks = groups * L.chunks;
     if (blocks > 0x7fffffffll) { g->err = "grid too large"; return RDDL_ERR_ARG; }
     rddl_program::Timed tm;
-    if (g->profiling) {
+    // (bounded: a caller that switches profiling on and never reads it stops accumulating events after 64 Ki launches)
+    const bool timing = g->profiling && g->timed.size() < (size_t)(1 << 16);
+    if (timing) {
       tm.launch = (int)(&L - g->launches.data());
       CK(cudaEventCreate(&tm.e0));
       CK(cudaEventCreate(&tm.e1));
@@ -1211,7 +1213,7 @@ static int run_plan(rddl_program* g, int plan, void* const* tensors, const doubl
     else rddl_level_interp<RDDL_MAX_REGS><<<(unsigned)blocks, 256, 0, stream>>>(A);
     ++g->launches_issued;
     CK(cudaGetLastError());
-    if (g->profiling) {
+    if (timing) {
       CK(cudaEventRecord(tm.e1, stream));
       g->timed.push_back(tm);
     }
